@@ -1,0 +1,483 @@
+"""CPU oracle for the RepText denoising step.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module.  The product package
+(``reptext_b200``) never does; it fails loudly when its CUDA library is missing.
+
+PARITY UNPINNED.  The reference (``RepText/*.py``) ships no tests, fixtures or
+golden vectors, and the arithmetic of its hot path lives in the un-vendored
+third-party package ``diffusers`` (not pinned by ``RepText/requirements.txt``;
+the authors' run log shows 0.36.0, ``main.ipynb:390``).  ``diffusers`` is not
+installable here (no network), so this file restates its published algorithm
+(``models/transformers/transformer_flux.py``, ``models/embeddings.py``,
+``models/normalization.py``, ``schedulers/scheduling_flow_match_euler_discrete.py``
+at 0.36.0) and anchors on the reference's own call sites:
+
+* ``RepText/controlnet_flux.py:216-413``  -> :func:`controlnet_forward`
+* ``RepText/pipeline_flux_controlnet.py:1017-1130`` -> :func:`denoise_t2i`
+* ``RepText/pipeline_flux_controlnet_inpaint.py:1140-1295`` -> :func:`denoise_inpaint`
+* ``RepText/pipeline_flux_controlnet.py:78-88, 535-570, 948-967, 1007-1013``
+  -> :func:`calculate_shift`, :func:`prepare_latent_image_ids`, :func:`pack_latents`,
+  :func:`unpack_latents`, :func:`make_sigmas`, :func:`regional_mask`
+* ``RepText/pipeline_flux_controlnet_inpaint.py:635-649`` -> :func:`glyph_latent_init`
+
+The block math is cross-checked against an independent implementation that IS on
+this box (torchtitan's BFL blocks) in ``tests/test_oracle_crosscheck.py`` and
+against the self-consistency invariants of SURVEY.md A.10 in
+``tests/test_oracle_invariants.py``.
+
+Everything is functional: a model is a ``dict[str, Tensor]`` with the diffusers
+state-dict key names plus a small config dict.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+
+# --------------------------------------------------------------------------- #
+# helpers
+# --------------------------------------------------------------------------- #
+def _lin(sd: SD, name: str, x: Tensor) -> Tensor:
+    return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
+
+
+def _ln(x: Tensor) -> Tensor:
+    # nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+    return F.layer_norm(x, (x.shape[-1],), None, None, 1e-6)
+
+
+def _rms(x: Tensor, w: Tensor) -> Tensor:
+    # torch.nn.RMSNorm(head_dim, eps=1e-6) as used by FluxAttention (diffusers >= 0.35)
+    return F.rms_norm(x, (x.shape[-1],), w, 1e-6)
+
+
+# --------------------------------------------------------------------------- #
+# A.1  timestep / guidance / pooled-text embedding
+# --------------------------------------------------------------------------- #
+def timestep_sinusoid(t: Tensor, dim: int = 256) -> Tensor:
+    """diffusers ``get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0)``."""
+    half = dim // 2
+    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half
+    emb = t[:, None].float() * torch.exp(exponent)[None, :]
+    return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+
+
+def time_text_embed(sd: SD, prefix: str, timestep: Tensor, guidance: Optional[Tensor], pooled: Tensor) -> Tensor:
+    """``CombinedTimestep(Guidance)TextProjEmbeddings.forward`` (controlnet_flux.py:66-71, :287-291)."""
+    p = prefix + "time_text_embed."
+    tp = timestep_sinusoid(timestep).to(pooled.dtype)
+    e = _lin(sd, p + "timestep_embedder.linear_2", F.silu(_lin(sd, p + "timestep_embedder.linear_1", tp)))
+    if guidance is not None:
+        gp = timestep_sinusoid(guidance).to(pooled.dtype)
+        e = e + _lin(sd, p + "guidance_embedder.linear_2", F.silu(_lin(sd, p + "guidance_embedder.linear_1", gp)))
+    pe = _lin(sd, p + "text_embedder.linear_2", F.silu(_lin(sd, p + "text_embedder.linear_1", pooled)))
+    return e + pe
+
+
+# --------------------------------------------------------------------------- #
+# A.2  3-axis RoPE
+# --------------------------------------------------------------------------- #
+def rope_table(ids: Tensor, axes_dim: Sequence[int], theta: float = 10000.0) -> Tuple[Tensor, Tensor]:
+    """``FluxPosEmbed.forward`` (controlnet_flux.py:65, :316-317): float64 outer product,
+    cos/sin repeat_interleave(2), cast to float32, concatenated over the axes."""
+    pos = ids.float()
+    cos_out, sin_out = [], []
+    for i, d in enumerate(axes_dim):
+        freqs = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float64, device=ids.device)[: d // 2] / d))
+        ang = torch.outer(pos[:, i], freqs)  # float32 x float64 -> float64
+        cos_out.append(ang.cos().repeat_interleave(2, dim=1).float())
+        sin_out.append(ang.sin().repeat_interleave(2, dim=1).float())
+    return torch.cat(cos_out, dim=-1), torch.cat(sin_out, dim=-1)
+
+
+def apply_rope(x: Tensor, rope: Tuple[Tensor, Tensor]) -> Tensor:
+    """``apply_rotary_emb(x, freqs, sequence_dim=1)`` on ``[B,S,H,hd]``: interleaved pairs."""
+    cos, sin = rope
+    cos = cos[None, :, None, :]
+    sin = sin[None, :, None, :]
+    xr, xi = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)
+    rot = torch.stack([-xi, xr], dim=-1).flatten(3)
+    return (x.float() * cos + rot.float() * sin).to(x.dtype)
+
+
+def _attention(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
+    """A.5: native SDPA on [B,H,S,hd], no mask, scale 1/sqrt(hd); returns [B,S,H*hd]."""
+    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
+    return o.transpose(1, 2).flatten(2, 3).to(q.dtype)
+
+
+# --------------------------------------------------------------------------- #
+# A.3  FluxTransformerBlock (double stream)
+# --------------------------------------------------------------------------- #
+def double_block(sd: SD, p: str, x: Tensor, c: Tensor, temb: Tensor, rope, heads: int) -> Tuple[Tensor, Tensor]:
+    """Returns (encoder_hidden_states, hidden_states) like diffusers."""
+    se = F.silu(temb)
+    sh1, sc1, g1, sh2, sc2, g2 = _lin(sd, p + "norm1.linear", se).chunk(6, dim=1)
+    csh1, csc1, cg1, csh2, csc2, cg2 = _lin(sd, p + "norm1_context.linear", se).chunk(6, dim=1)
+    xn = _ln(x) * (1 + sc1[:, None]) + sh1[:, None]
+    cn = _ln(c) * (1 + csc1[:, None]) + csh1[:, None]
+
+    def hv(t):
+        return t.unflatten(-1, (heads, -1))
+
+    q = _rms(hv(_lin(sd, p + "attn.to_q", xn)), sd[p + "attn.norm_q.weight"])
+    k = _rms(hv(_lin(sd, p + "attn.to_k", xn)), sd[p + "attn.norm_k.weight"])
+    v = hv(_lin(sd, p + "attn.to_v", xn))
+    cq = _rms(hv(_lin(sd, p + "attn.add_q_proj", cn)), sd[p + "attn.norm_added_q.weight"])
+    ck = _rms(hv(_lin(sd, p + "attn.add_k_proj", cn)), sd[p + "attn.norm_added_k.weight"])
+    cv = hv(_lin(sd, p + "attn.add_v_proj", cn))
+    Q = torch.cat([cq, q], dim=1)
+    K = torch.cat([ck, k], dim=1)
+    V = torch.cat([cv, v], dim=1)
+    if rope is not None:
+        Q, K = apply_rope(Q, rope), apply_rope(K, rope)
+    o = _attention(Q, K, V)
+    T = c.shape[1]
+    co, o = o[:, :T], o[:, T:]
+    o = _lin(sd, p + "attn.to_out.0", o)
+    co = _lin(sd, p + "attn.to_add_out", co)
+
+    x = x + g1[:, None] * o
+    xn2 = _ln(x) * (1 + sc2[:, None]) + sh2[:, None]
+    ff = _lin(sd, p + "ff.net.2", F.gelu(_lin(sd, p + "ff.net.0.proj", xn2), approximate="tanh"))
+    x = x + g2[:, None] * ff
+
+    c = c + cg1[:, None] * co
+    cn2 = _ln(c) * (1 + csc2[:, None]) + csh2[:, None]
+    cff = _lin(sd, p + "ff_context.net.2", F.gelu(_lin(sd, p + "ff_context.net.0.proj", cn2), approximate="tanh"))
+    c = c + cg2[:, None] * cff
+    if c.dtype == torch.float16:
+        c = c.clip(-65504, 65504)
+    return c, x
+
+
+# --------------------------------------------------------------------------- #
+# A.4  FluxSingleTransformerBlock
+# --------------------------------------------------------------------------- #
+def single_block_joint(sd: SD, p: str, h: Tensor, temb: Tensor, rope, heads: int) -> Tensor:
+    """Pre-0.35 call shape used by controlnet_flux.py:376-380: joint [c;x] in, joint out."""
+    sh, sc, g = _lin(sd, p + "norm.linear", F.silu(temb)).chunk(3, dim=1)
+    hn = _ln(h) * (1 + sc[:, None]) + sh[:, None]
+    m = F.gelu(_lin(sd, p + "proj_mlp", hn), approximate="tanh")
+
+    def hv(t):
+        return t.unflatten(-1, (heads, -1))
+
+    q = _rms(hv(_lin(sd, p + "attn.to_q", hn)), sd[p + "attn.norm_q.weight"])
+    k = _rms(hv(_lin(sd, p + "attn.to_k", hn)), sd[p + "attn.norm_k.weight"])
+    v = hv(_lin(sd, p + "attn.to_v", hn))
+    if rope is not None:
+        q, k = apply_rope(q, rope), apply_rope(k, rope)
+    a = _attention(q, k, v)
+    out = h + g[:, None] * _lin(sd, p + "proj_out", torch.cat([a, m], dim=2))
+    if out.dtype == torch.float16:
+        out = out.clip(-65504, 65504)
+    return out
+
+
+def single_block(sd: SD, p: str, x: Tensor, c: Tensor, temb: Tensor, rope, heads: int) -> Tuple[Tensor, Tensor]:
+    """diffusers >= 0.35 call shape: (hidden, encoder) -> (encoder, hidden)."""
+    T = c.shape[1]
+    h = single_block_joint(sd, p, torch.cat([c, x], dim=1), temb, rope, heads)
+    return h[:, :T], h[:, T:]
+
+
+# --------------------------------------------------------------------------- #
+# a1: FluxControlNetModel.forward  (RepText/controlnet_flux.py:216-413)
+# --------------------------------------------------------------------------- #
+def controlnet_forward(
+    sd: SD,
+    cfg: dict,
+    hidden_states: Tensor,
+    controlnet_cond: Tensor,
+    conditioning_scale: float,
+    encoder_hidden_states: Tensor,
+    pooled_projections: Tensor,
+    timestep: Tensor,
+    img_ids: Tensor,
+    txt_ids: Tensor,
+    guidance: Optional[Tensor],
+) -> Tuple[Optional[List[Tensor]], Optional[List[Tensor]]]:
+    heads = cfg["num_attention_heads"]
+    h = _lin(sd, "x_embedder", hidden_states)                        # :277
+    h = h + _lin(sd, "controlnet_x_embedder", controlnet_cond)      # :280
+    timestep = timestep.to(h.dtype) * 1000                           # :282
+    if guidance is not None and cfg.get("guidance_embeds", False):
+        guidance = guidance.to(h.dtype) * 1000                       # :284
+    else:
+        guidance = None
+    temb = time_text_embed(sd, "", timestep, guidance, pooled_projections)   # :287-291
+    c = _lin(sd, "context_embedder", encoder_hidden_states)         # :292
+    if txt_ids.ndim == 3:
+        txt_ids = txt_ids[0]
+    if img_ids.ndim == 3:
+        img_ids = img_ids[0]
+    rope = rope_table(torch.cat((txt_ids, img_ids), dim=0), cfg["axes_dims_rope"])  # :316-317
+
+    block_samples = []
+    for i in range(cfg["num_layers"]):                               # :320-349
+        c, h = double_block(sd, f"transformer_blocks.{i}.", h, c, temb, rope, heads)
+        block_samples.append(h)
+    T = c.shape[1]
+    hj = torch.cat([c, h], dim=1)                                    # :351
+    single_samples = []
+    for j in range(cfg["num_single_layers"]):                        # :354-381
+        hj = single_block_joint(sd, f"single_transformer_blocks.{j}.", hj, temb, rope, heads)
+        single_samples.append(hj[:, T:])
+    cb = [_lin(sd, f"controlnet_blocks.{i}", s) for i, s in enumerate(block_samples)]           # :385-387
+    cs = [_lin(sd, f"controlnet_single_blocks.{j}", s) for j, s in enumerate(single_samples)]  # :390-392
+    cb = [s * conditioning_scale for s in cb]                        # :395
+    cs = [s * conditioning_scale for s in cs]                        # :396
+    return (cb if cb else None), (cs if cs else None)                # :398-408
+
+
+# --------------------------------------------------------------------------- #
+# a12 / A.6: FluxTransformer2DModel.forward (diffusers 0.36.0, called at
+# RepText/pipeline_flux_controlnet.py:1092-1104)
+# --------------------------------------------------------------------------- #
+def transformer_forward(
+    sd: SD,
+    cfg: dict,
+    hidden_states: Tensor,
+    encoder_hidden_states: Tensor,
+    pooled_projections: Tensor,
+    timestep: Tensor,
+    img_ids: Tensor,
+    txt_ids: Tensor,
+    guidance: Optional[Tensor],
+    controlnet_block_samples: Optional[List[Tensor]] = None,
+    controlnet_single_block_samples: Optional[List[Tensor]] = None,
+) -> Tensor:
+    heads = cfg["num_attention_heads"]
+    x = _lin(sd, "x_embedder", hidden_states)
+    timestep = timestep.to(x.dtype) * 1000
+    if guidance is not None and cfg.get("guidance_embeds", False):
+        guidance = guidance.to(x.dtype) * 1000
+    else:
+        guidance = None
+    temb = time_text_embed(sd, "", timestep, guidance, pooled_projections)
+    c = _lin(sd, "context_embedder", encoder_hidden_states)
+    if txt_ids.ndim == 3:
+        txt_ids = txt_ids[0]
+    if img_ids.ndim == 3:
+        img_ids = img_ids[0]
+    rope = rope_table(torch.cat((txt_ids, img_ids), dim=0), cfg["axes_dims_rope"])
+
+    nl, ns = cfg["num_layers"], cfg["num_single_layers"]
+    for i in range(nl):
+        c, x = double_block(sd, f"transformer_blocks.{i}.", x, c, temb, rope, heads)
+        if controlnet_block_samples is not None:
+            interval = int(np.ceil(nl / len(controlnet_block_samples)))
+            x = x + controlnet_block_samples[i // interval]
+    for j in range(ns):
+        c, x = single_block(sd, f"single_transformer_blocks.{j}.", x, c, temb, rope, heads)
+        if controlnet_single_block_samples is not None:
+            interval = int(np.ceil(ns / len(controlnet_single_block_samples)))
+            x = x + controlnet_single_block_samples[j // interval]
+    # AdaLayerNormContinuous: chunk order is (scale, shift)
+    emb = _lin(sd, "norm_out.linear", F.silu(temb).to(x.dtype))
+    scale, shift = emb.chunk(2, dim=1)
+    x = _ln(x) * (1 + scale)[:, None, :] + shift[:, None, :]
+    return _lin(sd, "proj_out", x)
+
+
+# --------------------------------------------------------------------------- #
+# A.7: FlowMatchEulerDiscreteScheduler (FLUX.1-dev scheduler_config.json)
+# --------------------------------------------------------------------------- #
+SCHEDULER_CONFIG = dict(
+    num_train_timesteps=1000, shift=3.0, use_dynamic_shifting=True,
+    base_shift=0.5, max_shift=1.15, base_image_seq_len=256, max_image_seq_len=4096,
+)
+
+
+def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shift=0.5, max_shift=1.16):
+    """pipeline_flux_controlnet.py:78-88 (verbatim arithmetic)."""
+    m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    b = base_shift - m * base_seq_len
+    return image_seq_len * m + b
+
+
+def make_sigmas(num_inference_steps: int, image_seq_len: int, cfg: dict = SCHEDULER_CONFIG) -> Tuple[Tensor, Tensor]:
+    """pipeline_flux_controlnet.py:948-967 + scheduler.set_timesteps(sigmas=, mu=).
+    Returns (timesteps[n] fp32, sigmas[n+1] fp32 with trailing 0)."""
+    sig = np.linspace(1.0, 1 / num_inference_steps, num_inference_steps).astype(np.float32)
+    mu = calculate_shift(image_seq_len, cfg["base_image_seq_len"], cfg["max_image_seq_len"],
+                         cfg["base_shift"], cfg["max_shift"])
+    sig = math.exp(mu) / (math.exp(mu) + (1 / sig - 1) ** 1.0)
+    sig = torch.from_numpy(np.asarray(sig)).to(torch.float32)
+    timesteps = sig * cfg["num_train_timesteps"]
+    sigmas = torch.cat([sig, torch.zeros(1, dtype=torch.float32)])
+    return timesteps, sigmas
+
+
+def euler_step(model_output: Tensor, sigma: Tensor, sigma_next: Tensor, sample: Tensor) -> Tensor:
+    """scheduler.step (pipeline_flux_controlnet.py:1109).  NB torch type promotion: the product of the
+    0-dim fp32 ``dt`` and a bf16 ``model_output`` is a bf16 tensor (rounded before the fp32 add).  On
+    CPU torch also rounds ``dt`` itself to bf16 first; on CUDA (sigmas live on the CPU in diffusers, so
+    ``dt`` is a host scalar) it stays fp32.  In fp32 all forms coincide."""
+    sample = sample.to(torch.float32)
+    prev = sample + (sigma_next - sigma) * model_output
+    return prev.to(model_output.dtype)
+
+
+# --------------------------------------------------------------------------- #
+# a15: pack / unpack / ids ; a11 regional mask ; a17 glyph init
+# --------------------------------------------------------------------------- #
+def prepare_latent_image_ids(height: int, width: int, dtype=torch.float32) -> Tensor:
+    """pipeline_flux_controlnet.py:535-546 (height/width are LATENT sizes, i.e. 2*(px//16))."""
+    ids = torch.zeros(height // 2, width // 2, 3)
+    ids[..., 1] = ids[..., 1] + torch.arange(height // 2)[:, None]
+    ids[..., 2] = ids[..., 2] + torch.arange(width // 2)[None, :]
+    return ids.reshape(-1, 3).to(dtype)
+
+
+def pack_latents(latents: Tensor) -> Tensor:
+    """pipeline_flux_controlnet.py:550-555."""
+    b, ch, h, w = latents.shape
+    latents = latents.view(b, ch, h // 2, 2, w // 2, 2).permute(0, 2, 4, 1, 3, 5)
+    return latents.reshape(b, (h // 2) * (w // 2), ch * 4)
+
+
+def unpack_latents(latents: Tensor, height: int, width: int, vae_scale_factor: int = 16) -> Tensor:
+    """pipeline_flux_controlnet.py:559-570 (height/width are PIXEL sizes)."""
+    b, n, ch = latents.shape
+    h, w = height // vae_scale_factor, width // vae_scale_factor
+    latents = latents.view(b, h, w, ch // 4, 2, 2).permute(0, 3, 1, 4, 2, 5)
+    return latents.reshape(b, ch // 4, h * 2, w * 2)
+
+
+def regional_mask(mask_u8: np.ndarray, dtype=torch.float32) -> Tensor:
+    """pipeline_flux_controlnet.py:1007-1013: 0/255 box -> /255 -> bilinear x1/16 -> [1,N,1]."""
+    region = torch.from_numpy(np.array(mask_u8)) / 255.0
+    m = F.interpolate(region[None, None], scale_factor=1 / 16, mode="bilinear").reshape([1, -1, 1])
+    return m.to(dtype)
+
+
+def glyph_latent_init(image: Tensor, image_latents: Tensor, noise: Tensor, live: bool) -> Tensor:
+    """prepare_latents_reptext.  ``live=True`` is the inpaint pipeline
+    (pipeline_flux_controlnet_inpaint.py:635-649: ``noise = result``); ``live=False`` is the T2I
+    pipeline, which builds ``result`` and then packs ``noise`` (pipeline_flux_controlnet.py:643-656)."""
+    gm = (image > 0).any(dim=1, keepdim=True).repeat(1, 16, 1, 1).float()
+    gm = F.interpolate(gm, size=(noise.shape[-2], noise.shape[-1]), mode="bilinear", align_corners=False)
+    gm[gm > 0] = 1
+    gm[gm < 0] = 0
+    gm = gm > 0
+    result = torch.zeros_like(noise)
+    result[gm] = 0.10 * image_latents[gm] + 1.00 * noise[gm]
+    result[~gm] = noise[~gm]
+    return pack_latents(result if live else noise)
+
+
+# --------------------------------------------------------------------------- #
+# a10: T2I denoise loop body  (RepText/pipeline_flux_controlnet.py:1017-1130)
+# --------------------------------------------------------------------------- #
+def denoise_t2i(
+    tr_sd: SD, tr_cfg: dict, cn_sd: SD, cn_cfg: dict,
+    latents: Tensor, prompt_embeds: Tensor, pooled: Tensor,
+    control_image_list: List[Tensor], control_mask_list: List[Tensor],
+    text_ids: Tensor, img_ids: Tensor,
+    timesteps: Tensor, sigmas: Tensor,
+    guidance_scale: float, conditioning_scale: float = 1.0, conditioning_step: int = 30,
+    callback=None,
+) -> Tensor:
+    for i, t in enumerate(timesteps):
+        timestep = t.expand(latents.shape[0]).to(latents.dtype)                       # :1025
+        guidance = None
+        if tr_cfg.get("guidance_embeds", False):
+            guidance = torch.tensor([guidance_scale]).expand(latents.shape[0])        # :1029-1030
+        blk = sgl = None
+        for ci in range(len(control_image_list)):                                     # :1037
+            mask = control_mask_list[ci] if len(control_mask_list) > 0 else None
+            if i < conditioning_step:                                                 # :1042
+                b, s = controlnet_forward(cn_sd, cn_cfg, latents, control_image_list[ci], conditioning_scale,
+                                          prompt_embeds, pooled, timestep / 1000, img_ids, text_ids, guidance)
+            else:
+                b, s = None, None
+            if b is not None:                                                         # :1060-1064
+                b = [mask * x.to(latents.dtype) if mask is not None else x.to(latents.dtype) for x in b]
+            if s is not None:                                                         # :1065-1069
+                s = [mask * x.to(latents.dtype) if mask is not None else x.to(latents.dtype) for x in s]
+            if ci == 0:                                                               # :1072-1087
+                blk, sgl = b, s
+            else:
+                if b is not None and blk is not None:
+                    blk = [u + v for u, v in zip(blk, b)]
+                if s is not None and sgl is not None:
+                    sgl = [u + v for u, v in zip(sgl, s)]
+        noise_pred = transformer_forward(tr_sd, tr_cfg, latents, prompt_embeds, pooled, timestep / 1000,
+                                         img_ids, text_ids, guidance, blk, sgl)      # :1092-1104
+        latents = euler_step(noise_pred, sigmas[i], sigmas[i + 1], latents)           # :1109
+        if callback is not None:
+            callback(i, t, latents)                                                   # :1116-1123
+    return latents
+
+
+# --------------------------------------------------------------------------- #
+# a16: inpaint denoise loop body (RepText/pipeline_flux_controlnet_inpaint.py:1140-1295)
+# --------------------------------------------------------------------------- #
+def denoise_inpaint(
+    tr_sd: SD, tr_cfg: dict, cn_sd: SD, cn_cfg: dict, cni_sd: SD, cni_cfg: dict,
+    latents: Tensor, prompt_embeds: Tensor, pooled: Tensor,          # already cat([neg, pos]) when CFG (:1033-1035)
+    control_image_list: List[Tensor], control_mask_list: List[Tensor],
+    control_image_inpaint: Tensor,
+    text_ids: Tensor, img_ids: Tensor,
+    timesteps: Tensor, sigmas: Tensor,
+    guidance_scale: float, true_guidance_scale: float = 3.5,
+    conditioning_scale: float = 1.0, conditioning_step: int = 30, conditioning_scale_inpaint: float = 1.0,
+    callback=None,
+) -> Tensor:
+    do_cfg = guidance_scale > 1                                                      # :241-242
+    for i, t in enumerate(timesteps):
+        timestep = t.expand(latents.shape[0]).to(latents.dtype)                       # :1148
+        guidance = None
+        if tr_cfg.get("guidance_embeds", False):
+            guidance = torch.tensor([guidance_scale]).expand(latents.shape[0])        # :1152-1153
+        blk = sgl = None
+        for ci in range(len(control_image_list)):                                     # :1160
+            mask = control_mask_list[ci] if len(control_mask_list) > 0 else None
+            if i < conditioning_step:
+                b, s = controlnet_forward(cn_sd, cn_cfg, latents, control_image_list[ci], conditioning_scale,
+                                          prompt_embeds, pooled, timestep / 1000, img_ids, text_ids, guidance)
+            else:
+                b, s = None, None
+            if b is not None:
+                b = [mask * x.to(latents.dtype) if mask is not None else x.to(latents.dtype) for x in b]
+            if s is not None:
+                s = [mask * x.to(latents.dtype) if mask is not None else x.to(latents.dtype) for x in s]
+            if ci == 0:
+                blk, sgl = b, s
+            else:
+                if b is not None and blk is not None:
+                    blk = [u + v for u, v in zip(blk, b)]
+                if s is not None and sgl is not None:
+                    sgl = [u + v for u, v in zip(sgl, s)]
+        b, s = controlnet_forward(cni_sd, cni_cfg, latents, control_image_inpaint, conditioning_scale_inpaint,
+                                  prompt_embeds, pooled, timestep / 1000, img_ids, text_ids, guidance)  # :1214-1227
+        if b is not None:
+            b = [x.to(latents.dtype) for x in b]
+        if s is not None:
+            s = [x.to(latents.dtype) for x in s]
+        if b is not None and blk is not None:                                         # :1234-1238
+            blk = [u + v for u, v in zip(blk, b)]
+        if s is not None and sgl is not None:                                         # :1239-1245
+            sgl = [u + v for u, v in zip(sgl, s)]
+        noise_pred = transformer_forward(tr_sd, tr_cfg, latents, prompt_embeds, pooled, timestep / 1000,
+                                         img_ids, text_ids, guidance, blk, sgl)      # :1250-1262
+        if do_cfg:                                                                    # :1264-1270
+            uncond, text = noise_pred.chunk(2)
+            if i > 0:
+                noise_pred = uncond + true_guidance_scale * (text - uncond)
+            else:
+                noise_pred = text * 0.0
+        latents = euler_step(noise_pred, sigmas[i], sigmas[i + 1], latents)           # :1274
+        if callback is not None:
+            callback(i, t, latents)
+    return latents
