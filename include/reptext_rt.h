@@ -1,0 +1,213 @@
+/* reptext_rt.h — C-ABI of the B200-native RepText denoising-step runtime (librt_reptext.so).
+ *
+ * The reference has no FFI layer: its boundary is Python attribute calls made by the two pipelines on
+ * three registered modules (RepText/pipeline_flux_controlnet.py:209-218).  The Python shims in
+ * reptext_b200/ keep those call signatures and bind the entry points below with ctypes; every entry
+ * point cites the reference interface it replaces.  All pointers are DEVICE pointers unless marked
+ * host; no torch types cross this boundary.  Every function returns RT_OK (0) or a negative error
+ * code; rt_last_error() gives the message (the shim raises ValueError / RuntimeError like the
+ * reference does, e.g. RepText/controlnet_flux.py:297).  `stream` is a cudaStream_t.
+ */
+#ifndef REPTEXT_RT_H
+#define REPTEXT_RT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+#if defined(__GNUC__)
+#define RT_API __attribute__((visibility("default")))
+#else
+#define RT_API
+#endif
+
+enum { RT_OK = 0, RT_ERR_INVALID = -1, RT_ERR_CUDA = -2, RT_ERR_UNSUPPORTED = -3, RT_ERR_INTERNAL = -4 };
+enum { RT_F32 = 0, RT_BF16 = 1 };             /* storage dtype of weights and activations */
+enum { RT_TRANSFORMER = 0, RT_CONTROLNET = 1 };
+
+typedef struct rt_model rt_model;
+
+/* Fields are the register_to_config names of RepText/controlnet_flux.py:44-60. */
+typedef struct rt_model_config {
+  int kind;  /* RT_TRANSFORMER | RT_CONTROLNET */
+  int dtype; /* RT_F32 | RT_BF16 */
+  int in_channels;
+  int cond_channels; /* controlnet: in_channels + extra_condition_channels */
+  int out_channels;  /* transformer: proj_out features */
+  int num_layers;
+  int num_single_layers;
+  int num_attention_heads;
+  int attention_head_dim;
+  int joint_attention_dim;
+  int pooled_projection_dim;
+  int guidance_embeds;
+  int axes_dims_rope[3];
+} rt_model_config;
+
+/* ------------------------------------------------------------------------------------------------ */
+RT_API const char* rt_last_error(void); /* host string, valid until the next failing call on this thread */
+RT_API int rt_abi_version(void);
+RT_API long long rt_launch_count(void); /* number of this library's kernels launched so far (process-wide) */
+/* options: "force_simt" (0/1), "gemm_cta_group" (0 auto, 1, 2), "attn_variant" (0 auto, ...) */
+RT_API int rt_set_option(const char* name, int value);
+RT_API int rt_get_option(const char* name, int* value);
+
+/* ---- model life cycle: replaces FluxControlNetModel.__init__ / from_pretrained
+ *      (RepText/controlnet_flux.py:44-116, RepText/infer.py:30-33) and diffusers' FluxTransformer2DModel. */
+RT_API int rt_model_create(const rt_model_config* cfg, rt_model** out);
+/* Borrow a device tensor as parameter `name` (diffusers state-dict key).  The caller
+ * keeps it alive for the life of the model.  shape is a host array. */
+RT_API int rt_model_set_weight(rt_model* m, const char* name, const void* dev_ptr, const int64_t* shape, int ndim);
+RT_API int rt_model_finalize(rt_model* m, void* stream); /* checks every parameter is present, builds tables */
+RT_API int rt_model_destroy(rt_model* m);
+RT_API int64_t rt_model_workspace_bytes(const rt_model* m, int batch, int n_img, int n_txt);
+
+typedef struct rt_forward_args {
+  int batch;     /* effective batch of the embeddings (2 under true-CFG)                       */
+  int lat_batch; /* batch of hidden_states (1 or batch; 1 broadcasts — inpaint pipeline :1145) */
+  int t_batch;   /* batch of timestep / guidance (1 or batch)                                  */
+  int n_img, n_txt;
+  const void* hidden_states;         /* [lat_batch, n_img, in_channels]     */
+  const void* encoder_hidden_states; /* [batch, n_txt, joint_attention_dim] */
+  const void* pooled_projections;    /* [batch, pooled_projection_dim]      */
+  const void* timestep;              /* [t_batch] model dtype, sigma in [0,1] (the pipelines pass t/1000) */
+  const void* guidance;              /* [t_batch] model dtype, or NULL      */
+  const float* img_ids;              /* [n_img, 3] fp32 */
+  const float* txt_ids;              /* [n_txt, 3] fp32 */
+  void* workspace;
+  int64_t workspace_bytes;
+  void* stream;
+} rt_forward_args;
+
+/* FluxControlNetModel.forward — RepText/controlnet_flux.py:216-413, called at
+ * RepText/pipeline_flux_controlnet.py:1043-1056 and pipeline_flux_controlnet_inpaint.py:1167, :1214.
+ * block_samples: [num_layers, batch, n_img, D]; single_block_samples: [num_single_layers, batch, n_img, D]
+ * (NULL when num_single_layers == 0).  The conditioning scale (:395-396) is fused into the zero-linear
+ * epilogue.  mask ([n_img], model dtype, or NULL) fuses the pipelines' regional-mask multiply
+ * (pipeline_flux_controlnet.py:1060-1069) and accumulate != 0 fuses the multi-line sum (:1072-1087):
+ * out = (zero_linear(h) * scale * mask) + (accumulate ? out : 0). */
+RT_API int rt_controlnet_forward(rt_model* m, const rt_forward_args* a, const void* controlnet_cond, int cond_batch,
+                          float conditioning_scale, const void* mask, int accumulate, void* block_samples,
+                          void* single_block_samples);
+
+/* FluxTransformer2DModel.forward (diffusers 0.36.0) as called at
+ * RepText/pipeline_flux_controlnet.py:1092-1104.  controlnet_*_samples are host arrays of device
+ * pointers to [batch, n_img, D] tensors (or NULL / 0); sample i//ceil(L/n) is added after block i,
+ * fused into that block's last GEMM epilogue.  out: [batch, n_img, out_channels]. */
+RT_API int rt_transformer_forward(rt_model* m, const rt_forward_args* a, const void* const* controlnet_block_samples,
+                           int n_block_samples, const void* const* controlnet_single_block_samples,
+                           int n_single_block_samples, void* out);
+
+/* FlowMatchEulerDiscreteScheduler.step — called at RepText/pipeline_flux_controlnet.py:1109:
+ * out = dtype( float(sample) + dtype((sigma_next - sigma) * model_output) ); n elements. */
+RT_API int rt_euler_step(int dtype, const void* model_output, const void* sample, void* out, int64_t n, float sigma,
+                  float sigma_next, void* stream);
+/* true-CFG combine, RepText/pipeline_flux_controlnet_inpaint.py:1264-1270: v2 = [uncond; text] (2 x n);
+ * zero_pred != 0 is the i == 0 branch (noise_pred = text * 0). */
+RT_API int rt_cfg_combine(int dtype, const void* v2, void* out, int64_t n, float true_guidance_scale, int zero_pred,
+                   void* stream);
+/* CFG combine fused with the Euler step (same arithmetic, one pass) */
+RT_API int rt_cfg_euler_step(int dtype, const void* v2, const void* sample, void* out, int64_t n,
+                      float true_guidance_scale, int zero_pred, float sigma, float sigma_next, void* stream);
+/* Unfused regional-mask multiply + multi-line sum for ControlNet outputs that did not come from this
+ * library (pipeline_flux_controlnet.py:1060-1087): out = mask[r] * scale * x + (acc_in ? acc_in : 0). */
+RT_API int rt_mask_scale_add(int dtype, const void* x, const void* mask, const void* acc_in, void* out, int batch,
+                      int rows, int D, float scale, void* stream);
+/* Glyph-latent init blend, RepText/pipeline_flux_controlnet_inpaint.py:643-647:
+ * out = mask ? w_glyph * glyph_latents + w_noise * noise : noise  (mask: uint8 per element). */
+RT_API int rt_glyph_init_blend(int dtype, const void* noise, const void* glyph_latents, const unsigned char* mask,
+                        void* out, int64_t n, float w_glyph, float w_noise, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator-level entry points (used by the parity tests and by bench.py's roofline leg).
+ * ------------------------------------------------------------------------------------------------ */
+enum {
+  RT_EPI_BIAS = 0,        /* acc + bias                                                          */
+  RT_EPI_GELU = 1,        /* gelu_tanh(acc + bias)                                               */
+  RT_EPI_QKNORM_ROPE = 2, /* per head: rmsnorm(acc + bias) * w, then interleaved-pair RoPE       */
+  RT_EPI_GATE_RESID = 3,  /* out = out + gate[b, n] * (acc + bias) (+ extra[b, m, n]), in place  */
+  RT_EPI_SCALE_MASK = 4   /* out = (acc + bias) * scale * mask[m] (+ out if accumulate)          */
+};
+
+typedef struct rt_gemm_segment {
+  const void* W;    /* [n_end - n_begin, K] row-major (nn.Linear weight) */
+  const void* bias; /* [n_end - n_begin] or NULL */
+  int n_begin, n_end;
+  int mode;
+  void* out; /* [batch, rows, out_ld] */
+  int64_t out_batch_stride;
+  int out_ld;
+  int out_col0;
+  const void* norm_w; /* RT_EPI_QKNORM_ROPE: [head_dim] */
+} rt_gemm_segment;
+
+typedef struct rt_gemm_problem {
+  const void* A; /* [batch, a_rows_total, a_ld] */
+  int64_t a_batch_stride; /* 0 broadcasts one batch */
+  int a_ld;
+  int a_row0;
+  int a_rows_total;
+  int m_rows;
+  int out_row0;
+  int K;
+  int nseg;
+  rt_gemm_segment seg[4];
+  const float* gate; /* [batch, gate_ld] fp32 or NULL (= 1) */
+  int gate_ld;
+  const void* extra; /* optional addend; problem rows >= extra_row0 map to extra rows 0.. */
+  int64_t extra_batch_stride;
+  int extra_ld;
+  int extra_row0;
+  float scale;
+  const void* mask; /* [m_rows] or NULL */
+  int accumulate;
+} rt_gemm_problem;
+
+typedef struct rt_gemm_launch {
+  int dtype;
+  int batch;
+  int nprob;
+  rt_gemm_problem prob[2];
+  const float* rope; /* [rows, head_dim/2, 2] (cos, sin) fp32, indexed by out_row0 + m; NULL = no rope */
+  int head_dim;
+} rt_gemm_launch;
+
+/* impl: 0 auto, 1 SIMT, 2 tcgen05 cta_group::1, 3 tcgen05 cta_group::2 */
+RT_API int rt_gemm(const rt_gemm_launch* g, int impl, void* stream);
+
+typedef struct rt_attention_args {
+  int dtype;
+  const void* qkv; /* [batch, S, ld]; head h of q at column q_col0 + h*hd, etc. */
+  int64_t batch_stride;
+  int ld;
+  int q_col0, k_col0, v_col0;
+  void* out; /* [batch, S, out_ld]; head h at column out_col0 + h*hd */
+  int64_t out_batch_stride;
+  int out_ld, out_col0;
+  int batch, S, heads, hd;
+} rt_attention_args;
+/* impl: 0 auto, 1 SIMT, >= 2 tcgen05 variant (impl - 2) */
+RT_API int rt_attention(const rt_attention_args* a, int impl, void* stream);
+
+typedef struct rt_lnmod_group {
+  int row_begin, row_end;
+  const float* shift; /* [batch, ld] */
+  const float* scale;
+  int ld;
+} rt_lnmod_group;
+RT_API int rt_layernorm_modulate(int dtype, const void* x, int64_t x_batch_stride, int x_ld, void* out,
+                          int64_t out_batch_stride, int out_ld, int batch, int D, int ngroups,
+                          const rt_lnmod_group* groups /* host */, void* stream);
+/* FluxPosEmbed (RepText/controlnet_flux.py:65, :316-317): ids [S,3] fp32 -> out [S, sum(axes)/2, 2] fp32 */
+RT_API int rt_rope_table(const float* ids, int S, const int* axes_dims /* host, 3 */, float* out, void* stream);
+/* In-place per-head RMSNorm * w + RoPE on `heads` heads starting at column col0 (SIMT path's unfused form) */
+RT_API int rt_qknorm_rope(int dtype, void* buf, int64_t batch_stride, int ld, int col0, int batch, int row0, int rows,
+                   int heads, int hd, const void* norm_w, const float* rope, int rope_row0, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REPTEXT_RT_H */

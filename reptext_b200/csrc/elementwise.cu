@@ -1,0 +1,547 @@
+// HBM-bound kernels of the hot path: LayerNorm+modulation, grouped GEMV (AdaLN / time-text MLPs),
+// RoPE table, QK-RMSNorm+RoPE (unfused form), Euler step, CFG combine, regional mask, glyph blend.
+// All are coalesced 16-byte-per-thread kernels; grids are sized in multiples of the SM count.
+#include <cmath>
+
+#include "dtype_utils.cuh"
+#include "rt_internal.h"
+
+namespace rt {
+
+long long g_launch_count = 0;
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-6, no affine) + (1 + scale) * xn + shift.  One warp per row, row cached in
+// registers (up to 16 16-byte vectors per lane = D <= 4096 bf16 / 2048 fp32), else 3 passes over L1.
+// Reference: diffusers AdaLayerNormZero / AdaLayerNormZeroSingle / AdaLayerNormContinuous, reached
+// from RepText/controlnet_flux.py:343-348 via FluxTransformerBlock.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnMaxGroups = 2;
+struct LnGroups {
+  int n;
+  LnModGroup g[kLnMaxGroups];
+};
+
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) ln_mod_kernel(const T* __restrict__ x, long long x_bs, int x_ld,
+                                                     T* __restrict__ out, long long o_bs, int o_ld, int batch,
+                                                     int rows_total, int D, LnGroups groups) {
+  constexpr int N = VecT<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int nvec = D / N;  // D % N == 0 checked on the host
+  for (long long wrow = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+       wrow < (long long)batch * rows_total; wrow += (long long)gridDim.x * warps_per_block) {
+    const int b = (int)(wrow / rows_total);
+    const int lr = (int)(wrow % rows_total);
+    // map the linear row index onto the groups' row ranges
+    int r = -1, gi = 0, acc = 0;
+#pragma unroll
+    for (int k = 0; k < kLnMaxGroups; ++k) {
+      if (k < groups.n) {
+        int len = groups.g[k].row_end - groups.g[k].row_begin;
+        if (r < 0 && lr < acc + len) {
+          r = groups.g[k].row_begin + (lr - acc);
+          gi = k;
+        }
+        acc += len;
+      }
+    }
+    const LnModGroup& G = groups.g[gi];
+    const T* xr = x + (long long)b * x_bs + (long long)r * x_ld;
+    T* orow = out + (long long)b * o_bs + (long long)r * o_ld;
+    const float* sh = G.shift + (long long)b * G.ld;
+    const float* sc = G.scale + (long long)b * G.ld;
+
+    float v[MAXV][N];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
+        ldvec(xr + c * N, v[i]);
+#pragma unroll
+        for (int j = 0; j < N; ++j) s += v[i][j];
+      }
+    }
+    s = warp_sum(s);
+    const float mean = s / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          float d = v[i][j] - mean;
+          q += d * d;
+        }
+      }
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / (float)D + 1e-6f);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
+        float o[N];
+#pragma unroll
+        for (int j4 = 0; j4 < N; j4 += 4) {
+          float4 a = *reinterpret_cast<const float4*>(sc + c * N + j4);
+          float4 h = *reinterpret_cast<const float4*>(sh + c * N + j4);
+          o[j4 + 0] = (v[i][j4 + 0] - mean) * rstd * (1.f + a.x) + h.x;
+          o[j4 + 1] = (v[i][j4 + 1] - mean) * rstd * (1.f + a.y) + h.y;
+          o[j4 + 2] = (v[i][j4 + 2] - mean) * rstd * (1.f + a.z) + h.z;
+          o[j4 + 3] = (v[i][j4 + 3] - mean) * rstd * (1.f + a.w) + h.w;
+        }
+        stvec(orow + c * N, o);
+      }
+    }
+  }
+}
+
+void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out, long long o_bs, int o_ld, int batch,
+                   int D, int ngroups, const LnModGroup* groups, cudaStream_t stream) {
+  RT_REQUIRE(ngroups >= 1 && ngroups <= kLnMaxGroups, "ln_mod: 1..2 row groups");
+  LnGroups G;
+  G.n = ngroups;
+  int rows_total = 0;
+  for (int i = 0; i < ngroups; ++i) {
+    G.g[i] = groups[i];
+    rows_total += groups[i].row_end - groups[i].row_begin;
+    RT_REQUIRE(groups[i].ld % 4 == 0, "ln_mod: modulation ld must be a multiple of 4");
+  }
+  if (rows_total == 0 || batch == 0) return;
+  const long long total = (long long)batch * rows_total;
+  const int threads = 256, wpb = threads / 32;
+  long long blocks = (total + wpb - 1) / wpb;
+  long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  RT_DISPATCH_DTYPE(dtype, T, {
+    constexpr int N = VecT<T>::N;
+    RT_REQUIRE(D % N == 0 && x_ld % N == 0 && o_ld % N == 0, "ln_mod: D and lds must be multiples of the vector width");
+    const int nvec = D / N;
+    const int per_lane = (nvec + 31) / 32;
+    RT_REQUIRE(per_lane <= 16, "ln_mod: D too large");
+    if (per_lane <= 2)
+      ln_mod_kernel<T, 2><<<(int)blocks, threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld, batch,
+                                                               rows_total, D, G);
+    else if (per_lane <= 4)
+      ln_mod_kernel<T, 4><<<(int)blocks, threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld, batch,
+                                                               rows_total, D, G);
+    else if (per_lane <= 12)
+      ln_mod_kernel<T, 12><<<(int)blocks, threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld, batch,
+                                                                rows_total, D, G);
+    else
+      ln_mod_kernel<T, 16><<<(int)blocks, threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld, batch,
+                                                                rows_total, D, G);
+  });
+  RT_POST_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Grouped GEMV (M = batch <= 8 per pass): one warp per output row, weights streamed once with 16-byte
+// loads; x (fp32, tiny) comes through L1.  Used for the AdaLN modulation vectors of ALL blocks in one
+// launch and for the time/guidance/pooled MLPs (diffusers CombinedTimestepGuidanceTextProjEmbeddings,
+// RepText/controlnet_flux.py:287-291).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NB>
+__global__ void __launch_bounds__(256) gemv_grouped_kernel(const float* __restrict__ x, int x_ld, int b0, int K,
+                                                           const GemvJob* __restrict__ jobs,
+                                                           const int* __restrict__ prefix, int njobs, int total_rows,
+                                                           float* __restrict__ out, int out_ld, int silu_out,
+                                                           int accumulate) {
+  constexpr int N = VecT<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < total_rows; row += gridDim.x * wpb) {
+    int lo = 0, hi = njobs - 1;  // last job with prefix[j] <= row
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (prefix[mid] <= row) lo = mid; else hi = mid - 1;
+    }
+    const GemvJob J = jobs[lo];
+    const int r = row - prefix[lo];
+    const T* w = reinterpret_cast<const T*>(J.W) + (long long)r * K;
+    float acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+    for (int c = lane * N; c < K; c += 32 * N) {
+      float wv[N];
+      ldvec(w + c, wv);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float* xb = x + (long long)(b0 + b) * x_ld + c;
+#pragma unroll
+        for (int j = 0; j < N; j += 4) {
+          float4 xv = *reinterpret_cast<const float4*>(xb + j);
+          acc[b] += wv[j] * xv.x + wv[j + 1] * xv.y + wv[j + 2] * xv.z + wv[j + 3] * xv.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = warp_sum(acc[b]);
+    if (lane == 0) {
+      const float bias = J.bias ? to_f(reinterpret_cast<const T*>(J.bias)[r]) : 0.f;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float v = acc[b] + bias;
+        if (silu_out) v = v / (1.f + expf(-v));
+        float* o = out + (long long)(b0 + b) * out_ld + J.out_off + r;
+        *o = accumulate ? (*o + v) : v;
+      }
+    }
+  }
+}
+
+void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
+                         const int* prefix_dev, int njobs, int total_rows, float* out, int out_ld, int silu_out,
+                         int accumulate, cudaStream_t stream) {
+  if (batch == 0 || total_rows == 0) return;
+  RT_REQUIRE(x_ld % 4 == 0, "gemv: x_ld must be a multiple of 4");
+  const int threads = 256, wpb = threads / 32;
+  int blocks = (total_rows + wpb - 1) / wpb;
+  int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  RT_DISPATCH_DTYPE(wdtype, T, {
+    RT_REQUIRE(K % VecT<T>::N == 0, "gemv: K must be a multiple of the vector width");
+    int b0 = 0;
+    while (b0 < batch) {
+      int nb = batch - b0;
+      if (nb >= 4) {
+        gemv_grouped_kernel<T, 4><<<blocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
+                                                                  total_rows, out, out_ld, silu_out, accumulate);
+        b0 += 4;
+      } else if (nb >= 2) {
+        gemv_grouped_kernel<T, 2><<<blocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
+                                                                  total_rows, out, out_ld, silu_out, accumulate);
+        b0 += 2;
+      } else {
+        gemv_grouped_kernel<T, 1><<<blocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
+                                                                  total_rows, out, out_ld, silu_out, accumulate);
+        b0 += 1;
+      }
+      RT_POST_LAUNCH();
+    }
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Timestep sinusoid: diffusers get_timestep_embedding(256, flip_sin_to_cos=True, shift=0) applied to
+// T(t) * 1000 computed IN THE MODEL DTYPE (RepText/controlnet_flux.py:282-284: `timestep.to(dtype) * 1000`).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void time_sinusoid_kernel(const T* __restrict__ t, int t_batch, int batch, float* __restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * 128) return;
+  int b = idx / 128, j = idx % 128;
+  T tv = t[t_batch == 1 ? 0 : b];
+  float v = to_f(from_f<T>(to_f(tv) * 1000.f));
+  float f = expf(-logf(10000.f) * (float)j / 128.f);
+  float s, c;
+  sincosf(v * f, &s, &c);
+  out[b * 256 + j] = c;
+  out[b * 256 + 128 + j] = s;
+}
+void launch_time_sinusoid(int dtype, const void* t, int t_batch, int batch, float* out, cudaStream_t stream) {
+  if (batch == 0) return;
+  int n = batch * 128;
+  RT_DISPATCH_DTYPE(dtype, T,
+                    (time_sinusoid_kernel<T><<<(n + 127) / 128, 128, 0, stream>>>((const T*)t, t_batch, batch, out)));
+  RT_POST_LAUNCH();
+}
+
+template <typename T>
+__global__ void cast_to_f32_kernel(const T* __restrict__ x, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = to_f(x[i]);
+}
+void launch_cast_to_f32(int dtype, const void* x, float* out, long long n, cudaStream_t stream) {
+  if (n == 0) return;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  RT_DISPATCH_DTYPE(dtype, T, (cast_to_f32_kernel<T><<<blocks, 256, 0, stream>>>((const T*)x, out, n)));
+  RT_POST_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE table (FluxPosEmbed, RepText/controlnet_flux.py:65, :316-317): float64 angle, cos/sin to fp32.
+// Stored compactly as (cos, sin) per PAIR: [S, hd/2] float2 (the reference repeat_interleaves by 2).
+// ------------------------------------------------------------------------------------------------
+__global__ void rope_table_kernel(const float* __restrict__ ids, int S, int d0, int d1, int d2,
+                                  float2* __restrict__ out) {
+  const int half = (d0 + d1 + d2) / 2;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * half) return;
+  int s = idx / half, j = idx % half;
+  int axis, jj, d;
+  if (j < d0 / 2) { axis = 0; jj = j; d = d0; }
+  else if (j < (d0 + d1) / 2) { axis = 1; jj = j - d0 / 2; d = d1; }
+  else { axis = 2; jj = j - (d0 + d1) / 2; d = d2; }
+  double omega = 1.0 / pow(10000.0, (double)(2 * jj) / (double)d);
+  double ang = (double)ids[s * 3 + axis] * omega;
+  out[idx] = make_float2((float)cos(ang), (float)sin(ang));
+}
+void launch_rope_table(const float* ids, int S, const int* axes, float2* out, cudaStream_t stream) {
+  int half = (axes[0] + axes[1] + axes[2]) / 2;
+  int n = S * half;
+  if (n == 0) return;
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(ids, S, axes[0], axes[1], axes[2], out);
+  RT_POST_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Unfused QK-RMSNorm (eps 1e-6, over head_dim) * w + interleaved-pair RoPE, in place.  One warp per
+// (batch, row, head).  The tcgen05 GEMM fuses this into its epilogue; this form serves the SIMT path.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int EPL>  // elements per lane (hd = 32 * EPL), EPL even
+__global__ void __launch_bounds__(256) qknorm_rope_kernel(T* __restrict__ buf, long long bs, int ld, int col0,
+                                                          int batch, int row0, int rows, int heads,
+                                                          const T* __restrict__ w, const float2* __restrict__ rope,
+                                                          int rope_row0) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const long long total = (long long)batch * rows * heads;
+  constexpr int hd = 32 * EPL;
+  for (long long it = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); it < total;
+       it += (long long)gridDim.x * wpb) {
+    int h = (int)(it % heads);
+    long long br = it / heads;
+    int r = (int)(br % rows);
+    int b = (int)(br / rows);
+    T* p = buf + (long long)b * bs + (long long)(row0 + r) * ld + col0 + h * hd + lane * EPL;
+    float v[EPL];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      v[j] = to_f(p[j]);
+      ss += v[j] * v[j];
+    }
+    ss = warp_sum(ss);
+    const float rs = rsqrtf(ss / (float)hd + 1e-6f);
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) v[j] = v[j] * rs * to_f(w[lane * EPL + j]);
+    if (rope) {
+      const float2* rp = rope + (long long)(rope_row0 + r) * (hd / 2) + lane * (EPL / 2);
+#pragma unroll
+      for (int j = 0; j < EPL; j += 2) {
+        float2 cs = rp[j / 2];
+        float a = v[j], c = v[j + 1];
+        v[j] = a * cs.x - c * cs.y;
+        v[j + 1] = c * cs.x + a * cs.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) p[j] = from_f<T>(v[j]);
+  }
+}
+void launch_qknorm_rope(int dtype, void* buf, long long bs, int ld, int col0, int batch, int row0, int rows,
+                        int heads, int hd, const void* norm_w, const float2* rope, int rope_row0,
+                        cudaStream_t stream) {
+  long long total = (long long)batch * rows * heads;
+  if (total == 0) return;
+  RT_REQUIRE(hd == 64 || hd == 128, "qknorm_rope: head_dim must be 64 or 128");
+  int blocks = (int)((total + 7) / 8);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  RT_DISPATCH_DTYPE(dtype, T, {
+    if (hd == 64)
+      qknorm_rope_kernel<T, 2><<<blocks, 256, 0, stream>>>((T*)buf, bs, ld, col0, batch, row0, rows, heads,
+                                                           (const T*)norm_w, rope, rope_row0);
+    else
+      qknorm_rope_kernel<T, 4><<<blocks, 256, 0, stream>>>((T*)buf, bs, ld, col0, batch, row0, rows, heads,
+                                                           (const T*)norm_w, rope, rope_row0);
+  });
+  RT_POST_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
+// FlowMatch Euler step (scheduler.step at RepText/pipeline_flux_controlnet.py:1109) and true-CFG
+// (pipeline_flux_controlnet_inpaint.py:1264-1270).  16 bytes per thread per tensor, grid-stride.
+//   out = T( float(x) + float(T(dt * float(v))) )       (dt stays fp32: CUDA form, see oracle note)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) euler_kernel(const T* __restrict__ v, const T* __restrict__ x,
+                                                    T* __restrict__ out, long long n, float dt) {
+  constexpr int N = VecT<T>::N;
+  const long long nv = n / N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float a[N], b[N], o[N];
+    ldvec(v + i * N, a);
+    ldvec(x + i * N, b);
+#pragma unroll
+    for (int j = 0; j < N; ++j) o[j] = b[j] + to_f(from_f<T>(dt * a[j]));
+    stvec(out + i * N, o);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - nv * N)) {
+    long long i = nv * N + threadIdx.x;
+    out[i] = from_f<T>(to_f(x[i]) + to_f(from_f<T>(dt * to_f(v[i]))));
+  }
+}
+static int ew_blocks(long long nvec) {
+  long long b = (nvec + 255) / 256;
+  long long cap = (long long)sm_count() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+void launch_euler_step(int dtype, const void* v, const void* x, void* out, long long n, float sigma,
+                       float sigma_next, cudaStream_t stream) {
+  if (n == 0) return;
+  const float dt = sigma_next - sigma;
+  RT_DISPATCH_DTYPE(dtype, T, (euler_kernel<T><<<ew_blocks(n / VecT<T>::N), 256, 0, stream>>>(
+                                  (const T*)v, (const T*)x, (T*)out, n, dt)));
+  RT_POST_LAUNCH();
+}
+
+// noise_pred = uncond + s * (text - uncond)   (each op rounded to T like the reference's tensor ops)
+template <typename T>
+__device__ __forceinline__ float cfg_one(float u, float t, float s, int zero_pred) {
+  if (zero_pred) return to_f(from_f<T>(t * 0.f));
+  float d = to_f(from_f<T>(t - u));
+  float m = to_f(from_f<T>(s * d));
+  return to_f(from_f<T>(u + m));
+}
+template <typename T, bool kEuler>
+__global__ void __launch_bounds__(256) cfg_kernel(const T* __restrict__ v2, const T* __restrict__ x,
+                                                  T* __restrict__ out, long long n, float s, int zero_pred,
+                                                  float dt) {
+  constexpr int N = VecT<T>::N;
+  const long long nv = n / N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float u[N], t[N], o[N];
+    ldvec(v2 + i * N, u);
+    ldvec(v2 + n + i * N, t);
+    if constexpr (kEuler) {
+      float xv[N];
+      ldvec(x + i * N, xv);
+#pragma unroll
+      for (int j = 0; j < N; ++j) o[j] = xv[j] + to_f(from_f<T>(dt * cfg_one<T>(u[j], t[j], s, zero_pred)));
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) o[j] = cfg_one<T>(u[j], t[j], s, zero_pred);
+    }
+    stvec(out + i * N, o);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - nv * N)) {
+    long long i = nv * N + threadIdx.x;
+    float p = cfg_one<T>(to_f(v2[i]), to_f(v2[n + i]), s, zero_pred);
+    out[i] = kEuler ? from_f<T>(to_f(x[i]) + to_f(from_f<T>(dt * p))) : from_f<T>(p);
+  }
+}
+void launch_cfg_combine(int dtype, const void* v2, void* out, long long n, float s, int zero_pred,
+                        cudaStream_t stream) {
+  if (n == 0) return;
+  RT_REQUIRE((n * (long long)dtype_size(dtype)) % 16 == 0, "cfg: n*sizeof(T) must be a multiple of 16");
+  RT_DISPATCH_DTYPE(dtype, T, (cfg_kernel<T, false><<<ew_blocks(n / VecT<T>::N), 256, 0, stream>>>(
+                                  (const T*)v2, nullptr, (T*)out, n, s, zero_pred, 0.f)));
+  RT_POST_LAUNCH();
+}
+void launch_cfg_euler(int dtype, const void* v2, const void* x, void* out, long long n, float s, int zero_pred,
+                      float sigma, float sigma_next, cudaStream_t stream) {
+  if (n == 0) return;
+  RT_REQUIRE((n * (long long)dtype_size(dtype)) % 16 == 0, "cfg: n*sizeof(T) must be a multiple of 16");
+  RT_DISPATCH_DTYPE(dtype, T, (cfg_kernel<T, true><<<ew_blocks(n / VecT<T>::N), 256, 0, stream>>>(
+                                  (const T*)v2, (const T*)x, (T*)out, n, s, zero_pred, sigma_next - sigma)));
+  RT_POST_LAUNCH();
+}
+
+// out[b, r, :] = T(mask[r] * T(scale * x[b, r, :])) (+ acc_in[b, r, :])
+template <typename T>
+__global__ void __launch_bounds__(256) mask_scale_add_kernel(const T* __restrict__ x, const T* __restrict__ mask,
+                                                             const T* __restrict__ acc_in, T* __restrict__ out,
+                                                             int rows, int D, long long total_vec, float scale) {
+  constexpr int N = VecT<T>::N;
+  const int vpr = D / N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long row = i / vpr;
+    int r = (int)(row % rows);
+    float m = mask ? to_f(mask[r]) : 1.f;
+    float a[N], o[N];
+    ldvec(x + i * N, a);
+#pragma unroll
+    for (int j = 0; j < N; ++j) o[j] = to_f(from_f<T>(m * to_f(from_f<T>(scale * a[j]))));
+    if (acc_in) {
+      float c[N];
+      ldvec(acc_in + i * N, c);
+#pragma unroll
+      for (int j = 0; j < N; ++j) o[j] += c[j];
+    }
+    stvec(out + i * N, o);
+  }
+}
+void launch_mask_scale_add(int dtype, const void* x, const void* mask, const void* acc_in, void* out, int batch,
+                           int rows, int D, float scale, cudaStream_t stream) {
+  long long n = (long long)batch * rows * D;
+  if (n == 0) return;
+  RT_DISPATCH_DTYPE(dtype, T, {
+    RT_REQUIRE(D % VecT<T>::N == 0, "mask_scale_add: D must be a multiple of the vector width");
+    long long nv = n / VecT<T>::N;
+    mask_scale_add_kernel<T><<<ew_blocks(nv), 256, 0, stream>>>((const T*)x, (const T*)mask, (const T*)acc_in,
+                                                                (T*)out, rows, D, nv, scale);
+  });
+  RT_POST_LAUNCH();
+}
+
+// glyph-latent init: out = mask ? T(T(wg * z) + T(wn * noise)) : noise
+template <typename T>
+__global__ void __launch_bounds__(256) glyph_blend_kernel(const T* __restrict__ noise, const T* __restrict__ z,
+                                                          const unsigned char* __restrict__ mask, T* __restrict__ out,
+                                                          long long n, float wg, float wn) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float nz = to_f(noise[i]);
+    float r = nz;
+    if (mask[i]) r = to_f(from_f<T>(wg * to_f(z[i]))) + to_f(from_f<T>(wn * nz));
+    out[i] = from_f<T>(r);
+  }
+}
+void launch_glyph_blend(int dtype, const void* noise, const void* z, const unsigned char* mask, void* out,
+                        long long n, float wg, float wn, cudaStream_t stream) {
+  if (n == 0) return;
+  RT_DISPATCH_DTYPE(dtype, T, (glyph_blend_kernel<T><<<ew_blocks(n), 256, 0, stream>>>(
+                                  (const T*)noise, (const T*)z, mask, (T*)out, n, wg, wn)));
+  RT_POST_LAUNCH();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) copy_rows_kernel(const T* __restrict__ src, long long s_bs, int s_ld,
+                                                        int s_row0, T* __restrict__ dst, long long d_bs, int d_ld,
+                                                        int d_row0, int rows, int vpr, long long total_vec) {
+  constexpr int N = VecT<T>::N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % vpr);
+    long long row = i / vpr;
+    int r = (int)(row % rows);
+    int b = (int)(row / rows);
+    float a[N];
+    ldvec(src + (long long)b * s_bs + (long long)(s_row0 + r) * s_ld + c * N, a);
+    stvec(dst + (long long)b * d_bs + (long long)(d_row0 + r) * d_ld + c * N, a);
+  }
+}
+void launch_copy_rows(int dtype, const void* src, long long s_bs, int s_ld, int s_row0, void* dst, long long d_bs,
+                      int d_ld, int d_row0, int batch, int rows, int D, cudaStream_t stream) {
+  long long n = (long long)batch * rows * D;
+  if (n == 0) return;
+  RT_DISPATCH_DTYPE(dtype, T, {
+    constexpr int N = VecT<T>::N;
+    RT_REQUIRE(D % N == 0 && s_ld % N == 0 && d_ld % N == 0, "copy_rows: vector alignment");
+    long long nv = n / N;
+    copy_rows_kernel<T><<<ew_blocks(nv), 256, 0, stream>>>((const T*)src, s_bs, s_ld, s_row0, (T*)dst, d_bs, d_ld,
+                                                           d_row0, rows, D / N, nv);
+  });
+  RT_POST_LAUNCH();
+}
+
+}  // namespace rt

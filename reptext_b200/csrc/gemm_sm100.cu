@@ -1,0 +1,613 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> swizzled smem -> tcgen05.mma -> TMEM ->
+// fused epilogue -> global.  One launch covers up to two "problems" (text rows and image rows of the
+// joint sequence, each with its own weights) and up to four column segments per problem (q | k | v |
+// mlp, each with its own weight matrix, bias, epilogue mode and destination), so that the QKV(+MLP)
+// projections of a Flux block are ONE kernel without concatenated weight copies.
+//
+//   warp 0      TMA producer (one elected lane)            warp 2   TMEM allocator
+//   warp 1      tcgen05.mma issuer (one lane)              warps 4-7 epilogue (TMEM lane quadrant = warp % 4)
+//
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty
+// (MMA <-> epilogue), static persistent tile scheduler (tile = blockIdx.x + i * gridDim.x).
+// kCtaGroup == 2 pairs two CTAs of a cluster on a 256 x BN tile (tcgen05 cta_group::2): each CTA
+// loads its own 128 rows of A and HALF of the W tile, the leader issues the MMAs for both.
+//
+// Epilogues (reference semantics: diffusers FluxTransformerBlock / FluxSingleTransformerBlock,
+// reached from RepText/controlnet_flux.py:343-348, and controlnet_flux.py:385-396 for SCALE_MASK):
+//   BIAS, GELU(tanh), QK-RMSNorm + RoPE per 128-wide head, gate * x + residual (+ ControlNet
+//   residual), (x) * conditioning_scale * regional_mask (+ accumulate).
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "dtype_utils.cuh"
+#include "ptx_sm100.cuh"
+#include "rt_internal.h"
+
+namespace rt {
+
+namespace {
+
+constexpr int BM = 128;       // rows per CTA tile (= TMEM lanes)
+constexpr int BK = 64;        // k-block: 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int kMaxSeg = 4;
+
+struct alignas(64) TcSegment {
+  CUtensorMap tmW;  // 2D (K, rows), box (64, BN / cta_group)
+  const bf16* bias;
+  bf16* out;
+  const bf16* norm_w;
+  long long out_bs;
+  int n_begin, n_end, mode, out_ld, out_col0, pad_;
+};
+
+struct alignas(64) TcProblem {
+  CUtensorMap tmA;  // 3D (K, rows, batch), box (64, 128, 1)
+  TcSegment seg[kMaxSeg];
+  const float* gate;
+  const bf16* extra;
+  const bf16* mask;
+  long long e_bs;
+  int a_row0, a_bcast, m_rows, out_row0, K, nseg, gate_ld, e_ld, e_row0, accumulate;
+  float scale;
+  int tiles_m, tiles_n, tile_base, num_tiles;
+};
+
+struct alignas(64) TcParams {
+  TcProblem prob[2];
+  const float2* rope;
+  int nprob, batch, total_tiles, head_dim;
+};
+
+template <int BN, int kCtaGroup>
+struct Cfg {
+  static constexpr int kBRows = BN / kCtaGroup;             // W rows each CTA loads
+  static constexpr int kABytes = BM * BK * 2;               // 16 KB
+  static constexpr int kBBytes = kBRows * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
+  static constexpr int kAccStages = 2;
+  static constexpr int kTmemCols = (kAccStages * BN <= 32) ? 32 : (kAccStages * BN <= 64) ? 64
+                                   : (kAccStages * BN <= 128) ? 128 : (kAccStages * BN <= 256) ? 256 : 512;
+  static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+struct TileCoord {
+  int p, b, m0, n0, seg;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int t, int bn, int rows_per_tile) {
+  TileCoord c;
+  c.p = (P.nprob > 1 && t >= P.prob[1].tile_base) ? 1 : 0;
+  const TcProblem& pr = P.prob[c.p];
+  int tl = t - pr.tile_base;
+  int mt = tl % pr.tiles_m;
+  int rest = tl / pr.tiles_m;
+  c.b = rest % P.batch;
+  int nt = rest / P.batch;
+  c.m0 = mt * rows_per_tile;
+  c.n0 = nt * bn;
+  c.seg = 0;
+#pragma unroll
+  for (int s = 1; s < kMaxSeg; ++s)
+    if (s < pr.nseg && c.n0 >= pr.seg[s].n_begin) c.seg = s;
+  return c;
+}
+
+// ---- epilogue helpers: 32 consecutive columns of one row ------------------------------------------
+__device__ __forceinline__ void load_bf16x32(const bf16* p, float (&v)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t = __ldg(q + i);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[i * 8 + 2 * j] = ptx::bf16_lo(w[j]);
+      v[i * 8 + 2 * j + 1] = ptx::bf16_hi(w[j]);
+    }
+  }
+}
+__device__ __forceinline__ void load_bf16x32_rw(const bf16* p, float (&v)[32]) {  // data this kernel also writes
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t = q[i];
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[i * 8 + 2 * j] = ptx::bf16_lo(w[j]);
+      v[i * 8 + 2 * j + 1] = ptx::bf16_hi(w[j]);
+    }
+  }
+}
+__device__ __forceinline__ void store_bf16x32(bf16* p, const float (&v)[32]) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t;
+    t.x = ptx::pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]);
+    t.y = ptx::pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+    t.z = ptx::pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]);
+    t.w = ptx::pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+    q[i] = t;
+  }
+}
+__device__ __forceinline__ void tmem_load_f32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  ptx::tmem_ld_32x32b_x32(taddr, r);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + ptx::tanh_approx(inner));
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const TcParams& P, const TcProblem& pr, const TcSegment& sg,
+                                              uint32_t tacc, int b, int m, int n0) {
+  const bool row_ok = m < pr.m_rows;
+  const int nl0 = n0 - sg.n_begin;  // column within the segment
+  bf16* orow = sg.out + (long long)b * sg.out_bs + (long long)(pr.out_row0 + m) * sg.out_ld + sg.out_col0 + nl0;
+  const bf16* bias = sg.bias ? sg.bias + nl0 : nullptr;
+
+  if (sg.mode == EPI_QKNORM_ROPE) {
+    // one head = 128 columns; two passes over TMEM (reads are cheap) instead of 128 live registers
+    const float2* rp = P.rope ? P.rope + (long long)(pr.out_row0 + m) * 64 : nullptr;
+#pragma unroll 1
+    for (int hc = 0; hc < BN / 128; ++hc) {
+      float ss = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_load_f32x32(tacc + hc * 128 + c * 32, v);
+        if (bias) {
+          float bv[32];
+          load_bf16x32(bias + hc * 128 + c * 32, bv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += bv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ss += v[i] * v[i];
+      }
+      const float rs = rsqrtf(ss * (1.f / 128.f) + 1e-6f);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_load_f32x32(tacc + hc * 128 + c * 32, v);
+        if (bias) {
+          float bv[32];
+          load_bf16x32(bias + hc * 128 + c * 32, bv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += bv[i];
+        }
+        float wv[32];
+        load_bf16x32(sg.norm_w + c * 32, wv);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = v[i] * rs * wv[i];
+        if (rp && row_ok) {
+          const float4* r4 = reinterpret_cast<const float4*>(rp + c * 16);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 cs = __ldg(r4 + i);  // (cos0, sin0, cos1, sin1)
+            float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+            v[4 * i] = x0 * cs.x - x1 * cs.y;
+            v[4 * i + 1] = x1 * cs.x + x0 * cs.y;
+            v[4 * i + 2] = x2 * cs.z - x3 * cs.w;
+            v[4 * i + 3] = x3 * cs.z + x2 * cs.w;
+          }
+        }
+        if (row_ok) store_bf16x32(orow + hc * 128 + c * 32, v);
+      }
+    }
+    return;
+  }
+
+  const float* gate = (sg.mode == EPI_GATE_RESID && pr.gate) ? pr.gate + (long long)b * pr.gate_ld + n0 : nullptr;
+  const bf16* extra = nullptr;
+  if (sg.mode == EPI_GATE_RESID && pr.extra && m >= pr.e_row0)
+    extra = pr.extra + (long long)b * pr.e_bs + (long long)(m - pr.e_row0) * pr.e_ld + n0;
+  float mk = 1.f;
+  if (sg.mode == EPI_SCALE_MASK) {
+    mk = pr.scale;
+    if (pr.mask && row_ok) mk *= __bfloat162float(pr.mask[m]);
+  }
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    float v[32];
+    tmem_load_f32x32(tacc + c * 32, v);
+    if (bias) {
+      float bv[32];
+      load_bf16x32(bias + c * 32, bv);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += bv[i];
+    }
+    if (sg.mode == EPI_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_fast(v[i]);
+    } else if (sg.mode == EPI_GATE_RESID) {
+      if (gate) {
+        const float4* g4 = reinterpret_cast<const float4*>(gate + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 g = __ldg(g4 + i);
+          v[4 * i] *= g.x; v[4 * i + 1] *= g.y; v[4 * i + 2] *= g.z; v[4 * i + 3] *= g.w;
+        }
+      }
+      if (row_ok) {
+        float r[32];
+        load_bf16x32_rw(orow + c * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += r[i];
+        if (extra) {
+          load_bf16x32(extra + c * 32, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += r[i];
+        }
+      }
+    } else if (sg.mode == EPI_SCALE_MASK) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= mk;
+      if (pr.accumulate && row_ok) {
+        float r[32];
+        load_bf16x32_rw(orow + c * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += r[i];
+      }
+    }
+    if (row_ok) store_bf16x32(orow + c * 32, v);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+template <int BN, int kCtaGroup>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
+  using C = Cfg<BN, kCtaGroup>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tfull_bar = bars + 2 * C::kStages;
+  uint64_t* tempty_bar = bars + 2 * C::kStages + C::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 2 * C::kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCtaGroup == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x / kCtaGroup;
+  const int num_clusters = gridDim.x / kCtaGroup;
+  constexpr int kRowsPerTile = BM * kCtaGroup;
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < P.nprob; ++p) {
+      ptx::prefetch_tmap(&P.prob[p].tmA);
+      for (int s = 0; s < P.prob[p].nseg; ++s) ptx::prefetch_tmap(&P.prob[p].seg[s].tmW);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], kCtaGroup);  // leader's own arrive.expect_tx (+ the peer's remote arrive)
+      ptx::mbar_init(&empty_bar[i], 1);         // one tcgen05.commit
+    }
+    for (int i = 0; i < C::kAccStages; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);                         // one tcgen05.commit
+      ptx::mbar_init(&tempty_bar[i], kCtaGroup * kEpiThreads);  // every epilogue thread of the pair
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kCtaGroup>(tmem_slot, C::kTmemCols);
+  ptx::tc_fence_before();
+  if constexpr (kCtaGroup == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0, phase = 0;
+    for (int t = cluster_id; t < P.total_tiles; t += num_clusters) {
+      const TileCoord tc = decode_tile(P, t, BN, kRowsPerTile);
+      const TcProblem& pr = P.prob[tc.p];
+      const TcSegment& sg = pr.seg[tc.seg];
+      const int a_row = pr.a_row0 + tc.m0 + (int)cta_rank * BM;
+      const int a_b = pr.a_bcast ? 0 : tc.b;
+      const int w_row = (tc.n0 - sg.n_begin) + (int)cta_rank * C::kBRows;
+      const int nkb = (pr.K + BK - 1) / BK;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        void* sa = smem_a + stage * C::kABytes;
+        void* sb = smem_b + stage * C::kBBytes;
+        if constexpr (kCtaGroup == 1) {
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+          ptx::tma_load_3d(&pr.tmA, &full_bar[stage], sa, kb * BK, a_row, a_b);
+          ptx::tma_load_2d(&sg.tmW, &full_bar[stage], sb, kb * BK, w_row);
+        } else {
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+          ptx::tma_load_3d_2sm(&pr.tmA, &full_bar[stage], sa, kb * BK, a_row, a_b);
+          ptx::tma_load_2d_2sm(&sg.tmW, &full_bar[stage], sb, kb * BK, w_row);
+          if (!leader) ptx::mbar_arrive_cluster(&full_bar[stage], 0);
+        }
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * kCtaGroup, BN, 0, 0);
+    int stage = 0, phase = 0, iter = 0;
+    for (int t = cluster_id; t < P.total_tiles; t += num_clusters, ++iter) {
+      const TileCoord tc = decode_tile(P, t, BN, kRowsPerTile);
+      const int nkb = (P.prob[tc.p].K + BK - 1) / BK;
+      const int as = iter & 1, aphase = (iter >> 1) & 1;
+      ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint64_t adesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * C::kABytes), 0, 1024);
+        const uint64_t bdesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * C::kBBytes), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+          ptx::mma_bf16_ss<kCtaGroup>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        if constexpr (kCtaGroup == 1) {
+          ptx::mma_commit(&empty_bar[stage]);
+          if (kb == nkb - 1) ptx::mma_commit(&tfull_bar[as]);
+        } else {
+          ptx::mma_commit_2sm(&empty_bar[stage], 3);
+          if (kb == nkb - 1) ptx::mma_commit_2sm(&tfull_bar[as], 3);
+        }
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;
+    int iter = 0;
+    for (int t = cluster_id; t < P.total_tiles; t += num_clusters, ++iter) {
+      const TileCoord tc = decode_tile(P, t, BN, kRowsPerTile);
+      const TcProblem& pr = P.prob[tc.p];
+      const int as = iter & 1, aphase = (iter >> 1) & 1;
+      ptx::mbar_wait(&tfull_bar[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      const int m = tc.m0 + (int)cta_rank * BM + quad * 32 + lane;
+      epilogue_tile<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m, tc.n0);
+      ptx::tc_fence_before();
+      if constexpr (kCtaGroup == 1) ptx::mbar_arrive(&tempty_bar[as]);
+      else ptx::mbar_arrive_cluster(&tempty_bar[as], 0);
+    }
+  }
+
+  ptx::tc_fence_before();
+  if constexpr (kCtaGroup == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<kCtaGroup>(tmem_base, C::kTmemCols);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeFn>(p);
+  });
+  if (!fn) throw Error(RT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  return fn;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t d[3], s[2];
+  uint32_t box[3];
+  int rank;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rank == o.rank && d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2] && s[0] == o.s[0] &&
+           s[1] == o.s[1] && box[0] == o.box[0] && box[1] == o.box[1] && box[2] == o.box[2];
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.d[0]); mix(k.d[1]); mix(k.d[2]); mix(k.s[0]); mix(k.s[1]); mix(k.box[1]); mix(k.box[2]); mix(k.rank);
+    return h;
+  }
+};
+
+}  // namespace
+
+void encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                      const uint32_t* box) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{};
+  key.base = base;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.s[i] = strides_b[i];
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return; }
+  }
+  RT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  cuuint64_t gd[3], gs[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    RT_REQUIRE(strides_b[i] % 16 == 0, "TMA strides must be multiples of 16 bytes");
+    gs[i] = strides_b[i];
+  }
+  CUresult r = get_encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs,
+                               bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(RT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+}
+
+static int pick_bn(const GemmLaunch& L) {
+  for (int bn : {256, 128, 64}) {
+    bool ok = true;
+    for (int p = 0; p < L.nprob && ok; ++p)
+      for (int s = 0; s < L.prob[p].nseg && ok; ++s) {
+        const GemmSegment& S = L.prob[p].seg[s];
+        if (S.n_begin % bn || S.n_end % bn) ok = false;
+        if (S.mode == EPI_QKNORM_ROPE && bn < 128) ok = false;
+      }
+    if (ok) return bn;
+  }
+  return 0;
+}
+
+bool gemm_tc_supported(const GemmLaunch& L, std::string* why) {
+  auto fail = [&](const char* m) { if (why) *why = m; return false; };
+  if (L.dtype != RT_BF16) return fail("dtype is not bf16");
+  if (L.nprob < 1 || L.nprob > 2) return fail("nprob");
+  if (pick_bn(L) == 0) return fail("segment boundaries are not multiples of 64 (or 128 for qk-norm)");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  for (int p = 0; p < L.nprob; ++p) {
+    const GemmProblem& P = L.prob[p];
+    if (P.K % 8 || P.a_ld % 8 || P.a_batch_stride % 8) return fail("K / a_ld / a_batch_stride not multiples of 8");
+    if (!al16(P.A)) return fail("A not 16-byte aligned");
+    if (P.nseg < 1 || P.nseg > kMaxSeg) return fail("nseg");
+    if (P.gate && (!al16(P.gate) || P.gate_ld % 4)) return fail("gate alignment");
+    if (P.extra && (!al16(P.extra) || P.extra_ld % 8 || P.extra_batch_stride % 8)) return fail("extra alignment");
+    int expect = 0;
+    for (int s = 0; s < P.nseg; ++s) {
+      const GemmSegment& S = P.seg[s];
+      if (S.n_begin != expect || S.n_end <= S.n_begin) return fail("segments must tile [0, N) in order");
+      expect = S.n_end;
+      if (!al16(S.W) || !al16(S.out) || (S.bias && !al16(S.bias))) return fail("W / out / bias alignment");
+      if (S.out_ld % 8 || S.out_col0 % 8 || S.out_batch_stride % 8) return fail("out ld / col0 / stride alignment");
+      if (S.mode == EPI_QKNORM_ROPE) {
+        if (L.head_dim != 128) return fail("fused qk-norm needs head_dim 128");
+        if (!S.norm_w || !al16(S.norm_w)) return fail("norm_w");
+        if (L.rope && !al16(L.rope)) return fail("rope alignment");
+      }
+    }
+  }
+  return true;
+}
+
+template <int BN, int CG>
+static void launch_cfg(const TcParams& P, int num_sms, cudaStream_t stream) {
+  using C = Cfg<BN, CG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       C::kSmemBytes));
+    attr_set = true;
+  }
+  int clusters = num_sms / CG;
+  if (clusters > P.total_tiles) clusters = P.total_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, P));
+  count_launch();
+}
+
+void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_group) {
+  std::string why;
+  if (!gemm_tc_supported(L, &why)) throw Error(RT_ERR_UNSUPPORTED, "tcgen05 GEMM: " + why);
+  if (L.batch == 0) return;
+  const int bn = pick_bn(L);
+  int cg = force_cta_group ? force_cta_group : 1;
+  RT_REQUIRE(cg == 1 || cg == 2, "cta_group must be 1 or 2");
+  if (cg == 2 && bn < 128) cg = 1;  // each CTA must hold at least 64 rows of W
+
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    RT_CHECK_CUDA(cudaGetDevice(&dev));
+    RT_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+
+  TcParams P{};
+  P.nprob = L.nprob;
+  P.batch = L.batch;
+  P.rope = reinterpret_cast<const float2*>(L.rope);
+  P.head_dim = L.head_dim;
+  int tile_base = 0;
+  for (int p = 0; p < L.nprob; ++p) {
+    const GemmProblem& G = L.prob[p];
+    TcProblem& T = P.prob[p];
+    const bool bcast = G.a_batch_stride == 0;
+    uint64_t dims[3] = {(uint64_t)G.K, (uint64_t)G.a_rows_total, (uint64_t)(bcast ? 1 : L.batch)};
+    uint64_t strides[2] = {(uint64_t)G.a_ld * 2, (uint64_t)(bcast ? (long long)G.a_rows_total * G.a_ld : G.a_batch_stride) * 2};
+    uint32_t box[3] = {BK, BM, 1};
+    encode_tmap_bf16(&T.tmA, G.A, 3, dims, strides, box);
+    T.a_row0 = G.a_row0; T.a_bcast = bcast; T.m_rows = G.m_rows; T.out_row0 = G.out_row0; T.K = G.K;
+    T.nseg = G.nseg;
+    T.gate = G.gate; T.gate_ld = G.gate_ld;
+    T.extra = reinterpret_cast<const bf16*>(G.extra); T.e_bs = G.extra_batch_stride; T.e_ld = G.extra_ld;
+    T.e_row0 = G.extra_row0;
+    T.mask = reinterpret_cast<const bf16*>(G.mask); T.scale = G.scale; T.accumulate = G.accumulate;
+    for (int s = 0; s < G.nseg; ++s) {
+      const GemmSegment& S = G.seg[s];
+      TcSegment& D = T.seg[s];
+      uint64_t wd[2] = {(uint64_t)G.K, (uint64_t)(S.n_end - S.n_begin)};
+      uint64_t ws[1] = {(uint64_t)G.K * 2};
+      uint32_t wb[2] = {BK, (uint32_t)(bn / cg)};
+      encode_tmap_bf16(&D.tmW, S.W, 2, wd, ws, wb);
+      D.bias = reinterpret_cast<const bf16*>(S.bias);
+      D.out = reinterpret_cast<bf16*>(S.out);
+      D.norm_w = reinterpret_cast<const bf16*>(S.norm_w);
+      D.out_bs = S.out_batch_stride; D.n_begin = S.n_begin; D.n_end = S.n_end; D.mode = S.mode;
+      D.out_ld = S.out_ld; D.out_col0 = S.out_col0;
+    }
+    const int rows_per_tile = BM * cg;
+    T.tiles_m = (G.m_rows + rows_per_tile - 1) / rows_per_tile;
+    T.tiles_n = gemm_total_n(G) / bn;
+    T.tile_base = tile_base;
+    T.num_tiles = T.tiles_m * T.tiles_n * L.batch;
+    tile_base += T.num_tiles;
+  }
+  P.total_tiles = tile_base;
+  if (P.total_tiles == 0) return;
+
+#define RT_GEMM_CASE(BN_, CG_) \
+  if (bn == BN_ && cg == CG_) { launch_cfg<BN_, CG_>(P, num_sms, stream); return; }
+  RT_GEMM_CASE(256, 1)
+  RT_GEMM_CASE(128, 1)
+  RT_GEMM_CASE(64, 1)
+  RT_GEMM_CASE(256, 2)
+  RT_GEMM_CASE(128, 2)
+#undef RT_GEMM_CASE
+  throw Error(RT_ERR_INTERNAL, "no GEMM instantiation");
+}
+
+}  // namespace rt

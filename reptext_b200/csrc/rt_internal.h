@@ -1,0 +1,126 @@
+// Internal declarations shared by the kernels, the C++ runtime (model.cu) and the C-ABI (api.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/reptext_rt.h"
+
+namespace rt {
+
+// ------------------------------------------------------------------ errors
+void set_last_error(const std::string& msg);
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+#define RT_CHECK_CUDA(expr)                                                                              \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      throw ::rt::Error(RT_ERR_CUDA, std::string(#expr) + " -> " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                                         ":" + std::to_string(__LINE__) + ")");                          \
+  } while (0)
+#define RT_REQUIRE(cond, msg)                                                              \
+  do {                                                                                     \
+    if (!(cond)) throw ::rt::Error(RT_ERR_INVALID, std::string(msg) + " [" #cond "]");     \
+  } while (0)
+
+inline size_t dtype_size(int dt) { return dt == RT_BF16 ? 2 : 4; }
+int get_option(const char* name);
+
+// run f, translating exceptions into a status code + rt_last_error()
+template <typename F>
+inline int guarded(F&& f) {
+  try {
+    f();
+    return RT_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return RT_ERR_INTERNAL;
+  }
+}
+
+// ------------------------------------------------------------------ GEMM description
+// out[b, out_row0 + m, out_col0 + (n - n_begin)] = epilogue( sum_k A[b, a_row0 + m, k] * W_seg[n - n_begin, k] )
+// (structs are the public ones of include/reptext_rt.h)
+enum EpiMode : int {
+  EPI_BIAS = RT_EPI_BIAS,
+  EPI_GELU = RT_EPI_GELU,
+  EPI_QKNORM_ROPE = RT_EPI_QKNORM_ROPE,  // fused form exists on the tcgen05 path only
+  EPI_GATE_RESID = RT_EPI_GATE_RESID,
+  EPI_SCALE_MASK = RT_EPI_SCALE_MASK,
+};
+using GemmSegment = rt_gemm_segment;
+using GemmProblem = rt_gemm_problem;
+using GemmLaunch = rt_gemm_launch;
+
+int gemm_total_n(const GemmProblem& p);
+
+// kernels (each launches on `stream`; throws rt::Error)
+void launch_gemm_simt(const GemmLaunch& g, cudaStream_t stream);
+bool gemm_tc_supported(const GemmLaunch& g, std::string* why);
+void launch_gemm_tc(const GemmLaunch& g, cudaStream_t stream, int force_cta_group /*0 auto,1,2*/);
+void launch_gemm(const GemmLaunch& g, cudaStream_t stream);  // picks tcgen05 when supported
+extern long long g_launch_count;                             // kernels launched by this library
+
+// ------------------------------------------------------------------ other kernels
+using LnModGroup = rt_lnmod_group;
+// out[b, r, :] = LN(x[b, r, :]) * (1 + scale) + shift   (eps 1e-6, no affine)
+void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out, long long o_bs, int o_ld, int batch,
+                   int D, int ngroups, const LnModGroup* groups, cudaStream_t stream);
+
+// in-place per-head RMSNorm * w and RoPE on columns [col0, col0 + heads*hd) of buf (SIMT path)
+void launch_qknorm_rope(int dtype, void* buf, long long bs, int ld, int col0, int batch, int row0, int rows,
+                        int heads, int hd, const void* norm_w, const float2* rope, int rope_row0,
+                        cudaStream_t stream);
+
+// O[b, r, h*hd + d] = softmax(Q K^T / sqrt(hd)) V over the joint sequence; q/k/v live in one buffer
+using AttnArgs = rt_attention_args;
+void launch_attention_simt(const AttnArgs& a, cudaStream_t stream);
+bool attention_tc_supported(const AttnArgs& a, std::string* why);
+void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant);
+void launch_attention(const AttnArgs& a, cudaStream_t stream);
+
+// grouped GEMV: out[b, off + r] = dot(act(x[b, :]), W[r, :]) + bias[r]   (fp32 in/out, weights dtype T)
+struct GemvJob {
+  const void* W;
+  const void* bias;
+  int rows;
+  int out_off;
+};
+void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
+                         const int* job_row_prefix_dev, int njobs, int total_rows, float* out, int out_ld,
+                         int silu_in, int accumulate, cudaStream_t stream);
+
+void launch_time_sinusoid(int dtype, const void* t, int t_batch, int batch, float* out /*[batch,256]*/,
+                          cudaStream_t stream);
+void launch_cast_to_f32(int dtype, const void* x, float* out, long long n, cudaStream_t stream);
+void launch_rope_table(const float* ids /*[S,3]*/, int S, const int* axes /*3*/, float2* out /*[S, hd/2]*/,
+                       cudaStream_t stream);
+void launch_euler_step(int dtype, const void* v, const void* x, void* out, long long n, float sigma,
+                       float sigma_next, cudaStream_t stream);
+void launch_cfg_euler(int dtype, const void* v2 /*[2,n] uncond,text*/, const void* x, void* out, long long n,
+                      float true_scale, int zero_pred, float sigma, float sigma_next, cudaStream_t stream);
+void launch_cfg_combine(int dtype, const void* v2, void* out, long long n, float true_scale, int zero_pred,
+                        cudaStream_t stream);
+void launch_mask_scale_add(int dtype, const void* x, const void* mask, const void* acc_in, void* out, int batch,
+                           int rows, int D, float scale, cudaStream_t stream);
+void launch_glyph_blend(int dtype, const void* noise, const void* glyph_lat, const unsigned char* mask, void* out,
+                        long long n, float w_glyph, float w_noise, cudaStream_t stream);
+void launch_copy_rows(int dtype, const void* src, long long s_bs, int s_ld, int s_row0, void* dst, long long d_bs,
+                      int d_ld, int d_row0, int batch, int rows, int D, cudaStream_t stream);
+
+// ------------------------------------------------------------------ TMA descriptor encode (driver entry point)
+void encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                      const uint32_t* box);
+
+}  // namespace rt
