@@ -1,0 +1,171 @@
+"""ctypes binding of ``csrc/librt_reptext.so`` (C-ABI declared in ``include/reptext_rt.h``).
+
+There is NO CPU fallback: if the shared library is missing, or a call fails, this module raises.
+Tensors cross the boundary as raw device pointers + sizes; torch is used for device memory only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "librt_reptext.so")
+
+RT_F32, RT_BF16 = 0, 1
+RT_TRANSFORMER, RT_CONTROLNET = 0, 1
+EPI_BIAS, EPI_GELU, EPI_QKNORM_ROPE, EPI_GATE_RESID, EPI_SCALE_MASK = range(5)
+RT_ERR_INVALID = -1
+
+EXPORTS = [
+    "rt_last_error", "rt_abi_version", "rt_launch_count", "rt_set_option", "rt_get_option",
+    "rt_model_create", "rt_model_set_weight", "rt_model_finalize", "rt_model_destroy", "rt_model_workspace_bytes",
+    "rt_controlnet_forward", "rt_transformer_forward",
+    "rt_euler_step", "rt_cfg_combine", "rt_cfg_euler_step", "rt_mask_scale_add", "rt_glyph_init_blend",
+    "rt_gemm", "rt_attention", "rt_layernorm_modulate", "rt_rope_table", "rt_qknorm_rope",
+]
+
+
+class ModelConfig(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("dtype", C.c_int), ("in_channels", C.c_int), ("cond_channels", C.c_int),
+        ("out_channels", C.c_int), ("num_layers", C.c_int), ("num_single_layers", C.c_int),
+        ("num_attention_heads", C.c_int), ("attention_head_dim", C.c_int), ("joint_attention_dim", C.c_int),
+        ("pooled_projection_dim", C.c_int), ("guidance_embeds", C.c_int), ("axes_dims_rope", C.c_int * 3),
+    ]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int), ("lat_batch", C.c_int), ("t_batch", C.c_int), ("n_img", C.c_int), ("n_txt", C.c_int),
+        ("hidden_states", C.c_void_p), ("encoder_hidden_states", C.c_void_p), ("pooled_projections", C.c_void_p),
+        ("timestep", C.c_void_p), ("guidance", C.c_void_p), ("img_ids", C.c_void_p), ("txt_ids", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("stream", C.c_void_p),
+    ]
+
+
+class GemmSegment(C.Structure):
+    _fields_ = [
+        ("W", C.c_void_p), ("bias", C.c_void_p), ("n_begin", C.c_int), ("n_end", C.c_int), ("mode", C.c_int),
+        ("out", C.c_void_p), ("out_batch_stride", C.c_int64), ("out_ld", C.c_int), ("out_col0", C.c_int),
+        ("norm_w", C.c_void_p),
+    ]
+
+
+class GemmProblem(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("a_batch_stride", C.c_int64), ("a_ld", C.c_int), ("a_row0", C.c_int),
+        ("a_rows_total", C.c_int), ("m_rows", C.c_int), ("out_row0", C.c_int), ("K", C.c_int), ("nseg", C.c_int),
+        ("seg", GemmSegment * 4), ("gate", C.c_void_p), ("gate_ld", C.c_int), ("extra", C.c_void_p),
+        ("extra_batch_stride", C.c_int64), ("extra_ld", C.c_int), ("extra_row0", C.c_int), ("scale", C.c_float),
+        ("mask", C.c_void_p), ("accumulate", C.c_int),
+    ]
+
+
+class GemmLaunch(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int), ("batch", C.c_int), ("nprob", C.c_int), ("prob", GemmProblem * 2),
+        ("rope", C.c_void_p), ("head_dim", C.c_int),
+    ]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int), ("qkv", C.c_void_p), ("batch_stride", C.c_int64), ("ld", C.c_int), ("q_col0", C.c_int),
+        ("k_col0", C.c_int), ("v_col0", C.c_int), ("out", C.c_void_p), ("out_batch_stride", C.c_int64),
+        ("out_ld", C.c_int), ("out_col0", C.c_int), ("batch", C.c_int), ("S", C.c_int), ("heads", C.c_int),
+        ("hd", C.c_int),
+    ]
+
+
+class LnModGroup(C.Structure):
+    _fields_ = [("row_begin", C.c_int), ("row_end", C.c_int), ("shift", C.c_void_p), ("scale", C.c_void_p),
+                ("ld", C.c_int)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA runtime library.  Raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m reptext_b200.build` "
+            "(reptext_b200 has no CPU or PyTorch fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.rt_last_error.restype = C.c_char_p
+    L.rt_launch_count.restype = C.c_longlong
+    L.rt_model_workspace_bytes.restype = C.c_int64
+    L.rt_model_workspace_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.rt_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.rt_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    L.rt_model_create.argtypes = [C.POINTER(ModelConfig), C.POINTER(C.c_void_p)]
+    L.rt_model_set_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]
+    L.rt_model_finalize.argtypes = [C.c_void_p, C.c_void_p]
+    L.rt_model_destroy.argtypes = [C.c_void_p]
+    L.rt_controlnet_forward.argtypes = [C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p, C.c_int, C.c_float,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.rt_transformer_forward.argtypes = [C.c_void_p, C.POINTER(ForwardArgs), C.POINTER(C.c_void_p), C.c_int,
+                                         C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    L.rt_euler_step.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
+                                C.c_void_p]
+    L.rt_cfg_combine.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_void_p]
+    L.rt_cfg_euler_step.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int,
+                                    C.c_float, C.c_float, C.c_void_p]
+    L.rt_mask_scale_add.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_float, C.c_void_p]
+    L.rt_glyph_init_blend.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_float, C.c_float, C.c_void_p]
+    L.rt_gemm.argtypes = [C.POINTER(GemmLaunch), C.c_int, C.c_void_p]
+    L.rt_attention.argtypes = [C.POINTER(AttentionArgs), C.c_int, C.c_void_p]
+    L.rt_layernorm_modulate.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.POINTER(LnModGroup), C.c_void_p]
+    L.rt_rope_table.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+    L.rt_qknorm_rope.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(status: int) -> None:
+    """Translate a status code into the exception the reference would raise (ValueError for bad
+    arguments, e.g. RepText/controlnet_flux.py:297; RuntimeError otherwise)."""
+    if status == 0:
+        return
+    msg = lib().rt_last_error().decode("utf-8", "replace")
+    if status == RT_ERR_INVALID:
+        raise ValueError(msg)
+    raise RuntimeError(f"librt_reptext error {status}: {msg}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.bfloat16:
+        return RT_BF16
+    if dt == torch.float32:
+        return RT_F32
+    raise ValueError(f"unsupported dtype {dt}: the runtime computes in float32 or bfloat16")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError("reptext_b200 needs CUDA tensors (there is no CPU path)")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().rt_launch_count())
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().rt_set_option(name.encode(), int(value)))

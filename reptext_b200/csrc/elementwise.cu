@@ -133,7 +133,7 @@ void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out
     RT_REQUIRE(D % N == 0 && x_ld % N == 0 && o_ld % N == 0, "ln_mod: D and lds must be multiples of the vector width");
     const int nvec = D / N;
     const int per_lane = (nvec + 31) / 32;
-    RT_REQUIRE(per_lane <= 16, "ln_mod: D too large");
+    RT_REQUIRE(per_lane <= 24, "ln_mod: D too large");
     if (per_lane <= 2)
       ln_mod_kernel<T, 2><<<(int)blocks, threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld, batch,
                                                                rows_total, D, G);
@@ -143,8 +143,11 @@ void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out
     else if (per_lane <= 12)
       ln_mod_kernel<T, 12><<<(int)blocks, threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld, batch,
                                                                 rows_total, D, G);
-    else
+    else if (per_lane <= 16)
       ln_mod_kernel<T, 16><<<(int)blocks, threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld, batch,
+                                                                rows_total, D, G);
+    else
+      ln_mod_kernel<T, 24><<<(int)blocks, threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld, batch,
                                                                 rows_total, D, G);
   });
   RT_POST_LAUNCH();
@@ -259,6 +262,20 @@ void launch_time_sinusoid(int dtype, const void* t, int t_batch, int batch, floa
   int n = batch * 128;
   RT_DISPATCH_DTYPE(dtype, T,
                     (time_sinusoid_kernel<T><<<(n + 127) / 128, 128, 0, stream>>>((const T*)t, t_batch, batch, out)));
+  RT_POST_LAUNCH();
+}
+
+__global__ void silu_f32_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    out[i] = v / (1.f + expf(-v));
+  }
+}
+void launch_silu_f32(const float* x, float* out, long long n, cudaStream_t stream) {
+  if (n == 0) return;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  silu_f32_kernel<<<blocks, 256, 0, stream>>>(x, out, n);
   RT_POST_LAUNCH();
 }
 
@@ -380,12 +397,12 @@ __global__ void __launch_bounds__(256) euler_kernel(const T* __restrict__ v, con
     ldvec(v + i * N, a);
     ldvec(x + i * N, b);
 #pragma unroll
-    for (int j = 0; j < N; ++j) o[j] = b[j] + to_f(from_f<T>(dt * a[j]));
+    for (int j = 0; j < N; ++j) o[j] = __fadd_rn(b[j], to_f(from_f<T>(__fmul_rn(dt, a[j]))));
     stvec(out + i * N, o);
   }
   if (blockIdx.x == 0 && threadIdx.x < (int)(n - nv * N)) {
     long long i = nv * N + threadIdx.x;
-    out[i] = from_f<T>(to_f(x[i]) + to_f(from_f<T>(dt * to_f(v[i]))));
+    out[i] = from_f<T>(__fadd_rn(to_f(x[i]), to_f(from_f<T>(__fmul_rn(dt, to_f(v[i]))))));
   }
 }
 static int ew_blocks(long long nvec) {
@@ -407,10 +424,10 @@ void launch_euler_step(int dtype, const void* v, const void* x, void* out, long 
 // noise_pred = uncond + s * (text - uncond)   (each op rounded to T like the reference's tensor ops)
 template <typename T>
 __device__ __forceinline__ float cfg_one(float u, float t, float s, int zero_pred) {
-  if (zero_pred) return to_f(from_f<T>(t * 0.f));
-  float d = to_f(from_f<T>(t - u));
-  float m = to_f(from_f<T>(s * d));
-  return to_f(from_f<T>(u + m));
+  if (zero_pred) return to_f(from_f<T>(__fmul_rn(t, 0.f)));
+  float d = to_f(from_f<T>(__fsub_rn(t, u)));
+  float m = to_f(from_f<T>(__fmul_rn(s, d)));
+  return to_f(from_f<T>(__fadd_rn(u, m)));
 }
 template <typename T, bool kEuler>
 __global__ void __launch_bounds__(256) cfg_kernel(const T* __restrict__ v2, const T* __restrict__ x,
@@ -426,7 +443,8 @@ __global__ void __launch_bounds__(256) cfg_kernel(const T* __restrict__ v2, cons
       float xv[N];
       ldvec(x + i * N, xv);
 #pragma unroll
-      for (int j = 0; j < N; ++j) o[j] = xv[j] + to_f(from_f<T>(dt * cfg_one<T>(u[j], t[j], s, zero_pred)));
+      for (int j = 0; j < N; ++j)
+        o[j] = __fadd_rn(xv[j], to_f(from_f<T>(__fmul_rn(dt, cfg_one<T>(u[j], t[j], s, zero_pred)))));
     } else {
 #pragma unroll
       for (int j = 0; j < N; ++j) o[j] = cfg_one<T>(u[j], t[j], s, zero_pred);
@@ -436,7 +454,7 @@ __global__ void __launch_bounds__(256) cfg_kernel(const T* __restrict__ v2, cons
   if (blockIdx.x == 0 && threadIdx.x < (int)(n - nv * N)) {
     long long i = nv * N + threadIdx.x;
     float p = cfg_one<T>(to_f(v2[i]), to_f(v2[n + i]), s, zero_pred);
-    out[i] = kEuler ? from_f<T>(to_f(x[i]) + to_f(from_f<T>(dt * p))) : from_f<T>(p);
+    out[i] = kEuler ? from_f<T>(__fadd_rn(to_f(x[i]), to_f(from_f<T>(__fmul_rn(dt, p))))) : from_f<T>(p);
   }
 }
 void launch_cfg_combine(int dtype, const void* v2, void* out, long long n, float s, int zero_pred,
@@ -471,12 +489,12 @@ __global__ void __launch_bounds__(256) mask_scale_add_kernel(const T* __restrict
     float a[N], o[N];
     ldvec(x + i * N, a);
 #pragma unroll
-    for (int j = 0; j < N; ++j) o[j] = to_f(from_f<T>(m * to_f(from_f<T>(scale * a[j]))));
+    for (int j = 0; j < N; ++j) o[j] = to_f(from_f<T>(__fmul_rn(m, to_f(from_f<T>(__fmul_rn(scale, a[j]))))));
     if (acc_in) {
       float c[N];
       ldvec(acc_in + i * N, c);
 #pragma unroll
-      for (int j = 0; j < N; ++j) o[j] += c[j];
+      for (int j = 0; j < N; ++j) o[j] = __fadd_rn(o[j], c[j]);
     }
     stvec(out + i * N, o);
   }
@@ -502,7 +520,7 @@ __global__ void __launch_bounds__(256) glyph_blend_kernel(const T* __restrict__ 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float nz = to_f(noise[i]);
     float r = nz;
-    if (mask[i]) r = to_f(from_f<T>(wg * to_f(z[i]))) + to_f(from_f<T>(wn * nz));
+    if (mask[i]) r = __fadd_rn(to_f(from_f<T>(__fmul_rn(wg, to_f(z[i])))), to_f(from_f<T>(__fmul_rn(wn, nz))));
     out[i] = from_f<T>(r);
   }
 }

@@ -1,0 +1,598 @@
+// Model-level runtime: FluxControlNetModel.forward (RepText/controlnet_flux.py:216-413) and the
+// FluxTransformer2DModel.forward it conditions (diffusers 0.36.0, called at
+// RepText/pipeline_flux_controlnet.py:1092-1104), driven from C++ so that one forward is a straight
+// sequence of kernel launches on the caller's stream (graph-capturable: no allocation, no sync).
+//
+// HBM layout (all in the caller-provided workspace; T = text tokens, N = image tokens, S = T + N):
+//   x    [B, S, D]   residual stream, TEXT ROWS FIRST then image rows (the order attention uses)
+//   xn   [B, S, D]   LayerNorm + AdaLN-modulated copy feeding the projections
+//   qkv  [B, S, 3D]  q | k | v, head-major; q and k already RMS-normed and rotated by the GEMM epilogue
+//   cat  [B, S, 5D]  attention output (cols 0..D) | MLP hidden (cols D..5D): the single-stream block's
+//                    concat (proj_out reads it with K = 5D), and the double block's two scratch areas
+//   mod  [B, M] fp32 every block's AdaLN vectors, produced by ONE grouped GEMV per forward
+// A double block is 7 launches (2 LN-modulate, 4 grouped GEMMs over the text and image problems,
+// 1 attention); a single block is 4.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "dtype_utils.cuh"
+#include "rt_internal.h"
+
+namespace rt {
+namespace {
+
+struct Lin {
+  const void* W = nullptr;
+  const void* b = nullptr;
+  int n = 0, k = 0;
+};
+struct DoubleBlk {
+  Lin norm1, norm1c, q, k, v, aq, ak, av, o, ao, ff1, ff2, cff1, cff2;
+  const void *nq = nullptr, *nk = nullptr, *naq = nullptr, *nak = nullptr;
+  int mod_img = 0, mod_ctx = 0;
+};
+struct SingleBlk {
+  Lin norm, q, k, v, mlp, out;
+  const void *nq = nullptr, *nk = nullptr;
+  int mod = 0;
+};
+
+struct Workspace {
+  float *sin_t, *sin_g, *pooled, *hid, *temb, *temb_s, *mod;
+  float2* rope;
+  char *x, *xn, *qkv, *cat;
+};
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+}  // namespace
+}  // namespace rt
+
+using namespace rt;
+
+struct rt_model {
+  rt_model_config cfg{};
+  int D = 0, hd = 0, H = 0;
+  struct Wt {
+    const void* p;
+    std::vector<int64_t> shape;
+  };
+  std::map<std::string, Wt> w;
+  bool finalized = false;
+  Lin x_emb, ctx_emb, cnx_emb, t1, t2, g1, g2, p1, p2, norm_out, proj_out;
+  std::vector<DoubleBlk> dbl;
+  std::vector<SingleBlk> sgl;
+  std::vector<Lin> cn_blk, cn_sgl;
+  int mod_total = 0, mod_out = 0;
+  GemvJob* jobs_dev = nullptr;  // [0..5] = t1 g1 p1 t2 g2 p2, [6..] = AdaLN linears of every block
+  int* prefix_dev = nullptr;    // [0] = 0 (single-job launches), [1..] = row prefix of the AdaLN jobs
+  int n_mod_jobs = 0, mod_rows = 0;
+
+  ~rt_model() {
+    if (jobs_dev) cudaFree(jobs_dev);
+    if (prefix_dev) cudaFree(prefix_dev);
+  }
+};
+
+namespace rt {
+namespace {
+
+Lin get_linear(const rt_model& m, const std::string& name, int n, int k) {
+  auto iw = m.w.find(name + ".weight");
+  if (iw == m.w.end()) throw Error(RT_ERR_INVALID, "missing parameter " + name + ".weight");
+  const auto& sw = iw->second.shape;
+  if (sw.size() != 2 || sw[0] != n || sw[1] != k)
+    throw Error(RT_ERR_INVALID, "parameter " + name + ".weight has the wrong shape (expected [" + std::to_string(n) +
+                                    ", " + std::to_string(k) + "])");
+  Lin l;
+  l.W = iw->second.p;
+  l.n = n;
+  l.k = k;
+  auto ib = m.w.find(name + ".bias");
+  if (ib != m.w.end()) {
+    if (ib->second.shape.size() != 1 || ib->second.shape[0] != n)
+      throw Error(RT_ERR_INVALID, "parameter " + name + ".bias has the wrong shape");
+    l.b = ib->second.p;
+  }
+  return l;
+}
+const void* get_vec(const rt_model& m, const std::string& name, int n) {
+  auto it = m.w.find(name);
+  if (it == m.w.end()) throw Error(RT_ERR_INVALID, "missing parameter " + name);
+  if (it->second.shape.size() != 1 || it->second.shape[0] != n)
+    throw Error(RT_ERR_INVALID, "parameter " + name + " has the wrong shape");
+  return it->second.p;
+}
+
+size_t carve(const rt_model& m, int B, int N, int T, char* base, Workspace* ws) {
+  const size_t es = dtype_size(m.cfg.dtype);
+  const size_t S = (size_t)T + N, D = m.D;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes);
+    return base ? base + o : nullptr;
+  };
+  Workspace w{};
+  w.sin_t = (float*)take((size_t)B * 256 * 4);
+  w.sin_g = (float*)take((size_t)B * 256 * 4);
+  w.pooled = (float*)take((size_t)B * align_up(m.cfg.pooled_projection_dim, 4) * 4);
+  w.hid = (float*)take((size_t)B * 3 * D * 4);
+  w.temb = (float*)take((size_t)B * D * 4);
+  w.temb_s = (float*)take((size_t)B * D * 4);
+  w.mod = (float*)take((size_t)B * m.mod_total * 4);
+  w.rope = (float2*)take(S * (m.hd / 2) * sizeof(float2));
+  w.x = take((size_t)B * S * D * es);
+  w.xn = take((size_t)B * S * D * es);
+  w.qkv = take((size_t)B * S * 3 * D * es);
+  w.cat = take((size_t)B * S * 5 * D * es);
+  if (ws) *ws = w;
+  return off;
+}
+
+GemmSegment make_seg(const Lin& l, int n_begin, int mode, void* out, long long obs, int old, int ocol0,
+                     const void* norm_w = nullptr) {
+  GemmSegment s{};
+  s.W = l.W;
+  s.bias = l.b;
+  s.n_begin = n_begin;
+  s.n_end = n_begin + l.n;
+  s.mode = mode;
+  s.out = out;
+  s.out_batch_stride = obs;
+  s.out_ld = old;
+  s.out_col0 = ocol0;
+  s.norm_w = norm_w;
+  return s;
+}
+GemmProblem make_prob(const void* A, long long a_bs, int a_ld, int a_row0, int a_rows_total, int m_rows, int out_row0,
+                      int K) {
+  GemmProblem p{};
+  p.A = A;
+  p.a_batch_stride = a_bs;
+  p.a_ld = a_ld;
+  p.a_row0 = a_row0;
+  p.a_rows_total = a_rows_total;
+  p.m_rows = m_rows;
+  p.out_row0 = out_row0;
+  p.K = K;
+  p.scale = 1.f;
+  return p;
+}
+
+struct Ctx {
+  const rt_model& m;
+  Workspace ws;
+  int B, T, N, S, D, dt;
+  size_t es;
+  cudaStream_t st;
+  long long sD() const { return (long long)S * D; }
+};
+
+// temb = MLP_t(sin(1000 t)) + MLP_g(sin(1000 g)) + MLP_p(pooled)   (controlnet_flux.py:282-291), then the AdaLN
+// vectors of every block: mod = Linear_i(SiLU(temb)).
+void time_text_and_modulation(const Ctx& c, const rt_forward_args& a) {
+  const rt_model& m = c.m;
+  const Workspace& w = c.ws;
+  const int D = c.D, B = c.B, P = m.cfg.pooled_projection_dim;
+  const bool has_g = m.cfg.guidance_embeds != 0;
+  launch_time_sinusoid(c.dt, a.timestep, a.t_batch, B, w.sin_t, c.st);
+  if (has_g) launch_time_sinusoid(c.dt, a.guidance, a.t_batch, B, w.sin_g, c.st);
+  launch_cast_to_f32(c.dt, a.pooled_projections, w.pooled, (long long)B * P, c.st);
+  // first linears (+ SiLU) into hid = [h_t | h_g | h_p]
+  launch_gemv_grouped(c.dt, w.sin_t, 256, B, 256, m.jobs_dev + 0, m.prefix_dev, 1, D, w.hid, 3 * D, 1, 0, c.st);
+  if (has_g)
+    launch_gemv_grouped(c.dt, w.sin_g, 256, B, 256, m.jobs_dev + 1, m.prefix_dev, 1, D, w.hid, 3 * D, 1, 0, c.st);
+  launch_gemv_grouped(c.dt, w.pooled, P, B, P, m.jobs_dev + 2, m.prefix_dev, 1, D, w.hid, 3 * D, 1, 0, c.st);
+  // second linears accumulate into temb
+  launch_gemv_grouped(c.dt, w.hid, 3 * D, B, D, m.jobs_dev + 3, m.prefix_dev, 1, D, w.temb, D, 0, 0, c.st);
+  if (has_g)
+    launch_gemv_grouped(c.dt, w.hid + D, 3 * D, B, D, m.jobs_dev + 4, m.prefix_dev, 1, D, w.temb, D, 0, 1, c.st);
+  launch_gemv_grouped(c.dt, w.hid + 2 * D, 3 * D, B, D, m.jobs_dev + 5, m.prefix_dev, 1, D, w.temb, D, 0, 1, c.st);
+  launch_silu_f32(w.temb, w.temb_s, (long long)B * D, c.st);
+  launch_gemv_grouped(c.dt, w.temb_s, D, B, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, m.mod_rows, w.mod,
+                      m.mod_total, 0, 0, c.st);
+}
+
+void embed_inputs(const Ctx& c, const rt_forward_args& a, const void* cond, int cond_batch) {
+  const rt_model& m = c.m;
+  const int D = c.D, T = c.T, N = c.N, J = m.cfg.joint_attention_dim, Cin = m.cfg.in_channels;
+  // context_embedder (controlnet_flux.py:292) -> text rows of x
+  {
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
+    L.prob[0] = make_prob(a.encoder_hidden_states, (long long)T * J, J, 0, T, T, 0, J);
+    L.prob[0].nseg = 1;
+    L.prob[0].seg[0] = make_seg(m.ctx_emb, 0, EPI_BIAS, c.ws.x, c.sD(), D, 0);
+    launch_gemm(L, c.st);
+  }
+  // x_embedder (:277) -> image rows of x; batch-1 latents broadcast against batch-2 embeddings
+  {
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
+    const long long bs = (a.lat_batch == 1 && c.B > 1) ? 0 : (long long)N * Cin;
+    L.prob[0] = make_prob(a.hidden_states, bs, Cin, 0, N, N, T, Cin);
+    L.prob[0].nseg = 1;
+    L.prob[0].seg[0] = make_seg(m.x_emb, 0, EPI_BIAS, c.ws.x, c.sD(), D, 0);
+    launch_gemm(L, c.st);
+  }
+  if (cond) {  // + controlnet_x_embedder(controlnet_cond) (:280)
+    const int Cc = m.cfg.cond_channels;
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
+    const long long bs = (cond_batch == 1 && c.B > 1) ? 0 : (long long)N * Cc;
+    L.prob[0] = make_prob(cond, bs, Cc, 0, N, N, T, Cc);
+    L.prob[0].nseg = 1;
+    L.prob[0].seg[0] = make_seg(m.cnx_emb, 0, EPI_GATE_RESID, c.ws.x, c.sD(), D, 0);
+    launch_gemm(L, c.st);
+  }
+}
+
+void run_attention(const Ctx& c) {
+  AttnArgs t{};
+  t.dtype = c.dt;
+  t.qkv = c.ws.qkv; t.batch_stride = (long long)c.S * 3 * c.D; t.ld = 3 * c.D;
+  t.q_col0 = 0; t.k_col0 = c.D; t.v_col0 = 2 * c.D;
+  t.out = c.ws.cat; t.out_batch_stride = (long long)c.S * 5 * c.D; t.out_ld = 5 * c.D; t.out_col0 = 0;
+  t.batch = c.B; t.S = c.S; t.heads = c.m.H; t.hd = c.m.hd;
+  launch_attention(t, c.st);
+}
+
+// FluxTransformerBlock (diffusers).  `extra`: ControlNet residual added to the image rows
+// after the block ([B, N, D], or null) - fused into the last GEMM's epilogue.
+void double_block(const Ctx& c, const DoubleBlk& k, const void* extra) {
+  const Workspace& w = c.ws;
+  const int D = c.D, T = c.T, N = c.N, S = c.S, ld = c.m.mod_total;
+  const float* mi = w.mod + k.mod_img;
+  const float* mc = w.mod + k.mod_ctx;
+  const long long sD = c.sD(), s3D = 3 * sD, s5D = 5 * sD;
+  {
+    LnModGroup g[2] = {{0, T, mc, mc + D, ld}, {T, S, mi, mi + D, ld}};
+    launch_ln_mod(c.dt, w.x, sD, D, w.xn, sD, D, c.B, D, 2, g, c.st);
+  }
+  {
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 2; L.rope = reinterpret_cast<const float*>(w.rope); L.head_dim = c.m.hd;
+    GemmProblem& pt = L.prob[0];
+    pt = make_prob(w.xn, sD, D, 0, S, T, 0, D);
+    pt.nseg = 3;
+    pt.seg[0] = make_seg(k.aq, 0, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, 0, k.naq);
+    pt.seg[1] = make_seg(k.ak, D, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, D, k.nak);
+    pt.seg[2] = make_seg(k.av, 2 * D, EPI_BIAS, w.qkv, s3D, 3 * D, 2 * D);
+    GemmProblem& pi = L.prob[1];
+    pi = make_prob(w.xn, sD, D, T, S, N, T, D);
+    pi.nseg = 3;
+    pi.seg[0] = make_seg(k.q, 0, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, 0, k.nq);
+    pi.seg[1] = make_seg(k.k, D, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, D, k.nk);
+    pi.seg[2] = make_seg(k.v, 2 * D, EPI_BIAS, w.qkv, s3D, 3 * D, 2 * D);
+    launch_gemm(L, c.st);
+  }
+  run_attention(c);
+  {  // x += gate_msa * to_out(attn)
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 2;
+    L.prob[0] = make_prob(w.cat, s5D, 5 * D, 0, S, T, 0, D);
+    L.prob[0].nseg = 1;
+    L.prob[0].seg[0] = make_seg(k.ao, 0, EPI_GATE_RESID, w.x, sD, D, 0);
+    L.prob[0].gate = mc + 2 * D; L.prob[0].gate_ld = ld;
+    L.prob[1] = make_prob(w.cat, s5D, 5 * D, T, S, N, T, D);
+    L.prob[1].nseg = 1;
+    L.prob[1].seg[0] = make_seg(k.o, 0, EPI_GATE_RESID, w.x, sD, D, 0);
+    L.prob[1].gate = mi + 2 * D; L.prob[1].gate_ld = ld;
+    launch_gemm(L, c.st);
+  }
+  {
+    LnModGroup g[2] = {{0, T, mc + 3 * D, mc + 4 * D, ld}, {T, S, mi + 3 * D, mi + 4 * D, ld}};
+    launch_ln_mod(c.dt, w.x, sD, D, w.xn, sD, D, c.B, D, 2, g, c.st);
+  }
+  {  // MLP hidden -> cat[:, :, D:5D]
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 2;
+    L.prob[0] = make_prob(w.xn, sD, D, 0, S, T, 0, D);
+    L.prob[0].nseg = 1;
+    L.prob[0].seg[0] = make_seg(k.cff1, 0, EPI_GELU, w.cat, s5D, 5 * D, D);
+    L.prob[1] = make_prob(w.xn, sD, D, T, S, N, T, D);
+    L.prob[1].nseg = 1;
+    L.prob[1].seg[0] = make_seg(k.ff1, 0, EPI_GELU, w.cat, s5D, 5 * D, D);
+    launch_gemm(L, c.st);
+  }
+  {  // x += gate_mlp * ff2(hidden) (+ ControlNet residual on the image rows)
+    const char* h = w.cat + (size_t)D * c.es;
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 2;
+    L.prob[0] = make_prob(h, s5D, 5 * D, 0, S, T, 0, 4 * D);
+    L.prob[0].nseg = 1;
+    L.prob[0].seg[0] = make_seg(k.cff2, 0, EPI_GATE_RESID, w.x, sD, D, 0);
+    L.prob[0].gate = mc + 5 * D; L.prob[0].gate_ld = ld;
+    L.prob[1] = make_prob(h, s5D, 5 * D, T, S, N, T, 4 * D);
+    L.prob[1].nseg = 1;
+    L.prob[1].seg[0] = make_seg(k.ff2, 0, EPI_GATE_RESID, w.x, sD, D, 0);
+    L.prob[1].gate = mi + 5 * D; L.prob[1].gate_ld = ld;
+    if (extra) {
+      L.prob[1].extra = extra; L.prob[1].extra_batch_stride = (long long)N * D; L.prob[1].extra_ld = D;
+      L.prob[1].extra_row0 = 0;
+    }
+    launch_gemm(L, c.st);
+  }
+}
+
+// FluxSingleTransformerBlock on the joint sequence.  `extra` ([B, N, D]) is added to the
+// image rows (problem rows >= T).
+void single_block(const Ctx& c, const SingleBlk& k, const void* extra) {
+  const Workspace& w = c.ws;
+  const int D = c.D, T = c.T, N = c.N, S = c.S, ld = c.m.mod_total;
+  const float* md = w.mod + k.mod;
+  const long long sD = c.sD(), s3D = 3 * sD, s5D = 5 * sD;
+  {
+    LnModGroup g[1] = {{0, S, md, md + D, ld}};
+    launch_ln_mod(c.dt, w.x, sD, D, w.xn, sD, D, c.B, D, 1, g, c.st);
+  }
+  {  // q | k | v | mlp in one launch
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 1; L.rope = reinterpret_cast<const float*>(w.rope); L.head_dim = c.m.hd;
+    GemmProblem& p = L.prob[0];
+    p = make_prob(w.xn, sD, D, 0, S, S, 0, D);
+    p.nseg = 4;
+    p.seg[0] = make_seg(k.q, 0, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, 0, k.nq);
+    p.seg[1] = make_seg(k.k, D, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, D, k.nk);
+    p.seg[2] = make_seg(k.v, 2 * D, EPI_BIAS, w.qkv, s3D, 3 * D, 2 * D);
+    p.seg[3] = make_seg(k.mlp, 3 * D, EPI_GELU, w.cat, s5D, 5 * D, D);
+    launch_gemm(L, c.st);
+  }
+  run_attention(c);
+  {  // x += gate * proj_out([attn | mlp])
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
+    GemmProblem& p = L.prob[0];
+    p = make_prob(w.cat, s5D, 5 * D, 0, S, S, 0, 5 * D);
+    p.nseg = 1;
+    p.seg[0] = make_seg(k.out, 0, EPI_GATE_RESID, w.x, sD, D, 0);
+    p.gate = md + 2 * D; p.gate_ld = ld;
+    if (extra) {
+      p.extra = extra; p.extra_batch_stride = (long long)N * D; p.extra_ld = D; p.extra_row0 = T;
+    }
+    launch_gemm(L, c.st);
+  }
+}
+
+Ctx begin_forward(rt_model* m, const rt_forward_args* a) {
+  RT_REQUIRE(m && a, "null model / args");
+  RT_REQUIRE(m->finalized, "rt_model_finalize has not been called");
+  RT_REQUIRE(a->batch >= 1 && a->n_img >= 1 && a->n_txt >= 1, "batch, n_img and n_txt must be positive");
+  RT_REQUIRE(a->lat_batch == 1 || a->lat_batch == a->batch, "hidden_states batch must be 1 or the embedding batch");
+  RT_REQUIRE(a->t_batch == 1 || a->t_batch == a->batch, "timestep batch must be 1 or the embedding batch");
+  RT_REQUIRE(a->hidden_states && a->encoder_hidden_states && a->pooled_projections && a->timestep && a->img_ids &&
+                 a->txt_ids,
+             "null input tensor");
+  RT_REQUIRE(!m->cfg.guidance_embeds || a->guidance, "this model has guidance_embeds: `guidance` is required");
+  RT_REQUIRE(a->workspace, "null workspace");
+  Workspace ws;
+  size_t need = carve(*m, a->batch, a->n_img, a->n_txt, (char*)a->workspace, &ws);
+  RT_REQUIRE((size_t)a->workspace_bytes >= need, "workspace too small (see rt_model_workspace_bytes)");
+  RT_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  Ctx c{*m, ws, a->batch, a->n_txt, a->n_img, a->n_txt + a->n_img, m->D, m->cfg.dtype, dtype_size(m->cfg.dtype),
+        (cudaStream_t)a->stream};
+  // FluxPosEmbed over cat(txt_ids, img_ids) (controlnet_flux.py:316-317)
+  launch_rope_table(a->txt_ids, c.T, m->cfg.axes_dims_rope, ws.rope, c.st);
+  launch_rope_table(a->img_ids, c.N, m->cfg.axes_dims_rope, ws.rope + (size_t)c.T * (m->hd / 2), c.st);
+  time_text_and_modulation(c, *a);
+  return c;
+}
+
+}  // namespace
+}  // namespace rt
+
+extern "C" {
+
+int rt_model_create(const rt_model_config* cfg, rt_model** out) {
+  return guarded([&] {
+    RT_REQUIRE(cfg && out, "null argument");
+    RT_REQUIRE(cfg->kind == RT_TRANSFORMER || cfg->kind == RT_CONTROLNET, "kind");
+    RT_REQUIRE(cfg->dtype == RT_F32 || cfg->dtype == RT_BF16, "dtype");
+    RT_REQUIRE(cfg->num_layers >= 0 && cfg->num_single_layers >= 0, "layer counts");
+    RT_REQUIRE(cfg->num_attention_heads > 0 && (cfg->attention_head_dim == 64 || cfg->attention_head_dim == 128),
+               "attention_head_dim must be 64 or 128");
+    RT_REQUIRE(cfg->axes_dims_rope[0] + cfg->axes_dims_rope[1] + cfg->axes_dims_rope[2] == cfg->attention_head_dim,
+               "sum(axes_dims_rope) must equal attention_head_dim");
+    RT_REQUIRE(cfg->in_channels > 0 && cfg->joint_attention_dim > 0 && cfg->pooled_projection_dim > 0, "dims");
+    RT_REQUIRE(cfg->pooled_projection_dim % 4 == 0, "pooled_projection_dim must be a multiple of 4");
+    if (cfg->kind == RT_CONTROLNET) RT_REQUIRE(cfg->cond_channels > 0, "cond_channels");
+    else RT_REQUIRE(cfg->out_channels > 0, "out_channels");
+    auto* m = new rt_model();
+    m->cfg = *cfg;
+    m->hd = cfg->attention_head_dim;
+    m->H = cfg->num_attention_heads;
+    m->D = m->hd * m->H;
+    *out = m;
+  });
+}
+
+int rt_model_set_weight(rt_model* m, const char* name, const void* dev_ptr, const int64_t* shape, int ndim) {
+  return guarded([&] {
+    RT_REQUIRE(m && name && dev_ptr && shape && ndim >= 1 && ndim <= 2, "set_weight: bad argument");
+    RT_REQUIRE(!m->finalized, "set_weight after finalize");
+    RT_REQUIRE((reinterpret_cast<uintptr_t>(dev_ptr) & 15) == 0, "parameters must be 16-byte aligned");
+    rt_model::Wt w{dev_ptr, std::vector<int64_t>(shape, shape + ndim)};
+    m->w[name] = w;
+  });
+}
+
+int rt_model_finalize(rt_model* m, void* stream) {
+  return guarded([&] {
+    RT_REQUIRE(m && !m->finalized, "finalize: bad model");
+    const rt_model_config& c = m->cfg;
+    const int D = m->D, hd = m->hd;
+    const std::string tte = "time_text_embed.";
+    m->x_emb = get_linear(*m, "x_embedder", D, c.in_channels);
+    m->ctx_emb = get_linear(*m, "context_embedder", D, c.joint_attention_dim);
+    m->t1 = get_linear(*m, tte + "timestep_embedder.linear_1", D, 256);
+    m->t2 = get_linear(*m, tte + "timestep_embedder.linear_2", D, D);
+    if (c.guidance_embeds) {
+      m->g1 = get_linear(*m, tte + "guidance_embedder.linear_1", D, 256);
+      m->g2 = get_linear(*m, tte + "guidance_embedder.linear_2", D, D);
+    }
+    m->p1 = get_linear(*m, tte + "text_embedder.linear_1", D, c.pooled_projection_dim);
+    m->p2 = get_linear(*m, tte + "text_embedder.linear_2", D, D);
+
+    std::vector<GemvJob> jobs(6);
+    auto job = [](const Lin& l, int off) { return GemvJob{l.W, l.b, l.n, off}; };
+    jobs[0] = job(m->t1, 0);
+    jobs[1] = c.guidance_embeds ? job(m->g1, D) : GemvJob{nullptr, nullptr, 0, 0};
+    jobs[2] = job(m->p1, 2 * D);
+    jobs[3] = job(m->t2, 0);
+    jobs[4] = c.guidance_embeds ? job(m->g2, 0) : GemvJob{nullptr, nullptr, 0, 0};
+    jobs[5] = job(m->p2, 0);
+    std::vector<int> prefix = {0};
+    int off = 0, rows = 0;
+    auto add_mod = [&](const Lin& l) {
+      int o = off;
+      jobs.push_back(job(l, off));
+      prefix.push_back(rows);
+      off += l.n;
+      rows += l.n;
+      return o;
+    };
+
+    m->dbl.resize(c.num_layers);
+    for (int i = 0; i < c.num_layers; ++i) {
+      const std::string p = "transformer_blocks." + std::to_string(i) + ".";
+      DoubleBlk& b = m->dbl[i];
+      b.norm1 = get_linear(*m, p + "norm1.linear", 6 * D, D);
+      b.norm1c = get_linear(*m, p + "norm1_context.linear", 6 * D, D);
+      b.q = get_linear(*m, p + "attn.to_q", D, D);
+      b.k = get_linear(*m, p + "attn.to_k", D, D);
+      b.v = get_linear(*m, p + "attn.to_v", D, D);
+      b.aq = get_linear(*m, p + "attn.add_q_proj", D, D);
+      b.ak = get_linear(*m, p + "attn.add_k_proj", D, D);
+      b.av = get_linear(*m, p + "attn.add_v_proj", D, D);
+      b.o = get_linear(*m, p + "attn.to_out.0", D, D);
+      b.ao = get_linear(*m, p + "attn.to_add_out", D, D);
+      b.nq = get_vec(*m, p + "attn.norm_q.weight", hd);
+      b.nk = get_vec(*m, p + "attn.norm_k.weight", hd);
+      b.naq = get_vec(*m, p + "attn.norm_added_q.weight", hd);
+      b.nak = get_vec(*m, p + "attn.norm_added_k.weight", hd);
+      b.ff1 = get_linear(*m, p + "ff.net.0.proj", 4 * D, D);
+      b.ff2 = get_linear(*m, p + "ff.net.2", D, 4 * D);
+      b.cff1 = get_linear(*m, p + "ff_context.net.0.proj", 4 * D, D);
+      b.cff2 = get_linear(*m, p + "ff_context.net.2", D, 4 * D);
+      b.mod_img = add_mod(b.norm1);
+      b.mod_ctx = add_mod(b.norm1c);
+    }
+    m->sgl.resize(c.num_single_layers);
+    for (int j = 0; j < c.num_single_layers; ++j) {
+      const std::string p = "single_transformer_blocks." + std::to_string(j) + ".";
+      SingleBlk& b = m->sgl[j];
+      b.norm = get_linear(*m, p + "norm.linear", 3 * D, D);
+      b.q = get_linear(*m, p + "attn.to_q", D, D);
+      b.k = get_linear(*m, p + "attn.to_k", D, D);
+      b.v = get_linear(*m, p + "attn.to_v", D, D);
+      b.nq = get_vec(*m, p + "attn.norm_q.weight", hd);
+      b.nk = get_vec(*m, p + "attn.norm_k.weight", hd);
+      b.mlp = get_linear(*m, p + "proj_mlp", 4 * D, D);
+      b.out = get_linear(*m, p + "proj_out", D, 5 * D);
+      b.mod = add_mod(b.norm);
+    }
+    if (c.kind == RT_TRANSFORMER) {
+      m->norm_out = get_linear(*m, "norm_out.linear", 2 * D, D);
+      m->proj_out = get_linear(*m, "proj_out", c.out_channels, D);
+      m->mod_out = add_mod(m->norm_out);
+    } else {
+      m->cnx_emb = get_linear(*m, "controlnet_x_embedder", D, c.cond_channels);
+      for (int i = 0; i < c.num_layers; ++i)
+        m->cn_blk.push_back(get_linear(*m, "controlnet_blocks." + std::to_string(i), D, D));
+      for (int j = 0; j < c.num_single_layers; ++j)
+        m->cn_sgl.push_back(get_linear(*m, "controlnet_single_blocks." + std::to_string(j), D, D));
+    }
+    m->mod_total = off > 0 ? off : 4;
+    m->mod_rows = rows;
+    m->n_mod_jobs = (int)jobs.size() - 6;
+    RT_CHECK_CUDA(cudaMalloc(&m->jobs_dev, jobs.size() * sizeof(GemvJob)));
+    RT_CHECK_CUDA(cudaMalloc(&m->prefix_dev, prefix.size() * sizeof(int)));
+    RT_CHECK_CUDA(cudaMemcpyAsync(m->jobs_dev, jobs.data(), jobs.size() * sizeof(GemvJob), cudaMemcpyHostToDevice,
+                                  (cudaStream_t)stream));
+    RT_CHECK_CUDA(cudaMemcpyAsync(m->prefix_dev, prefix.data(), prefix.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                  (cudaStream_t)stream));
+    RT_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // the host vectors die here
+    m->finalized = true;
+  });
+}
+
+int rt_model_destroy(rt_model* m) {
+  return guarded([&] { delete m; });
+}
+
+int64_t rt_model_workspace_bytes(const rt_model* m, int batch, int n_img, int n_txt) {
+  if (!m || !m->finalized || batch < 1 || n_img < 1 || n_txt < 1) return -1;
+  return (int64_t)carve(*m, batch, n_img, n_txt, nullptr, nullptr);
+}
+
+int rt_controlnet_forward(rt_model* m, const rt_forward_args* a, const void* controlnet_cond, int cond_batch,
+                          float conditioning_scale, const void* mask, int accumulate, void* block_samples,
+                          void* single_block_samples) {
+  return guarded([&] {
+    RT_REQUIRE(m && m->cfg.kind == RT_CONTROLNET, "not a ControlNet model");
+    RT_REQUIRE(controlnet_cond && (cond_batch == 1 || (a && cond_batch == a->batch)), "controlnet_cond batch");
+    RT_REQUIRE(m->cfg.num_layers == 0 || block_samples, "block_samples is null");
+    RT_REQUIRE(m->cfg.num_single_layers == 0 || single_block_samples, "single_block_samples is null");
+    Ctx c = begin_forward(m, a);
+    embed_inputs(c, *a, controlnet_cond, cond_batch);
+    const int D = c.D, T = c.T, N = c.N, S = c.S;
+    const long long sample_elems = (long long)c.B * N * D;
+    auto zero_linear = [&](const Lin& zl, void* out) {  // controlnet_flux.py:385-396 (+ pipeline mask / sum)
+      GemmLaunch L{};
+      L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
+      GemmProblem& p = L.prob[0];
+      p = make_prob(c.ws.x, c.sD(), D, T, S, N, 0, D);
+      p.nseg = 1;
+      p.seg[0] = make_seg(zl, 0, EPI_SCALE_MASK, out, (long long)N * D, D, 0);
+      p.scale = conditioning_scale;
+      p.mask = mask;
+      p.accumulate = accumulate;
+      launch_gemm(L, c.st);
+    };
+    for (int i = 0; i < m->cfg.num_layers; ++i) {
+      double_block(c, m->dbl[i], nullptr);
+      zero_linear(m->cn_blk[i], (char*)block_samples + (size_t)i * sample_elems * c.es);
+    }
+    for (int j = 0; j < m->cfg.num_single_layers; ++j) {
+      single_block(c, m->sgl[j], nullptr);
+      zero_linear(m->cn_sgl[j], (char*)single_block_samples + (size_t)j * sample_elems * c.es);
+    }
+  });
+}
+
+int rt_transformer_forward(rt_model* m, const rt_forward_args* a, const void* const* controlnet_block_samples,
+                           int n_block_samples, const void* const* controlnet_single_block_samples,
+                           int n_single_block_samples, void* out) {
+  return guarded([&] {
+    RT_REQUIRE(m && m->cfg.kind == RT_TRANSFORMER, "not a transformer model");
+    RT_REQUIRE(out, "null output");
+    RT_REQUIRE(n_block_samples >= 0 && n_single_block_samples >= 0, "negative sample count");
+    RT_REQUIRE(n_block_samples == 0 || controlnet_block_samples, "controlnet_block_samples is null");
+    RT_REQUIRE(n_single_block_samples == 0 || controlnet_single_block_samples, "controlnet_single_block_samples");
+    Ctx c = begin_forward(m, a);
+    embed_inputs(c, *a, nullptr, 0);
+    const int D = c.D, T = c.T, N = c.N, S = c.S, nl = m->cfg.num_layers, ns = m->cfg.num_single_layers;
+    // residual injection: sample[i // ceil(L / n)] after block i (diffusers FluxTransformer2DModel.forward)
+    const int iv_d = n_block_samples ? (nl + n_block_samples - 1) / n_block_samples : 1;
+    const int iv_s = n_single_block_samples ? (ns + n_single_block_samples - 1) / n_single_block_samples : 1;
+    for (int i = 0; i < nl; ++i)
+      double_block(c, m->dbl[i], n_block_samples ? controlnet_block_samples[i / iv_d] : nullptr);
+    for (int j = 0; j < ns; ++j)
+      single_block(c, m->sgl[j], n_single_block_samples ? controlnet_single_block_samples[j / iv_s] : nullptr);
+    // norm_out (AdaLayerNormContinuous: chunk order scale, shift) + proj_out on the image rows
+    const float* mo = c.ws.mod + m->mod_out;
+    LnModGroup g[1] = {{T, S, mo + D, mo, m->mod_total}};
+    launch_ln_mod(c.dt, c.ws.x, c.sD(), D, c.ws.xn, c.sD(), D, c.B, D, 1, g, c.st);
+    const int Co = m->cfg.out_channels;
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
+    L.prob[0] = make_prob(c.ws.xn, c.sD(), D, T, S, N, 0, D);
+    L.prob[0].nseg = 1;
+    L.prob[0].seg[0] = make_seg(m->proj_out, 0, EPI_BIAS, out, (long long)N * Co, Co, 0);
+    launch_gemm(L, c.st);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+"""Host-side mirrors of the two modules the reference pipelines call every step.
+
+* :class:`FluxControlNetModel` keeps the call signature of ``RepText/controlnet_flux.py:216-229`` and the
+  return convention of ``:398-413``.
+* :class:`FluxTransformer2DModel` keeps the signature diffusers 0.36.0 exposes and the reference uses at
+  ``RepText/pipeline_flux_controlnet.py:1092-1104``.
+
+Both are thin: they validate arguments (raising what the reference raises), hand raw device pointers to the
+C-ABI (``include/reptext_rt.h``) and wrap the result buffers as tensors.  All arithmetic is in
+``csrc/*.cu``; there is no PyTorch fallback - without the built library, or on a CPU tensor, they raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+
+from . import _lib as L
+from . import weights as W
+
+_WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """One scratch buffer per (device, stream): the pipelines run the ControlNet and the transformer
+    back to back on one stream, so they share it.  It only ever grows."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.0) + 256, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+@dataclass
+class FluxControlNetOutput:
+    """``RepText/controlnet_flux.py:35-38``."""
+    controlnet_block_samples: Optional[List[torch.Tensor]]
+    controlnet_single_block_samples: Optional[List[torch.Tensor]]
+
+
+@dataclass
+class Transformer2DModelOutput:
+    sample: torch.Tensor
+
+
+class FrozenConfig(SimpleNamespace):
+    """Attribute- and item-style access, like diffusers' ``FrozenDict`` config."""
+
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+    def get(self, k, default=None):
+        return getattr(self, k, default)
+
+
+class _RuntimeModel:
+    """Common part: owns the parameter tensors (diffusers state-dict names) and the native handle."""
+
+    _kind = "transformer"
+
+    def __init__(self, config: dict, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 dtype: torch.dtype = torch.bfloat16, device: Union[str, torch.device] = "cuda"):
+        self.config = FrozenConfig(**config)
+        self._cfg = dict(config)
+        self._dtype = dtype
+        self._device = torch.device(device)
+        self._handle: Optional[C.c_void_p] = None
+        self._params: Dict[str, torch.Tensor] = {}
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # ---- nn.Module-like surface the pipelines touch -------------------------------------------------
+    @property
+    def dtype(self) -> torch.dtype:
+        return self._dtype
+
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    def to(self, *args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.dtype) and a != self._dtype:
+                raise ValueError("reptext_b200 models are built for one dtype; pass dtype= at construction")
+            if isinstance(a, (str, torch.device)) and torch.device(a).type != "cuda":
+                raise ValueError("reptext_b200 models live on a CUDA device (there is no CPU path)")
+        return self
+
+    def eval(self):
+        return self
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return dict(self._params)
+
+    def parameters(self):
+        return iter(self._params.values())
+
+    @classmethod
+    def from_config(cls, config: dict, **kw):
+        return cls(config, **kw)
+
+    @classmethod
+    def random_init(cls, config: dict, seed: int = 0, dtype: torch.dtype = torch.bfloat16, device="cuda",
+                    zero_init: bool = False):
+        """Seeded random-init weights with the FLUX.1-dev / RepText architecture (no network for checkpoints)."""
+        sd = W.random_state_dict(config, cls._kind, seed=seed, dtype=dtype, device=device, zero_init=zero_init)
+        return cls(config, sd, dtype=dtype, device=device)
+
+    # ---- native handle ------------------------------------------------------------------------------
+    def _native_config(self) -> L.ModelConfig:
+        c = self._cfg
+        nc = L.ModelConfig()
+        nc.kind = L.RT_CONTROLNET if self._kind == "controlnet" else L.RT_TRANSFORMER
+        nc.dtype = L.dtype_code(self._dtype)
+        nc.in_channels = c["in_channels"]
+        nc.cond_channels = c["in_channels"] + c.get("extra_condition_channels", 0)
+        nc.out_channels = (c.get("out_channels") or c["in_channels"]) * c.get("patch_size", 1) ** 2
+        nc.num_layers = c["num_layers"]
+        nc.num_single_layers = c["num_single_layers"]
+        nc.num_attention_heads = c["num_attention_heads"]
+        nc.attention_head_dim = c["attention_head_dim"]
+        nc.joint_attention_dim = c["joint_attention_dim"]
+        nc.pooled_projection_dim = c["pooled_projection_dim"]
+        nc.guidance_embeds = int(bool(c.get("guidance_embeds", False)))
+        for i, a in enumerate(c["axes_dims_rope"]):
+            nc.axes_dims_rope[i] = int(a)
+        return nc
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True) -> None:
+        lib = L.lib()
+        want = {k: tuple(s) for k, s, _ in W.param_table(self._cfg, self._kind)}
+        missing = [k for k in want if k not in sd]
+        unexpected = [k for k in sd if k not in want]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing keys {missing[:4]}..., unexpected keys {unexpected[:4]}...")
+        if self._handle is not None:
+            L.check(lib.rt_model_destroy(self._handle))
+            self._handle = None
+        h = C.c_void_p()
+        nc = self._native_config()
+        L.check(lib.rt_model_create(C.byref(nc), C.byref(h)))
+        self._params = {}
+        for k, shape in want.items():
+            t = sd[k]
+            if tuple(t.shape) != shape:
+                raise RuntimeError(f"load_state_dict: {k} has shape {tuple(t.shape)}, expected {shape}")
+            t = t.detach().to(device=self._device, dtype=self._dtype).contiguous()
+            self._params[k] = t
+            shp = (C.c_int64 * t.dim())(*t.shape)
+            L.check(lib.rt_model_set_weight(h, k.encode(), L.ptr(t), shp, t.dim()))
+        L.check(lib.rt_model_finalize(h, L.stream_ptr()))
+        self._handle = h
+
+    def __del__(self):
+        try:
+            if self._handle is not None and L._lib is not None:
+                L._lib.rt_model_destroy(self._handle)
+        except Exception:
+            pass
+
+    # ---- argument marshalling -----------------------------------------------------------------------
+    def _check(self, name: str, t: torch.Tensor, last: Optional[int] = None, dtype: Optional[torch.dtype] = None):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"`{name}` must be a torch.Tensor")
+        if not t.is_cuda:
+            raise ValueError(f"`{name}` must be a CUDA tensor (reptext_b200 has no CPU path)")
+        if last is not None and t.shape[-1] != last:
+            raise ValueError(f"`{name}` has {t.shape[-1]} features, the model expects {last}")
+        return t.to(dtype or self._dtype).contiguous()
+
+    def _forward_args(self, hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
+                      guidance, keep: list) -> L.ForwardArgs:
+        c = self._cfg
+        if self._handle is None:
+            raise RuntimeError("model has no weights: call load_state_dict() or use random_init()")
+        hs = self._check("hidden_states", hidden_states, c["in_channels"])
+        enc = self._check("encoder_hidden_states", encoder_hidden_states, c["joint_attention_dim"])
+        pooled = self._check("pooled_projections", pooled_projections, c["pooled_projection_dim"])
+        if hs.dim() != 3 or enc.dim() != 3 or pooled.dim() != 2:
+            raise ValueError("hidden_states / encoder_hidden_states must be 3-D and pooled_projections 2-D")
+        if txt_ids.ndim == 3:   # deprecated batched ids (controlnet_flux.py:302-315)
+            txt_ids = txt_ids[0]
+        if img_ids.ndim == 3:
+            img_ids = img_ids[0]
+        B = enc.shape[0]
+        if pooled.shape[0] != B:
+            raise ValueError("pooled_projections and encoder_hidden_states disagree on the batch size")
+        if hs.shape[0] not in (1, B):
+            raise ValueError("hidden_states batch must be 1 or match encoder_hidden_states")
+        N, T = hs.shape[1], enc.shape[1]
+        if img_ids.shape[0] != N or txt_ids.shape[0] != T:
+            raise ValueError("img_ids / txt_ids do not match the token counts")
+        ts = self._check("timestep", timestep.reshape(-1))
+        if ts.numel() not in (1, B):
+            raise ValueError("timestep must have 1 or batch elements")
+        g = None
+        if c.get("guidance_embeds", False):
+            if guidance is None:
+                raise ValueError("this model was built with guidance_embeds=True: `guidance` is required")
+            g = self._check("guidance", guidance.reshape(-1))
+            if g.numel() != ts.numel():
+                g = g.expand(ts.numel()).contiguous() if g.numel() == 1 else g
+            if g.numel() != ts.numel():
+                raise ValueError("guidance and timestep disagree on the batch size")
+        ii = self._check("img_ids", img_ids, 3, torch.float32)
+        ti = self._check("txt_ids", txt_ids, 3, torch.float32)
+        nbytes = L.lib().rt_model_workspace_bytes(self._handle, B, N, T)
+        ws = _workspace(hs.device, nbytes)
+        base = (ws.data_ptr() + 255) // 256 * 256
+        a = L.ForwardArgs()
+        a.batch, a.lat_batch, a.t_batch, a.n_img, a.n_txt = B, hs.shape[0], ts.numel(), N, T
+        a.hidden_states, a.encoder_hidden_states, a.pooled_projections = L.ptr(hs), L.ptr(enc), L.ptr(pooled)
+        a.timestep, a.guidance, a.img_ids, a.txt_ids = L.ptr(ts), L.ptr(g), L.ptr(ii), L.ptr(ti)
+        a.workspace, a.workspace_bytes, a.stream = base, ws.numel() - (base - ws.data_ptr()), L.stream_ptr()
+        keep.extend([hs, enc, pooled, ts, g, ii, ti, ws])
+        return a
+
+
+class FluxControlNetModel(_RuntimeModel):
+    """Drop-in for ``RepText/controlnet_flux.py:41`` (inference path)."""
+
+    _kind = "controlnet"
+
+    def __init__(self, config: dict, state_dict=None, dtype=torch.bfloat16, device="cuda"):
+        if config.get("num_mode") is not None:
+            raise NotImplementedError("ControlNet-Union (num_mode) is outside the RepText hot path")
+        super().__init__(config, state_dict, dtype, device)
+        self.union = False
+
+    @property
+    def inner_dim(self) -> int:
+        return self._cfg["num_attention_heads"] * self._cfg["attention_head_dim"]
+
+    @torch.no_grad()
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        controlnet_cond: torch.Tensor,
+        controlnet_mode: torch.Tensor = None,
+        conditioning_scale: float = 1.0,
+        encoder_hidden_states: torch.Tensor = None,
+        pooled_projections: torch.Tensor = None,
+        timestep: torch.Tensor = None,
+        img_ids: torch.Tensor = None,
+        txt_ids: torch.Tensor = None,
+        guidance: torch.Tensor = None,
+        joint_attention_kwargs: Optional[Dict[str, Any]] = None,
+        return_dict: bool = True,
+        *,
+        regional_mask: Optional[torch.Tensor] = None,
+        accumulate_into: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None,
+    ):
+        """Same arguments as the reference.  Two keyword-only extensions let the pipelines fuse their
+        per-step host work into the zero-linear epilogue: ``regional_mask`` ([1, N, 1]; the multiply at
+        ``pipeline_flux_controlnet.py:1060-1069``) and ``accumulate_into`` (the stacked outputs of a previous
+        text line; the sum at ``:1072-1087``)."""
+        if controlnet_mode is not None:
+            raise ValueError("`controlnet_mode` is only valid for ControlNet-Union models (num_mode is None here)")
+        if joint_attention_kwargs:
+            extra = set(joint_attention_kwargs) - {"scale"}
+            if extra:
+                raise NotImplementedError(f"joint_attention_kwargs {sorted(extra)} are not supported")
+        c = self._cfg
+        keep: list = []
+        a = self._forward_args(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
+                               guidance if c.get("guidance_embeds") else None, keep)
+        cond = self._check("controlnet_cond", controlnet_cond, c["in_channels"] + c.get("extra_condition_channels", 0))
+        if cond.dim() != 3 or cond.shape[1] != a.n_img or cond.shape[0] not in (1, a.batch):
+            raise ValueError("controlnet_cond must be [1 or batch, n_img, in_channels + extra_condition_channels]")
+        B, N, D = a.batch, a.n_img, self.inner_dim
+        nl, ns = c["num_layers"], c["num_single_layers"]
+        acc_b, acc_s = accumulate_into if accumulate_into is not None else (None, None)
+
+        def out_buf(n, acc):
+            if n == 0:
+                return None
+            if acc is not None:
+                if tuple(acc.shape) != (n, B, N, D) or acc.dtype != self._dtype or not acc.is_contiguous():
+                    raise ValueError("accumulate_into must be the stacked [layers, B, N, D] output of a previous call")
+                return acc
+            return torch.empty(n, B, N, D, dtype=self._dtype, device=cond.device)
+
+        blocks, singles = out_buf(nl, acc_b), out_buf(ns, acc_s)
+        mask = None
+        if regional_mask is not None:
+            mask = self._check("regional_mask", regional_mask.reshape(-1))
+            if mask.numel() != N:
+                raise ValueError("regional_mask must have one value per image token")
+        L.check(L.lib().rt_controlnet_forward(self._handle, C.byref(a), L.ptr(cond), cond.shape[0],
+                                              float(conditioning_scale), L.ptr(mask),
+                                              int(accumulate_into is not None), L.ptr(blocks), L.ptr(singles)))
+        bl = list(blocks.unbind(0)) if blocks is not None else None
+        sl = list(singles.unbind(0)) if singles is not None else None
+        if bl is not None:
+            bl[0]._rt_stacked = blocks          # lets the pipeline pass the stack back as accumulate_into
+        if sl is not None:
+            sl[0]._rt_stacked = singles
+        if not return_dict:
+            return (bl, sl)
+        return FluxControlNetOutput(controlnet_block_samples=bl, controlnet_single_block_samples=sl)
+
+    __call__ = forward
+
+
+class FluxTransformer2DModel(_RuntimeModel):
+    """Drop-in for diffusers' ``FluxTransformer2DModel`` as the reference pipelines call it."""
+
+    _kind = "transformer"
+
+    @torch.no_grad()
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        encoder_hidden_states: torch.Tensor = None,
+        pooled_projections: torch.Tensor = None,
+        timestep: torch.Tensor = None,
+        img_ids: torch.Tensor = None,
+        txt_ids: torch.Tensor = None,
+        guidance: torch.Tensor = None,
+        joint_attention_kwargs: Optional[Dict[str, Any]] = None,
+        controlnet_block_samples=None,
+        controlnet_single_block_samples=None,
+        return_dict: bool = True,
+        controlnet_blocks_repeat: bool = False,
+    ):
+        if controlnet_blocks_repeat:
+            raise NotImplementedError("controlnet_blocks_repeat is not used by the RepText pipelines")
+        if joint_attention_kwargs:
+            extra = set(joint_attention_kwargs) - {"scale"}
+            if extra:
+                raise NotImplementedError(f"joint_attention_kwargs {sorted(extra)} are not supported")
+        c = self._cfg
+        keep: list = []
+        a = self._forward_args(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
+                               guidance if c.get("guidance_embeds") else None, keep)
+        B, N, D = a.batch, a.n_img, c["num_attention_heads"] * c["attention_head_dim"]
+
+        def ptr_array(samples, what):
+            if samples is None or len(samples) == 0:
+                return None, 0
+            arr = (C.c_void_p * len(samples))()
+            for i, s in enumerate(samples):
+                s = self._check(what, s, D)
+                if tuple(s.shape) != (B, N, D):
+                    raise ValueError(f"{what}[{i}] must be [batch, n_img, {D}]")
+                keep.append(s)
+                arr[i] = L.ptr(s)
+            return arr, len(samples)
+
+        bp, nb = ptr_array(controlnet_block_samples, "controlnet_block_samples")
+        sp, nsg = ptr_array(controlnet_single_block_samples, "controlnet_single_block_samples")
+        co = (c.get("out_channels") or c["in_channels"]) * c.get("patch_size", 1) ** 2
+        out = torch.empty(B, N, co, dtype=self._dtype, device=self._device)
+        L.check(L.lib().rt_transformer_forward(self._handle, C.byref(a), bp, nb, sp, nsg, L.ptr(out)))
+        if not return_dict:
+            return (out,)
+        return Transformer2DModelOutput(sample=out)
+
+    __call__ = forward

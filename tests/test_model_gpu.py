@@ -1,0 +1,166 @@
+"""Model-level parity on the GPU through the C-ABI: FluxControlNetModel.forward and
+FluxTransformer2DModel.forward against the oracle (oracle/flux_oracle.py) on identical random-init weights.
+
+Bars (BASELINE.json north_star): <= 1e-4 rel-L2 against the fp32 oracle on the tiny config (fp32 kernels);
+<= 1e-2 in bf16 (tcgen05 kernels), checked against the fp32 oracle evaluated on the same bf16-rounded weights.
+"""
+import pytest
+import torch
+
+from util import rel_l2, synth_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(tr_cfg, cn_cfg, dtype, seed=100):
+    from reptext_b200 import models, weights
+    tr_sd = weights.random_state_dict(tr_cfg, "transformer", seed=seed)
+    cn_sd = weights.random_state_dict(cn_cfg, "controlnet", seed=seed + 1)
+    if dtype == torch.bfloat16:  # both sides see the same bf16-rounded parameters
+        tr_sd = {k: v.to(dtype).float() for k, v in tr_sd.items()}
+        cn_sd = {k: v.to(dtype).float() for k, v in cn_sd.items()}
+    tr = models.FluxTransformer2DModel(tr_cfg, tr_sd, dtype=dtype)
+    cn = models.FluxControlNetModel(cn_cfg, cn_sd, dtype=dtype)
+    return tr, cn, tr_sd, cn_sd
+
+
+def _oracle_time(v, dtype):
+    """the reference rounds `timestep.to(dtype) * 1000` IN THE MODEL DTYPE
+    (controlnet_flux.py:282-284).  The fp32 oracle is fed that rounded value so that both sides embed
+    the same timestep (bf16(0.62) * 1000 is 620 in bf16, not 621.09)."""
+    if dtype == torch.float32:
+        return v
+    return (v.to(dtype) * 1000).float() / 1000
+
+
+def _oracle_on(device, sd):
+    return {k: v.to(device) for k, v in sd.items()}
+
+
+CASES = [
+    # name, transformer cfg, controlnet cfg, H, W, T, dtype, tol
+    ("tiny_fp32", "TINY_TRANSFORMER", "TINY_CONTROLNET", 256, 256, 64, torch.float32, 1e-4),
+    ("tiny_fp32_ragged", "TINY_TRANSFORMER", "TINY_CONTROLNET", 208, 176, 40, torch.float32, 1e-4),
+    ("small128_bf16", "SMALL128_TRANSFORMER", "SMALL128_CONTROLNET", 256, 256, 128, torch.bfloat16, 1e-2),
+    ("small128_bf16_ragged", "SMALL128_TRANSFORMER", "SMALL128_CONTROLNET", 208, 176, 72, torch.bfloat16, 1e-2),
+    ("tiny_bf16_simt", "TINY_TRANSFORMER", "TINY_CONTROLNET", 256, 256, 64, torch.bfloat16, 1e-2),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_controlnet_and_transformer_forward(case):
+    from oracle import flux_oracle as O
+    from reptext_b200 import config
+    name, trn, cnn, H, Wd, T, dtype, tol = case
+    TR, CN = getattr(config, trn), getattr(config, cnn)
+    tr, cn, tr_sd, cn_sd = _build(TR, CN, dtype)
+    x = synth_inputs(TR, CN, H, Wd, T, seed=7, batch=2, n_lines=2)
+    if dtype == torch.bfloat16:
+        x = {k: ([t.to(dtype).float() for t in v] if isinstance(v, list) else (v.to(dtype).float() if torch.is_tensor(v) else v))
+             for k, v in x.items()}
+    dev = "cuda"
+    t = torch.tensor([0.62, 0.62])
+    g = torch.tensor([3.5, 3.5])
+    to, go = _oracle_time(t, dtype).to("cuda"), _oracle_time(g, dtype).to("cuda")
+    # ---------------- oracle (fp32, on the GPU through stock torch: same function, faster than the CPU)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        osd_tr, osd_cn = _oracle_on(dev, tr_sd), _oracle_on(dev, cn_sd)
+        xg = {k: ([t_.to(dev) for t_ in v] if isinstance(v, list) else (v.to(dev) if torch.is_tensor(v) else v))
+              for k, v in x.items()}
+        with torch.no_grad():
+            ob, os_ = O.controlnet_forward(osd_cn, CN, xg["latents"], xg["conds"][0], 0.8, xg["prompt_embeds"],
+                                           xg["pooled"], to, xg["img_ids"], xg["txt_ids"], go)
+            onp = O.transformer_forward(osd_tr, TR, xg["latents"], xg["prompt_embeds"], xg["pooled"], to,
+                                        xg["img_ids"], xg["txt_ids"], go, ob, None)
+            onp0 = O.transformer_forward(osd_tr, TR, xg["latents"], xg["prompt_embeds"], xg["pooled"], to,
+                                         xg["img_ids"], xg["txt_ids"], go, None, None)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert os_ is None
+    # ---------------- CUDA path
+    c = lambda v: v.to(dev, dtype)
+    kw = dict(encoder_hidden_states=c(xg["prompt_embeds"]), pooled_projections=c(xg["pooled"]), timestep=c(t),
+              img_ids=c(xg["img_ids"]), txt_ids=c(xg["txt_ids"]), guidance=g.to(dev))
+    blocks, singles = cn(hidden_states=c(xg["latents"]), controlnet_cond=c(xg["conds"][0]), conditioning_scale=0.8,
+                         return_dict=False, **kw)
+    assert singles is None and len(blocks) == CN["num_layers"]
+    for i, (got, want) in enumerate(zip(blocks, ob)):
+        assert got.shape == want.shape and got.dtype == dtype
+        assert rel_l2(got.float(), want) < tol, (name, "controlnet block", i, rel_l2(got.float(), want))
+    # the oracle's samples go into the transformer, so that its error is measured on its own
+    np0 = tr(hidden_states=c(xg["latents"]), return_dict=False, **kw)[0]
+    assert rel_l2(np0.float(), onp0) < tol, (name, "transformer", rel_l2(np0.float(), onp0))
+    np1 = tr(hidden_states=c(xg["latents"]), controlnet_block_samples=[c(s) for s in ob], return_dict=False, **kw)[0]
+    assert rel_l2(np1.float(), onp) < tol, (name, "transformer + residuals", rel_l2(np1.float(), onp))
+    assert rel_l2(onp, onp0) > 10 * tol  # the residual injection is visible at this tolerance
+    # ---------------- fused regional mask + multi-line sum == the pipeline's host-side form
+    m0, m1 = c(xg["masks"][0]), c(xg["masks"][1])
+    b0, _ = cn(hidden_states=c(xg["latents"]), controlnet_cond=c(xg["conds"][0]), conditioning_scale=0.8,
+               return_dict=False, regional_mask=m0, **kw)
+    stacked = b0[0]._rt_stacked
+    b01, _ = cn(hidden_states=c(xg["latents"]), controlnet_cond=c(xg["conds"][1]), conditioning_scale=0.8,
+                return_dict=False, regional_mask=m1, accumulate_into=(stacked, None), **kw)
+    with torch.no_grad():
+        ob1, _ = O.controlnet_forward(osd_cn, CN, xg["latents"], xg["conds"][1], 0.8, xg["prompt_embeds"],
+                                      xg["pooled"], to, xg["img_ids"], xg["txt_ids"], go)
+    for i in range(len(ob)):
+        want = xg["masks"][0] * ob[i] + xg["masks"][1] * ob1[i]
+        assert rel_l2(b01[i].float(), want) < tol, (name, "mask+sum", i)
+
+
+@pytest.mark.parametrize("dtype,trn,cnn,tol", [(torch.float32, "TINY_TRANSFORMER", "TINY_INPAINT_CONTROLNET", 1e-4),
+                                                (torch.bfloat16, "SMALL128_TRANSFORMER", "SMALL128_CONTROLNET", 1e-2)])
+def test_batch1_latents_broadcast_against_batch2_embeddings(dtype, trn, cnn, tol):
+    """Inpaint pipeline true-CFG (pipeline_flux_controlnet_inpaint.py:1145): latents are NOT doubled."""
+    from oracle import flux_oracle as O
+    from reptext_b200 import config
+    TR, CN = getattr(config, trn), getattr(config, cnn)
+    tr, cn, tr_sd, cn_sd = _build(TR, CN, dtype)
+    x = synth_inputs(TR, CN, 128, 192, 48, seed=9, batch=2, n_lines=1)
+    dev = "cuda"
+    r = (lambda v: v.to(dtype).float()) if dtype == torch.bfloat16 else (lambda v: v)
+    lat1 = r(x["latents"][:1]).to(dev)
+    pe, po = r(x["prompt_embeds"]).to(dev), r(x["pooled"]).to(dev)
+    cond = r(x["conds"][0][:1]).to(dev)
+    t, g = torch.tensor([0.3]).to(dev), torch.tensor([3.5]).to(dev)
+    to, go = _oracle_time(t, dtype), _oracle_time(g, dtype)
+    ii, ti = x["img_ids"].to(dev), x["txt_ids"].to(dev)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ob, _ = O.controlnet_forward(_oracle_on(dev, cn_sd), CN, lat1, torch.cat([cond] * 2), 1.0, pe, po, to, ii, ti, go)
+            onp = O.transformer_forward(_oracle_on(dev, tr_sd), TR, lat1, pe, po, to, ii, ti, go, ob, None)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    c = lambda v: v.to(dev, dtype)
+    kw = dict(encoder_hidden_states=c(pe), pooled_projections=c(po), timestep=c(t), img_ids=ii, txt_ids=ti, guidance=g)
+    bl, _ = cn(hidden_states=c(lat1), controlnet_cond=c(torch.cat([cond] * 2)), return_dict=False, **kw)
+    for got, want in zip(bl, ob):
+        assert got.shape[0] == 2 and rel_l2(got.float(), want) < tol
+    got = tr(hidden_states=c(lat1), controlnet_block_samples=[c(s) for s in ob], return_dict=False, **kw)[0]
+    assert got.shape == onp.shape and rel_l2(got.float(), onp) < tol
+
+
+def test_model_argument_errors():
+    from reptext_b200 import config, models
+    cn = models.FluxControlNetModel.random_init(config.TINY_CONTROLNET, dtype=torch.float32)
+    x = synth_inputs(config.TINY_TRANSFORMER, config.TINY_CONTROLNET, 64, 64, 8, batch=1)
+    dev = "cuda"
+    kw = dict(hidden_states=x["latents"].to(dev), controlnet_cond=x["conds"][0].to(dev),
+              encoder_hidden_states=x["prompt_embeds"].to(dev), pooled_projections=x["pooled"].to(dev),
+              timestep=torch.tensor([0.5], device=dev), img_ids=x["img_ids"].to(dev), txt_ids=x["txt_ids"].to(dev),
+              guidance=torch.tensor([3.5], device=dev))
+    cn(**kw)
+    with pytest.raises(ValueError):   # controlnet_flux.py:297 raises ValueError on a mode/union mismatch
+        cn(**dict(kw, controlnet_mode=torch.zeros(1, 1, dtype=torch.long, device=dev)))
+    with pytest.raises(ValueError):
+        cn(**dict(kw, guidance=None))
+    with pytest.raises(ValueError):
+        cn(**dict(kw, controlnet_cond=x["conds"][0][:, :, :100].to(dev)))
+    with pytest.raises(ValueError):
+        cn(**dict(kw, hidden_states=x["latents"]))  # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        models.FluxControlNetModel(config.TINY_CONTROLNET, {"x_embedder.weight": torch.zeros(1)}, dtype=torch.float32)
