@@ -205,13 +205,17 @@ def controlnet_forward(
     img_ids: Tensor,
     txt_ids: Tensor,
     guidance: Optional[Tensor],
+    time_dtype: Optional[torch.dtype] = None,
 ) -> Tuple[Optional[List[Tensor]], Optional[List[Tensor]]]:
+    """``time_dtype``: evaluate ``timestep.to(dtype) * 1000`` in that dtype (the reference does it in the MODEL
+    dtype, so a bf16 run embeds bf16-rounded timesteps - SURVEY.md 3.4 quirk 6); None = the dtype of the weights."""
     heads = cfg["num_attention_heads"]
     h = _lin(sd, "x_embedder", hidden_states)                        # :277
     h = h + _lin(sd, "controlnet_x_embedder", controlnet_cond)      # :280
-    timestep = timestep.to(h.dtype) * 1000                           # :282
+    td = time_dtype or h.dtype
+    timestep = (timestep.to(td) * 1000).to(h.dtype)                  # :282
     if guidance is not None and cfg.get("guidance_embeds", False):
-        guidance = guidance.to(h.dtype) * 1000                       # :284
+        guidance = (guidance.to(td) * 1000).to(h.dtype)              # :284
     else:
         guidance = None
     temb = time_text_embed(sd, "", timestep, guidance, pooled_projections)   # :287-291
@@ -255,12 +259,14 @@ def transformer_forward(
     guidance: Optional[Tensor],
     controlnet_block_samples: Optional[List[Tensor]] = None,
     controlnet_single_block_samples: Optional[List[Tensor]] = None,
+    time_dtype: Optional[torch.dtype] = None,
 ) -> Tensor:
     heads = cfg["num_attention_heads"]
     x = _lin(sd, "x_embedder", hidden_states)
-    timestep = timestep.to(x.dtype) * 1000
+    td = time_dtype or x.dtype
+    timestep = (timestep.to(td) * 1000).to(x.dtype)
     if guidance is not None and cfg.get("guidance_embeds", False):
-        guidance = guidance.to(x.dtype) * 1000
+        guidance = (guidance.to(td) * 1000).to(x.dtype)
     else:
         guidance = None
     temb = time_text_embed(sd, "", timestep, guidance, pooled_projections)
@@ -386,19 +392,21 @@ def denoise_t2i(
     text_ids: Tensor, img_ids: Tensor,
     timesteps: Tensor, sigmas: Tensor,
     guidance_scale: float, conditioning_scale: float = 1.0, conditioning_step: int = 30,
-    callback=None,
+    callback=None, time_dtype: Optional[torch.dtype] = None,
 ) -> Tensor:
+    """``time_dtype`` (default: the latents' dtype) is the dtype the reference would hold ``timestep`` in."""
+    td = time_dtype or latents.dtype
     for i, t in enumerate(timesteps):
-        timestep = t.expand(latents.shape[0]).to(latents.dtype)                       # :1025
+        timestep = t.expand(latents.shape[0]).to(td)                                  # :1025
         guidance = None
         if tr_cfg.get("guidance_embeds", False):
-            guidance = torch.tensor([guidance_scale]).expand(latents.shape[0])        # :1029-1030
+            guidance = torch.tensor([guidance_scale], device=latents.device).expand(latents.shape[0])        # :1029-1030
         blk = sgl = None
         for ci in range(len(control_image_list)):                                     # :1037
             mask = control_mask_list[ci] if len(control_mask_list) > 0 else None
             if i < conditioning_step:                                                 # :1042
                 b, s = controlnet_forward(cn_sd, cn_cfg, latents, control_image_list[ci], conditioning_scale,
-                                          prompt_embeds, pooled, timestep / 1000, img_ids, text_ids, guidance)
+                                          prompt_embeds, pooled, timestep / 1000, img_ids, text_ids, guidance, td)
             else:
                 b, s = None, None
             if b is not None:                                                         # :1060-1064
@@ -413,7 +421,7 @@ def denoise_t2i(
                 if s is not None and sgl is not None:
                     sgl = [u + v for u, v in zip(sgl, s)]
         noise_pred = transformer_forward(tr_sd, tr_cfg, latents, prompt_embeds, pooled, timestep / 1000,
-                                         img_ids, text_ids, guidance, blk, sgl)      # :1092-1104
+                                         img_ids, text_ids, guidance, blk, sgl, td)      # :1092-1104
         latents = euler_step(noise_pred, sigmas[i], sigmas[i + 1], latents)           # :1109
         if callback is not None:
             callback(i, t, latents)                                                   # :1116-1123
@@ -432,20 +440,21 @@ def denoise_inpaint(
     timesteps: Tensor, sigmas: Tensor,
     guidance_scale: float, true_guidance_scale: float = 3.5,
     conditioning_scale: float = 1.0, conditioning_step: int = 30, conditioning_scale_inpaint: float = 1.0,
-    callback=None,
+    callback=None, time_dtype: Optional[torch.dtype] = None,
 ) -> Tensor:
     do_cfg = guidance_scale > 1                                                      # :241-242
+    td = time_dtype or latents.dtype
     for i, t in enumerate(timesteps):
-        timestep = t.expand(latents.shape[0]).to(latents.dtype)                       # :1148
+        timestep = t.expand(latents.shape[0]).to(td)                                  # :1148
         guidance = None
         if tr_cfg.get("guidance_embeds", False):
-            guidance = torch.tensor([guidance_scale]).expand(latents.shape[0])        # :1152-1153
+            guidance = torch.tensor([guidance_scale], device=latents.device).expand(latents.shape[0])        # :1152-1153
         blk = sgl = None
         for ci in range(len(control_image_list)):                                     # :1160
             mask = control_mask_list[ci] if len(control_mask_list) > 0 else None
             if i < conditioning_step:
                 b, s = controlnet_forward(cn_sd, cn_cfg, latents, control_image_list[ci], conditioning_scale,
-                                          prompt_embeds, pooled, timestep / 1000, img_ids, text_ids, guidance)
+                                          prompt_embeds, pooled, timestep / 1000, img_ids, text_ids, guidance, td)
             else:
                 b, s = None, None
             if b is not None:
@@ -460,7 +469,7 @@ def denoise_inpaint(
                 if s is not None and sgl is not None:
                     sgl = [u + v for u, v in zip(sgl, s)]
         b, s = controlnet_forward(cni_sd, cni_cfg, latents, control_image_inpaint, conditioning_scale_inpaint,
-                                  prompt_embeds, pooled, timestep / 1000, img_ids, text_ids, guidance)  # :1214-1227
+                                  prompt_embeds, pooled, timestep / 1000, img_ids, text_ids, guidance, td)  # :1214-1227
         if b is not None:
             b = [x.to(latents.dtype) for x in b]
         if s is not None:
@@ -470,7 +479,7 @@ def denoise_inpaint(
         if s is not None and sgl is not None:                                         # :1239-1245
             sgl = [u + v for u, v in zip(sgl, s)]
         noise_pred = transformer_forward(tr_sd, tr_cfg, latents, prompt_embeds, pooled, timestep / 1000,
-                                         img_ids, text_ids, guidance, blk, sgl)      # :1250-1262
+                                         img_ids, text_ids, guidance, blk, sgl, td)      # :1250-1262
         if do_cfg:                                                                    # :1264-1270
             uncond, text = noise_pred.chunk(2)
             if i > 0:

@@ -1,0 +1,319 @@
+"""Shared host-side orchestration of the two RepText pipelines.
+
+Everything here is the reference's own once-per-call preparation and per-step control flow
+(``RepText/pipeline_flux_controlnet.py:882-1148``, ``RepText/pipeline_flux_controlnet_inpaint.py:981-1313``)
+restated over the B200 runtime: per step it issues
+
+    controlnet(...)  per text line   -> rt_controlnet_forward   (mask * scale and the multi-line sum fused)
+    controlnet_inpaint(...)          -> rt_controlnet_forward   (accumulating into the same residuals)
+    transformer(...)                 -> rt_transformer_forward  (residual injection fused)
+    scheduler.step(...) [+ true CFG] -> rt_euler_step / rt_cfg_euler_step
+
+The reference's quirks are kept on purpose: the T2I glyph-latent init is dead code, the inpaint
+one is live; ``control_guidance_start/end`` have no effect; the gate is ``i < controlnet_conditioning_step``;
+true-CFG step 0 predicts zero; inpaint residuals are dropped when no text-line residuals exist.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .models import FluxControlNetModel
+from .pipeline_utils import DiffusionPipeline, FluxPipelineOutput, VaeImageProcessor, randn_tensor
+
+
+def calculate_shift(image_seq_len, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
+                    max_shift: float = 1.16):
+    """``pipeline_flux_controlnet.py:78-88``: mu is linear in the number of image tokens."""
+    slope = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    return image_seq_len * slope + (base_shift - slope * base_seq_len)
+
+
+def retrieve_timesteps(scheduler, num_inference_steps=None, device=None, timesteps=None, sigmas=None, **kwargs):
+    """``pipeline_flux_controlnet.py:104-160``."""
+    if timesteps is not None and sigmas is not None:
+        raise ValueError("Only one of `timesteps` or `sigmas` can be passed. Please choose one to set custom values")
+    if timesteps is not None:
+        scheduler.set_timesteps(timesteps=timesteps, device=device, **kwargs)
+    elif sigmas is not None:
+        scheduler.set_timesteps(sigmas=sigmas, device=device, **kwargs)
+    else:
+        scheduler.set_timesteps(num_inference_steps, device=device, **kwargs)
+    return scheduler.timesteps, len(scheduler.timesteps)
+
+
+def retrieve_latents(encoder_output, generator=None, sample_mode: str = "sample"):
+    if hasattr(encoder_output, "latent_dist") and sample_mode == "sample":
+        return encoder_output.latent_dist.sample(generator)
+    if hasattr(encoder_output, "latent_dist") and sample_mode == "argmax":
+        return encoder_output.latent_dist.mode()
+    if hasattr(encoder_output, "latents"):
+        return encoder_output.latents
+    raise AttributeError("Could not access latents of provided encoder_output")
+
+
+class RepTextPipelineBase(DiffusionPipeline):
+    _callback_tensor_inputs = ["latents", "prompt_embeds"]
+    _inpaint = False
+
+    def _setup(self):
+        vae = getattr(self, "vae", None)
+        self.vae_scale_factor = 2 ** len(vae.config.block_out_channels) if vae is not None else 16
+        self.image_processor = VaeImageProcessor(vae_scale_factor=self.vae_scale_factor)
+        tok = getattr(self, "tokenizer", None)
+        self.tokenizer_max_length = tok.model_max_length if tok is not None else 77
+        self.default_sample_size = 64
+        self._guidance_scale = 1.0
+        self._joint_attention_kwargs = None
+        self._interrupt = False
+        self._num_timesteps = 0
+
+    # ---- properties of the reference ----------------------------------------------------------------
+    @property
+    def do_classifier_free_guidance(self):
+        return self._guidance_scale > 1
+
+    @property
+    def guidance_scale(self):
+        return self._guidance_scale
+
+    @property
+    def joint_attention_kwargs(self):
+        return self._joint_attention_kwargs
+
+    @property
+    def num_timesteps(self):
+        return self._num_timesteps
+
+    @property
+    def interrupt(self):
+        return self._interrupt
+
+    # ---- once-per-call helpers ----------------------------------------------------------------------
+    def check_inputs(self, prompt, prompt_2, height, width, prompt_embeds=None, pooled_prompt_embeds=None,
+                     callback_on_step_end_tensor_inputs=None, max_sequence_length=None):
+        """Same conditions and exception types as ``pipeline_flux_controlnet.py:486-531``."""
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if callback_on_step_end_tensor_inputs is not None:
+            bad = [k for k in callback_on_step_end_tensor_inputs if k not in self._callback_tensor_inputs]
+            if bad:
+                raise ValueError(f"`callback_on_step_end_tensor_inputs` has to be in {self._callback_tensor_inputs}, "
+                                 f"but found {bad}")
+        if prompt is not None and prompt_embeds is not None:
+            raise ValueError("Cannot forward both `prompt` and `prompt_embeds`. Please make sure to only forward one.")
+        if prompt_2 is not None and prompt_embeds is not None:
+            raise ValueError("Cannot forward both `prompt_2` and `prompt_embeds`. Please make sure to only forward one.")
+        if prompt is None and prompt_embeds is None:
+            raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both undefined.")
+        if prompt is not None and not isinstance(prompt, (str, list)):
+            raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
+        if prompt_2 is not None and not isinstance(prompt_2, (str, list)):
+            raise ValueError(f"`prompt_2` has to be of type `str` or `list` but is {type(prompt_2)}")
+        if prompt_embeds is not None and pooled_prompt_embeds is None:
+            raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
+        if max_sequence_length is not None and max_sequence_length > 512:
+            raise ValueError(f"`max_sequence_length` cannot be greater than 512 but is {max_sequence_length}")
+
+    def _encode_text(self, prompt, num_images_per_prompt, max_sequence_length):
+        enc = getattr(self, "text_encoder", None)
+        if enc is None or not hasattr(enc, "encode"):
+            raise ValueError("no text encoder is attached to this pipeline: pass `prompt_embeds` and "
+                             "`pooled_prompt_embeds` (the T5 / CLIP encoders are outside the accelerated path)")
+        prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+        pe, po = enc.encode(prompts, max_sequence_length)
+        pe = pe.repeat_interleave(num_images_per_prompt, dim=0)
+        po = po.repeat_interleave(num_images_per_prompt, dim=0)
+        return pe, po
+
+    def _text_ids(self, n_txt: int, device) -> torch.Tensor:
+        enc = getattr(self, "text_encoder", None)
+        dtype = enc.dtype if enc is not None and hasattr(enc, "dtype") else self.transformer.dtype
+        return torch.zeros(n_txt, 3).to(device=device, dtype=dtype)      # :449-451
+
+    @staticmethod
+    def _prepare_latent_image_ids(batch_size, height, width, device, dtype):
+        """``:535-546``: (0, row, col) per 2x2 latent patch."""
+        rows, cols = height // 2, width // 2
+        ids = torch.zeros(rows, cols, 3)
+        ids[..., 1] += torch.arange(rows)[:, None]
+        ids[..., 2] += torch.arange(cols)[None, :]
+        return ids.reshape(rows * cols, 3).to(device=device, dtype=dtype)
+
+    @staticmethod
+    def _pack_latents(latents, batch_size, num_channels_latents, height, width):
+        """``:550-555``: [B, C, H, W] -> [B, (H/2)(W/2), 4C]."""
+        x = latents.view(batch_size, num_channels_latents, height // 2, 2, width // 2, 2).permute(0, 2, 4, 1, 3, 5)
+        return x.reshape(batch_size, (height // 2) * (width // 2), num_channels_latents * 4)
+
+    @staticmethod
+    def _unpack_latents(latents, height, width, vae_scale_factor):
+        """``:559-570``."""
+        b, _, ch = latents.shape
+        h, w = height // vae_scale_factor, width // vae_scale_factor
+        x = latents.view(b, h, w, ch // 4, 2, 2).permute(0, 3, 1, 4, 2, 5)
+        return x.reshape(b, ch // 4, h * 2, w * 2)
+
+    def _encode_vae_image(self, image: torch.Tensor, generator):
+        if isinstance(generator, list):
+            lat = torch.cat([retrieve_latents(self.vae.encode(image[i:i + 1]), generator=generator[i])
+                             for i in range(image.shape[0])], dim=0)
+        else:
+            lat = retrieve_latents(self.vae.encode(image), generator=generator)
+        return (lat - self.vae.config.shift_factor) * self.vae.config.scaling_factor
+
+    def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
+        """``:573-605``."""
+        height = 2 * (int(height) // self.vae_scale_factor)
+        width = 2 * (int(width) // self.vae_scale_factor)
+        ids = self._prepare_latent_image_ids(batch_size, height, width, device, dtype)
+        if latents is not None:
+            return latents.to(device=device, dtype=dtype), ids
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
+                             f"effective batch size of {batch_size}.")
+        noise = randn_tensor((batch_size, num_channels_latents, height, width), generator=generator, device=device,
+                             dtype=dtype)
+        return self._pack_latents(noise, batch_size, num_channels_latents, height, width), ids
+
+    def prepare_latents_reptext(self, image, batch_size, num_channels_latents, height, width, dtype, device, generator,
+                                latents=None):
+        """Glyph-latent init (``:608-660``; inpaint ``:608-655``).  The T2I pipeline computes the blend and then
+        packs the plain noise (dead code upstream); the inpaint pipeline packs the blend."""
+        height = 2 * (int(height) // self.vae_scale_factor)
+        width = 2 * (int(width) // self.vae_scale_factor)
+        image = image.to(device=device, dtype=dtype)
+        image_latents = self._encode_vae_image(image=image, generator=generator)
+        n0 = image_latents.shape[0]
+        if batch_size > n0 and batch_size % n0 == 0:
+            image_latents = torch.cat([image_latents] * (batch_size // n0), dim=0)
+        elif batch_size > n0:
+            raise ValueError(f"Cannot duplicate `image` of batch size {n0} to {batch_size} text prompts.")
+        ids = self._prepare_latent_image_ids(batch_size, height, width, device, dtype)
+        if latents is not None:
+            return latents.to(device=device, dtype=dtype), ids
+        noise = randn_tensor((batch_size, num_channels_latents, height, width), generator=generator, device=device,
+                             dtype=dtype)
+        if self._inpaint:
+            gm = (image > 0).any(dim=1, keepdim=True).repeat(1, 16, 1, 1).float()
+            gm = F.interpolate(gm, size=(noise.shape[-2], noise.shape[-1]), mode="bilinear", align_corners=False)
+            gm = (gm > 0).expand_as(noise).contiguous().to(torch.uint8)
+            noise = ops.glyph_init_blend(noise.contiguous(), image_latents.to(dtype).contiguous(), gm, 0.10, 1.00)
+        return self._pack_latents(noise, batch_size, num_channels_latents, height, width), ids
+
+    def _repeat(self, x, batch_size, num_images_per_prompt):
+        return x.repeat_interleave(batch_size if x.shape[0] == 1 else num_images_per_prompt, dim=0)
+
+    def prepare_image(self, image, width, height, batch_size, num_images_per_prompt, device, dtype,
+                      image_position=None, do_classifier_free_guidance=False, guess_mode=False):
+        """Canny + position images -> VAE latents -> channel concat -> pack (``:663-731``).  The posterior is
+        sampled with the GLOBAL RNG, like upstream."""
+        if not isinstance(image, torch.Tensor):
+            image = self.image_processor.preprocess(image, height=height, width=width)
+        image = self._repeat(image, batch_size, num_images_per_prompt).to(device=device, dtype=dtype)
+        if not isinstance(image_position, torch.Tensor):
+            image_position = self.image_processor.preprocess(image_position, height=height, width=width)
+        image_position = self._repeat(image_position, batch_size, num_images_per_prompt).to(device=device, dtype=dtype)
+        image_position = image_position.repeat(1, 3, 1, 1)
+        cfg = self.vae.config
+
+        def enc(x):
+            z = self.vae.encode(x.to(self.vae.dtype)).latent_dist.sample()
+            return ((z - cfg.shift_factor) * cfg.scaling_factor).to(dtype)
+
+        control = torch.cat([enc(image), enc(image_position)], dim=1)
+        packed = self._pack_latents(control, batch_size * num_images_per_prompt, control.shape[1], control.shape[2],
+                                    control.shape[3])
+        if do_classifier_free_guidance:
+            packed = torch.cat([packed] * 2)
+        return packed, height, width
+
+    def _regional_masks(self, control_mask, device, dtype) -> List[torch.Tensor]:
+        """``:1007-1013``: 0/255 box -> [0, 1] -> bilinear x1/16 -> [1, N, 1]."""
+        out = []
+        if control_mask is not None:
+            for m in control_mask:
+                region = torch.from_numpy(np.array(m)) / 255.0
+                mk = F.interpolate(region[None, None], scale_factor=1 / 16, mode="bilinear").reshape([1, -1, 1])
+                out.append(mk.to(device=device, dtype=dtype))
+        return out
+
+    # ---- the hot loop -------------------------------------------------------------------------------
+    def _denoise(self, *, latents, latent_image_ids, text_ids, prompt_embeds, pooled_prompt_embeds, timesteps,
+                 num_inference_steps, guidance_scale, control_image_list, control_mask_list, control_mode,
+                 controlnet_conditioning_scale, controlnet_conditioning_step, callback_on_step_end,
+                 callback_on_step_end_tensor_inputs, control_image_inpaint=None,
+                 controlnet_conditioning_scale_inpaint=1.0, true_guidance_scale=3.5):
+        device = latents.device
+        num_warmup_steps = max(len(timesteps) - num_inference_steps * self.scheduler.order, 0)
+        do_cfg = self._inpaint and self.do_classifier_free_guidance
+        guidance_const = None
+        if self.transformer.config.guidance_embeds:
+            # the reference rebuilds this 1-element tensor every step (:1029); it is step-invariant
+            guidance_const = torch.tensor([guidance_scale], device=device)
+        common = dict(controlnet_mode=control_mode, joint_attention_kwargs=self.joint_attention_kwargs,
+                      return_dict=False)
+        with self.progress_bar(total=num_inference_steps) as progress_bar:
+            for i, t in enumerate(timesteps):
+                if self.interrupt:
+                    continue
+                timestep = t.expand(latents.shape[0]).to(latents.dtype)
+                guidance = guidance_const.expand(latents.shape[0]) if guidance_const is not None else None
+                step_kw = dict(hidden_states=latents, timestep=timestep / 1000, guidance=guidance,
+                               pooled_projections=pooled_prompt_embeds, encoder_hidden_states=prompt_embeds,
+                               txt_ids=text_ids, img_ids=latent_image_ids)
+                blocks = singles = None          # python lists of per-block tensors, or None
+                stack_b = stack_s = None         # the same data as one [L, B, N, D] tensor
+                if i < controlnet_conditioning_step:
+                    for ci, cond in enumerate(control_image_list):
+                        mask = control_mask_list[ci] if len(control_mask_list) > 0 else None
+                        acc = (stack_b, stack_s) if ci > 0 else None
+                        blocks, singles = self.controlnet(controlnet_cond=cond,
+                                                          conditioning_scale=controlnet_conditioning_scale,
+                                                          regional_mask=mask, accumulate_into=acc, **step_kw, **common)
+                        stack_b = blocks[0]._rt_stacked if blocks is not None else None
+                        stack_s = singles[0]._rt_stacked if singles is not None else None
+                if control_image_inpaint is not None and (blocks is not None or singles is not None):
+                    # second ControlNet (inpaint :1214-1245); its residuals only survive when text-line residuals exist
+                    blocks, singles = self.controlnet_inpaint(controlnet_cond=control_image_inpaint,
+                                                              conditioning_scale=controlnet_conditioning_scale_inpaint,
+                                                              accumulate_into=(stack_b, stack_s), **step_kw, **common)
+                noise_pred = self.transformer(controlnet_block_samples=blocks, controlnet_single_block_samples=singles,
+                                              joint_attention_kwargs=self.joint_attention_kwargs, return_dict=False,
+                                              **step_kw)[0]
+                if do_cfg:   # :1264-1270, fused with the Euler step
+                    latents = self.scheduler.step_cfg(noise_pred, t, latents, true_guidance_scale, zero_pred=(i == 0))
+                else:
+                    latents = self.scheduler.step(noise_pred, t, latents, return_dict=False)[0]
+                if callback_on_step_end is not None:
+                    local = dict(latents=latents, prompt_embeds=prompt_embeds)
+                    outs = callback_on_step_end(self, i, t, {k: local[k] for k in callback_on_step_end_tensor_inputs})
+                    outs = outs or {}
+                    latents = outs.pop("latents", latents)
+                    prompt_embeds = outs.pop("prompt_embeds", prompt_embeds)
+                if i == len(timesteps) - 1 or ((i + 1) > num_warmup_steps and (i + 1) % self.scheduler.order == 0):
+                    progress_bar.update()
+        return latents
+
+    def _finish(self, latents, height, width, output_type, return_dict):
+        if output_type == "latent":
+            image = latents
+        else:
+            z = self._unpack_latents(latents, height, width, self.vae_scale_factor)
+            z = (z / self.vae.config.scaling_factor) + self.vae.config.shift_factor
+            image = self.vae.decode(z, return_dict=False)[0]
+            image = self.image_processor.postprocess(image, output_type=output_type)
+        self.maybe_free_model_hooks()
+        if not return_dict:
+            return (image,)
+        return FluxPipelineOutput(images=image)
+
+    def _require_controlnet(self, net, name):
+        # the reference only defines control_image_list under this isinstance (:928-929); anything else NameErrors
+        if not isinstance(net, FluxControlNetModel):
+            raise TypeError(f"`{name}` must be a reptext_b200 FluxControlNetModel (multi-ControlNet wrappers are not "
+                            "used by the RepText pipelines)")

@@ -53,6 +53,8 @@ SMALL128_CONTROLNET = dict(
     num_mode=None, extra_conditioning_channels=0, extra_condition_channels=64,
 )
 
+SMALL128_INPAINT_CONTROLNET = dict(SMALL128_CONTROLNET, extra_condition_channels=4)
+
 # FLUX.1-dev scheduler_config.json
 SCHEDULER = dict(
     num_train_timesteps=1000, shift=3.0, use_dynamic_shifting=True,

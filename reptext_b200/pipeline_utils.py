@@ -1,0 +1,240 @@
+"""Minimal host-side pieces the reference pipelines take from diffusers (which is not installable here):
+a ``DiffusionPipeline`` base (``register_modules``, ``_execution_device``, ``progress_bar``,
+``maybe_free_model_hooks``), ``VaeImageProcessor`` (PIL / numpy / tensor -> [-1, 1] NCHW and back),
+``randn_tensor``, and stand-ins for the modules OUTSIDE the hot path - the VAE and the CLIP / T5 text
+encoders (SURVEY.md section 8f "next") - so that the reference-shaped ``__call__`` runs end to end on synthetic
+data.  The stand-ins are deterministic and cheap; they make no claim to be FLUX's VAE or T5.
+"""
+from __future__ import annotations
+
+import contextlib
+import hashlib
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .models import FrozenConfig
+
+try:  # PIL is host-side glyph rendering's library; present in this image
+    import PIL.Image
+except Exception:  # pragma: no cover
+    PIL = None
+
+
+def randn_tensor(shape, generator=None, device=None, dtype=None):
+    """diffusers.utils.torch_utils.randn_tensor: draw on the generator's device, then move."""
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    if isinstance(generator, (list, tuple)):
+        shape1 = (1,) + tuple(shape[1:])
+        parts = [randn_tensor(shape1, g, device, dtype) for g in generator]
+        return torch.cat(parts, dim=0)
+    gdev = generator.device if generator is not None else device
+    t = torch.randn(tuple(shape), generator=generator, device=gdev, dtype=dtype)
+    return t.to(device)
+
+
+@dataclass
+class FluxPipelineOutput:
+    images: Union[List, np.ndarray, torch.Tensor]
+
+
+class _Progress:
+    def __init__(self, total, disable):
+        self.total, self.n, self.disable = total, 0, disable
+
+    def update(self, k=1):
+        self.n += k
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+class DiffusionPipeline:
+    """The slice of diffusers' DiffusionPipeline the reference touches (pipeline_flux_controlnet.py:209-218,
+    :906, :1016, :1143)."""
+
+    def __init__(self):
+        self._modules_registered: List[str] = []
+        self._progress_bar_config = {}
+
+    def register_modules(self, **modules):
+        for name, m in modules.items():
+            setattr(self, name, m)
+            self._modules_registered.append(name)
+
+    @property
+    def components(self):
+        return {k: getattr(self, k) for k in self._modules_registered}
+
+    @property
+    def _execution_device(self) -> torch.device:
+        for name in ("transformer", "controlnet"):
+            m = getattr(self, name, None)
+            if m is not None and hasattr(m, "device"):
+                return torch.device(m.device)
+        return torch.device("cuda")
+
+    @property
+    def device(self):
+        return self._execution_device
+
+    def to(self, *args, **kwargs):
+        for name in self._modules_registered:
+            m = getattr(self, name)
+            if hasattr(m, "to"):
+                m.to(*args, **kwargs)
+        return self
+
+    def set_progress_bar_config(self, **kwargs):
+        self._progress_bar_config = kwargs
+
+    def progress_bar(self, iterable=None, total=None):
+        return _Progress(total, self._progress_bar_config.get("disable", True))
+
+    def maybe_free_model_hooks(self):
+        pass
+
+    def enable_model_cpu_offload(self, *a, **k):
+        raise NotImplementedError("weights stay resident in HBM (180 GB per B200); CPU offload is not provided")
+
+
+class VaeImageProcessor:
+    """PIL / numpy / tensor -> float NCHW in [-1, 1] (or [0, 1] masks), resized to (height, width)."""
+
+    def __init__(self, vae_scale_factor: int = 8, do_resize: bool = True, do_normalize: bool = True,
+                 do_binarize: bool = False, do_convert_grayscale: bool = False, do_convert_rgb: bool = False):
+        self.config = FrozenConfig(vae_scale_factor=vae_scale_factor, do_resize=do_resize, do_normalize=do_normalize,
+                                   do_binarize=do_binarize, do_convert_grayscale=do_convert_grayscale,
+                                   do_convert_rgb=do_convert_rgb)
+
+    def _one(self, img) -> torch.Tensor:
+        c = self.config
+        if PIL is not None and isinstance(img, PIL.Image.Image):
+            if c.do_convert_grayscale:
+                img = img.convert("L")
+            elif c.do_convert_rgb:
+                img = img.convert("RGB")
+            arr = np.array(img).astype(np.float32) / 255.0
+        elif isinstance(img, np.ndarray):
+            arr = img.astype(np.float32)
+            if arr.max() > 1.0:
+                arr = arr / 255.0
+        elif isinstance(img, torch.Tensor):
+            t = img.float()
+            if t.dim() == 2:
+                t = t[None]
+            return t if t.dim() == 3 else t[0]
+        else:
+            raise ValueError(f"unsupported image type {type(img)}")
+        if arr.ndim == 2:
+            arr = arr[..., None]
+        if c.do_convert_grayscale and arr.shape[-1] == 3:
+            arr = arr.mean(-1, keepdims=True)
+        return torch.from_numpy(arr).permute(2, 0, 1)
+
+    def preprocess(self, image, height: Optional[int] = None, width: Optional[int] = None) -> torch.Tensor:
+        c = self.config
+        imgs = image if isinstance(image, (list, tuple)) else [image]
+        if isinstance(image, torch.Tensor) and image.dim() == 4:
+            x = image.float()
+        else:
+            x = torch.stack([self._one(i) for i in imgs])
+        if c.do_resize and height is not None and width is not None and tuple(x.shape[-2:]) != (height, width):
+            x = F.interpolate(x, size=(height, width), mode="bilinear", align_corners=False)
+        if c.do_normalize:
+            x = 2.0 * x - 1.0
+        if c.do_binarize:
+            x = (x >= 0.5).to(x.dtype)
+        return x
+
+    def postprocess(self, image: torch.Tensor, output_type: str = "pil"):
+        if output_type in ("latent", "pt"):
+            return image
+        x = (image.float() / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).cpu().numpy()
+        if output_type == "np":
+            return x
+        if output_type == "pil":
+            return [PIL.Image.fromarray((im * 255).round().astype("uint8").squeeze()) for im in x]
+        raise ValueError(f"unknown output_type {output_type}")
+
+
+# ------------------------------------------------------------------------------------------------------
+# Stand-ins for modules outside the hot path
+# ------------------------------------------------------------------------------------------------------
+class _LatentDist:
+    def __init__(self, mean: torch.Tensor, std: float):
+        self.mean, self.std = mean, std
+
+    def sample(self, generator=None) -> torch.Tensor:
+        noise = randn_tensor(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
+class SyntheticVAE:
+    """Stand-in with AutoencoderKL's interface (``encode(x).latent_dist.sample()``, ``decode(z)``,
+    ``config.{shift_factor, scaling_factor, block_out_channels}``, ``dtype``): 8x average pooling and a fixed
+    3 -> 16 channel mix.  NOT the FLUX VAE (out of scope)."""
+
+    def __init__(self, dtype=torch.bfloat16, device="cuda", latent_channels: int = 16, posterior_std: float = 0.0):
+        self.dtype, self.device = dtype, torch.device(device)
+        self.config = FrozenConfig(shift_factor=0.1159, scaling_factor=0.3611, block_out_channels=(128, 256, 512, 512),
+                                   latent_channels=latent_channels)
+        g = torch.Generator().manual_seed(1234)
+        self._mix = torch.randn(latent_channels, 3, generator=g).to(self.device)
+        self._std = posterior_std
+
+    def to(self, *a, **k):
+        return self
+
+    def encode(self, x: torch.Tensor):
+        x = x.to(self.device, torch.float32)
+        if x.shape[1] == 1:
+            x = x.repeat(1, 3, 1, 1)
+        p = F.avg_pool2d(x, 8)
+        z = torch.einsum("oc,bchw->bohw", self._mix, p)
+        return FrozenConfig(latent_dist=_LatentDist(z.to(self.dtype), self._std))
+
+    def decode(self, z: torch.Tensor, return_dict: bool = True):
+        z = z.to(self.device, torch.float32)
+        img = torch.einsum("oc,bohw->bchw", self._mix, z) / self._mix.shape[0]
+        img = F.interpolate(img, scale_factor=8, mode="nearest").clamp(-1, 1).to(self.dtype)
+        return (img,) if not return_dict else FrozenConfig(sample=img)
+
+
+class SyntheticTextEncoders:
+    """Stand-in for CLIP + T5: prompt -> deterministic pseudo-random (prompt_embeds [B, L, joint_dim],
+    pooled [B, pooled_dim]) seeded by a hash of the prompt.  NOT a language model (out of scope, 8f.3)."""
+
+    def __init__(self, joint_attention_dim: int, pooled_projection_dim: int, dtype=torch.bfloat16, device="cuda"):
+        self.joint, self.pooled = joint_attention_dim, pooled_projection_dim
+        self.dtype, self.device = dtype, torch.device(device)
+
+    def to(self, *a, **k):
+        return self
+
+    def _gen(self, text: str) -> torch.Generator:
+        seed = int.from_bytes(hashlib.sha256(text.encode("utf-8")).digest()[:7], "little")
+        return torch.Generator().manual_seed(seed)
+
+    def encode(self, prompts: Sequence[str], max_sequence_length: int):
+        pe, po = [], []
+        for p in prompts:
+            g = self._gen(p)
+            pe.append(torch.randn(max_sequence_length, self.joint, generator=g))
+            po.append(torch.randn(self.pooled, generator=g))
+        return (torch.stack(pe).to(self.device, self.dtype), torch.stack(po).to(self.device, self.dtype))
+
+
+@contextlib.contextmanager
+def no_grad():
+    with torch.no_grad():
+        yield
