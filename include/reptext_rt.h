@@ -51,9 +51,15 @@ typedef struct rt_model_config {
 RT_API const char* rt_last_error(void); /* host string, valid until the next failing call on this thread */
 RT_API int rt_abi_version(void);
 RT_API long long rt_launch_count(void); /* number of this library's kernels launched so far (process-wide) */
-/* options: "force_simt" (0/1), "gemm_cta_group" (0 auto, 1, 2), "attn_variant" (0 auto, ...) */
+/* options: "force_simt" (0/1), "gemm_cta_group" (0 auto, 1, 2), "attn_variant" (0 auto, ...), "profile" (0/1) */
 RT_API int rt_set_option(const char* name, int value);
 RT_API int rt_get_option(const char* name, int* value);
+
+/* Per-class device timing for the roofline report (bench.py): with option "profile" = 1 every launch of a class
+ * is bracketed by CUDA events on its own stream.  class: 0 tcgen05 GEMM, 1 SIMT GEMM, 2 tcgen05 attention,
+ * 3 SIMT attention, 4 LayerNorm-modulate, 5 grouped GEMV, 6 elementwise.  work = algorithmic FLOPs (0-3) or bytes. */
+RT_API int rt_profile_reset(void);
+RT_API int rt_profile_read(int cls, double* ms, double* work, long long* count);
 
 /* ---- model life cycle: replaces FluxControlNetModel.__init__ / from_pretrained
  *      (RepText/controlnet_flux.py:44-116, RepText/infer.py:30-33) and diffusers' FluxTransformer2DModel. */

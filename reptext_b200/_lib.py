@@ -21,6 +21,7 @@ RT_ERR_INVALID = -1
 
 EXPORTS = [
     "rt_last_error", "rt_abi_version", "rt_launch_count", "rt_set_option", "rt_get_option",
+    "rt_profile_reset", "rt_profile_read",
     "rt_model_create", "rt_model_set_weight", "rt_model_finalize", "rt_model_destroy", "rt_model_workspace_bytes",
     "rt_controlnet_forward", "rt_transformer_forward",
     "rt_euler_step", "rt_cfg_combine", "rt_cfg_euler_step", "rt_mask_scale_add", "rt_glyph_init_blend",
@@ -104,6 +105,7 @@ def lib() -> C.CDLL:
     L.rt_model_workspace_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.rt_set_option.argtypes = [C.c_char_p, C.c_int]
     L.rt_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    L.rt_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.rt_model_create.argtypes = [C.POINTER(ModelConfig), C.POINTER(C.c_void_p)]
     L.rt_model_set_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]
     L.rt_model_finalize.argtypes = [C.c_void_p, C.c_void_p]
@@ -169,3 +171,22 @@ def launch_count() -> int:
 
 def set_option(name: str, value: int) -> None:
     check(lib().rt_set_option(name.encode(), int(value)))
+
+
+PROF_CLASSES = ["gemm_tcgen05", "gemm_simt", "attention_tcgen05", "attention_simt", "layernorm_modulate", "gemv",
+                "elementwise"]
+
+
+def profile_reset() -> None:
+    check(lib().rt_profile_reset())
+
+
+def profile_read() -> dict:
+    """{class name: (total ms, total algorithmic work, launches)} since the last reset (option "profile")."""
+    out = {}
+    for i, name in enumerate(PROF_CLASSES):
+        ms, work, n = C.c_double(), C.c_double(), C.c_longlong()
+        check(lib().rt_profile_read(i, C.byref(ms), C.byref(work), C.byref(n)))
+        if n.value:
+            out[name] = (ms.value, work.value, n.value)
+    return out

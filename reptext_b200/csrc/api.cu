@@ -3,6 +3,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <vector>
 
 #include "dtype_utils.cuh"
 #include "rt_internal.h"
@@ -13,7 +14,8 @@ static thread_local std::string t_last_error;
 void set_last_error(const std::string& msg) { t_last_error = msg; }
 
 static std::map<std::string, int>& options() {
-  static std::map<std::string, int> o = {{"force_simt", 0}, {"gemm_cta_group", 0}, {"attn_variant", 0}};
+  static std::map<std::string, int> o = {{"force_simt", 0}, {"gemm_cta_group", 0}, {"attn_variant", 0},
+                                         {"profile", 0}};
   return o;
 }
 int get_option(const char* name) {
@@ -21,18 +23,55 @@ int get_option(const char* name) {
   return it == options().end() ? 0 : it->second;
 }
 
+// ---- per-class timing ----------------------------------------------------------------------------
+struct ProfRec {
+  int cls;
+  double work;
+  cudaEvent_t e0, e1;
+};
+static std::vector<ProfRec>& prof_recs() {
+  static std::vector<ProfRec> r;
+  return r;
+}
+static std::mutex g_prof_mu;
+ProfScope::ProfScope(int cls, double work, cudaStream_t s) : cls_(cls), work_(work), s_(s) {
+  if (!get_option("profile")) return;
+  if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) { e0_ = e1_ = nullptr; return; }
+  cudaEventRecord(e0_, s_);
+}
+ProfScope::~ProfScope() {
+  if (!e0_) return;
+  cudaEventRecord(e1_, s_);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  prof_recs().push_back({cls_, work_, e0_, e1_});
+}
+
+static double gemm_flops(const GemmLaunch& g) {
+  double f = 0;
+  for (int p = 0; p < g.nprob; ++p)
+    f += 2.0 * g.batch * (double)g.prob[p].m_rows * gemm_total_n(g.prob[p]) * g.prob[p].K;
+  return f;
+}
+
 void launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
-  if (!get_option("force_simt") && gemm_tc_supported(g, nullptr))
+  if (!get_option("force_simt") && gemm_tc_supported(g, nullptr)) {
+    ProfScope ps(PROF_GEMM_TC, gemm_flops(g), stream);
     launch_gemm_tc(g, stream, get_option("gemm_cta_group"));
-  else
+  } else {
+    ProfScope ps(PROF_GEMM_SIMT, gemm_flops(g), stream);
     launch_gemm_simt(g, stream);
+  }
 }
 
 void launch_attention(const AttnArgs& a, cudaStream_t stream) {
-  if (!get_option("force_simt") && attention_tc_supported(a, nullptr))
+  const double flops = 4.0 * a.batch * a.heads * (double)a.S * a.S * a.hd;
+  if (!get_option("force_simt") && attention_tc_supported(a, nullptr)) {
+    ProfScope ps(PROF_ATTN_TC, flops, stream);
     launch_attention_tc(a, stream, get_option("attn_variant"));
-  else
+  } else {
+    ProfScope ps(PROF_ATTN_SIMT, flops, stream);
     launch_attention_simt(a, stream);
+  }
 }
 
 }  // namespace rt
@@ -55,6 +94,37 @@ int rt_get_option(const char* name, int* value) {
   return guarded([&] {
     RT_REQUIRE(name && value && options().count(name), "unknown option");
     *value = options()[name];
+  });
+}
+
+int rt_profile_reset(void) {
+  return guarded([&] {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : prof_recs()) {
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+    prof_recs().clear();
+  });
+}
+int rt_profile_read(int cls, double* ms, double* work, long long* count) {
+  return guarded([&] {
+    RT_REQUIRE(cls >= 0 && cls < PROF_NCLS && ms && work && count, "profile_read: bad argument");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double t = 0, w = 0;
+    long long n = 0;
+    for (auto& r : prof_recs()) {
+      if (r.cls != cls) continue;
+      RT_CHECK_CUDA(cudaEventSynchronize(r.e1));
+      float f = 0;
+      RT_CHECK_CUDA(cudaEventElapsedTime(&f, r.e0, r.e1));
+      t += f;
+      w += r.work;
+      ++n;
+    }
+    *ms = t;
+    *work = w;
+    *count = n;
   });
 }
 

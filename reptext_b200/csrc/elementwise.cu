@@ -123,6 +123,7 @@ void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out
     RT_REQUIRE(groups[i].ld % 4 == 0, "ln_mod: modulation ld must be a multiple of 4");
   }
   if (rows_total == 0 || batch == 0) return;
+  ProfScope ps(PROF_LN, 2.0 * batch * rows_total * (double)D * dtype_size(dtype), stream);
   const long long total = (long long)batch * rows_total;
   const int threads = 256, wpb = threads / 32;
   long long blocks = (total + wpb - 1) / wpb;
@@ -212,6 +213,7 @@ void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K,
                          const int* prefix_dev, int njobs, int total_rows, float* out, int out_ld, int silu_out,
                          int accumulate, cudaStream_t stream) {
   if (batch == 0 || total_rows == 0) return;
+  ProfScope ps(PROF_GEMV, (double)total_rows * K * dtype_size(wdtype), stream);
   RT_REQUIRE(x_ld % 4 == 0, "gemv: x_ld must be a multiple of 4");
   const int threads = 256, wpb = threads / 32;
   int blocks = (total_rows + wpb - 1) / wpb;

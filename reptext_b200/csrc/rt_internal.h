@@ -120,6 +120,20 @@ void launch_glyph_blend(int dtype, const void* noise, const void* glyph_lat, con
 void launch_copy_rows(int dtype, const void* src, long long s_bs, int s_ld, int s_row0, void* dst, long long d_bs,
                       int d_ld, int d_row0, int batch, int rows, int D, cudaStream_t stream);
 
+// ------------------------------------------------------------------ per-class device timing (option "profile")
+// When the option is on, every launch of a class is bracketed by CUDA events on ITS stream; bench.py reads
+// the per-class sums (rt_profile_read) for the roofline line.  Off by default (zero overhead).
+enum ProfClass : int { PROF_GEMM_TC = 0, PROF_GEMM_SIMT, PROF_ATTN_TC, PROF_ATTN_SIMT, PROF_LN, PROF_GEMV, PROF_ELEM,
+                       PROF_NCLS };
+struct ProfScope {
+  ProfScope(int cls, double work, cudaStream_t s);
+  ~ProfScope();
+  int cls_;
+  double work_;
+  cudaStream_t s_;
+  cudaEvent_t e0_ = nullptr, e1_ = nullptr;
+};
+
 // ------------------------------------------------------------------ TMA descriptor encode (driver entry point)
 void encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
                       const uint32_t* box);
