@@ -301,21 +301,23 @@ def run_b200(args, wl):
         res = out.images.to("cpu", non_blocking=False)
         return res
 
-    one_image(2)
-    barrier()
-    d2h[0] = 0
-    t0 = time.perf_counter()
-    e0.record()
-    res = one_image(STEPS_PER_IMAGE)
-    e1.record()
-    barrier()
-    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0)], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * STEPS_PER_IMAGE / (float(e2e_ms.item()) / 1000.0)
-    h2d_total = sum(t.numel() * t.element_size() for t in (h_pe, h_po, h_lat, canny, pos)) + mask_img.size * 4
-    h2d_step = h2d_total / STEPS_PER_IMAGE
-    d2h_step = (d2h[0] + res.numel() * res.element_size()) / STEPS_PER_IMAGE
+    e2e_value = h2d_step = d2h_step = None
+    if not args.no_e2e:
+        one_image(2)
+        barrier()
+        d2h[0] = 0
+        t0 = time.perf_counter()
+        e0.record()
+        res = one_image(STEPS_PER_IMAGE)
+        e1.record()
+        barrier()
+        e2e_ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0)], device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e_value = world * STEPS_PER_IMAGE / (float(e2e_ms.item()) / 1000.0)
+        h2d_total = sum(t.numel() * t.element_size() for t in (h_pe, h_po, h_lat, canny, pos)) + mask_img.size * 4
+        h2d_step = h2d_total / STEPS_PER_IMAGE
+        d2h_step = (d2h[0] + res.numel() * res.element_size()) / STEPS_PER_IMAGE
 
     # ---- the only collective: gather the output latents of all ranks (after the timed regions)
     if world > 1:
@@ -369,6 +371,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the pipeline end-to-end leg (profiling runs only)")
     args = ap.parse_args()
     wl = workload(args.workload)
     if args.impl == "reference":

@@ -1,6 +1,319 @@
-// placeholder, replaced below
+// Joint text+image flash attention for sm_100a: non-causal, no mask, head_dim 128, bf16 in / fp32 softmax.
+// (diffusers dispatch_attention_fn -> F.scaled_dot_product_attention as reached from FluxTransformerBlock /
+//  FluxSingleTransformerBlock, RepText/controlnet_flux.py:343-348)
+//
+// One CTA owns TWO 128-row query tiles (A, B) of one (batch, head) and walks the key/value sequence in
+// 128-key tiles.  q and k arrive already RMS-normed and rotated (fused into the QKV GEMM epilogue), so this
+// kernel reads q | k | v straight out of the [B, S, 3D] projection buffer with TMA - no concat / permute copies.
+//
+//   warp 0        TMA producer: Q once, then K and V rings (2 stages each), 128B-swizzled tiles
+//   warp 1        tcgen05.mma issuer:  S = Q K^T  (SS, both operands K-major)
+//                                      O += P V   (TS: P read from TMEM, V MN-major from smem)
+//   warp 2        TMEM allocator (all 512 columns: S_A | S_B | O_A | O_B, 128 fp32 columns each)
+//   warps 4-7     softmax warpgroup for tile A: thread r owns query row r (TMEM lane r)
+//   warps 8-11    softmax warpgroup for tile B
+//
+// The tensor pipe ping-pongs between the two tiles: while warpgroup A runs exp2 on S_A[j+1] the MMA warp
+// issues P_B V and Q_B K^T.  P (bf16) overwrites the first 64 columns of its own S buffer; the in-order
+// execution of tcgen05.mma makes "P V(j) then Q K^T(j+1) into the same columns" safe.  The running max
+// is only raised when it grows by more than 2^8 (lazy rescale), so O is almost never read back.
+#include "dtype_utils.cuh"
+#include "ptx_sm100.cuh"
 #include "rt_internal.h"
+
 namespace rt {
-bool attention_tc_supported(const AttnArgs& a, std::string* why) { if (why) *why = "not built yet"; return false; }
-void launch_attention_tc(const AttnArgs&, cudaStream_t, int) { throw Error(RT_ERR_UNSUPPORTED, "tcgen05 attention not built"); }
+namespace {
+
+constexpr int HD = 128;
+constexpr int BQ = 128;   // rows per query tile
+constexpr int BKV = 128;  // keys per tile
+constexpr int kStages = 2;
+constexpr int kThreads = 384;
+constexpr int kTileBytes = BQ * HD * 2;       // 32 KB: two 16 KB sub-tiles of 64 columns (one swizzle row each)
+constexpr int kSubBytes = kTileBytes / 2;
+constexpr int kSmemTiles = 2 + 2 * kStages;   // Q_A Q_B | K ring | V ring
+constexpr int kNumBars = 1 + 4 * kStages + 2 + 2 + 1;
+constexpr int kSmemBytes = kSmemTiles * kTileBytes + kNumBars * 8 + 16 + 1024;
+
+struct AttnParams {
+  CUtensorMap tm;  // (col, row, batch) over the qkv buffer, box (64, 128, 1), SWIZZLE_128B
+  bf16* out;
+  long long out_bs;
+  int out_ld, out_col0;
+  int q_col0, k_col0, v_col0;
+  int S, heads, n_qpairs;
+  float scale_log2;  // log2(e) / sqrt(head_dim)
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  ptx::tmem_ld_32x32b_x32(taddr, r);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+__global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_constant__ AttnParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint8_t* smem_q = smem;                                    // 2 tiles
+  uint8_t* smem_k = smem + 2 * kTileBytes;                   // kStages tiles
+  uint8_t* smem_v = smem + (2 + kStages) * kTileBytes;       // kStages tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + kStages;
+  uint64_t* v_full = k_empty + kStages;
+  uint64_t* v_empty = v_full + kStages;
+  uint64_t* s_full = v_empty + kStages;  // [2]
+  uint64_t* p_full = s_full + 2;         // [2]
+  uint64_t* o_full = p_full + 2;         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qp = blockIdx.x % P.n_qpairs;
+  const int bh = blockIdx.x / P.n_qpairs;
+  const int h = bh % P.heads, b = bh / P.heads;
+  const int q0 = qp * 2 * BQ;
+  const int n_kv = (P.S + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&P.tm);
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 128);
+    }
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    ptx::mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub)
+        ptx::tma_load_3d(&P.tm, q_full, smem_q + t * kTileBytes + sub * kSubBytes, P.q_col0 + h * HD + sub * 64,
+                         q0 + t * BQ, b);
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % kStages, ph = (j / kStages) & 1;
+      ptx::mbar_wait(&k_empty[st], ph ^ 1);
+      ptx::mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub)
+        ptx::tma_load_3d(&P.tm, &k_full[st], smem_k + st * kTileBytes + sub * kSubBytes, P.k_col0 + h * HD + sub * 64,
+                         j * BKV, b);
+      ptx::mbar_wait(&v_empty[st], ph ^ 1);
+      ptx::mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub)
+        ptx::tma_load_3d(&P.tm, &v_full[st], smem_v + st * kTileBytes + sub * kSubBytes, P.v_col0 + h * HD + sub * 64,
+                         j * BKV, b);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);  // A, B K-major
+    constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, HD, 0, 1);   // A from TMEM, B (= V) MN-major
+    auto issue_qk = [&](int t, int st) {
+      const uint32_t qa = ptx::smem_u32(smem_q + t * kTileBytes), ka = ptx::smem_u32(smem_k + st * kTileBytes);
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        const uint32_t off = (kk >> 2) * kSubBytes + (kk & 3) * 32;
+        ptx::mma_bf16_ss<1>(tmem + t * 128, ptx::make_smem_desc_sw128(qa + off, 0, 1024),
+                            ptx::make_smem_desc_sw128(ka + off, 0, 1024), idesc_qk, kk != 0 ? 1u : 0u);
+      }
+    };
+    auto issue_pv = [&](int t, int st, bool acc) {
+      const uint32_t va = ptx::smem_u32(smem_v + st * kTileBytes);
+#pragma unroll
+      for (int kk = 0; kk < BKV / 16; ++kk) {
+        // 16 keys = two 8-row core groups (SBO 1024 B); 128 head-dim columns = two 64-column sub-tiles (LBO 16 KB)
+        ptx::mma_bf16_ts(tmem + 256 + t * 128, tmem + t * 128 + kk * 8,
+                         ptx::make_smem_desc_sw128(va + kk * 2048, kSubBytes, 1024), idesc_pv,
+                         (acc || kk != 0) ? 1u : 0u);
+      }
+    };
+    ptx::mbar_wait(q_full, 0);
+    ptx::mbar_wait(&k_full[0], 0);
+    ptx::tc_fence_after();
+    issue_qk(0, 0);
+    ptx::mma_commit(&s_full[0]);
+    issue_qk(1, 0);
+    ptx::mma_commit(&s_full[1]);
+    ptx::mma_commit(&k_empty[0]);
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % kStages, ph = (j / kStages) & 1;
+      const int nst = (j + 1) % kStages, nph = ((j + 1) / kStages) & 1;
+      const bool more = j + 1 < n_kv;
+      ptx::mbar_wait(&v_full[st], ph);
+      ptx::mbar_wait(&p_full[0], j & 1);
+      ptx::tc_fence_after();
+      issue_pv(0, st, j > 0);
+      if (more) {
+        ptx::mbar_wait(&k_full[nst], nph);
+        ptx::tc_fence_after();
+        issue_qk(0, nst);
+        ptx::mma_commit(&s_full[0]);
+      }
+      ptx::mbar_wait(&p_full[1], j & 1);
+      ptx::tc_fence_after();
+      issue_pv(1, st, j > 0);
+      ptx::mma_commit(&v_empty[st]);
+      if (more) {
+        issue_qk(1, nst);
+        ptx::mma_commit(&s_full[1]);
+        ptx::mma_commit(&k_empty[nst]);
+      }
+    }
+    ptx::mma_commit(o_full);
+  } else if (warp >= 4) {
+    // ===================== softmax warpgroups =====================
+    const int t = (warp - 4) >> 2;  // 0: tile A, 1: tile B
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t s_addr = tmem + lane_off + t * 128;
+    const uint32_t o_addr = tmem + lane_off + 256 + t * 128;
+    const int row = q0 + t * BQ + quad * 32 + lane;
+    const float c = P.scale_log2;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      ptx::mbar_wait(&s_full[t], j & 1);
+      ptx::tc_fence_after();
+      const int n_valid = P.S - j * BKV;  // < 128 only on the last tile
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        float v[32];
+        tmem_ld32(s_addr + ch * 32, v);
+        if (n_valid < BKV) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ch * 32 + i >= n_valid) v[i] = -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+      }
+      const float mx_s = mx * c;
+      if (j == 0) {
+        m_ref = mx_s;
+      } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
+        const float m_new = fmaxf(m_ref, mx_s);
+        const float f = ptx::ex2_approx(m_ref - m_new);
+        l *= f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(o_addr + ch * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          ptx::tmem_st_32x32b_x32(o_addr + ch * 32, r);
+        }
+        m_ref = m_new;
+      }
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        float v[32];
+        tmem_ld32(s_addr + ch * 32, v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ptx::ex2_approx(fmaf(v[2 * i], c, -m_ref));
+          float p1 = ptx::ex2_approx(fmaf(v[2 * i + 1], c, -m_ref));
+          if (n_valid < BKV) {
+            if (ch * 32 + 2 * i >= n_valid) p0 = 0.f;
+            if (ch * 32 + 2 * i + 1 >= n_valid) p1 = 0.f;
+          }
+          l += p0 + p1;
+          pk[i] = ptx::pack_bf16x2(p0, p1);
+        }
+        ptx::tmem_st_32x32b_x16(s_addr + ch * 16, pk);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&p_full[t]);
+    }
+    // ---- epilogue: O / l -> bf16 -> global
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    bf16* orow = P.out + (long long)b * P.out_bs + (long long)row * P.out_ld + P.out_col0 + h * HD;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      float v[32];
+      tmem_ld32(o_addr + ch * 32, v);
+      if (row < P.S) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = ptx::pack_bf16x2(v[8 * i + 0] * inv, v[8 * i + 1] * inv);
+          u.y = ptx::pack_bf16x2(v[8 * i + 2] * inv, v[8 * i + 3] * inv);
+          u.z = ptx::pack_bf16x2(v[8 * i + 4] * inv, v[8 * i + 5] * inv);
+          u.w = ptx::pack_bf16x2(v[8 * i + 6] * inv, v[8 * i + 7] * inv);
+          dst[i] = u;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<1>(tmem, 512);
+}
+
+}  // namespace
+
+bool attention_tc_supported(const AttnArgs& a, std::string* why) {
+  auto fail = [&](const char* m) { if (why) *why = m; return false; };
+  if (a.dtype != RT_BF16) return fail("dtype is not bf16");
+  if (a.hd != HD) return fail("head_dim is not 128");
+  if (a.ld % 8 || a.batch_stride % 8 || a.q_col0 % 8 || a.k_col0 % 8 || a.v_col0 % 8) return fail("qkv alignment");
+  if (a.out_ld % 8 || a.out_col0 % 8 || a.out_batch_stride % 8) return fail("out alignment");
+  if ((reinterpret_cast<uintptr_t>(a.qkv) & 15) || (reinterpret_cast<uintptr_t>(a.out) & 15)) return fail("pointer alignment");
+  if (a.S < 1) return fail("empty sequence");
+  return true;
+}
+
+void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
+  (void)variant;
+  std::string why;
+  if (!attention_tc_supported(a, &why)) throw Error(RT_ERR_UNSUPPORTED, "tcgen05 attention: " + why);
+  if (a.batch == 0) return;
+  AttnParams P{};
+  const int cols = a.ld;  // the map spans whole rows of the projection buffer; q / k / v are column offsets
+  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)a.S, (uint64_t)a.batch};
+  uint64_t strides[2] = {(uint64_t)a.ld * 2, (uint64_t)a.batch_stride * 2};
+  uint32_t box[3] = {64, 128, 1};
+  encode_tmap_bf16(&P.tm, a.qkv, 3, dims, strides, box);
+  P.out = reinterpret_cast<bf16*>(a.out);
+  P.out_bs = a.out_batch_stride; P.out_ld = a.out_ld; P.out_col0 = a.out_col0;
+  P.q_col0 = a.q_col0; P.k_col0 = a.k_col0; P.v_col0 = a.v_col0;
+  P.S = a.S; P.heads = a.heads;
+  P.n_qpairs = (a.S + 2 * BQ - 1) / (2 * BQ);
+  P.scale_log2 = 1.4426950408889634f / sqrtf((float)a.hd);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RT_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const long long grid = (long long)P.n_qpairs * a.heads * a.batch;
+  attn_tc_kernel<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(P);
+  RT_POST_LAUNCH();
+}
+
+}  // namespace rt

@@ -180,7 +180,15 @@ def test_gemm_rejects_bad_arguments(ops):
 @pytest.mark.parametrize("dtype,hd,S,impl", [(torch.float32, 64, 320, 1), (torch.float32, 128, 100, 1),
                                              (torch.bfloat16, 128, 384, 1), (torch.bfloat16, 64, 77, 1)])
 def test_attention_simt(ops, dtype, hd, S, impl):
-    B, H = 2, 3
+    _attention_case(ops, dtype, hd, S, impl, 2, 3)
+
+
+@pytest.mark.parametrize("S,B,H", [(256, 1, 1), (384, 2, 3), (320, 1, 2), (100, 1, 1), (4608, 1, 2), (1111, 2, 2)])
+def test_attention_tcgen05(ops, S, B, H):
+    _attention_case(ops, torch.bfloat16, 128, S, 2, B, H)
+
+
+def _attention_case(ops, dtype, hd, S, impl, B, H):
     qkv = _rand((B, S, 3 * H * hd + 8), dtype, 1)
     out = ops.attention(qkv, H, hd, 0, H * hd, 2 * H * hd, impl=impl)
     q, k, v = [qkv[:, :, i * H * hd:(i + 1) * H * hd].float().view(B, S, H, hd).transpose(1, 2) for i in range(3)]
