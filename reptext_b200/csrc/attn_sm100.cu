@@ -53,6 +53,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 2^x for x <= ~8 on the FMA pipe (Cody-Waite split + cubic minimax, rel. error ~1e-4, far inside bf16's 2^-9):
+// the MUFU unit (16 ex2 / clk / SM) is the co-bottleneck of this kernel, so a fixed share of the exponentials
+// is computed here instead.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float xi = __fadd_rd(x, 12582912.f);  // 1.5 * 2^23 + floor(x)
+  const float f = x - (xi - 12582912.f);      // [0, 1)
+  float p = fmaf(0.077119089663028717f, f, 0.227564394474029541f);
+  p = fmaf(p, f, 0.695146143436431885f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xi) << 23));
+}
+
+// kDebug: 0 = product; 1 / 2 / 3 are timing experiments (no exp2 / no row max / neither; wrong results).
+// kPolyEvery: every kPolyEvery-th PAIR of exponentials goes to exp2_poly (0 = none).
+template <int kDebug, int kPolyEvery>
 __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_constant__ AttnParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
@@ -100,6 +116,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     ptx::mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
@@ -124,64 +142,80 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
         ptx::tma_load_3d(&P.tm, &v_full[st], smem_v + st * kTileBytes + sub * kSubBytes, P.v_col0 + h * HD + sub * 64,
                          j * BKV, b);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The whole warp runs the loop (so that descriptor arithmetic stays on the uniform datapath); one elected
+    // lane issues the tcgen05 instructions.
     constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);  // A, B K-major
     constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, HD, 0, 1);   // A from TMEM, B (= V) MN-major
+    const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_q), 0, 1024);
+    const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_k), 0, 1024);
+    const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_v), kSubBytes, 1024);
+    constexpr uint32_t kTile16 = kTileBytes >> 4, kSub16 = kSubBytes >> 4;
     auto issue_qk = [&](int t, int st) {
-      const uint32_t qa = ptx::smem_u32(smem_q + t * kTileBytes), ka = ptx::smem_u32(smem_k + st * kTileBytes);
+      const uint64_t qa = q_desc + (uint64_t)(t * kTile16), ka = k_desc + (uint64_t)(st * kTile16);
 #pragma unroll
       for (int kk = 0; kk < HD / 16; ++kk) {
-        const uint32_t off = (kk >> 2) * kSubBytes + (kk & 3) * 32;
-        ptx::mma_bf16_ss<1>(tmem + t * 128, ptx::make_smem_desc_sw128(qa + off, 0, 1024),
-                            ptx::make_smem_desc_sw128(ka + off, 0, 1024), idesc_qk, kk != 0 ? 1u : 0u);
+        const uint32_t off = (kk >> 2) * kSub16 + (kk & 3) * 2;  // (addr >> 4) units
+        ptx::mma_bf16_ss<1>(tmem + t * 128, qa + off, ka + off, idesc_qk, kk != 0 ? 1u : 0u);
       }
     };
-    auto issue_pv = [&](int t, int st, bool acc) {
-      const uint32_t va = ptx::smem_u32(smem_v + st * kTileBytes);
+    auto issue_pv = [&](int t, int st, uint32_t acc) {
+      const uint64_t va = v_desc + (uint64_t)(st * kTile16);
 #pragma unroll
       for (int kk = 0; kk < BKV / 16; ++kk) {
         // 16 keys = two 8-row core groups (SBO 1024 B); 128 head-dim columns = two 64-column sub-tiles (LBO 16 KB)
-        ptx::mma_bf16_ts(tmem + 256 + t * 128, tmem + t * 128 + kk * 8,
-                         ptx::make_smem_desc_sw128(va + kk * 2048, kSubBytes, 1024), idesc_pv,
-                         (acc || kk != 0) ? 1u : 0u);
+        ptx::mma_bf16_ts(tmem + 256 + t * 128, tmem + t * 128 + kk * 8, va + (uint64_t)(kk * 128), idesc_pv,
+                         kk != 0 ? 1u : acc);
       }
     };
     ptx::mbar_wait(q_full, 0);
     ptx::mbar_wait(&k_full[0], 0);
     ptx::tc_fence_after();
-    issue_qk(0, 0);
-    ptx::mma_commit(&s_full[0]);
-    issue_qk(1, 0);
-    ptx::mma_commit(&s_full[1]);
-    ptx::mma_commit(&k_empty[0]);
+    if (ptx::elect_one()) {
+      issue_qk(0, 0);
+      ptx::mma_commit(&s_full[0]);
+      issue_qk(1, 0);
+      ptx::mma_commit(&s_full[1]);
+      ptx::mma_commit(&k_empty[0]);
+    }
+    __syncwarp();
     for (int j = 0; j < n_kv; ++j) {
       const int st = j % kStages, ph = (j / kStages) & 1;
       const int nst = (j + 1) % kStages, nph = ((j + 1) / kStages) & 1;
       const bool more = j + 1 < n_kv;
+      const uint32_t acc = j > 0 ? 1u : 0u;
       ptx::mbar_wait(&v_full[st], ph);
       ptx::mbar_wait(&p_full[0], j & 1);
+      if (more) ptx::mbar_wait(&k_full[nst], nph);
       ptx::tc_fence_after();
-      issue_pv(0, st, j > 0);
-      if (more) {
-        ptx::mbar_wait(&k_full[nst], nph);
-        ptx::tc_fence_after();
-        issue_qk(0, nst);
-        ptx::mma_commit(&s_full[0]);
+      if (ptx::elect_one()) {
+        issue_pv(0, st, acc);
+        if (more) {
+          issue_qk(0, nst);
+          ptx::mma_commit(&s_full[0]);
+        }
       }
+      __syncwarp();
       ptx::mbar_wait(&p_full[1], j & 1);
       ptx::tc_fence_after();
-      issue_pv(1, st, j > 0);
-      ptx::mma_commit(&v_empty[st]);
-      if (more) {
-        issue_qk(1, nst);
-        ptx::mma_commit(&s_full[1]);
-        ptx::mma_commit(&k_empty[nst]);
+      if (ptx::elect_one()) {
+        issue_pv(1, st, acc);
+        ptx::mma_commit(&v_empty[st]);
+        if (more) {
+          issue_qk(1, nst);
+          ptx::mma_commit(&s_full[1]);
+          ptx::mma_commit(&k_empty[nst]);
+        }
       }
+      __syncwarp();
     }
-    ptx::mma_commit(o_full);
-  } else if (warp >= 4) {
+    if (ptx::elect_one()) ptx::mma_commit(o_full);
+    __syncwarp();
+  }
+  } else {
     // ===================== softmax warpgroups =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int t = (warp - 4) >> 2;  // 0: tile A, 1: tile B
     const int quad = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
@@ -194,20 +228,33 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
       ptx::mbar_wait(&s_full[t], j & 1);
       ptx::tc_fence_after();
       const int n_valid = P.S - j * BKV;  // < 128 only on the last tile
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        float v[32];
-        tmem_ld32(s_addr + ch * 32, v);
-        if (n_valid < BKV) {
+      // the whole score row (128 fp32) in registers: ONE TMEM round trip per tile
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      ptx::tmem_ld_32x32b_x32(s_addr, s0);
+      ptx::tmem_ld_32x32b_x32(s_addr + 32, s1);
+      ptx::tmem_ld_32x32b_x32(s_addr + 64, s2);
+      ptx::tmem_ld_32x32b_x32(s_addr + 96, s3);
+      ptx::tmem_ld_wait();
+      if (n_valid < BKV) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (ch * 32 + i >= n_valid) v[i] = -INFINITY;
+        for (int i = 0; i < 32; ++i) {
+          if (i >= n_valid) s0[i] = 0xff800000u;  // -inf
+          if (32 + i >= n_valid) s1[i] = 0xff800000u;
+          if (64 + i >= n_valid) s2[i] = 0xff800000u;
+          if (96 + i >= n_valid) s3[i] = 0xff800000u;
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
       }
-      const float mx_s = mx * c;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (!(kDebug & 2))
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+        mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
+        mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+      }
+      float mx_s = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+      if (kDebug & 2) mx_s = 0.f;
       if (j == 0) {
         m_ref = mx_s;
       } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
@@ -215,34 +262,42 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
         const float f = ptx::ex2_approx(m_ref - m_new);
         l *= f;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(o_addr + ch * 32, r);
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(o_addr + ch * 16, r);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-          ptx::tmem_st_32x32b_x32(o_addr + ch * 32, r);
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          ptx::tmem_st_32x32b_x16(o_addr + ch * 16, r);
         }
         m_ref = m_new;
       }
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        float v[32];
-        tmem_ld32(s_addr + ch * 32, v);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ptx::ex2_approx(fmaf(v[2 * i], c, -m_ref));
-          float p1 = ptx::ex2_approx(fmaf(v[2 * i + 1], c, -m_ref));
-          if (n_valid < BKV) {
-            if (ch * 32 + 2 * i >= n_valid) p0 = 0.f;
-            if (ch * 32 + 2 * i + 1 >= n_valid) p1 = 0.f;
-          }
-          l += p0 + p1;
-          pk[i] = ptx::pack_bf16x2(p0, p1);
-        }
-        ptx::tmem_st_32x32b_x16(s_addr + ch * 16, pk);
+      float l0 = 0.f, l1 = 0.f;
+#define RT_SOFTMAX_CHUNK(SV, COL)                                                            \
+      {                                                                                      \
+        uint32_t pk[16];                                                                     \
+        _Pragma("unroll") for (int i = 0; i < 16; ++i) {                                     \
+          float p0 = fmaf(__uint_as_float(SV[2 * i]), c, -m_ref);                            \
+          float p1 = fmaf(__uint_as_float(SV[2 * i + 1]), c, -m_ref);                        \
+          if (!(kDebug & 1)) {                                                               \
+            if (kPolyEvery > 0 && (i % kPolyEvery) == kPolyEvery - 1) {                      \
+              p0 = exp2_poly(p0); p1 = exp2_poly(p1);                                        \
+            } else {                                                                         \
+              p0 = ptx::ex2_approx(p0); p1 = ptx::ex2_approx(p1);                            \
+            }                                                                                \
+          }                                                                                  \
+          l0 += p0;                                                                          \
+          l1 += p1;                                                                          \
+          pk[i] = ptx::pack_bf16x2(p0, p1);                                                  \
+        }                                                                                    \
+        ptx::tmem_st_32x32b_x16(s_addr + COL, pk);                                           \
       }
+      RT_SOFTMAX_CHUNK(s0, 0)
+      RT_SOFTMAX_CHUNK(s1, 16)
+      RT_SOFTMAX_CHUNK(s2, 32)
+      RT_SOFTMAX_CHUNK(s3, 48)
+#undef RT_SOFTMAX_CHUNK
+      l += l0 + l1;
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&p_full[t]);
@@ -290,7 +345,6 @@ bool attention_tc_supported(const AttnArgs& a, std::string* why) {
 }
 
 void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
-  (void)variant;
   std::string why;
   if (!attention_tc_supported(a, &why)) throw Error(RT_ERR_UNSUPPORTED, "tcgen05 attention: " + why);
   if (a.batch == 0) return;
@@ -306,13 +360,21 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
   P.S = a.S; P.heads = a.heads;
   P.n_qpairs = (a.S + 2 * BQ - 1) / (2 * BQ);
   P.scale_log2 = 1.4426950408889634f / sqrtf((float)a.hd);
+  using KernelFn = void (*)(const AttnParams);
+  // variant 0 = product configuration; 1-3 timing experiments; 4.. = other exp2_poly shares (tuning)
+  static const KernelFn table[] = {attn_tc_kernel<0, 0>, attn_tc_kernel<1, 0>, attn_tc_kernel<2, 0>, attn_tc_kernel<3, 0>,
+                                   attn_tc_kernel<0, 4>, attn_tc_kernel<0, 2>, attn_tc_kernel<0, 3>, attn_tc_kernel<0, 5>,
+                                   attn_tc_kernel<0, 8>};
+  constexpr int kNumVariants = sizeof(table) / sizeof(table[0]);
   static bool attr_set = false;
   if (!attr_set) {
-    RT_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    for (int i = 0; i < kNumVariants; ++i)
+      RT_CHECK_CUDA(cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
+  RT_REQUIRE(variant >= 0 && variant < kNumVariants, "attention: unknown variant");
   const long long grid = (long long)P.n_qpairs * a.heads * a.batch;
-  attn_tc_kernel<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(P);
+  table[variant]<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(P);
   RT_POST_LAUNCH();
 }
 
