@@ -241,7 +241,7 @@ void run_attention(const Ctx& c) {
 
 // FluxTransformerBlock (diffusers).  `extra`: ControlNet residual added to the image rows
 // after the block ([B, N, D], or null) - fused into the last GEMM's epilogue.
-void double_block(const Ctx& c, const DoubleBlk& k, const void* extra) {
+void double_block_pre(const Ctx& c, const DoubleBlk& k) {
   const Workspace& w = c.ws;
   const int D = c.D, T = c.T, N = c.N, S = c.S, ld = c.m.mod_total;
   const float* mi = w.mod + k.mod_img;
@@ -268,7 +268,14 @@ void double_block(const Ctx& c, const DoubleBlk& k, const void* extra) {
     pi.seg[2] = make_seg(k.v, 2 * D, EPI_BIAS, w.qkv, s3D, 3 * D, 2 * D);
     launch_gemm(L, c.st);
   }
-  run_attention(c);
+}
+
+void double_block_post(const Ctx& c, const DoubleBlk& k, const void* extra) {
+  const Workspace& w = c.ws;
+  const int D = c.D, T = c.T, N = c.N, S = c.S, ld = c.m.mod_total;
+  const float* mi = w.mod + k.mod_img;
+  const float* mc = w.mod + k.mod_ctx;
+  const long long sD = c.sD(), s5D = 5 * sD;
   {  // x += gate_msa * to_out(attn)
     GemmLaunch L{};
     L.dtype = c.dt; L.batch = c.B; L.nprob = 2;
@@ -319,7 +326,7 @@ void double_block(const Ctx& c, const DoubleBlk& k, const void* extra) {
 
 // FluxSingleTransformerBlock on the joint sequence.  `extra` ([B, N, D]) is added to the
 // image rows (problem rows >= T).
-void single_block(const Ctx& c, const SingleBlk& k, const void* extra) {
+void single_block_pre(const Ctx& c, const SingleBlk& k) {
   const Workspace& w = c.ws;
   const int D = c.D, T = c.T, N = c.N, S = c.S, ld = c.m.mod_total;
   const float* md = w.mod + k.mod;
@@ -340,7 +347,13 @@ void single_block(const Ctx& c, const SingleBlk& k, const void* extra) {
     p.seg[3] = make_seg(k.mlp, 3 * D, EPI_GELU, w.cat, s5D, 5 * D, D);
     launch_gemm(L, c.st);
   }
-  run_attention(c);
+}
+
+void single_block_post(const Ctx& c, const SingleBlk& k, const void* extra) {
+  const Workspace& w = c.ws;
+  const int D = c.D, T = c.T, N = c.N, S = c.S, ld = c.m.mod_total;
+  const float* md = w.mod + k.mod;
+  const long long sD = c.sD(), s5D = 5 * sD;
   {  // x += gate * proj_out([attn | mlp])
     GemmLaunch L{};
     L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
@@ -354,6 +367,17 @@ void single_block(const Ctx& c, const SingleBlk& k, const void* extra) {
     }
     launch_gemm(L, c.st);
   }
+}
+
+void double_block(const Ctx& c, const DoubleBlk& k, const void* extra) {
+  double_block_pre(c, k);
+  run_attention(c);
+  double_block_post(c, k, extra);
+}
+void single_block(const Ctx& c, const SingleBlk& k, const void* extra) {
+  single_block_pre(c, k);
+  run_attention(c);
+  single_block_post(c, k, extra);
 }
 
 Ctx begin_forward(rt_model* m, const rt_forward_args* a) {
