@@ -35,6 +35,14 @@ def workload(name: str):
         return dict(name="cfg2: FLUX.1-dev-arch (19+38 blocks, D=3072) + RepText ControlNet (6+0), 1024x1024, "
                          "N=4096 image + T=512 text tokens, 1 text line, bf16, batch 1 per GPU",
                     TR=config.FLUX_DEV, CN=config.REPTEXT_CONTROLNET, H=1024, W=1024, T=512)
+    if name == "cfg5":  # BASELINE.json configs[4]: ONE 1536x1536 sample, tokens + attention heads sharded over all ranks
+        return dict(name="cfg5: FLUX.1-dev-arch + RepText ControlNet, 1536x1536, N=9216 image + T=512 text tokens, "
+                         "1 text line, bf16, batch 1; ONE sample sequence-parallel over all GPUs (heads sharded in "
+                         "attention, exchanges fused into the GEMM / attention epilogues as NVLink peer stores)",
+                    TR=config.FLUX_DEV, CN=config.REPTEXT_CONTROLNET, H=1536, W=1536, T=512, sp=True)
+    if name == "cfg5_small":  # debugging aid: the sequence-parallel path on the 8-head test pair
+        return dict(name="cfg5_small (debug): SP8 pair, 512x256", TR=config.SP8_TRANSFORMER, CN=config.SP8_CONTROLNET,
+                    H=512, W=256, T=64, sp=True)
     if name == "cfg2_small":  # debugging aid only: same code path, 2+2 blocks, D=256
         return dict(name="cfg2_small (debug): 2+2 blocks, D=256, 256x256", TR=config.SMALL128_TRANSFORMER,
                     CN=config.SMALL128_CONTROLNET, H=256, W=256, T=128)
@@ -201,6 +209,9 @@ def run_b200(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
+    for kv in filter(None, os.environ.get("RT_OPTIONS", "").split(",")):   # A/B aid, e.g. RT_OPTIONS=attn_variant=4
+        k, v = kv.split("=")
+        _lib.set_option(k.strip(), int(v))
     dt = torch.bfloat16
     TR, CN, H, W, T = wl["TR"], wl["CN"], wl["H"], wl["W"], wl["T"]
     N = (H // 16) * (W // 16)
@@ -223,6 +234,21 @@ def run_b200(args, wl):
     lat, pe, po, cond = [t.to(dev, non_blocking=True) for t in (h_lat, h_pe, h_po, h_cond)]
     img_ids = pipe._prepare_latent_image_ids(1, 2 * (H // 16), 2 * (W // 16), dev, dt)
     txt_ids = torch.zeros(T, 3, device=dev, dtype=dt)
+    sp = None
+    sp_kw = {}
+    if wl.get("sp") and world > 1:
+        # one sample for the whole job: every rank holds the SAME inputs (seeded alike) and keeps its token shard
+        from reptext_b200 import parallel
+        g = torch.Generator().manual_seed(1000)
+        full = [torch.randn(1, N, TR["in_channels"], generator=g).to(dt), torch.randn(1, T, TR["joint_attention_dim"], generator=g).to(dt),
+                torch.randn(1, TR["pooled_projection_dim"], generator=g).to(dt),
+                torch.randn(1, N, CN["in_channels"] + CN["extra_condition_channels"], generator=g).to(dt)]
+        h_lat, h_pe, h_po, h_cond = [pin(t) for t in full]
+        sp = parallel.SequenceParallelGroup()
+        sp_kw = dict(sp=sp)
+        sh = lambda t, d=1: parallel.shard_tokens(t.to(dev), rank, world, d)
+        lat, pe, po, cond = sh(h_lat), sh(h_pe), h_po.to(dev), sh(h_cond)
+        mask, img_ids, txt_ids = sh(mask.reshape(1, -1, 1)), sh(img_ids, 0), sh(txt_ids, 0)
     guidance = torch.tensor([3.5], device=dev)
     import numpy as np
     from reptext_b200._pipeline_common import calculate_shift
@@ -236,8 +262,8 @@ def run_b200(args, wl):
         t = tsd[i % STEPS_PER_IMAGE]
         kw = dict(hidden_states=latents, encoder_hidden_states=pe, pooled_projections=po,
                   timestep=(t.expand(1).to(dt)) / 1000, guidance=guidance, img_ids=img_ids, txt_ids=txt_ids)
-        bl, sl = cn(controlnet_cond=cond, conditioning_scale=1.0, regional_mask=mask, return_dict=False, **kw)
-        v = tr(controlnet_block_samples=bl, controlnet_single_block_samples=sl, return_dict=False, **kw)[0]
+        bl, sl = cn(controlnet_cond=cond, conditioning_scale=1.0, regional_mask=mask, return_dict=False, **kw, **sp_kw)
+        v = tr(controlnet_block_samples=bl, controlnet_single_block_samples=sl, return_dict=False, **kw, **sp_kw)[0]
         j = i % STEPS_PER_IMAGE
         return ops.euler_step(v, latents, sig[j], sig[j + 1])
 
@@ -268,7 +294,10 @@ def run_b200(args, wl):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total = float(tmax.item())
-    value = world * args.steps / (ms_total / 1000.0)
+    n_samples = 1 if sp is not None else world        # sequence-parallel: the whole job is ONE sample
+    value = n_samples * args.steps / (ms_total / 1000.0)
+    if sp is not None:
+        sp.check()
     finite = bool(torch.isfinite(x.float()).all().item())
 
     # ---- per-class device time of the same K steps (separate pass: events around every launch)
@@ -303,6 +332,7 @@ def run_b200(args, wl):
 
     e2e_value = h2d_step = d2h_step = None
     if not args.no_e2e:
+        pipe.enable_sequence_parallel(sp)
         one_image(2)
         barrier()
         d2h[0] = 0
@@ -314,19 +344,24 @@ def run_b200(args, wl):
         e2e_ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0)], device=dev)
         if world > 1:
             dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        e2e_value = world * STEPS_PER_IMAGE / (float(e2e_ms.item()) / 1000.0)
+        e2e_value = n_samples * STEPS_PER_IMAGE / (float(e2e_ms.item()) / 1000.0)
         h2d_total = sum(t.numel() * t.element_size() for t in (h_pe, h_po, h_lat, canny, pos)) + mask_img.size * 4
         h2d_step = h2d_total / STEPS_PER_IMAGE
         d2h_step = (d2h[0] + res.numel() * res.element_size()) / STEPS_PER_IMAGE
 
     # ---- the only collective: gather the output latents of all ranks (after the timed regions)
-    if world > 1:
+    if sp is not None:
+        from reptext_b200 import parallel
+        x = parallel.gather_tokens(x)
+        sp.close()
+    elif world > 1:
         outs = [torch.empty_like(x) for _ in range(world)]
         dist.all_gather(outs, x)
 
     if rank == 0:
         pk = peaks()
         flops = step_flops(TR, CN, N, T)
+        gpus_per_sample = world if sp is not None else 1
         gem = prof.get("gemm_tcgen05", (0.0, 0.0, 0))
         roof = None
         if gem[0] > 0:
@@ -346,13 +381,17 @@ def run_b200(args, wl):
             v_cpu, sample = cpu_oracle_steps_per_s(wl)
             cpu = dict(value=v_cpu, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample)
         step_ms = ms_total / args.steps
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                    ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+        line = dict(metric=METRIC.replace("1024x1024", f"{H}x{W}"), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=step_ms, higher_is_better=True, scaling="strong" if sp is not None else "weak",
+                    vs_baseline=None, dtype="bf16",
                     data="synthetic (random-init weights of the named architecture, randn latents / embeddings)",
-                    config=dict(workload=wl["name"], parallelism=f"dp{world} (independent samples, no data-path collective)",
+                    config=dict(workload=wl["name"],
+                                parallelism=(f"sp{world} (one sample; tokens and attention heads sharded; peer stores + flag "
+                                             "barriers, NCCL only gathers the final latents)" if sp is not None else
+                                             f"dp{world} (independent samples, no data-path collective)"),
                                 l2="not flushed: each step streams 32 GB of weights, far larger than the 126 MB L2",
                                 flops_per_step=flops, images_per_s=value / STEPS_PER_IMAGE,
-                                tensor_util_whole_step=flops / (step_ms / 1000.0) / 1e12 / pk["bf16_sustained"],
+                                tensor_util_whole_step=flops / gpus_per_sample / (step_ms / 1000.0) / 1e12 / pk["bf16_sustained"],
                                 finite_output=finite),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_step, d2h_bytes_per_step=d2h_step,
                              how="FluxControlNetPipeline.__call__, one 28-step image from pinned host inputs, latents "

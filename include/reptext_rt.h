@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 #if defined(__GNUC__)
 #define RT_API __attribute__((visibility("default")))
 #else
@@ -50,8 +50,14 @@ typedef struct rt_model_config {
 /* ------------------------------------------------------------------------------------------------ */
 RT_API const char* rt_last_error(void); /* host string, valid until the next failing call on this thread */
 RT_API int rt_abi_version(void);
+/* sizeof() of a public struct, so that a binding can check its mirror: 0 rt_model_config, 1 rt_forward_args,
+ * 2 rt_sp_group, 3 rt_controlnet_call, 4 rt_transformer_call, 5 rt_gemm_segment, 6 rt_gemm_problem,
+ * 7 rt_gemm_launch, 8 rt_attention_args, 9 rt_lnmod_group; -1 for an unknown index. */
+RT_API int rt_struct_size(int which);
 RT_API long long rt_launch_count(void); /* number of this library's kernels launched so far (process-wide) */
-/* options: "force_simt" (0/1), "gemm_cta_group" (0 auto, 1, 2), "attn_variant" (0 auto, ...), "profile" (0/1) */
+/* options: "force_simt" (0/1), "gemm_cta_group" (0 auto, 1, 2), "attn_variant" (0 auto, ...), "profile" (0/1);
+ * A/B and timing aids: "ln_warp_rows" (1 = warp-per-row LayerNorm), "gemv_single_row" (1 = one row per warp),
+ * "gemm_debug" (timing experiments that produce WRONG results: 1 no epilogue, 2 k-block 0 only) */
 RT_API int rt_set_option(const char* name, int value);
 RT_API int rt_get_option(const char* name, int* value);
 
@@ -86,7 +92,40 @@ typedef struct rt_forward_args {
   void* workspace;
   int64_t workspace_bytes;
   void* stream;
+  const struct rt_sp_group* sp; /* NULL: the whole sequence is on this GPU.  Otherwise n_img / n_txt / the row
+                                   dimension of every tensor are THIS rank's token shard (see rt_sp_group). */
 } rt_forward_args;
+
+/* ---- sequence-parallel execution of ONE sample over `world` GPUs (BASELINE.json configs[4]: 1536x1536, 9216
+ *      image + 512 text tokens).  The reference has no such mode; the layout is Ulysses-style: every rank owns
+ *      n_txt text rows + n_img image rows for all token-wise work (embeds, AdaLN, LayerNorm, every GEMM) and
+ *      heads [rank*H/world, (rank+1)*H/world) over the WHOLE sequence for attention.  The two exchanges per
+ *      block are not separate collectives: the QKV GEMM epilogue stores each head's q|k|v columns straight into
+ *      the owning rank's workspace and the attention epilogue stores each output row straight into the owning
+ *      rank's workspace (peer stores over NVLink); a flag barrier between the phases orders them.
+ *      Requirements: bf16, head_dim 128, H % world == 0, identical (batch, n_img, n_txt) on every rank, and
+ *      every rank's workspace mapped in every process (rt_ipc_*).  RoPE follows the ids each rank passes, so
+ *      img_ids / txt_ids are simply the shard's rows. */
+#define RT_SP_MAX_RANKS 8
+#define RT_SP_FLAG_WORDS 16 /* [0..7] arrival epochs written by rank i, [8] this rank's epoch, [9] time-out flag */
+typedef struct rt_sp_group {
+  int world, rank;
+  void* peer_workspace[RT_SP_MAX_RANKS];               /* rank i's workspace as mapped in this process ([rank] = own) */
+  unsigned long long* peer_flags[RT_SP_MAX_RANKS];     /* rank i's RT_SP_FLAG_WORDS words, zeroed once at set-up     */
+  int lockstep; /* 1: one process drives every rank in phase order on ONE stream (rt_*_forward_lockstep; tests and
+                   single-GPU validation of the exchange indexing): stream order replaces the flag barriers */
+} rt_sp_group;
+
+/* Device memory that other processes on the node can map (cudaMalloc + CUDA IPC).  handle64: 64 host bytes. */
+RT_API int rt_ipc_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);
+RT_API int rt_ipc_open(const unsigned char* handle64, void** dev_ptr);
+RT_API int rt_ipc_close(void* dev_ptr);
+RT_API int rt_ipc_free(void* dev_ptr);
+/* All-ranks barrier on `stream` (one tiny kernel: release-store of this rank's epoch into every peer's flag
+ * block, acquire-spin on its own).  A rank that waits longer than ~10 s sets its time-out flag and moves on;
+ * rt_sp_status synchronises the stream and reports it. */
+RT_API int rt_sp_barrier(const rt_sp_group* g, void* stream);
+RT_API int rt_sp_status(const rt_sp_group* g, void* stream, int* timed_out);
 
 /* FluxControlNetModel.forward — RepText/controlnet_flux.py:216-413, called at
  * RepText/pipeline_flux_controlnet.py:1043-1056 and pipeline_flux_controlnet_inpaint.py:1167, :1214.
@@ -106,6 +145,30 @@ RT_API int rt_controlnet_forward(rt_model* m, const rt_forward_args* a, const vo
 RT_API int rt_transformer_forward(rt_model* m, const rt_forward_args* a, const void* const* controlnet_block_samples,
                            int n_block_samples, const void* const* controlnet_single_block_samples,
                            int n_single_block_samples, void* out);
+
+/* Lock-step forms of the two forwards: calls[i] carries rank i's arguments (calls[i].a.sp->rank == i,
+ * lockstep == 1, every workspace on the current device); the phases of all ranks are issued in order on
+ * calls[0].a.stream.  Same arithmetic and the same peer-store indexing as the multi-process mode. */
+typedef struct rt_controlnet_call {
+  rt_forward_args a;
+  const void* controlnet_cond;
+  int cond_batch;
+  float conditioning_scale;
+  const void* mask;
+  int accumulate;
+  void* block_samples;
+  void* single_block_samples;
+} rt_controlnet_call;
+typedef struct rt_transformer_call {
+  rt_forward_args a;
+  const void* const* controlnet_block_samples;
+  int n_block_samples;
+  const void* const* controlnet_single_block_samples;
+  int n_single_block_samples;
+  void* out;
+} rt_transformer_call;
+RT_API int rt_controlnet_forward_lockstep(rt_model* m, int world, const rt_controlnet_call* calls);
+RT_API int rt_transformer_forward_lockstep(rt_model* m, int world, const rt_transformer_call* calls);
 
 /* FlowMatchEulerDiscreteScheduler.step — called at RepText/pipeline_flux_controlnet.py:1109:
  * out = dtype( float(sample) + dtype((sigma_next - sigma) * model_output) ); n elements. */
@@ -148,6 +211,9 @@ typedef struct rt_gemm_segment {
   int out_ld;
   int out_col0;
   const void* norm_w; /* RT_EPI_QKNORM_ROPE: [head_dim] */
+  int scatter; /* 1 (tcgen05 path, BIAS / QKNORM_ROPE only): column block c = (n - n_begin) / sp_cols of this segment
+                  goes to launch.sp_out[c] at row sp_row0 + out_row0 + m, column out_col0 + (n - n_begin) % sp_cols;
+                  `out` is ignored, out_batch_stride / out_ld describe the destination buffers */
 } rt_gemm_segment;
 
 typedef struct rt_gemm_problem {
@@ -179,6 +245,9 @@ typedef struct rt_gemm_launch {
   rt_gemm_problem prob[2];
   const float* rope; /* [rows, head_dim/2, 2] (cos, sin) fp32, indexed by out_row0 + m; NULL = no rope */
   int head_dim;
+  int sp_cols; /* scatter segments: columns per destination (a multiple of 128); 0 = no scatter segment */
+  int sp_row0; /* row offset of this rank's rows in the destination buffers */
+  void* sp_out[8]; /* destination buffers (peer-mapped device pointers) */
 } rt_gemm_launch;
 
 /* impl: 0 auto, 1 SIMT, 2 tcgen05 cta_group::1, 3 tcgen05 cta_group::2 */
@@ -194,6 +263,9 @@ typedef struct rt_attention_args {
   int64_t out_batch_stride;
   int out_ld, out_col0;
   int batch, S, heads, hd;
+  int sp_rows; /* > 0 (tcgen05 path): output row r goes to sp_out[r / sp_rows] at row r % sp_rows (same out_ld,
+                  out_col0, out_batch_stride); `out` is ignored */
+  void* sp_out[8];
 } rt_attention_args;
 /* impl: 0 auto, 1 SIMT, >= 2 tcgen05 variant (impl - 2) */
 RT_API int rt_attention(const rt_attention_args* a, int impl, void* stream);

@@ -20,10 +20,12 @@ EPI_BIAS, EPI_GELU, EPI_QKNORM_ROPE, EPI_GATE_RESID, EPI_SCALE_MASK = range(5)
 RT_ERR_INVALID = -1
 
 EXPORTS = [
-    "rt_last_error", "rt_abi_version", "rt_launch_count", "rt_set_option", "rt_get_option",
+    "rt_last_error", "rt_abi_version", "rt_struct_size", "rt_launch_count", "rt_set_option", "rt_get_option",
     "rt_profile_reset", "rt_profile_read",
     "rt_model_create", "rt_model_set_weight", "rt_model_finalize", "rt_model_destroy", "rt_model_workspace_bytes",
     "rt_controlnet_forward", "rt_transformer_forward",
+    "rt_controlnet_forward_lockstep", "rt_transformer_forward_lockstep",
+    "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free", "rt_sp_barrier", "rt_sp_status",
     "rt_euler_step", "rt_cfg_combine", "rt_cfg_euler_step", "rt_mask_scale_add", "rt_glyph_init_blend",
     "rt_gemm", "rt_attention", "rt_layernorm_modulate", "rt_rope_table", "rt_qknorm_rope",
 ]
@@ -38,12 +40,41 @@ class ModelConfig(C.Structure):
     ]
 
 
+SP_MAX_RANKS = 8
+SP_FLAG_WORDS = 16
+
+
+class SpGroup(C.Structure):
+    """``rt_sp_group``: one sample's tokens sharded over ``world`` GPUs (sequence-parallel attention)."""
+    _fields_ = [
+        ("world", C.c_int), ("rank", C.c_int), ("peer_workspace", C.c_void_p * SP_MAX_RANKS),
+        ("peer_flags", C.c_void_p * SP_MAX_RANKS), ("lockstep", C.c_int),
+    ]
+
+
 class ForwardArgs(C.Structure):
     _fields_ = [
         ("batch", C.c_int), ("lat_batch", C.c_int), ("t_batch", C.c_int), ("n_img", C.c_int), ("n_txt", C.c_int),
         ("hidden_states", C.c_void_p), ("encoder_hidden_states", C.c_void_p), ("pooled_projections", C.c_void_p),
         ("timestep", C.c_void_p), ("guidance", C.c_void_p), ("img_ids", C.c_void_p), ("txt_ids", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("stream", C.c_void_p),
+        ("sp", C.POINTER(SpGroup)),
+    ]
+
+
+class ControlNetCall(C.Structure):
+    _fields_ = [
+        ("a", ForwardArgs), ("controlnet_cond", C.c_void_p), ("cond_batch", C.c_int),
+        ("conditioning_scale", C.c_float), ("mask", C.c_void_p), ("accumulate", C.c_int),
+        ("block_samples", C.c_void_p), ("single_block_samples", C.c_void_p),
+    ]
+
+
+class TransformerCall(C.Structure):
+    _fields_ = [
+        ("a", ForwardArgs), ("controlnet_block_samples", C.POINTER(C.c_void_p)), ("n_block_samples", C.c_int),
+        ("controlnet_single_block_samples", C.POINTER(C.c_void_p)), ("n_single_block_samples", C.c_int),
+        ("out", C.c_void_p),
     ]
 
 
@@ -51,7 +82,7 @@ class GemmSegment(C.Structure):
     _fields_ = [
         ("W", C.c_void_p), ("bias", C.c_void_p), ("n_begin", C.c_int), ("n_end", C.c_int), ("mode", C.c_int),
         ("out", C.c_void_p), ("out_batch_stride", C.c_int64), ("out_ld", C.c_int), ("out_col0", C.c_int),
-        ("norm_w", C.c_void_p),
+        ("norm_w", C.c_void_p), ("scatter", C.c_int),
     ]
 
 
@@ -68,7 +99,8 @@ class GemmProblem(C.Structure):
 class GemmLaunch(C.Structure):
     _fields_ = [
         ("dtype", C.c_int), ("batch", C.c_int), ("nprob", C.c_int), ("prob", GemmProblem * 2),
-        ("rope", C.c_void_p), ("head_dim", C.c_int),
+        ("rope", C.c_void_p), ("head_dim", C.c_int), ("sp_cols", C.c_int), ("sp_row0", C.c_int),
+        ("sp_out", C.c_void_p * SP_MAX_RANKS),
     ]
 
 
@@ -77,7 +109,7 @@ class AttentionArgs(C.Structure):
         ("dtype", C.c_int), ("qkv", C.c_void_p), ("batch_stride", C.c_int64), ("ld", C.c_int), ("q_col0", C.c_int),
         ("k_col0", C.c_int), ("v_col0", C.c_int), ("out", C.c_void_p), ("out_batch_stride", C.c_int64),
         ("out_ld", C.c_int), ("out_col0", C.c_int), ("batch", C.c_int), ("S", C.c_int), ("heads", C.c_int),
-        ("hd", C.c_int),
+        ("hd", C.c_int), ("sp_rows", C.c_int), ("sp_out", C.c_void_p * SP_MAX_RANKS),
     ]
 
 
@@ -114,6 +146,14 @@ def lib() -> C.CDLL:
                                         C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.rt_transformer_forward.argtypes = [C.c_void_p, C.POINTER(ForwardArgs), C.POINTER(C.c_void_p), C.c_int,
                                          C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    L.rt_controlnet_forward_lockstep.argtypes = [C.c_void_p, C.c_int, C.POINTER(ControlNetCall)]
+    L.rt_transformer_forward_lockstep.argtypes = [C.c_void_p, C.c_int, C.POINTER(TransformerCall)]
+    L.rt_ipc_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]
+    L.rt_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.rt_ipc_close.argtypes = [C.c_void_p]
+    L.rt_ipc_free.argtypes = [C.c_void_p]
+    L.rt_sp_barrier.argtypes = [C.POINTER(SpGroup), C.c_void_p]
+    L.rt_sp_status.argtypes = [C.POINTER(SpGroup), C.c_void_p, C.POINTER(C.c_int)]
     L.rt_euler_step.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                 C.c_void_p]
     L.rt_cfg_combine.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_void_p]
@@ -130,6 +170,11 @@ def lib() -> C.CDLL:
     L.rt_rope_table.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     L.rt_qknorm_rope.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    for i, st in enumerate((ModelConfig, ForwardArgs, SpGroup, ControlNetCall, TransformerCall, GemmSegment,
+                            GemmProblem, GemmLaunch, AttentionArgs, LnModGroup)):
+        if L.rt_struct_size(i) != C.sizeof(st):
+            raise RuntimeError(f"ctypes mirror of {st.__name__} is {C.sizeof(st)} bytes, the library says "
+                               f"{L.rt_struct_size(i)}: _lib.py and include/reptext_rt.h are out of step")
     _lib = L
     return L
 

@@ -257,6 +257,23 @@ class RepTextPipelineBase(DiffusionPipeline):
             guidance_const = torch.tensor([guidance_scale], device=device)
         common = dict(controlnet_mode=control_mode, joint_attention_kwargs=self.joint_attention_kwargs,
                       return_dict=False)
+        sp = getattr(self, "_sp", None)
+        sp_kw = {}
+        if sp is not None:
+            # sequence-parallel mode (BASELINE.json configs[4]): every rank keeps a contiguous block of the image
+            # and of the text tokens for the whole loop; only the finished latents are gathered (NCCL).
+            from .parallel import shard_tokens
+            r, w = sp.rank, sp.world
+            latents = shard_tokens(latents, r, w)
+            latent_image_ids = shard_tokens(latent_image_ids, r, w, dim=0)
+            text_ids = shard_tokens(text_ids, r, w, dim=0)
+            prompt_embeds = shard_tokens(prompt_embeds, r, w)
+            control_image_list = [shard_tokens(c, r, w) for c in control_image_list]
+            control_mask_list = [shard_tokens(m.reshape(1, -1, 1), r, w) for m in control_mask_list]
+            if control_image_inpaint is not None:
+                control_image_inpaint = shard_tokens(control_image_inpaint, r, w)
+            sp_kw = dict(sp=sp)
+            common.update(sp_kw)
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(timesteps):
                 if self.interrupt:
@@ -284,7 +301,7 @@ class RepTextPipelineBase(DiffusionPipeline):
                                                               accumulate_into=(stack_b, stack_s), **step_kw, **common)
                 noise_pred = self.transformer(controlnet_block_samples=blocks, controlnet_single_block_samples=singles,
                                               joint_attention_kwargs=self.joint_attention_kwargs, return_dict=False,
-                                              **step_kw)[0]
+                                              **step_kw, **sp_kw)[0]
                 if do_cfg:   # :1264-1270, fused with the Euler step
                     latents = self.scheduler.step_cfg(noise_pred, t, latents, true_guidance_scale, zero_pred=(i == 0))
                 else:
@@ -297,7 +314,18 @@ class RepTextPipelineBase(DiffusionPipeline):
                     prompt_embeds = outs.pop("prompt_embeds", prompt_embeds)
                 if i == len(timesteps) - 1 or ((i + 1) > num_warmup_steps and (i + 1) % self.scheduler.order == 0):
                     progress_bar.update()
+        if sp is not None:
+            from .parallel import gather_tokens
+            sp.check()
+            latents = gather_tokens(latents, sp.group)
         return latents
+
+    def enable_sequence_parallel(self, sp_group) -> None:
+        """Run ONE sample on all ranks of ``sp_group`` (:class:`reptext_b200.parallel.SequenceParallelGroup`): tokens
+        sharded across GPUs, attention heads sharded across GPUs inside every block.  Every rank must make the same
+        ``__call__`` with the same arguments and seed; every rank gets the full latents back.  ``None`` switches back
+        to one GPU per sample.  Callbacks see this rank's token shard."""
+        self._sp = sp_group
 
     def _finish(self, latents, height, width, output_type, return_dict):
         if output_type == "latent":

@@ -53,6 +53,10 @@ SMALL128_CONTROLNET = dict(
     num_mode=None, extra_conditioning_channels=0, extra_condition_channels=64,
 )
 
+# eight heads of 128: the smallest pair whose heads shard over 2, 4 and 8 ranks (sequence-parallel tests)
+SP8_TRANSFORMER = dict(SMALL128_TRANSFORMER, num_attention_heads=8, num_layers=1, num_single_layers=2)
+SP8_CONTROLNET = dict(SMALL128_CONTROLNET, num_attention_heads=8, num_layers=1)
+
 SMALL128_INPAINT_CONTROLNET = dict(SMALL128_CONTROLNET, extra_condition_channels=4)
 
 # FLUX.1-dev scheduler_config.json

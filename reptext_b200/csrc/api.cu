@@ -15,7 +15,7 @@ void set_last_error(const std::string& msg) { t_last_error = msg; }
 
 static std::map<std::string, int>& options() {
   static std::map<std::string, int> o = {{"force_simt", 0}, {"gemm_cta_group", 0}, {"attn_variant", 0},
-                                         {"profile", 0}};
+                                         {"profile", 0}, {"ln_warp_rows", 0}, {"gemv_single_row", 0}, {"gemm_debug", 0}};
   return o;
 }
 int get_option(const char* name) {
@@ -82,6 +82,21 @@ extern "C" {
 
 const char* rt_last_error(void) { return t_last_error.c_str(); }
 int rt_abi_version(void) { return RT_ABI_VERSION; }
+int rt_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(rt_model_config);
+    case 1: return (int)sizeof(rt_forward_args);
+    case 2: return (int)sizeof(rt_sp_group);
+    case 3: return (int)sizeof(rt_controlnet_call);
+    case 4: return (int)sizeof(rt_transformer_call);
+    case 5: return (int)sizeof(rt_gemm_segment);
+    case 6: return (int)sizeof(rt_gemm_problem);
+    case 7: return (int)sizeof(rt_gemm_launch);
+    case 8: return (int)sizeof(rt_attention_args);
+    case 9: return (int)sizeof(rt_lnmod_group);
+    default: return -1;
+  }
+}
 long long rt_launch_count(void) { return g_launch_count; }
 
 int rt_set_option(const char* name, int value) {
@@ -185,7 +200,7 @@ int rt_gemm(const rt_gemm_launch* g, int impl, void* stream) {
 
 int rt_attention(const rt_attention_args* a, int impl, void* stream) {
   return guarded([&] {
-    RT_REQUIRE(a && a->qkv && a->out, "attention: null argument");
+    RT_REQUIRE(a && a->qkv && (a->out || a->sp_rows > 0), "attention: null argument");
     cudaStream_t s = (cudaStream_t)stream;
     if (impl == 0) launch_attention(*a, s);
     else if (impl == 1) launch_attention_simt(*a, s);

@@ -43,6 +43,9 @@ struct AttnParams {
   int q_col0, k_col0, v_col0;
   int S, heads, n_qpairs;
   float scale_log2;  // log2(e) / sqrt(head_dim)
+  // sequence-parallel mode: output row r belongs to rank r / sp_rows and is stored straight into that rank's buffer
+  int sp_rows;
+  bf16* sp_out[RT_SP_MAX_RANKS];
 };
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -306,7 +309,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
     const float inv = 1.f / l;
-    bf16* orow = P.out + (long long)b * P.out_bs + (long long)row * P.out_ld + P.out_col0 + h * HD;
+    bf16* orow;
+    if (P.sp_rows > 0) {
+      const int dest = min(row / P.sp_rows, RT_SP_MAX_RANKS - 1);  // rows >= S are never stored
+      orow = P.sp_out[dest] + (long long)b * P.out_bs + (long long)(row - dest * P.sp_rows) * P.out_ld + P.out_col0 +
+             h * HD;
+    } else {
+      orow = P.out + (long long)b * P.out_bs + (long long)row * P.out_ld + P.out_col0 + h * HD;
+    }
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
       float v[32];
@@ -339,7 +349,15 @@ bool attention_tc_supported(const AttnArgs& a, std::string* why) {
   if (a.hd != HD) return fail("head_dim is not 128");
   if (a.ld % 8 || a.batch_stride % 8 || a.q_col0 % 8 || a.k_col0 % 8 || a.v_col0 % 8) return fail("qkv alignment");
   if (a.out_ld % 8 || a.out_col0 % 8 || a.out_batch_stride % 8) return fail("out alignment");
-  if ((reinterpret_cast<uintptr_t>(a.qkv) & 15) || (reinterpret_cast<uintptr_t>(a.out) & 15)) return fail("pointer alignment");
+  if (reinterpret_cast<uintptr_t>(a.qkv) & 15) return fail("pointer alignment");
+  if (a.sp_rows > 0) {
+    const int ndest = (a.S + a.sp_rows - 1) / a.sp_rows;
+    if (ndest > RT_SP_MAX_RANKS) return fail("sp_rows: more destinations than RT_SP_MAX_RANKS");
+    for (int d = 0; d < ndest; ++d)
+      if (!a.sp_out[d] || (reinterpret_cast<uintptr_t>(a.sp_out[d]) & 15)) return fail("sp_out pointer missing or misaligned");
+  } else if (!a.out || (reinterpret_cast<uintptr_t>(a.out) & 15)) {
+    return fail("pointer alignment");
+  }
   if (a.S < 1) return fail("empty sequence");
   return true;
 }
@@ -358,6 +376,8 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
   P.out_bs = a.out_batch_stride; P.out_ld = a.out_ld; P.out_col0 = a.out_col0;
   P.q_col0 = a.q_col0; P.k_col0 = a.k_col0; P.v_col0 = a.v_col0;
   P.S = a.S; P.heads = a.heads;
+  P.sp_rows = a.sp_rows > 0 ? a.sp_rows : 0;
+  for (int i = 0; i < RT_SP_MAX_RANKS; ++i) P.sp_out[i] = reinterpret_cast<bf16*>(a.sp_out[i]);
   P.n_qpairs = (a.S + 2 * BQ - 1) / (2 * BQ);
   P.scale_log2 = 1.4426950408889634f / sqrtf((float)a.hd);
   using KernelFn = void (*)(const AttnParams);

@@ -111,6 +111,114 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const T* __restrict__ x, lo
   }
 }
 
+
+// CTA form for rows that fit one 16-byte vector per thread (D <= 8192 bf16 / 4096 fp32): thread t owns columns
+// [t*N, t*N+N) of EVERY row its CTA processes, so the (1 + scale) / shift vectors live in registers and are read
+// once per CTA instead of once per row (per row they are 4x the bytes of the row itself in bf16).  kR rows are in
+// flight per iteration; mean and variance are two block reductions (two-pass, like torch's LayerNorm).
+template <typename T, int kR, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads) ln_mod_cta_kernel(const T* __restrict__ x, long long x_bs, int x_ld,
+                                                          T* __restrict__ out, long long o_bs, int o_ld, int batch,
+                                                          int rows_total, int D, LnGroups groups, int rows_per_cta) {
+  constexpr int N = VecT<T>::N;
+  __shared__ float red[2][kR][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const bool active = tid * N < D;
+  const long long lin_end = min((long long)(blockIdx.x + 1) * rows_per_cta, (long long)batch * rows_total);
+  const float inv_d = 1.f / (float)D;
+  int cur_key = -1;
+  float sc1[N], sh[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) { sc1[j] = 1.f; sh[j] = 0.f; }
+  for (long long lin = (long long)blockIdx.x * rows_per_cta; lin < lin_end;) {
+    const int b = (int)(lin / rows_total);
+    const int lr = (int)(lin % rows_total);
+    int gi = 0, r = 0, left = 0, acc = 0, g_ld = 0;
+    const float *g_scale = nullptr, *g_shift = nullptr;
+#pragma unroll
+    for (int k = 0; k < kLnMaxGroups; ++k) {
+      if (k < groups.n) {
+        const int len = groups.g[k].row_end - groups.g[k].row_begin;
+        if (left == 0 && lr < acc + len) {
+          gi = k;
+          r = groups.g[k].row_begin + (lr - acc);
+          left = acc + len - lr;
+          g_scale = groups.g[k].scale; g_shift = groups.g[k].shift; g_ld = groups.g[k].ld;
+        }
+        acc += len;
+      }
+    }
+    const int n = min(kR, min((int)(lin_end - lin), left));  // rows of this iteration: one (batch, group)
+    if (b * kLnMaxGroups + gi != cur_key) {
+      cur_key = b * kLnMaxGroups + gi;
+      if (active) {
+        const float* scp = g_scale + (long long)b * g_ld + tid * N;
+        const float* shp = g_shift + (long long)b * g_ld + tid * N;
+#pragma unroll
+        for (int j4 = 0; j4 < N; j4 += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(scp + j4);
+          const float4 h = *reinterpret_cast<const float4*>(shp + j4);
+          sc1[j4] = 1.f + a.x; sc1[j4 + 1] = 1.f + a.y; sc1[j4 + 2] = 1.f + a.z; sc1[j4 + 3] = 1.f + a.w;
+          sh[j4] = h.x; sh[j4 + 1] = h.y; sh[j4 + 2] = h.z; sh[j4 + 3] = h.w;
+        }
+      }
+    }
+    const T* xr = x + (long long)b * x_bs + (long long)r * x_ld + tid * N;
+    float v[kR][N];
+    float part[kR];
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+      part[i] = 0.f;
+      if (active && i < n) {
+        ldvec(xr + (long long)i * x_ld, v[i]);
+#pragma unroll
+        for (int j = 0; j < N; ++j) part[i] += v[i][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[i][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+      part[i] = warp_sum(part[i]);
+      if (lane == 0) red[0][i][warp] = part[i];
+    }
+    __syncthreads();
+    float mean[kR];
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += red[0][i][w];
+      mean[i] = t * inv_d;
+      float q = 0.f;
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float d = v[i][j] - mean[i];
+          q += d * d;
+        }
+      }
+      q = warp_sum(q);
+      if (lane == 0) red[1][i][warp] = q;
+    }
+    __syncthreads();
+    T* orow = out + (long long)b * o_bs + (long long)r * o_ld + tid * N;
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += red[1][i][w];
+      const float rstd = rsqrtf(t * inv_d + 1e-6f);
+      if (active && i < n) {
+        float o[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[j] = (v[i][j] - mean[i]) * rstd * sc1[j] + sh[j];
+        stvec(orow + (long long)i * o_ld, o);
+      }
+    }
+    lin += n;
+  }
+}
+
 void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out, long long o_bs, int o_ld, int batch,
                    int D, int ngroups, const LnModGroup* groups, cudaStream_t stream) {
   RT_REQUIRE(ngroups >= 1 && ngroups <= kLnMaxGroups, "ln_mod: 1..2 row groups");
@@ -133,6 +241,22 @@ void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out
     constexpr int N = VecT<T>::N;
     RT_REQUIRE(D % N == 0 && x_ld % N == 0 && o_ld % N == 0, "ln_mod: D and lds must be multiples of the vector width");
     const int nvec = D / N;
+    if (nvec <= 1024 && nvec >= 64 && !get_option("ln_warp_rows")) {
+      constexpr int kR = 4;
+      const int cta_threads = (nvec + 31) / 32 * 32;
+      const long long cap_cta = (long long)sm_count() * (cta_threads <= 512 ? 4 : 2);
+      long long rpc = (total + cap_cta - 1) / cap_cta;
+      rpc = (rpc + kR - 1) / kR * kR;
+      const long long grid = (total + rpc - 1) / rpc;
+      if (cta_threads <= 512)
+        ln_mod_cta_kernel<T, kR, 512><<<(int)grid, cta_threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs,
+                                                                             o_ld, batch, rows_total, D, G, (int)rpc);
+      else
+        ln_mod_cta_kernel<T, kR, 1024><<<(int)grid, cta_threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs,
+                                                                              o_ld, batch, rows_total, D, G, (int)rpc);
+      RT_POST_LAUNCH();
+      return;
+    }
     const int per_lane = (nvec + 31) / 32;
     RT_REQUIRE(per_lane <= 24, "ln_mod: D too large");
     if (per_lane <= 2)
@@ -209,9 +333,73 @@ __global__ void __launch_bounds__(256) gemv_grouped_kernel(const float* __restri
   }
 }
 
+
+// kR consecutive output rows per warp: the activation chunk (fp32, L1-resident) is loaded once for kR weight
+// rows instead of once per row, and kR independent 16-byte weight loads are in flight per lane per iteration.
+// Rows never straddle a job (the host checks rows % kR == 0 for every job).
+template <typename T, int NB, int kR>
+__global__ void __launch_bounds__(256) gemv_grouped_rows_kernel(const float* __restrict__ x, int x_ld, int b0, int K,
+                                                                const GemvJob* __restrict__ jobs,
+                                                                const int* __restrict__ prefix, int njobs,
+                                                                int total_rows, float* __restrict__ out, int out_ld,
+                                                                int silu_out, int accumulate) {
+  constexpr int N = VecT<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = (blockIdx.x * wpb + (threadIdx.x >> 5)) * kR; row < total_rows; row += gridDim.x * wpb * kR) {
+    int lo = 0, hi = njobs - 1;  // last job with prefix[j] <= row
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (prefix[mid] <= row) lo = mid; else hi = mid - 1;
+    }
+    const GemvJob J = jobs[lo];
+    const int r = row - prefix[lo];
+    const T* w = reinterpret_cast<const T*>(J.W) + (long long)r * K;
+    float acc[kR][NB];
+#pragma unroll
+    for (int i = 0; i < kR; ++i)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) acc[i][b] = 0.f;
+#pragma unroll 2
+    for (int c = lane * N; c < K; c += 32 * N) {
+      float wv[kR][N];
+#pragma unroll
+      for (int i = 0; i < kR; ++i) ldvec(w + (long long)i * K + c, wv[i]);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float* xb = x + (long long)(b0 + b) * x_ld + c;
+#pragma unroll
+        for (int j = 0; j < N; j += 4) {
+          const float4 xv = *reinterpret_cast<const float4*>(xb + j);
+#pragma unroll
+          for (int i = 0; i < kR; ++i)
+            acc[i][b] += wv[i][j] * xv.x + wv[i][j + 1] * xv.y + wv[i][j + 2] * xv.z + wv[i][j + 3] * xv.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kR; ++i)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) acc[i][b] = warp_sum(acc[i][b]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kR; ++i) {
+        const float bias = J.bias ? to_f(reinterpret_cast<const T*>(J.bias)[r + i]) : 0.f;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          float v = acc[i][b] + bias;
+          if (silu_out) v = v / (1.f + expf(-v));
+          float* o = out + (long long)(b0 + b) * out_ld + J.out_off + r + i;
+          *o = accumulate ? (*o + v) : v;
+        }
+      }
+    }
+  }
+}
+
 void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
                          const int* prefix_dev, int njobs, int total_rows, float* out, int out_ld, int silu_out,
-                         int accumulate, cudaStream_t stream) {
+                         int accumulate, cudaStream_t stream, bool rows_multiple_of_4) {
   if (batch == 0 || total_rows == 0) return;
   ProfScope ps(PROF_GEMV, (double)total_rows * K * dtype_size(wdtype), stream);
   RT_REQUIRE(x_ld % 4 == 0, "gemv: x_ld must be a multiple of 4");
@@ -222,9 +410,21 @@ void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K,
   RT_DISPATCH_DTYPE(wdtype, T, {
     RT_REQUIRE(K % VecT<T>::N == 0, "gemv: K must be a multiple of the vector width");
     int b0 = 0;
+    constexpr int kR = 4;
+    const bool multi = rows_multiple_of_4 && total_rows % kR == 0 && !get_option("gemv_single_row");
+    int mblocks = (total_rows / kR + wpb - 1) / wpb;
+    if (mblocks > cap) mblocks = cap;
     while (b0 < batch) {
       int nb = batch - b0;
-      if (nb >= 4) {
+      if (multi && nb >= 2) {
+        gemv_grouped_rows_kernel<T, 2, kR><<<mblocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
+                                                                            total_rows, out, out_ld, silu_out, accumulate);
+        b0 += 2;
+      } else if (multi) {
+        gemv_grouped_rows_kernel<T, 1, kR><<<mblocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
+                                                                            total_rows, out, out_ld, silu_out, accumulate);
+        b0 += 1;
+      } else if (nb >= 4) {
         gemv_grouped_kernel<T, 4><<<blocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
                                                                   total_rows, out, out_ld, silu_out, accumulate);
         b0 += 4;

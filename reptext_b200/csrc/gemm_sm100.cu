@@ -41,7 +41,7 @@ struct alignas(64) TcSegment {
   bf16* out;
   const bf16* norm_w;
   long long out_bs;
-  int n_begin, n_end, mode, out_ld, out_col0, pad_;
+  int n_begin, n_end, mode, out_ld, out_col0, scatter;
 };
 
 struct alignas(64) TcProblem {
@@ -60,6 +60,10 @@ struct alignas(64) TcParams {
   TcProblem prob[2];
   const float2* rope;
   int nprob, batch, total_tiles, head_dim;
+  // sequence-parallel scatter (rt_gemm_segment::scatter): destination buffers, columns per destination, row offset
+  bf16* sp_out[RT_SP_MAX_RANKS];
+  int sp_cols, sp_row0;
+  int debug;  // option "gemm_debug" (timing experiments, wrong results): 1 = no epilogue, 2 = every k-block loads k = 0
 };
 
 template <int BN, int kCtaGroup>
@@ -157,12 +161,21 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const TcProblem
   const int nl0 = n0 - sg.n_begin;  // column within the segment
   bf16* orow = sg.out + (long long)b * sg.out_bs + (long long)(pr.out_row0 + m) * sg.out_ld + sg.out_col0 + nl0;
   const bf16* bias = sg.bias ? sg.bias + nl0 : nullptr;
+  // Sequence-parallel scatter: the 32-column chunk starting at segment column `col` belongs to rank col / sp_cols
+  // and is stored straight into that rank's buffer (a peer-mapped pointer: the store crosses NVLink).
+  auto out_chunk = [&](int col) -> bf16* {
+    if (!sg.scatter) return orow + (col - nl0);
+    const int dest = col / P.sp_cols;
+    return P.sp_out[dest] + (long long)b * sg.out_bs + (long long)(P.sp_row0 + pr.out_row0 + m) * sg.out_ld +
+           sg.out_col0 + (col - dest * P.sp_cols);
+  };
 
   if (sg.mode == EPI_QKNORM_ROPE) {
     // one head = 128 columns; two passes over TMEM (reads are cheap) instead of 128 live registers
     const float2* rp = P.rope ? P.rope + (long long)(pr.out_row0 + m) * 64 : nullptr;
 #pragma unroll 1
     for (int hc = 0; hc < BN / 128; ++hc) {
+      bf16* ohead = out_chunk(nl0 + hc * 128);
       float ss = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -204,7 +217,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const TcProblem
             v[4 * i + 3] = x3 * cs.z + x2 * cs.w;
           }
         }
-        if (row_ok) store_bf16x32(orow + hc * 128 + c * 32, v);
+        if (row_ok) store_bf16x32(ohead + c * 32, v);
       }
     }
     return;
@@ -262,7 +275,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const TcProblem
         for (int i = 0; i < 32; ++i) v[i] += r[i];
       }
     }
-    if (row_ok) store_bf16x32(orow + c * 32, v);
+    if (row_ok) store_bf16x32(sg.mode == EPI_BIAS ? out_chunk(nl0 + c * 32) : orow + c * 32, v);
   }
 }
 
@@ -332,14 +345,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         void* sa = smem_a + stage * C::kABytes;
         void* sb = smem_b + stage * C::kBBytes;
+        const int k0 = (P.debug & 2) ? 0 : kb * BK;
         if constexpr (kCtaGroup == 1) {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-          ptx::tma_load_3d(&pr.tmA, &full_bar[stage], sa, kb * BK, a_row, a_b);
-          ptx::tma_load_2d(&sg.tmW, &full_bar[stage], sb, kb * BK, w_row);
+          ptx::tma_load_3d(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b);
+          ptx::tma_load_2d(&sg.tmW, &full_bar[stage], sb, k0, w_row);
         } else {
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-          ptx::tma_load_3d_2sm(&pr.tmA, &full_bar[stage], sa, kb * BK, a_row, a_b);
-          ptx::tma_load_2d_2sm(&sg.tmW, &full_bar[stage], sb, kb * BK, w_row);
+          ptx::tma_load_3d_2sm(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b);
+          ptx::tma_load_2d_2sm(&sg.tmW, &full_bar[stage], sb, k0, w_row);
         }
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
@@ -387,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
       const int m = tc.m0 + (int)cta_rank * BM + quad * 32 + lane;
-      epilogue_tile<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m, tc.n0);
+      if (!(P.debug & 1)) epilogue_tile<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m, tc.n0);
       ptx::tc_fence_before();
       if constexpr (kCtaGroup == 1) ptx::mbar_arrive(&tempty_bar[as]);
       else ptx::mbar_arrive_cluster(&tempty_bar[as], 0);
@@ -503,8 +517,17 @@ bool gemm_tc_supported(const GemmLaunch& L, std::string* why) {
       const GemmSegment& S = P.seg[s];
       if (S.n_begin != expect || S.n_end <= S.n_begin) return fail("segments must tile [0, N) in order");
       expect = S.n_end;
-      if (!al16(S.W) || !al16(S.out) || (S.bias && !al16(S.bias))) return fail("W / out / bias alignment");
+      if (!al16(S.W) || (!S.scatter && (!S.out || !al16(S.out))) || (S.bias && !al16(S.bias)))
+        return fail("W / out / bias alignment");
       if (S.out_ld % 8 || S.out_col0 % 8 || S.out_batch_stride % 8) return fail("out ld / col0 / stride alignment");
+      if (S.scatter) {
+        if (S.mode != EPI_BIAS && S.mode != EPI_QKNORM_ROPE) return fail("scatter needs a BIAS or QKNORM_ROPE segment");
+        if (L.sp_cols <= 0 || L.sp_cols % 128) return fail("sp_cols must be a positive multiple of 128");
+        const int ndest = (S.n_end - S.n_begin + L.sp_cols - 1) / L.sp_cols;
+        if (ndest > RT_SP_MAX_RANKS) return fail("scatter: more destinations than RT_SP_MAX_RANKS");
+        for (int d = 0; d < ndest; ++d)
+          if (!L.sp_out[d] || !al16(L.sp_out[d])) return fail("scatter: sp_out pointer missing or misaligned");
+      }
       if (S.mode == EPI_QKNORM_ROPE) {
         if (L.head_dim != 128) return fail("fused qk-norm needs head_dim 128");
         if (!S.norm_w || !al16(S.norm_w)) return fail("norm_w");
@@ -572,6 +595,9 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
   P.batch = L.batch;
   P.rope = reinterpret_cast<const float2*>(L.rope);
   P.head_dim = L.head_dim;
+  P.sp_cols = L.sp_cols; P.sp_row0 = L.sp_row0;
+  P.debug = get_option("gemm_debug");
+  for (int i = 0; i < RT_SP_MAX_RANKS; ++i) P.sp_out[i] = reinterpret_cast<bf16*>(L.sp_out[i]);
   int tile_base = 0;
   for (int p = 0; p < L.nprob; ++p) {
     const GemmProblem& G = L.prob[p];
@@ -598,7 +624,7 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
       D.out = reinterpret_cast<bf16*>(S.out);
       D.norm_w = reinterpret_cast<const bf16*>(S.norm_w);
       D.out_bs = S.out_batch_stride; D.n_begin = S.n_begin; D.n_end = S.n_end; D.mode = S.mode;
-      D.out_ld = S.out_ld; D.out_col0 = S.out_col0;
+      D.out_ld = S.out_ld; D.out_col0 = S.out_col0; D.scatter = S.scatter;
     }
     const int rows_per_tile = BM * cg;
     T.tiles_m = (G.m_rows + rows_per_tile - 1) / rows_per_tile;

@@ -167,8 +167,32 @@ struct Ctx {
   int B, T, N, S, D, dt;
   size_t es;
   cudaStream_t st;
+  // sequence-parallel mode (rt_sp_group): P ranks, this is rank r; T / N / S above are THIS rank's rows, the
+  // attention runs over Sg = P * S rows and Dl = D / P of the head columns.  peer_qkv / peer_cat: every rank's
+  // exchange buffers as mapped here.
+  const rt_sp_group* sp = nullptr;
+  int P = 1, r = 0, Sg = 0, Dl = 0;
+  char* peer_qkv[RT_SP_MAX_RANKS] = {};
+  char* peer_cat[RT_SP_MAX_RANKS] = {};
   long long sD() const { return (long long)S * D; }
 };
+
+// The q | k | v segments of a projection launch: local [B, S, 3D] layout, or (sequence-parallel) scattered by head
+// block into every rank's [B, Sg, 3 Dl] exchange buffer at this rank's row range.
+void set_qkv_targets(const Ctx& c, GemmLaunch& L) {
+  if (c.P == 1) return;
+  L.sp_cols = c.Dl;
+  L.sp_row0 = c.r * c.S;
+  for (int i = 0; i < c.P; ++i) L.sp_out[i] = c.peer_qkv[i];
+}
+GemmSegment make_qkv_seg(const Ctx& c, const Lin& l, int which /*0 q, 1 k, 2 v*/, const void* norm_w) {
+  const int mode = norm_w ? EPI_QKNORM_ROPE : EPI_BIAS;
+  if (c.P == 1)
+    return make_seg(l, which * c.D, mode, c.ws.qkv, 3 * c.sD(), 3 * c.D, which * c.D, norm_w);
+  GemmSegment s = make_seg(l, which * c.D, mode, nullptr, (long long)c.Sg * 3 * c.Dl, 3 * c.Dl, which * c.Dl, norm_w);
+  s.scatter = 1;
+  return s;
+}
 
 // temb = MLP_t(sin(1000 t)) + MLP_g(sin(1000 g)) + MLP_p(pooled)   (controlnet_flux.py:282-291), then the AdaLN
 // vectors of every block: mod = Linear_i(SiLU(temb)).
@@ -192,7 +216,7 @@ void time_text_and_modulation(const Ctx& c, const rt_forward_args& a) {
   launch_gemv_grouped(c.dt, w.hid + 2 * D, 3 * D, B, D, m.jobs_dev + 5, m.prefix_dev, 1, D, w.temb, D, 0, 1, c.st);
   launch_silu_f32(w.temb, w.temb_s, (long long)B * D, c.st);
   launch_gemv_grouped(c.dt, w.temb_s, D, B, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, m.mod_rows, w.mod,
-                      m.mod_total, 0, 0, c.st);
+                      m.mod_total, 0, 0, c.st, /*rows_multiple_of_4=*/D % 4 == 0);  // every AdaLN job has k*D rows
 }
 
 void embed_inputs(const Ctx& c, const rt_forward_args& a, const void* cond, int cond_batch) {
@@ -232,10 +256,22 @@ void embed_inputs(const Ctx& c, const rt_forward_args& a, const void* cond, int 
 void run_attention(const Ctx& c) {
   AttnArgs t{};
   t.dtype = c.dt;
-  t.qkv = c.ws.qkv; t.batch_stride = (long long)c.S * 3 * c.D; t.ld = 3 * c.D;
-  t.q_col0 = 0; t.k_col0 = c.D; t.v_col0 = 2 * c.D;
-  t.out = c.ws.cat; t.out_batch_stride = (long long)c.S * 5 * c.D; t.out_ld = 5 * c.D; t.out_col0 = 0;
-  t.batch = c.B; t.S = c.S; t.heads = c.m.H; t.hd = c.m.hd;
+  t.out_batch_stride = (long long)c.S * 5 * c.D; t.out_ld = 5 * c.D;
+  t.batch = c.B; t.hd = c.m.hd;
+  if (c.P == 1) {
+    t.qkv = c.ws.qkv; t.batch_stride = (long long)c.S * 3 * c.D; t.ld = 3 * c.D;
+    t.q_col0 = 0; t.k_col0 = c.D; t.v_col0 = 2 * c.D;
+    t.out = c.ws.cat; t.out_col0 = 0;
+    t.S = c.S; t.heads = c.m.H;
+  } else {
+    // this rank's heads over the whole sequence; output rows go back to the rank that owns the token
+    t.qkv = c.ws.qkv; t.batch_stride = (long long)c.Sg * 3 * c.Dl; t.ld = 3 * c.Dl;
+    t.q_col0 = 0; t.k_col0 = c.Dl; t.v_col0 = 2 * c.Dl;
+    t.out = nullptr; t.out_col0 = c.r * c.Dl;
+    t.S = c.Sg; t.heads = c.m.H / c.P;
+    t.sp_rows = c.S;
+    for (int i = 0; i < c.P; ++i) t.sp_out[i] = c.peer_cat[i];
+  }
   launch_attention(t, c.st);
 }
 
@@ -246,7 +282,7 @@ void double_block_pre(const Ctx& c, const DoubleBlk& k) {
   const int D = c.D, T = c.T, N = c.N, S = c.S, ld = c.m.mod_total;
   const float* mi = w.mod + k.mod_img;
   const float* mc = w.mod + k.mod_ctx;
-  const long long sD = c.sD(), s3D = 3 * sD, s5D = 5 * sD;
+  const long long sD = c.sD();
   {
     LnModGroup g[2] = {{0, T, mc, mc + D, ld}, {T, S, mi, mi + D, ld}};
     launch_ln_mod(c.dt, w.x, sD, D, w.xn, sD, D, c.B, D, 2, g, c.st);
@@ -254,18 +290,19 @@ void double_block_pre(const Ctx& c, const DoubleBlk& k) {
   {
     GemmLaunch L{};
     L.dtype = c.dt; L.batch = c.B; L.nprob = 2; L.rope = reinterpret_cast<const float*>(w.rope); L.head_dim = c.m.hd;
+    set_qkv_targets(c, L);
     GemmProblem& pt = L.prob[0];
     pt = make_prob(w.xn, sD, D, 0, S, T, 0, D);
     pt.nseg = 3;
-    pt.seg[0] = make_seg(k.aq, 0, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, 0, k.naq);
-    pt.seg[1] = make_seg(k.ak, D, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, D, k.nak);
-    pt.seg[2] = make_seg(k.av, 2 * D, EPI_BIAS, w.qkv, s3D, 3 * D, 2 * D);
+    pt.seg[0] = make_qkv_seg(c, k.aq, 0, k.naq);
+    pt.seg[1] = make_qkv_seg(c, k.ak, 1, k.nak);
+    pt.seg[2] = make_qkv_seg(c, k.av, 2, nullptr);
     GemmProblem& pi = L.prob[1];
     pi = make_prob(w.xn, sD, D, T, S, N, T, D);
     pi.nseg = 3;
-    pi.seg[0] = make_seg(k.q, 0, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, 0, k.nq);
-    pi.seg[1] = make_seg(k.k, D, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, D, k.nk);
-    pi.seg[2] = make_seg(k.v, 2 * D, EPI_BIAS, w.qkv, s3D, 3 * D, 2 * D);
+    pi.seg[0] = make_qkv_seg(c, k.q, 0, k.nq);
+    pi.seg[1] = make_qkv_seg(c, k.k, 1, k.nk);
+    pi.seg[2] = make_qkv_seg(c, k.v, 2, nullptr);
     launch_gemm(L, c.st);
   }
 }
@@ -330,7 +367,7 @@ void single_block_pre(const Ctx& c, const SingleBlk& k) {
   const Workspace& w = c.ws;
   const int D = c.D, T = c.T, N = c.N, S = c.S, ld = c.m.mod_total;
   const float* md = w.mod + k.mod;
-  const long long sD = c.sD(), s3D = 3 * sD, s5D = 5 * sD;
+  const long long sD = c.sD(), s5D = 5 * sD;
   {
     LnModGroup g[1] = {{0, S, md, md + D, ld}};
     launch_ln_mod(c.dt, w.x, sD, D, w.xn, sD, D, c.B, D, 1, g, c.st);
@@ -338,12 +375,13 @@ void single_block_pre(const Ctx& c, const SingleBlk& k) {
   {  // q | k | v | mlp in one launch
     GemmLaunch L{};
     L.dtype = c.dt; L.batch = c.B; L.nprob = 1; L.rope = reinterpret_cast<const float*>(w.rope); L.head_dim = c.m.hd;
+    set_qkv_targets(c, L);
     GemmProblem& p = L.prob[0];
     p = make_prob(w.xn, sD, D, 0, S, S, 0, D);
     p.nseg = 4;
-    p.seg[0] = make_seg(k.q, 0, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, 0, k.nq);
-    p.seg[1] = make_seg(k.k, D, EPI_QKNORM_ROPE, w.qkv, s3D, 3 * D, D, k.nk);
-    p.seg[2] = make_seg(k.v, 2 * D, EPI_BIAS, w.qkv, s3D, 3 * D, 2 * D);
+    p.seg[0] = make_qkv_seg(c, k.q, 0, k.nq);
+    p.seg[1] = make_qkv_seg(c, k.k, 1, k.nk);
+    p.seg[2] = make_qkv_seg(c, k.v, 2, nullptr);
     p.seg[3] = make_seg(k.mlp, 3 * D, EPI_GELU, w.cat, s5D, 5 * D, D);
     launch_gemm(L, c.st);
   }
@@ -369,17 +407,6 @@ void single_block_post(const Ctx& c, const SingleBlk& k, const void* extra) {
   }
 }
 
-void double_block(const Ctx& c, const DoubleBlk& k, const void* extra) {
-  double_block_pre(c, k);
-  run_attention(c);
-  double_block_post(c, k, extra);
-}
-void single_block(const Ctx& c, const SingleBlk& k, const void* extra) {
-  single_block_pre(c, k);
-  run_attention(c);
-  single_block_post(c, k, extra);
-}
-
 Ctx begin_forward(rt_model* m, const rt_forward_args* a) {
   RT_REQUIRE(m && a, "null model / args");
   RT_REQUIRE(m->finalized, "rt_model_finalize has not been called");
@@ -397,11 +424,146 @@ Ctx begin_forward(rt_model* m, const rt_forward_args* a) {
   RT_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "workspace must be 256-byte aligned");
   Ctx c{*m, ws, a->batch, a->n_txt, a->n_img, a->n_txt + a->n_img, m->D, m->cfg.dtype, dtype_size(m->cfg.dtype),
         (cudaStream_t)a->stream};
+  if (a->sp && a->sp->world > 1) {
+    const rt_sp_group& g = *a->sp;
+    RT_REQUIRE(g.world <= RT_SP_MAX_RANKS && g.rank >= 0 && g.rank < g.world, "sp group: world / rank");
+    RT_REQUIRE(m->cfg.dtype == RT_BF16 && m->hd == 128, "sequence-parallel mode needs bf16 and head_dim 128");
+    RT_REQUIRE(m->H % g.world == 0, "sequence-parallel mode: the head count must be a multiple of the world size");
+    RT_REQUIRE(g.peer_workspace[g.rank] == a->workspace, "sp group: peer_workspace[rank] must be this call's workspace");
+    c.sp = &g;
+    c.P = g.world;
+    c.r = g.rank;
+    c.Sg = c.S * g.world;
+    c.Dl = m->D / g.world;
+    for (int i = 0; i < g.world; ++i) {
+      RT_REQUIRE(g.peer_workspace[i] && (reinterpret_cast<uintptr_t>(g.peer_workspace[i]) & 255) == 0,
+                 "sp group: peer workspace missing or not 256-byte aligned");
+      RT_REQUIRE(g.lockstep || g.peer_flags[i], "sp group: null flag pointer");
+      Workspace pw;
+      carve(*m, a->batch, a->n_img, a->n_txt, (char*)g.peer_workspace[i], &pw);  // every rank carves identically
+      c.peer_qkv[i] = pw.qkv;
+      c.peer_cat[i] = pw.cat;
+    }
+  }
   // FluxPosEmbed over cat(txt_ids, img_ids) (controlnet_flux.py:316-317)
   launch_rope_table(a->txt_ids, c.T, m->cfg.axes_dims_rope, ws.rope, c.st);
   launch_rope_table(a->img_ids, c.N, m->cfg.axes_dims_rope, ws.rope + (size_t)c.T * (m->hd / 2), c.st);
   time_text_and_modulation(c, *a);
   return c;
+}
+
+// ---- phased execution -------------------------------------------------------------------------------------
+// One block = pre (LayerNorm-modulate + QKV(+MLP) projection) | attention | post (output projections, MLP).
+// `cs` holds ONE context (single GPU, or this process's rank of a sequence-parallel group) or, in lock-step
+// mode, the contexts of every rank: each phase is issued for all of them before the next one starts.  Between
+// the phases of a real multi-process group sits the flag barrier that orders the peer stores.
+void phase_sync(const std::vector<Ctx>& cs) {
+  if (cs.size() == 1 && cs[0].P > 1 && !cs[0].sp->lockstep) launch_sp_barrier(*cs[0].sp, cs[0].st);
+}
+template <class Pre, class Post>
+void run_block(const std::vector<Ctx>& cs, Pre pre, Post post) {
+  for (size_t i = 0; i < cs.size(); ++i) pre(cs[i], i);
+  phase_sync(cs);
+  for (size_t i = 0; i < cs.size(); ++i) run_attention(cs[i]);
+  phase_sync(cs);
+  for (size_t i = 0; i < cs.size(); ++i) post(cs[i], i);
+}
+
+void check_lockstep(int world, size_t ncalls, const rt_forward_args* const* args) {
+  RT_REQUIRE(world >= 1 && world <= RT_SP_MAX_RANKS && ncalls == (size_t)world, "lockstep: world");
+  if (world == 1) return;
+  for (int i = 0; i < world; ++i) {
+    const rt_forward_args* a = args[i];
+    RT_REQUIRE(a->sp && a->sp->lockstep && a->sp->world == world && a->sp->rank == i,
+               "lockstep: calls[i].a.sp must be a lock-step group with rank == i");
+    RT_REQUIRE(a->stream == args[0]->stream, "lockstep: every rank must use the same stream");
+    RT_REQUIRE(a->batch == args[0]->batch && a->n_img == args[0]->n_img && a->n_txt == args[0]->n_txt,
+               "lockstep: every rank must hold the same shard shape");
+  }
+}
+
+void controlnet_forward_impl(rt_model* m, const std::vector<const rt_controlnet_call*>& calls) {
+  RT_REQUIRE(m && m->cfg.kind == RT_CONTROLNET, "not a ControlNet model");
+  std::vector<Ctx> cs;
+  for (const rt_controlnet_call* k : calls) {
+    RT_REQUIRE(k->controlnet_cond && (k->cond_batch == 1 || k->cond_batch == k->a.batch), "controlnet_cond batch");
+    RT_REQUIRE(m->cfg.num_layers == 0 || k->block_samples, "block_samples is null");
+    RT_REQUIRE(m->cfg.num_single_layers == 0 || k->single_block_samples, "single_block_samples is null");
+    cs.push_back(begin_forward(m, &k->a));
+    embed_inputs(cs.back(), k->a, k->controlnet_cond, k->cond_batch);
+  }
+  auto zero_linear = [&](const Ctx& c, const rt_controlnet_call& k, const Lin& zl, void* base, int idx) {
+    // controlnet_flux.py:385-396 (+ the pipelines' regional mask and multi-line sum)
+    const long long sample_elems = (long long)c.B * c.N * c.D;
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
+    GemmProblem& p = L.prob[0];
+    p = make_prob(c.ws.x, c.sD(), c.D, c.T, c.S, c.N, 0, c.D);
+    p.nseg = 1;
+    p.seg[0] = make_seg(zl, 0, EPI_SCALE_MASK, (char*)base + (size_t)idx * sample_elems * c.es, (long long)c.N * c.D,
+                        c.D, 0);
+    p.scale = k.conditioning_scale;
+    p.mask = k.mask;
+    p.accumulate = k.accumulate;
+    launch_gemm(L, c.st);
+  };
+  for (int i = 0; i < m->cfg.num_layers; ++i)
+    run_block(cs, [&](const Ctx& c, size_t) { double_block_pre(c, m->dbl[i]); },
+              [&](const Ctx& c, size_t r) {
+                double_block_post(c, m->dbl[i], nullptr);
+                zero_linear(c, *calls[r], m->cn_blk[i], calls[r]->block_samples, i);
+              });
+  for (int j = 0; j < m->cfg.num_single_layers; ++j)
+    run_block(cs, [&](const Ctx& c, size_t) { single_block_pre(c, m->sgl[j]); },
+              [&](const Ctx& c, size_t r) {
+                single_block_post(c, m->sgl[j], nullptr);
+                zero_linear(c, *calls[r], m->cn_sgl[j], calls[r]->single_block_samples, j);
+              });
+}
+
+void transformer_forward_impl(rt_model* m, const std::vector<const rt_transformer_call*>& calls) {
+  RT_REQUIRE(m && m->cfg.kind == RT_TRANSFORMER, "not a transformer model");
+  std::vector<Ctx> cs;
+  for (const rt_transformer_call* k : calls) {
+    RT_REQUIRE(k->out, "null output");
+    RT_REQUIRE(k->n_block_samples >= 0 && k->n_single_block_samples >= 0, "negative sample count");
+    RT_REQUIRE(k->n_block_samples == 0 || k->controlnet_block_samples, "controlnet_block_samples is null");
+    RT_REQUIRE(k->n_single_block_samples == 0 || k->controlnet_single_block_samples, "controlnet_single_block_samples");
+    RT_REQUIRE(k->n_block_samples == calls[0]->n_block_samples &&
+                   k->n_single_block_samples == calls[0]->n_single_block_samples, "ranks disagree on the sample counts");
+    cs.push_back(begin_forward(m, &k->a));
+    embed_inputs(cs.back(), k->a, nullptr, 0);
+  }
+  const int nl = m->cfg.num_layers, ns = m->cfg.num_single_layers;
+  const int nbs = calls[0]->n_block_samples, nss = calls[0]->n_single_block_samples;
+  // residual injection: sample[i // ceil(L / n)] after block i (diffusers FluxTransformer2DModel.forward)
+  const int iv_d = nbs ? (nl + nbs - 1) / nbs : 1;
+  const int iv_s = nss ? (ns + nss - 1) / nss : 1;
+  for (int i = 0; i < nl; ++i)
+    run_block(cs, [&](const Ctx& c, size_t) { double_block_pre(c, m->dbl[i]); },
+              [&](const Ctx& c, size_t r) {
+                double_block_post(c, m->dbl[i], nbs ? calls[r]->controlnet_block_samples[i / iv_d] : nullptr);
+              });
+  for (int j = 0; j < ns; ++j)
+    run_block(cs, [&](const Ctx& c, size_t) { single_block_pre(c, m->sgl[j]); },
+              [&](const Ctx& c, size_t r) {
+                single_block_post(c, m->sgl[j], nss ? calls[r]->controlnet_single_block_samples[j / iv_s] : nullptr);
+              });
+  // norm_out (AdaLayerNormContinuous: chunk order scale, shift) + proj_out on the image rows
+  for (size_t r = 0; r < cs.size(); ++r) {
+    const Ctx& c = cs[r];
+    const int D = c.D, T = c.T, N = c.N, S = c.S;
+    const float* mo = c.ws.mod + m->mod_out;
+    LnModGroup g[1] = {{T, S, mo + D, mo, m->mod_total}};
+    launch_ln_mod(c.dt, c.ws.x, c.sD(), D, c.ws.xn, c.sD(), D, c.B, D, 1, g, c.st);
+    const int Co = m->cfg.out_channels;
+    GemmLaunch L{};
+    L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
+    L.prob[0] = make_prob(c.ws.xn, c.sD(), D, T, S, N, 0, D);
+    L.prob[0].nseg = 1;
+    L.prob[0].seg[0] = make_seg(m->proj_out, 0, EPI_BIAS, calls[r]->out, (long long)N * Co, Co, 0);
+    launch_gemm(L, c.st);
+  }
 }
 
 }  // namespace
@@ -555,34 +717,11 @@ int rt_controlnet_forward(rt_model* m, const rt_forward_args* a, const void* con
                           float conditioning_scale, const void* mask, int accumulate, void* block_samples,
                           void* single_block_samples) {
   return guarded([&] {
-    RT_REQUIRE(m && m->cfg.kind == RT_CONTROLNET, "not a ControlNet model");
-    RT_REQUIRE(controlnet_cond && (cond_batch == 1 || (a && cond_batch == a->batch)), "controlnet_cond batch");
-    RT_REQUIRE(m->cfg.num_layers == 0 || block_samples, "block_samples is null");
-    RT_REQUIRE(m->cfg.num_single_layers == 0 || single_block_samples, "single_block_samples is null");
-    Ctx c = begin_forward(m, a);
-    embed_inputs(c, *a, controlnet_cond, cond_batch);
-    const int D = c.D, T = c.T, N = c.N, S = c.S;
-    const long long sample_elems = (long long)c.B * N * D;
-    auto zero_linear = [&](const Lin& zl, void* out) {  // controlnet_flux.py:385-396 (+ pipeline mask / sum)
-      GemmLaunch L{};
-      L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
-      GemmProblem& p = L.prob[0];
-      p = make_prob(c.ws.x, c.sD(), D, T, S, N, 0, D);
-      p.nseg = 1;
-      p.seg[0] = make_seg(zl, 0, EPI_SCALE_MASK, out, (long long)N * D, D, 0);
-      p.scale = conditioning_scale;
-      p.mask = mask;
-      p.accumulate = accumulate;
-      launch_gemm(L, c.st);
-    };
-    for (int i = 0; i < m->cfg.num_layers; ++i) {
-      double_block(c, m->dbl[i], nullptr);
-      zero_linear(m->cn_blk[i], (char*)block_samples + (size_t)i * sample_elems * c.es);
-    }
-    for (int j = 0; j < m->cfg.num_single_layers; ++j) {
-      single_block(c, m->sgl[j], nullptr);
-      zero_linear(m->cn_sgl[j], (char*)single_block_samples + (size_t)j * sample_elems * c.es);
-    }
+    RT_REQUIRE(a, "null args");
+    RT_REQUIRE(!a->sp || !a->sp->lockstep, "a lock-step group runs through rt_controlnet_forward_lockstep");
+    rt_controlnet_call k{*a, controlnet_cond, cond_batch, conditioning_scale, mask, accumulate, block_samples,
+                         single_block_samples};
+    controlnet_forward_impl(m, {&k});
   });
 }
 
@@ -590,32 +729,33 @@ int rt_transformer_forward(rt_model* m, const rt_forward_args* a, const void* co
                            int n_block_samples, const void* const* controlnet_single_block_samples,
                            int n_single_block_samples, void* out) {
   return guarded([&] {
-    RT_REQUIRE(m && m->cfg.kind == RT_TRANSFORMER, "not a transformer model");
-    RT_REQUIRE(out, "null output");
-    RT_REQUIRE(n_block_samples >= 0 && n_single_block_samples >= 0, "negative sample count");
-    RT_REQUIRE(n_block_samples == 0 || controlnet_block_samples, "controlnet_block_samples is null");
-    RT_REQUIRE(n_single_block_samples == 0 || controlnet_single_block_samples, "controlnet_single_block_samples");
-    Ctx c = begin_forward(m, a);
-    embed_inputs(c, *a, nullptr, 0);
-    const int D = c.D, T = c.T, N = c.N, S = c.S, nl = m->cfg.num_layers, ns = m->cfg.num_single_layers;
-    // residual injection: sample[i // ceil(L / n)] after block i (diffusers FluxTransformer2DModel.forward)
-    const int iv_d = n_block_samples ? (nl + n_block_samples - 1) / n_block_samples : 1;
-    const int iv_s = n_single_block_samples ? (ns + n_single_block_samples - 1) / n_single_block_samples : 1;
-    for (int i = 0; i < nl; ++i)
-      double_block(c, m->dbl[i], n_block_samples ? controlnet_block_samples[i / iv_d] : nullptr);
-    for (int j = 0; j < ns; ++j)
-      single_block(c, m->sgl[j], n_single_block_samples ? controlnet_single_block_samples[j / iv_s] : nullptr);
-    // norm_out (AdaLayerNormContinuous: chunk order scale, shift) + proj_out on the image rows
-    const float* mo = c.ws.mod + m->mod_out;
-    LnModGroup g[1] = {{T, S, mo + D, mo, m->mod_total}};
-    launch_ln_mod(c.dt, c.ws.x, c.sD(), D, c.ws.xn, c.sD(), D, c.B, D, 1, g, c.st);
-    const int Co = m->cfg.out_channels;
-    GemmLaunch L{};
-    L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
-    L.prob[0] = make_prob(c.ws.xn, c.sD(), D, T, S, N, 0, D);
-    L.prob[0].nseg = 1;
-    L.prob[0].seg[0] = make_seg(m->proj_out, 0, EPI_BIAS, out, (long long)N * Co, Co, 0);
-    launch_gemm(L, c.st);
+    RT_REQUIRE(a, "null args");
+    RT_REQUIRE(!a->sp || !a->sp->lockstep, "a lock-step group runs through rt_transformer_forward_lockstep");
+    rt_transformer_call k{*a, controlnet_block_samples, n_block_samples, controlnet_single_block_samples,
+                          n_single_block_samples, out};
+    transformer_forward_impl(m, {&k});
+  });
+}
+
+int rt_controlnet_forward_lockstep(rt_model* m, int world, const rt_controlnet_call* calls) {
+  return guarded([&] {
+    RT_REQUIRE(calls && world >= 1 && world <= RT_SP_MAX_RANKS, "lockstep: bad argument");
+    std::vector<const rt_controlnet_call*> v;
+    std::vector<const rt_forward_args*> args;
+    for (int i = 0; i < world; ++i) { v.push_back(calls + i); args.push_back(&calls[i].a); }
+    check_lockstep(world, v.size(), args.data());
+    controlnet_forward_impl(m, v);
+  });
+}
+
+int rt_transformer_forward_lockstep(rt_model* m, int world, const rt_transformer_call* calls) {
+  return guarded([&] {
+    RT_REQUIRE(calls && world >= 1 && world <= RT_SP_MAX_RANKS, "lockstep: bad argument");
+    std::vector<const rt_transformer_call*> v;
+    std::vector<const rt_forward_args*> args;
+    for (int i = 0; i < world; ++i) { v.push_back(calls + i); args.push_back(&calls[i].a); }
+    check_lockstep(world, v.size(), args.data());
+    transformer_forward_impl(m, v);
   });
 }
 

@@ -99,7 +99,7 @@ struct GemvJob {
 };
 void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
                          const int* job_row_prefix_dev, int njobs, int total_rows, float* out, int out_ld,
-                         int silu_out, int accumulate, cudaStream_t stream);
+                         int silu_out, int accumulate, cudaStream_t stream, bool rows_multiple_of_4 = false);
 void launch_silu_f32(const float* x, float* out, long long n, cudaStream_t stream);
 
 void launch_time_sinusoid(int dtype, const void* t, int t_batch, int batch, float* out /*[batch,256]*/,
@@ -119,6 +119,9 @@ void launch_glyph_blend(int dtype, const void* noise, const void* glyph_lat, con
                         long long n, float w_glyph, float w_noise, cudaStream_t stream);
 void launch_copy_rows(int dtype, const void* src, long long s_bs, int s_ld, int s_row0, void* dst, long long d_bs,
                       int d_ld, int d_row0, int batch, int rows, int D, cudaStream_t stream);
+
+// cross-GPU flag barrier of the sequence-parallel mode (sp.cu)
+void launch_sp_barrier(const rt_sp_group& g, cudaStream_t stream);
 
 // ------------------------------------------------------------------ per-class device timing (option "profile")
 // When the option is on, every launch of a class is bracketed by CUDA events on ITS stream; bench.py reads

@@ -108,6 +108,7 @@ void launch_gemm_simt(const GemmLaunch& L, cudaStream_t stream) {
     if (P.m_rows == 0 || L.batch == 0) continue;
     for (int si = 0; si < P.nseg; ++si) {
       const GemmSegment& S = P.seg[si];
+      if (S.scatter) throw Error(RT_ERR_UNSUPPORTED, "sequence-parallel scatter exists on the tcgen05 GEMM only");
       SimtGemmArgs g;
       g.A = P.A; g.a_bs = P.a_batch_stride; g.a_ld = P.a_ld; g.a_row0 = P.a_row0;
       g.W = S.W; g.bias = S.bias;
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(256) attn_simt_kernel(AttnArgs a) {
 
 void launch_attention_simt(const AttnArgs& a, cudaStream_t stream) {
   if (a.batch == 0 || a.S == 0) return;
+  if (a.sp_rows > 0) throw Error(RT_ERR_UNSUPPORTED, "sequence-parallel scatter exists on the tcgen05 attention only");
   RT_REQUIRE(a.hd == 64 || a.hd == 128, "attention: head_dim must be 64 or 128");
   dim3 grid((a.S + 31) / 32, a.heads, a.batch);
   size_t smem = (size_t)(32 * (a.hd + 1) + 32 * a.hd + 32 * a.hd) * sizeof(float);

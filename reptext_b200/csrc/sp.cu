@@ -1,0 +1,142 @@
+// Sequence-parallel plumbing (include/reptext_rt.h, rt_sp_group): the cross-GPU flag barrier that orders the
+// peer stores of the fused QKV-GEMM / attention epilogues, and the CUDA-IPC helpers that make one rank's
+// workspace addressable from the other ranks' processes.  The reference has no multi-GPU mode;
+// the exchange pattern is the head <-> token re-partition of the joint attention
+// (diffusers FluxTransformerBlock / FluxSingleTransformerBlock, reached from RepText/controlnet_flux.py:343-348).
+#include <cstring>
+
+#include "dtype_utils.cuh"
+#include "rt_internal.h"
+
+namespace rt {
+namespace {
+
+struct BarrierParams {
+  unsigned long long* flags[RT_SP_MAX_RANKS];
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One warp.  Every earlier kernel of this stream has completed (stream order), so its peer stores are performed;
+// the system-scope fence + release stores publish them, the acquire loads on the other side make them visible
+// to every later kernel of the waiting rank's stream.  Epochs only grow, so there is nothing to reset and a
+// barrier can never be satisfied by a stale value.
+__global__ void sp_barrier_kernel(const BarrierParams p) {
+  unsigned long long* mine = p.flags[p.rank];
+  const int lane = threadIdx.x;
+  unsigned long long epoch = 0;
+  if (lane == 0) {
+    epoch = mine[8] + 1;
+    mine[8] = epoch;
+  }
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  __threadfence_system();
+  if (lane < p.world && lane != p.rank) st_release_sys(p.flags[lane] + p.rank, epoch);
+  if (lane < p.world && lane != p.rank) {
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(mine + lane) < epoch) {
+      __nanosleep(64);
+      if (globaltimer_ns() - t0 > 10000000000ull) {  // 10 s: a peer died; flag it instead of hanging the GPU
+        mine[9] = 1;
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+
+}  // namespace
+
+void launch_sp_barrier(const rt_sp_group& g, cudaStream_t stream) {
+  RT_REQUIRE(g.world >= 2 && g.world <= RT_SP_MAX_RANKS && g.rank >= 0 && g.rank < g.world, "sp group: world / rank");
+  BarrierParams p{};
+  p.world = g.world;
+  p.rank = g.rank;
+  for (int i = 0; i < g.world; ++i) {
+    RT_REQUIRE(g.peer_flags[i], "sp group: null flag pointer");
+    p.flags[i] = g.peer_flags[i];
+  }
+  sp_barrier_kernel<<<1, 32, 0, stream>>>(p);
+  RT_POST_LAUNCH();
+}
+
+}  // namespace rt
+
+using namespace rt;
+
+extern "C" {
+
+int rt_sp_barrier(const rt_sp_group* g, void* stream) {
+  return guarded([&] {
+    RT_REQUIRE(g, "sp_barrier: null group");
+    RT_REQUIRE(!g->lockstep, "sp_barrier: a lock-step group has no peers to wait for");
+    launch_sp_barrier(*g, (cudaStream_t)stream);
+  });
+}
+
+int rt_sp_status(const rt_sp_group* g, void* stream, int* timed_out) {
+  return guarded([&] {
+    RT_REQUIRE(g && timed_out && g->rank >= 0 && g->rank < RT_SP_MAX_RANKS && g->peer_flags[g->rank], "sp_status: bad argument");
+    unsigned long long v = 0;
+    RT_CHECK_CUDA(cudaMemcpyAsync(&v, g->peer_flags[g->rank] + 9, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    RT_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *timed_out = v != 0;
+  });
+}
+
+int rt_ipc_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64) {
+  return guarded([&] {
+    RT_REQUIRE(bytes > 0 && dev_ptr && handle64, "ipc_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    void* p = nullptr;
+    RT_CHECK_CUDA(cudaMalloc(&p, (size_t)bytes));
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+      cudaFree(p);
+      throw Error(RT_ERR_CUDA, std::string("ipc_alloc: ") + cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+  });
+}
+
+int rt_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+  return guarded([&] {
+    RT_REQUIRE(handle64 && dev_ptr, "ipc_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    RT_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = p;
+  });
+}
+
+int rt_ipc_close(void* dev_ptr) {
+  return guarded([&] {
+    if (dev_ptr) RT_CHECK_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  });
+}
+
+int rt_ipc_free(void* dev_ptr) {
+  return guarded([&] {
+    if (dev_ptr) RT_CHECK_CUDA(cudaFree(dev_ptr));
+  });
+}
+
+}  // extern "C"

@@ -174,7 +174,9 @@ class _RuntimeModel:
         return t.to(dtype or self._dtype).contiguous()
 
     def _forward_args(self, hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
-                      guidance, keep: list) -> L.ForwardArgs:
+                      guidance, keep: list, sp=None, sp_rank: Optional[int] = None) -> L.ForwardArgs:
+        """``sp``: a :class:`reptext_b200.parallel.SequenceParallelGroup` (or ``LockstepGroup``); every tensor then
+        holds this rank's token shard and the group's peer-mapped buffer is the workspace."""
         c = self._cfg
         if self._handle is None:
             raise RuntimeError("model has no weights: call load_state_dict() or use random_init()")
@@ -210,13 +212,26 @@ class _RuntimeModel:
         ii = self._check("img_ids", img_ids, 3, torch.float32)
         ti = self._check("txt_ids", txt_ids, 3, torch.float32)
         nbytes = L.lib().rt_model_workspace_bytes(self._handle, B, N, T)
-        ws = _workspace(hs.device, nbytes)
-        base = (ws.data_ptr() + 255) // 256 * 256
         a = L.ForwardArgs()
+        if sp is None:
+            ws = _workspace(hs.device, nbytes)
+            base = (ws.data_ptr() + 255) // 256 * 256
+            a.workspace, a.workspace_bytes = base, ws.numel() - (base - ws.data_ptr())
+        else:
+            if self._dtype != torch.bfloat16 or c["attention_head_dim"] != 128:
+                raise ValueError("sequence-parallel mode needs a bf16 model with attention_head_dim 128")
+            if c["num_attention_heads"] % sp.world:
+                raise ValueError(f"{c['num_attention_heads']} heads cannot be sharded over {sp.world} ranks")
+            ws = None
+            sp.ensure_workspace(nbytes)          # collective on a multi-process group; a no-op once large enough
+            grp = sp.struct(sp_rank)
+            a.workspace, a.workspace_bytes = grp.peer_workspace[grp.rank], sp.workspace_bytes
+            a.sp = C.pointer(grp)
+            keep.append(grp)
         a.batch, a.lat_batch, a.t_batch, a.n_img, a.n_txt = B, hs.shape[0], ts.numel(), N, T
         a.hidden_states, a.encoder_hidden_states, a.pooled_projections = L.ptr(hs), L.ptr(enc), L.ptr(pooled)
         a.timestep, a.guidance, a.img_ids, a.txt_ids = L.ptr(ts), L.ptr(g), L.ptr(ii), L.ptr(ti)
-        a.workspace, a.workspace_bytes, a.stream = base, ws.numel() - (base - ws.data_ptr()), L.stream_ptr()
+        a.stream = L.stream_ptr()
         keep.extend([hs, enc, pooled, ts, g, ii, ti, ws])
         return a
 
@@ -254,11 +269,47 @@ class FluxControlNetModel(_RuntimeModel):
         *,
         regional_mask: Optional[torch.Tensor] = None,
         accumulate_into: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None,
+        sp=None,
     ):
         """Same arguments as the reference.  Two keyword-only extensions let the pipelines fuse their
         per-step host work into the zero-linear epilogue: ``regional_mask`` ([1, N, 1]; the multiply at
         ``pipeline_flux_controlnet.py:1060-1069``) and ``accumulate_into`` (the stacked outputs of a previous
-        text line; the sum at ``:1072-1087``)."""
+        text line; the sum at ``:1072-1087``).  ``sp``: sequence-parallel group (every tensor is then this rank's
+        token shard; BASELINE.json configs[4])."""
+        call, keep, (blocks, singles) = self._marshal(
+            hidden_states, controlnet_cond, controlnet_mode, conditioning_scale, encoder_hidden_states,
+            pooled_projections, timestep, img_ids, txt_ids, guidance, joint_attention_kwargs, regional_mask,
+            accumulate_into, sp, None)
+        L.check(L.lib().rt_controlnet_forward(self._handle, C.byref(call.a), call.controlnet_cond, call.cond_batch,
+                                              call.conditioning_scale, call.mask, call.accumulate,
+                                              call.block_samples, call.single_block_samples))
+        return self._wrap(blocks, singles, return_dict)
+
+    def forward_lockstep(self, group, per_rank: List[dict], return_dict: bool = False):
+        """Every rank's forward driven in phase order by this process on one GPU (``LockstepGroup``): the same
+        peer-store indexing as the multi-process mode without needing several GPUs.  ``per_rank[i]`` holds rank i's
+        keyword arguments of :meth:`forward`."""
+        calls = (L.ControlNetCall * group.world)()
+        keep, outs = [], []
+        for r, kw in enumerate(per_rank):
+            kw = dict(kw)
+            call, k, bufs = self._marshal(
+                kw.pop("hidden_states"), kw.pop("controlnet_cond"), kw.pop("controlnet_mode", None),
+                kw.pop("conditioning_scale", 1.0), kw.pop("encoder_hidden_states"), kw.pop("pooled_projections"),
+                kw.pop("timestep"), kw.pop("img_ids"), kw.pop("txt_ids"), kw.pop("guidance", None),
+                kw.pop("joint_attention_kwargs", None), kw.pop("regional_mask", None),
+                kw.pop("accumulate_into", None), group, r)
+            if kw:
+                raise TypeError(f"unexpected arguments {sorted(kw)}")
+            calls[r] = call
+            keep.append(k)
+            outs.append(bufs)
+        L.check(L.lib().rt_controlnet_forward_lockstep(self._handle, group.world, calls))
+        return [self._wrap(b, s_, return_dict) for b, s_ in outs]
+
+    def _marshal(self, hidden_states, controlnet_cond, controlnet_mode, conditioning_scale, encoder_hidden_states,
+                 pooled_projections, timestep, img_ids, txt_ids, guidance, joint_attention_kwargs, regional_mask,
+                 accumulate_into, sp, sp_rank):
         if controlnet_mode is not None:
             raise ValueError("`controlnet_mode` is only valid for ControlNet-Union models (num_mode is None here)")
         if joint_attention_kwargs:
@@ -268,7 +319,7 @@ class FluxControlNetModel(_RuntimeModel):
         c = self._cfg
         keep: list = []
         a = self._forward_args(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
-                               guidance if c.get("guidance_embeds") else None, keep)
+                               guidance if c.get("guidance_embeds") else None, keep, sp, sp_rank)
         cond = self._check("controlnet_cond", controlnet_cond, c["in_channels"] + c.get("extra_condition_channels", 0))
         if cond.dim() != 3 or cond.shape[1] != a.n_img or cond.shape[0] not in (1, a.batch):
             raise ValueError("controlnet_cond must be [1 or batch, n_img, in_channels + extra_condition_channels]")
@@ -291,9 +342,17 @@ class FluxControlNetModel(_RuntimeModel):
             mask = self._check("regional_mask", regional_mask.reshape(-1))
             if mask.numel() != N:
                 raise ValueError("regional_mask must have one value per image token")
-        L.check(L.lib().rt_controlnet_forward(self._handle, C.byref(a), L.ptr(cond), cond.shape[0],
-                                              float(conditioning_scale), L.ptr(mask),
-                                              int(accumulate_into is not None), L.ptr(blocks), L.ptr(singles)))
+        call = L.ControlNetCall()
+        call.a = a
+        call.controlnet_cond, call.cond_batch = L.ptr(cond), cond.shape[0]
+        call.conditioning_scale, call.mask = float(conditioning_scale), L.ptr(mask)
+        call.accumulate = int(accumulate_into is not None)
+        call.block_samples, call.single_block_samples = L.ptr(blocks), L.ptr(singles)
+        keep.extend([cond, mask])
+        return call, keep, (blocks, singles)
+
+    @staticmethod
+    def _wrap(blocks, singles, return_dict):
         bl = list(blocks.unbind(0)) if blocks is not None else None
         sl = list(singles.unbind(0)) if singles is not None else None
         if bl is not None:
@@ -327,7 +386,41 @@ class FluxTransformer2DModel(_RuntimeModel):
         controlnet_single_block_samples=None,
         return_dict: bool = True,
         controlnet_blocks_repeat: bool = False,
+        *,
+        sp=None,
     ):
+        call, keep, out = self._marshal(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids,
+                                        txt_ids, guidance, joint_attention_kwargs, controlnet_block_samples,
+                                        controlnet_single_block_samples, controlnet_blocks_repeat, sp, None)
+        L.check(L.lib().rt_transformer_forward(self._handle, C.byref(call.a), call.controlnet_block_samples,
+                                               call.n_block_samples, call.controlnet_single_block_samples,
+                                               call.n_single_block_samples, call.out))
+        if not return_dict:
+            return (out,)
+        return Transformer2DModelOutput(sample=out)
+
+    def forward_lockstep(self, group, per_rank: List[dict]) -> List[torch.Tensor]:
+        """See :meth:`FluxControlNetModel.forward_lockstep`.  Returns every rank's ``[B, N_local, C]`` output."""
+        calls = (L.TransformerCall * group.world)()
+        keep, outs = [], []
+        for r, kw in enumerate(per_rank):
+            kw = dict(kw)
+            call, k, out = self._marshal(
+                kw.pop("hidden_states"), kw.pop("encoder_hidden_states"), kw.pop("pooled_projections"),
+                kw.pop("timestep"), kw.pop("img_ids"), kw.pop("txt_ids"), kw.pop("guidance", None),
+                kw.pop("joint_attention_kwargs", None), kw.pop("controlnet_block_samples", None),
+                kw.pop("controlnet_single_block_samples", None), False, group, r)
+            if kw:
+                raise TypeError(f"unexpected arguments {sorted(kw)}")
+            calls[r] = call
+            keep.append(k)
+            outs.append(out)
+        L.check(L.lib().rt_transformer_forward_lockstep(self._handle, group.world, calls))
+        return outs
+
+    def _marshal(self, hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
+                 joint_attention_kwargs, controlnet_block_samples, controlnet_single_block_samples,
+                 controlnet_blocks_repeat, sp, sp_rank):
         if controlnet_blocks_repeat:
             raise NotImplementedError("controlnet_blocks_repeat is not used by the RepText pipelines")
         if joint_attention_kwargs:
@@ -337,7 +430,7 @@ class FluxTransformer2DModel(_RuntimeModel):
         c = self._cfg
         keep: list = []
         a = self._forward_args(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
-                               guidance if c.get("guidance_embeds") else None, keep)
+                               guidance if c.get("guidance_embeds") else None, keep, sp, sp_rank)
         B, N, D = a.batch, a.n_img, c["num_attention_heads"] * c["attention_head_dim"]
 
         def ptr_array(samples, what):
@@ -353,12 +446,15 @@ class FluxTransformer2DModel(_RuntimeModel):
             return arr, len(samples)
 
         bp, nb = ptr_array(controlnet_block_samples, "controlnet_block_samples")
-        sp, nsg = ptr_array(controlnet_single_block_samples, "controlnet_single_block_samples")
+        spp, nsg = ptr_array(controlnet_single_block_samples, "controlnet_single_block_samples")
         co = (c.get("out_channels") or c["in_channels"]) * c.get("patch_size", 1) ** 2
         out = torch.empty(B, N, co, dtype=self._dtype, device=self._device)
-        L.check(L.lib().rt_transformer_forward(self._handle, C.byref(a), bp, nb, sp, nsg, L.ptr(out)))
-        if not return_dict:
-            return (out,)
-        return Transformer2DModelOutput(sample=out)
+        call = L.TransformerCall()
+        call.a = a
+        call.controlnet_block_samples, call.n_block_samples = bp, nb
+        call.controlnet_single_block_samples, call.n_single_block_samples = spp, nsg
+        call.out = L.ptr(out)
+        keep.extend([bp, spp])
+        return call, keep, out
 
     __call__ = forward

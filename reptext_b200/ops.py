@@ -24,6 +24,7 @@ class Segment:
     mode: int = L.EPI_BIAS
     out_col0: int = 0
     norm_w: Optional[torch.Tensor] = None
+    scatter: bool = False                # sequence-parallel: head blocks go to gemm(..., sp_out=[...]) buffers
 
 
 @dataclass
@@ -70,6 +71,7 @@ def _fill_problem(dst: L.GemmProblem, p: Problem, keep: list) -> None:
         sg.out_ld = s.out.stride(1)
         sg.out_col0 = s.out_col0
         sg.norm_w = L.ptr(s.norm_w)
+        sg.scatter = int(s.scatter)
     dst.gate = L.ptr(p.gate)
     dst.gate_ld = p.gate.stride(0) if p.gate is not None else 0
     dst.extra = L.ptr(p.extra)
@@ -84,8 +86,10 @@ def _fill_problem(dst: L.GemmProblem, p: Problem, keep: list) -> None:
 
 
 def gemm(problems: Sequence[Problem], batch: int, dtype: torch.dtype, rope: Optional[torch.Tensor] = None,
-         head_dim: int = 0, impl: int = IMPL_AUTO) -> None:
-    """One launch of the (grouped) projection GEMM with fused epilogues; see ``rt_gemm``."""
+         head_dim: int = 0, impl: int = IMPL_AUTO, sp_out: Optional[Sequence[torch.Tensor]] = None, sp_cols: int = 0,
+         sp_row0: int = 0) -> None:
+    """One launch of the (grouped) projection GEMM with fused epilogues; see ``rt_gemm``.  ``sp_out`` / ``sp_cols`` /
+    ``sp_row0``: destinations of ``Segment(scatter=True)`` segments (their ``out`` only supplies the strides)."""
     g = L.GemmLaunch()
     g.dtype = L.dtype_code(dtype)
     g.batch = batch
@@ -95,6 +99,9 @@ def gemm(problems: Sequence[Problem], batch: int, dtype: torch.dtype, rope: Opti
         _fill_problem(g.prob[i], p, keep)
     g.rope = L.ptr(rope)
     g.head_dim = head_dim
+    g.sp_cols, g.sp_row0 = sp_cols, sp_row0
+    for i, t in enumerate(sp_out or []):
+        g.sp_out[i] = L.ptr(t)
     L.check(L.lib().rt_gemm(C.byref(g), impl, L.stream_ptr()))
 
 
@@ -107,8 +114,11 @@ def linear(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 
 def attention(qkv: torch.Tensor, heads: int, hd: int, q_col0: int, k_col0: int, v_col0: int,
-              out: Optional[torch.Tensor] = None, out_col0: int = 0, impl: int = IMPL_AUTO) -> torch.Tensor:
-    """Joint non-causal attention over [batch, S, ld] with q/k/v at column offsets (head-major)."""
+              out: Optional[torch.Tensor] = None, out_col0: int = 0, impl: int = IMPL_AUTO,
+              sp_out: Optional[Sequence[torch.Tensor]] = None, sp_rows: int = 0) -> torch.Tensor:
+    """Joint non-causal attention over [batch, S, ld] with q/k/v at column offsets (head-major).  ``sp_out`` /
+    ``sp_rows``: sequence-parallel row scatter (output row r goes to ``sp_out[r // sp_rows]``; ``out`` only supplies
+    the strides)."""
     B, S, _ = qkv.shape
     if out is None:
         out = torch.empty(B, S, heads * hd, dtype=qkv.dtype, device=qkv.device)
@@ -123,6 +133,9 @@ def attention(qkv: torch.Tensor, heads: int, hd: int, q_col0: int, k_col0: int, 
     a.out_ld = out.stride(1)
     a.out_col0 = out_col0
     a.batch, a.S, a.heads, a.hd = B, S, heads, hd
+    a.sp_rows = sp_rows
+    for i, t in enumerate(sp_out or []):
+        a.sp_out[i] = L.ptr(t)
     L.check(L.lib().rt_attention(C.byref(a), impl, L.stream_ptr()))
     return out
 

@@ -72,3 +72,159 @@ def run_sharded(samples: Sequence, fn: Callable[[int, object], torch.Tensor], gr
     if not outs:
         raise ValueError("fewer samples than ranks")
     return gather_samples(torch.stack(outs, dim=0), len(samples), group)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Sequence-parallel mode (BASELINE.json configs[4]: one 1536x1536 sample, 9216 image + 512 text tokens, on 8 GPUs)
+# ---------------------------------------------------------------------------------------------------------
+# Tokens are sharded in contiguous row blocks (rank r owns rows [r*n/P, (r+1)*n/P) of the image tokens and of the text
+# tokens); the attention of every block runs head-sharded over the whole sequence.  The head <-> token exchanges are
+# peer stores issued by the QKV-GEMM and attention epilogues (include/reptext_rt.h, rt_sp_group) - NCCL only gathers
+# the final latents.
+
+def shard_tokens(t: torch.Tensor, rank: int, world: int, dim: int = 1) -> torch.Tensor:
+    """This rank's contiguous block of the token dimension."""
+    n = t.shape[dim]
+    if n % world:
+        raise ValueError(f"{n} tokens cannot be split evenly over {world} ranks")
+    step = n // world
+    return t.narrow(dim, rank * step, step).contiguous()
+
+
+def gather_tokens(local: torch.Tensor, group=None, dim: int = 1) -> torch.Tensor:
+    """Inverse of :func:`shard_tokens` on every rank (all-gather; NCCL on GPUs, gloo in the CPU tests)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    parts = [torch.empty_like(local) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    return torch.cat(parts, dim=dim)
+
+
+class _SpBase:
+    world: int
+    workspace_bytes: int = 0
+
+    def struct(self, rank=None):
+        raise NotImplementedError
+
+    def ensure_workspace(self, nbytes: int) -> None:
+        raise NotImplementedError
+
+
+class LockstepGroup(_SpBase):
+    """All ``world`` ranks of a sequence-parallel group driven by ONE process on ONE GPU (the models'
+    ``forward_lockstep``).  Every rank has its own workspace, the kernels scatter between them exactly as they do
+    between GPUs; stream order stands in for the cross-GPU barriers.  Used to validate the exchange indexing where
+    only one GPU is available."""
+
+    def __init__(self, world: int, device="cuda"):
+        from . import _lib as L
+        if not (1 <= world <= L.SP_MAX_RANKS):
+            raise ValueError(f"world must be 1..{L.SP_MAX_RANKS}")
+        self.world = world
+        self.device = torch.device(device)
+        self._bufs: List[torch.Tensor] = []
+        self.workspace_bytes = 0
+
+    def ensure_workspace(self, nbytes: int) -> None:
+        if nbytes <= self.workspace_bytes:
+            return
+        self._bufs = [torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+        self.workspace_bytes = nbytes
+
+    def struct(self, rank=None):
+        from . import _lib as L
+        g = L.SpGroup()
+        g.world, g.rank, g.lockstep = self.world, int(rank), 1
+        for i, b in enumerate(self._bufs):
+            g.peer_workspace[i] = (b.data_ptr() + 255) // 256 * 256
+        return g
+
+
+class SequenceParallelGroup(_SpBase):
+    """One process per GPU.  Owns this rank's peer-mappable workspace (``rt_ipc_alloc``), the other ranks' mappings
+    of theirs (``rt_ipc_open``; handles travel over ``torch.distributed``) and the barrier flag words."""
+
+    FLAG_BYTES = 4096
+
+    def __init__(self, group=None):
+        from . import _lib as L
+        if not dist.is_initialized():
+            raise RuntimeError("SequenceParallelGroup needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if not (2 <= self.world <= L.SP_MAX_RANKS):
+            raise ValueError(f"sequence-parallel world size must be 2..{L.SP_MAX_RANKS}")
+        self._own = None
+        self._peers: List[Optional[int]] = []
+        self.workspace_bytes = 0
+
+    def _release(self):
+        from . import _lib as L
+        lib = L.lib()
+        for i, p in enumerate(self._peers):
+            if p is not None and i != self.rank:
+                lib.rt_ipc_close(p)
+        self._peers = []
+        if self._own is not None:
+            lib.rt_ipc_free(self._own)
+            self._own = None
+        self.workspace_bytes = 0
+
+    def ensure_workspace(self, nbytes: int) -> None:
+        """COLLECTIVE when the buffer has to grow (every rank asks for the same size in the same order)."""
+        import ctypes as C
+        from . import _lib as L
+        if nbytes <= self.workspace_bytes:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)          # nobody still uses the old mapping
+        self._release()
+        lib = L.lib()
+        total = self.FLAG_BYTES + (nbytes + 255) // 256 * 256
+        p = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        L.check(lib.rt_ipc_alloc(total, C.byref(p), handle))
+        self._own = p.value
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=self.group)
+        self._peers = []
+        for i, h in enumerate(handles):
+            if i == self.rank:
+                self._peers.append(self._own)
+            else:
+                q = C.c_void_p()
+                L.check(lib.rt_ipc_open(h, C.byref(q)))
+                self._peers.append(q.value)
+        self.workspace_bytes = nbytes
+        dist.barrier(group=self.group)          # every mapping exists before the first peer store
+
+    def struct(self, rank=None):
+        from . import _lib as L
+        g = L.SpGroup()
+        g.world, g.rank, g.lockstep = self.world, self.rank, 0
+        for i, p in enumerate(self._peers):
+            g.peer_flags[i] = p
+            g.peer_workspace[i] = p + self.FLAG_BYTES
+        return g
+
+    def barrier(self) -> None:
+        import ctypes as C
+        from . import _lib as L
+        L.check(L.lib().rt_sp_barrier(C.byref(self.struct()), L.stream_ptr()))
+
+    def check(self) -> None:
+        """Synchronise and raise if a barrier on this rank ever timed out (a peer died or fell out of step)."""
+        import ctypes as C
+        from . import _lib as L
+        bad = C.c_int(0)
+        L.check(L.lib().rt_sp_status(C.byref(self.struct()), L.stream_ptr(), C.byref(bad)))
+        if bad.value:
+            raise RuntimeError("sequence-parallel barrier timed out: a peer rank is not making progress")
+
+    def close(self) -> None:
+        if self._own is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            self._release()

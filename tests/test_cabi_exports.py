@@ -23,7 +23,7 @@ def test_library_builds_loads_and_exports_the_header():
     assert not missing, missing
     assert sorted(_lib.EXPORTS) == names           # the ctypes binding covers exactly the header
     lib.rt_abi_version.restype = ctypes.c_int
-    assert lib.rt_abi_version() == 1                # host-only call
+    assert lib.rt_abi_version() == 2                # host-only call
 
 
 def test_host_only_entry_points_validate_arguments():
