@@ -313,7 +313,7 @@ def run_b200(args, wl):
 
     # ---- end to end through the public pipeline API: host (pinned) inputs, one 28-step image, latents read back
     #      to the host after EVERY step (callback_on_step_end, the reference's own per-step tap) and at the end.
-    h_tap = torch.empty(1, N, TR["in_channels"], dtype=dt).pin_memory()
+    h_tap = torch.empty(1, N // (world if sp is not None else 1), TR["in_channels"], dtype=dt).pin_memory()
     canny = pin(torch.rand(1, 3, H, W, generator=g) * 2 - 1)
     pos = pin((torch.from_numpy(mask_img)[None, None].float() / 255.0) * 2 - 1)
     d2h = [0]

@@ -305,33 +305,47 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
       ptx::tc_fence_before();
       ptx::mbar_arrive(&p_full[t]);
     }
-    // ---- epilogue: O / l -> bf16 -> global
+    // ---- epilogue: O / l -> bf16 -> shared (row-wise) -> global (2 rows x 256 B per warp instruction).
+    // TMEM gives each thread one ROW; storing it directly would write 32 rows x 16 B per instruction - 32 lines for
+    // the LSU and, when the destination is a peer GPU (sequence-parallel mode), 16-byte NVLink packets.  All MMAs
+    // have completed (o_full), so the Q / K tiles are dead: each softmax warp stages its 32 x 128 block there.
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
     const float inv = 1.f / l;
-    bf16* orow;
-    if (P.sp_rows > 0) {
-      const int dest = min(row / P.sp_rows, RT_SP_MAX_RANKS - 1);  // rows >= S are never stored
-      orow = P.sp_out[dest] + (long long)b * P.out_bs + (long long)(row - dest * P.sp_rows) * P.out_ld + P.out_col0 +
-             h * HD;
-    } else {
-      orow = P.out + (long long)b * P.out_bs + (long long)row * P.out_ld + P.out_col0 + h * HD;
-    }
+    constexpr int kPitch = HD * 2 + 16;  // 272 B: conflict-free row-wise writes and transposed reads
+    uint8_t* stage = smem + (warp - 4) * (32 * kPitch);
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
       float v[32];
       tmem_ld32(o_addr + ch * 32, v);
-      if (row < P.S) {
-        uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+      uint4* dst = reinterpret_cast<uint4*>(stage + lane * kPitch + ch * 64);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = ptx::pack_bf16x2(v[8 * i + 0] * inv, v[8 * i + 1] * inv);
-          u.y = ptx::pack_bf16x2(v[8 * i + 2] * inv, v[8 * i + 3] * inv);
-          u.z = ptx::pack_bf16x2(v[8 * i + 4] * inv, v[8 * i + 5] * inv);
-          u.w = ptx::pack_bf16x2(v[8 * i + 6] * inv, v[8 * i + 7] * inv);
-          dst[i] = u;
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = ptx::pack_bf16x2(v[8 * i + 0] * inv, v[8 * i + 1] * inv);
+        u.y = ptx::pack_bf16x2(v[8 * i + 2] * inv, v[8 * i + 3] * inv);
+        u.z = ptx::pack_bf16x2(v[8 * i + 4] * inv, v[8 * i + 5] * inv);
+        u.w = ptx::pack_bf16x2(v[8 * i + 6] * inv, v[8 * i + 7] * inv);
+        dst[i] = u;
+      }
+    }
+    __syncwarp();
+    const int row0 = q0 + t * BQ + quad * 32;  // first row of this warp
+    const int rr = lane >> 4, cc = lane & 15;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int r = it * 2 + rr;
+      const int grow = row0 + r;
+      if (grow < P.S) {
+        bf16* orow;
+        if (P.sp_rows > 0) {
+          const int dest = grow / P.sp_rows;
+          orow = P.sp_out[dest] + (long long)b * P.out_bs + (long long)(grow - dest * P.sp_rows) * P.out_ld +
+                 P.out_col0 + h * HD;
+        } else {
+          orow = P.out + (long long)b * P.out_bs + (long long)grow * P.out_ld + P.out_col0 + h * HD;
         }
+        *reinterpret_cast<uint4*>(orow + cc * 8) = *reinterpret_cast<const uint4*>(stage + r * kPitch + cc * 16);
       }
     }
   }

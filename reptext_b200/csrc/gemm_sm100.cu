@@ -63,7 +63,8 @@ struct alignas(64) TcParams {
   // sequence-parallel scatter (rt_gemm_segment::scatter): destination buffers, columns per destination, row offset
   bf16* sp_out[RT_SP_MAX_RANKS];
   int sp_cols, sp_row0;
-  int debug;  // option "gemm_debug" (timing experiments, wrong results): 1 = no epilogue, 2 = every k-block loads k = 0
+  int debug;  // option "gemm_debug": 1 = no epilogue, 2 = every k-block loads k = 0 (timing experiments, wrong
+              // results); 4 = direct row-per-thread epilogue stores instead of the staged ones (A/B, same results)
 };
 
 template <int BN, int kCtaGroup>
@@ -76,8 +77,9 @@ struct Cfg {
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (kAccStages * BN <= 32) ? 32 : (kAccStages * BN <= 64) ? 64
                                    : (kAccStages * BN <= 128) ? 128 : (kAccStages * BN <= 256) ? 256 : 512;
-  static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kBarBytes = ((2 * kStages + 2 * kAccStages) * 8 + 16 + 127) / 128 * 128;
+  static constexpr int kEpiStageOff = kStages * kStageBytes + kBarBytes;  // per-warp epilogue staging tiles
+  static constexpr int kSmemBytes = kEpiStageOff + 4 * 32 * 144 + 1024;    // + alignment slack
 };
 
 struct TileCoord {
@@ -279,6 +281,203 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const TcProblem
   }
 }
 
+
+// ---- staged epilogue ------------------------------------------------------------------------------------
+// TMEM hands every thread ONE ROW of the accumulator, so a direct store writes 32 rows x 16 B per warp instruction:
+// 32 separate lines for the LSU and - when the destination is a peer GPU's memory (sequence-parallel scatter), where
+// no L2 merges partial lines - 16-byte NVLink packets.  Instead each epilogue warp owns a 32-row x 64-column bf16
+// staging tile in shared memory (row pitch 144 B: conflict-free for the row-wise writes and for the transposed
+// reads), fills it row-wise and copies it out 4 rows x 128 B per instruction.  Residual operands (in-place
+// gate * x + residual, accumulate) take the same road in the other direction first; values are still rounded once.
+constexpr int kStagePitch = 144;
+constexpr int kStageWarpBytes = 32 * kStagePitch;
+
+__device__ __forceinline__ void stage_put32(uint8_t* stage, int lane, int half, const float (&v)[32]) {
+  uint4* q = reinterpret_cast<uint4*>(stage + lane * kStagePitch + half * 64);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t;
+    t.x = ptx::pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]);
+    t.y = ptx::pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+    t.z = ptx::pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]);
+    t.w = ptx::pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+    q[i] = t;
+  }
+}
+__device__ __forceinline__ void stage_get32(const uint8_t* stage, int lane, int half, float (&v)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(stage + lane * kStagePitch + half * 64);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 t = q[i];
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[i * 8 + 2 * j] = ptx::bf16_lo(w[j]);
+      v[i * 8 + 2 * j + 1] = ptx::bf16_hi(w[j]);
+    }
+  }
+}
+// g: (first row of this warp, first column of the 64-column group); 8 passes of 4 rows x 128 B
+__device__ __forceinline__ void stage_store(const uint8_t* stage, int lane, bf16* g, long long ld, int rows_valid) {
+  const int rr = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rr;
+    if (r < rows_valid)
+      *reinterpret_cast<uint4*>(g + (long long)r * ld + ch * 8) =
+          *reinterpret_cast<const uint4*>(stage + r * kStagePitch + ch * 16);
+  }
+}
+__device__ __forceinline__ void stage_load(uint8_t* stage, int lane, const bf16* g, long long ld, int rows_valid) {
+  const int rr = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rr;
+    if (r < rows_valid)
+      *reinterpret_cast<uint4*>(stage + r * kStagePitch + ch * 16) =
+          *reinterpret_cast<const uint4*>(g + (long long)r * ld + ch * 8);
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const TcProblem& pr, const TcSegment& sg,
+                                                     uint32_t tacc, int b, int m0w, int lane, int n0, uint8_t* stage) {
+  const int m = m0w + lane;
+  const bool row_ok = m < pr.m_rows;
+  const int rows_valid = min(max(pr.m_rows - m0w, 0), 32);
+  if (rows_valid == 0) return;  // warp-uniform
+  const int nl0 = n0 - sg.n_begin;  // column within the segment
+  const bf16* bias = sg.bias ? sg.bias + nl0 : nullptr;
+  // (first row of this warp, segment column `col`); with scatter the 64-column group starting at `col` lives in
+  // rank (col / sp_cols)'s buffer - a peer-mapped pointer, the store crosses NVLink
+  auto gptr = [&](int col) -> bf16* {
+    const long long row = pr.out_row0 + m0w;
+    if (!sg.scatter) return sg.out + (long long)b * sg.out_bs + row * sg.out_ld + sg.out_col0 + col;
+    const int dest = col / P.sp_cols;
+    return P.sp_out[dest] + (long long)b * sg.out_bs + (P.sp_row0 + row) * sg.out_ld + sg.out_col0 +
+           (col - dest * P.sp_cols);
+  };
+
+  if (sg.mode == EPI_QKNORM_ROPE) {
+    // one head = 128 columns; two passes over TMEM (reads are cheap) instead of 128 live registers
+    const float2* rp = P.rope ? P.rope + (long long)(pr.out_row0 + m) * 64 : nullptr;
+#pragma unroll 1
+    for (int hc = 0; hc < BN / 128; ++hc) {
+      float ss = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_load_f32x32(tacc + hc * 128 + c * 32, v);
+        if (bias) {
+          float bv[32];
+          load_bf16x32(bias + hc * 128 + c * 32, bv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += bv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ss += v[i] * v[i];
+      }
+      const float rs = rsqrtf(ss * (1.f / 128.f) + 1e-6f);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_load_f32x32(tacc + hc * 128 + c * 32, v);
+        if (bias) {
+          float bv[32];
+          load_bf16x32(bias + hc * 128 + c * 32, bv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += bv[i];
+        }
+        float wv[32];
+        load_bf16x32(sg.norm_w + c * 32, wv);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = v[i] * rs * wv[i];
+        if (rp && row_ok) {
+          const float4* r4 = reinterpret_cast<const float4*>(rp + c * 16);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 cs = __ldg(r4 + i);  // (cos0, sin0, cos1, sin1)
+            float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+            v[4 * i] = x0 * cs.x - x1 * cs.y;
+            v[4 * i + 1] = x1 * cs.x + x0 * cs.y;
+            v[4 * i + 2] = x2 * cs.z - x3 * cs.w;
+            v[4 * i + 3] = x3 * cs.z + x2 * cs.w;
+          }
+        }
+        stage_put32(stage, lane, c & 1, v);
+        if (c & 1) {
+          __syncwarp();
+          stage_store(stage, lane, gptr(nl0 + hc * 128 + (c >> 1) * 64), sg.out_ld, rows_valid);
+          __syncwarp();
+        }
+      }
+    }
+    return;
+  }
+
+  const float* gate = (sg.mode == EPI_GATE_RESID && pr.gate) ? pr.gate + (long long)b * pr.gate_ld + n0 : nullptr;
+  const bf16* extra = nullptr;
+  if (sg.mode == EPI_GATE_RESID && pr.extra && m >= pr.e_row0 && row_ok)
+    extra = pr.extra + (long long)b * pr.e_bs + (long long)(m - pr.e_row0) * pr.e_ld + n0;
+  float mk = 1.f;
+  if (sg.mode == EPI_SCALE_MASK) {
+    mk = pr.scale;
+    if (pr.mask && row_ok) mk *= __bfloat162float(pr.mask[m]);
+  }
+  const bool resid = sg.mode == EPI_GATE_RESID || (sg.mode == EPI_SCALE_MASK && pr.accumulate);
+#pragma unroll 1
+  for (int g = 0; g < BN / 64; ++g) {
+    bf16* gp = gptr(nl0 + g * 64);
+    if (resid) {
+      stage_load(stage, lane, gp, sg.out_ld, rows_valid);
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int c = g * 2 + half;
+      float v[32];
+      tmem_load_f32x32(tacc + c * 32, v);
+      if (bias) {
+        float bv[32];
+        load_bf16x32(bias + c * 32, bv);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += bv[i];
+      }
+      if (sg.mode == EPI_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_fast(v[i]);
+      } else if (sg.mode == EPI_GATE_RESID) {
+        if (gate) {
+          const float4* g4 = reinterpret_cast<const float4*>(gate + c * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 gv = __ldg(g4 + i);
+            v[4 * i] *= gv.x; v[4 * i + 1] *= gv.y; v[4 * i + 2] *= gv.z; v[4 * i + 3] *= gv.w;
+          }
+        }
+      } else if (sg.mode == EPI_SCALE_MASK) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= mk;
+      }
+      if (resid) {
+        float r[32];
+        stage_get32(stage, lane, half, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += r[i];
+        if (extra) {
+          load_bf16x32(extra + c * 32, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += r[i];
+        }
+      }
+      stage_put32(stage, lane, half, v);
+    }
+    __syncwarp();
+    stage_store(stage, lane, gp, sg.out_ld, rows_valid);
+    __syncwarp();
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 template <int BN, int kCtaGroup>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
@@ -400,8 +599,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      const int m = tc.m0 + (int)cta_rank * BM + quad * 32 + lane;
-      if (!(P.debug & 1)) epilogue_tile<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m, tc.n0);
+      const int m0w = tc.m0 + (int)cta_rank * BM + quad * 32;
+      if (P.debug & 1) {
+        // timing experiment: accumulators are dropped
+      } else if (P.debug & 4) {
+        epilogue_tile<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w + lane, tc.n0);
+      } else {
+        epilogue_tile_staged<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w, lane, tc.n0,
+                                 smem + C::kEpiStageOff + quad * kStageWarpBytes);
+      }
       ptx::tc_fence_before();
       if constexpr (kCtaGroup == 1) ptx::mbar_arrive(&tempty_bar[as]);
       else ptx::mbar_arrive_cluster(&tempty_bar[as], 0);

@@ -159,6 +159,7 @@ class SequenceParallelGroup(_SpBase):
         self._own = None
         self._peers: List[Optional[int]] = []
         self.workspace_bytes = 0
+        self.ensure_workspace(1 << 20)          # the flag words exist from the start (barrier() works right away)
 
     def _release(self):
         from . import _lib as L

@@ -163,5 +163,8 @@ def test_multi_process_sequence_parallel_pipeline_matches_single_gpu():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
            "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tests", "sp_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "sp_worker.log"), "w") as fh:
+        fh.write(r.stdout + "\n---- stderr ----\n" + r.stderr)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SP_WORKER_OK" in r.stdout
