@@ -114,108 +114,203 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const T* __restrict__ x, lo
 
 // CTA form for rows that fit one 16-byte vector per thread (D <= 8192 bf16 / 4096 fp32): thread t owns columns
 // [t*N, t*N+N) of EVERY row its CTA processes, so the (1 + scale) / shift vectors live in registers and are read
-// once per CTA instead of once per row (per row they are 4x the bytes of the row itself in bf16).  kR rows are in
-// flight per iteration; mean and variance are two block reductions (two-pass, like torch's LayerNorm).
-template <typename T, int kR, int kMaxThreads>
-__global__ void __launch_bounds__(kMaxThreads) ln_mod_cta_kernel(const T* __restrict__ x, long long x_bs, int x_ld,
-                                                          T* __restrict__ out, long long o_bs, int o_ld, int batch,
-                                                          int rows_total, int D, LnGroups groups, int rows_per_cta) {
-  constexpr int N = VecT<T>::N;
+// once per CTA instead of once per row (per row they are 4x the bytes of the row itself in bf16).  The kernel is
+// written for instruction count (the warp-per-row form issues ~290 instructions per thread and row and is
+// issue-bound, ncu r1): packed fp32x2 math, a 4-row butterfly for the warp reductions, 13-instruction cross-warp
+// reductions, and the next 4 rows are already in flight while the current 4 are reduced.  Mean and variance are two
+// passes over the registers (like torch's LayerNorm).
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+// sums of 4 independent values over the warp; every lane of lane-group g = lane >> 3 ends with the total of value g
+__device__ __forceinline__ float warp_sum4(const float (&p)[4], int lane) {
+  const bool hi16 = lane & 16, hi8 = lane & 8;
+  const float s0 = hi16 ? p[0] : p[2], s1 = hi16 ? p[1] : p[3];
+  const float k0 = hi16 ? p[2] : p[0], k1 = hi16 ? p[3] : p[1];
+  const float q0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+  const float q1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+  const float send = hi8 ? q0 : q1, keep = hi8 ? q1 : q0;
+  float t = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 4);
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  return t;
+}
+
+template <typename T>
+struct RawVec;
+template <>
+struct RawVec<bf16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const bf16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void zero() { u = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void unpack(float2 (&v)[4]) const {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = f2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float2 (&o)[4]) {
+    uint4 t;
+    __nv_bfloat162 h0 = __float22bfloat162_rn(o[0]), h1 = __float22bfloat162_rn(o[1]);
+    __nv_bfloat162 h2 = __float22bfloat162_rn(o[2]), h3 = __float22bfloat162_rn(o[3]);
+    t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
+    t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+template <>
+struct RawVec<float> {
+  float4 u;
+  __device__ __forceinline__ void load(const float* p) { u = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void zero() { u = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void unpack(float2 (&v)[2]) const { v[0] = f2(u.x, u.y); v[1] = f2(u.z, u.w); }
+  static __device__ __forceinline__ void store(float* p, const float2 (&o)[2]) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+  }
+};
+
+template <typename T, int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ln_mod_cta_kernel(const T* __restrict__ x, long long x_bs, int x_ld,
+                                                                 T* __restrict__ out, long long o_bs, int o_ld,
+                                                                 int batch, int rows_total, int D, LnGroups groups,
+                                                                 int rows_per_cta) {
+  constexpr int N = VecT<T>::N, H = N / 2, kR = 4;
   __shared__ float red[2][kR][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const bool active = tid * N < D;
-  const long long lin_end = min((long long)(blockIdx.x + 1) * rows_per_cta, (long long)batch * rows_total);
+  const int lin_begin = blockIdx.x * rows_per_cta;
+  const int lin_end = min(lin_begin + rows_per_cta, batch * rows_total);
   const float inv_d = 1.f / (float)D;
-  int cur_key = -1;
-  float sc1[N], sh[N];
+
+  // position of a linear row index: batch b, group gi, row r, rows left in this (batch, group)
+  int b = 0, r = 0, left = 0, g_ld = 0;
+  const float *g_scale = nullptr, *g_shift = nullptr;
+  auto locate = [&](int lin) {
+    b = lin / rows_total;
+    int lr = lin - b * rows_total;
+    bool found = false;
 #pragma unroll
-  for (int j = 0; j < N; ++j) { sc1[j] = 1.f; sh[j] = 0.f; }
-  for (long long lin = (long long)blockIdx.x * rows_per_cta; lin < lin_end;) {
-    const int b = (int)(lin / rows_total);
-    const int lr = (int)(lin % rows_total);
-    int gi = 0, r = 0, left = 0, acc = 0, g_ld = 0;
-    const float *g_scale = nullptr, *g_shift = nullptr;
-#pragma unroll
-    for (int k = 0; k < kLnMaxGroups; ++k) {
-      if (k < groups.n) {
-        const int len = groups.g[k].row_end - groups.g[k].row_begin;
-        if (left == 0 && lr < acc + len) {
-          gi = k;
-          r = groups.g[k].row_begin + (lr - acc);
-          left = acc + len - lr;
+    for (int k = 0; k < kLnMaxGroups; ++k) {  // static indices only: `groups` stays in the constant bank
+      const int len = groups.g[k].row_end - groups.g[k].row_begin;
+      if (!found && k < groups.n) {
+        if (lr < len) {
+          found = true;
+          r = groups.g[k].row_begin + lr;
+          left = len - lr;
           g_scale = groups.g[k].scale; g_shift = groups.g[k].shift; g_ld = groups.g[k].ld;
+        } else {
+          lr -= len;
         }
-        acc += len;
       }
     }
-    const int n = min(kR, min((int)(lin_end - lin), left));  // rows of this iteration: one (batch, group)
-    if (b * kLnMaxGroups + gi != cur_key) {
-      cur_key = b * kLnMaxGroups + gi;
-      if (active) {
-        const float* scp = g_scale + (long long)b * g_ld + tid * N;
-        const float* shp = g_shift + (long long)b * g_ld + tid * N;
+  };
+  float2 sc1[H], sh[H];
+  auto load_mod = [&]() {
+    if (active) {
+      const float* scp = g_scale + (long long)b * g_ld + tid * N;
+      const float* shp = g_shift + (long long)b * g_ld + tid * N;
 #pragma unroll
-        for (int j4 = 0; j4 < N; j4 += 4) {
-          const float4 a = *reinterpret_cast<const float4*>(scp + j4);
-          const float4 h = *reinterpret_cast<const float4*>(shp + j4);
-          sc1[j4] = 1.f + a.x; sc1[j4 + 1] = 1.f + a.y; sc1[j4 + 2] = 1.f + a.z; sc1[j4 + 3] = 1.f + a.w;
-          sh[j4] = h.x; sh[j4 + 1] = h.y; sh[j4 + 2] = h.z; sh[j4 + 3] = h.w;
-        }
+      for (int j = 0; j < H; j += 2) {
+        const float4 a = *reinterpret_cast<const float4*>(scp + 2 * j);
+        const float4 h = *reinterpret_cast<const float4*>(shp + 2 * j);
+        sc1[j] = f2(1.f + a.x, 1.f + a.y); sc1[j + 1] = f2(1.f + a.z, 1.f + a.w);
+        sh[j] = f2(h.x, h.y); sh[j + 1] = f2(h.z, h.w);
       }
     }
+  };
+  if (lin_begin >= lin_end) return;
+  locate(lin_begin);
+  load_mod();
+
+  RawVec<T> cur[kR], nxt[kR];
+  int n = min(kR, min(lin_end - lin_begin, left));
+  {
     const T* xr = x + (long long)b * x_bs + (long long)r * x_ld + tid * N;
-    float v[kR][N];
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+      if (active && i < n) cur[i].load(xr + (long long)i * x_ld); else cur[i].zero();
+    }
+  }
+  for (int lin = lin_begin; lin < lin_end;) {
+    // ---- where the NEXT iteration reads; issue its loads now
+    const int b0 = b, r0 = r, n0 = n;
+    const int lin_next = lin + n0;
+    int n_next = 0;
+    bool mod_changes = false;
+    if (lin_next < lin_end) {
+      if (left > n0) { r += n0; left -= n0; } else { locate(lin_next); mod_changes = true; }
+      n_next = min(kR, min(lin_end - lin_next, left));
+      const T* xr = x + (long long)b * x_bs + (long long)r * x_ld + tid * N;
+#pragma unroll
+      for (int i = 0; i < kR; ++i) {
+        if (active && i < n_next) nxt[i].load(xr + (long long)i * x_ld); else nxt[i].zero();
+      }
+    }
+    // ---- mean
+    float2 v[kR][H];
     float part[kR];
 #pragma unroll
     for (int i = 0; i < kR; ++i) {
-      part[i] = 0.f;
-      if (active && i < n) {
-        ldvec(xr + (long long)i * x_ld, v[i]);
+      cur[i].unpack(v[i]);
+      float2 a = v[i][0];
 #pragma unroll
-        for (int j = 0; j < N; ++j) part[i] += v[i][j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < N; ++j) v[i][j] = 0.f;
-      }
+      for (int j = 1; j < H; ++j) a = __fadd2_rn(a, v[i][j]);
+      part[i] = a.x + a.y;
     }
-#pragma unroll
-    for (int i = 0; i < kR; ++i) {
-      part[i] = warp_sum(part[i]);
-      if (lane == 0) red[0][i][warp] = part[i];
-    }
+    float t = warp_sum4(part, lane);
+    if ((lane & 7) == 0) red[0][lane >> 3][warp] = t;
     __syncthreads();
+    {
+      float a = 0.f;
+      for (int w = lane & 7; w < nwarps; w += 8) a += red[0][lane >> 3][w];
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      t = a;
+    }
     float mean[kR];
 #pragma unroll
-    for (int i = 0; i < kR; ++i) {
-      float t = 0.f;
-      for (int w = 0; w < nwarps; ++w) t += red[0][i][w];
-      mean[i] = t * inv_d;
-      float q = 0.f;
-      if (active) {
+    for (int i = 0; i < kR; ++i) mean[i] = __shfl_sync(0xffffffffu, t, i * 8) * inv_d;
+    // ---- variance (v becomes x - mean)
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          const float d = v[i][j] - mean[i];
-          q += d * d;
-        }
+    for (int i = 0; i < kR; ++i) {
+      const float2 nm = f2(-mean[i], -mean[i]);
+      float2 q = f2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        v[i][j] = __fadd2_rn(v[i][j], nm);
+        q = __ffma2_rn(v[i][j], v[i][j], q);
       }
-      q = warp_sum(q);
-      if (lane == 0) red[1][i][warp] = q;
+      part[i] = active ? q.x + q.y : 0.f;
     }
+    t = warp_sum4(part, lane);
+    if ((lane & 7) == 0) red[1][lane >> 3][warp] = t;
     __syncthreads();
-    T* orow = out + (long long)b * o_bs + (long long)r * o_ld + tid * N;
+    {
+      float a = 0.f;
+      for (int w = lane & 7; w < nwarps; w += 8) a += red[1][lane >> 3][w];
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      t = a;
+    }
+    // ---- normalise, modulate, store
+    T* orow = out + (long long)b0 * o_bs + (long long)r0 * o_ld + tid * N;
 #pragma unroll
     for (int i = 0; i < kR; ++i) {
-      float t = 0.f;
-      for (int w = 0; w < nwarps; ++w) t += red[1][i][w];
-      const float rstd = rsqrtf(t * inv_d + 1e-6f);
-      if (active && i < n) {
-        float o[N];
+      const float rstd = rsqrtf(__shfl_sync(0xffffffffu, t, i * 8) * inv_d + 1e-6f);
+      if (active && i < n0) {
+        const float2 rs = f2(rstd, rstd);
+        float2 o[H];
 #pragma unroll
-        for (int j = 0; j < N; ++j) o[j] = (v[i][j] - mean[i]) * rstd * sc1[j] + sh[j];
-        stvec(orow + (long long)i * o_ld, o);
+        for (int j = 0; j < H; ++j) o[j] = __ffma2_rn(v[i][j], __fmul2_rn(rs, sc1[j]), sh[j]);
+        RawVec<T>::store(orow + (long long)i * o_ld, o);
       }
     }
-    lin += n;
+    if (mod_changes) load_mod();   // the next rows belong to another (batch, group)
+#pragma unroll
+    for (int i = 0; i < kR; ++i) cur[i] = nxt[i];
+    n = n_next;
+    lin = lin_next;
   }
 }
 
@@ -244,16 +339,17 @@ void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out
     if (nvec <= 1024 && nvec >= 64 && !get_option("ln_warp_rows")) {
       constexpr int kR = 4;
       const int cta_threads = (nvec + 31) / 32 * 32;
-      const long long cap_cta = (long long)sm_count() * (cta_threads <= 512 ? 4 : 2);
+      const long long cap_cta = (long long)sm_count() * (cta_threads <= 384 ? 2 : 1);
       long long rpc = (total + cap_cta - 1) / cap_cta;
       rpc = (rpc + kR - 1) / kR * kR;
       const long long grid = (total + rpc - 1) / rpc;
-      if (cta_threads <= 512)
-        ln_mod_cta_kernel<T, kR, 512><<<(int)grid, cta_threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs,
-                                                                             o_ld, batch, rows_total, D, G, (int)rpc);
+      RT_REQUIRE(total < (1ll << 31), "ln_mod: too many rows");
+      if (cta_threads <= 384)
+        ln_mod_cta_kernel<T, 384, 2><<<(int)grid, cta_threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld,
+                                                                            batch, rows_total, D, G, (int)rpc);
       else
-        ln_mod_cta_kernel<T, kR, 1024><<<(int)grid, cta_threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs,
-                                                                              o_ld, batch, rows_total, D, G, (int)rpc);
+        ln_mod_cta_kernel<T, 1024, 1><<<(int)grid, cta_threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld,
+                                                                             batch, rows_total, D, G, (int)rpc);
       RT_POST_LAUNCH();
       return;
     }
