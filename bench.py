@@ -209,9 +209,7 @@ def run_b200(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
-    for kv in filter(None, os.environ.get("RT_OPTIONS", "").split(",")):   # A/B aid, e.g. RT_OPTIONS=attn_variant=4
-        k, v = kv.split("=")
-        _lib.set_option(k.strip(), int(v))
+    # (A/B aid: RT_OPTIONS=attn_variant=20,... is applied by _lib.lib() at load time)
     dt = torch.bfloat16
     TR, CN, H, W, T = wl["TR"], wl["CN"], wl["H"], wl["W"], wl["T"]
     N = (H // 16) * (W // 16)

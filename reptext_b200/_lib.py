@@ -176,6 +176,10 @@ def lib() -> C.CDLL:
             raise RuntimeError(f"ctypes mirror of {st.__name__} is {C.sizeof(st)} bytes, the library says "
                                f"{L.rt_struct_size(i)}: _lib.py and include/reptext_rt.h are out of step")
     _lib = L
+    # A/B aid: RT_OPTIONS="attn_variant=20,gemm_cta_group=1" applies rt_set_option at load time
+    for kv in filter(None, os.environ.get("RT_OPTIONS", "").split(",")):
+        k, v = kv.split("=")
+        check(L.rt_set_option(k.strip().encode(), int(v)))
     return L
 
 

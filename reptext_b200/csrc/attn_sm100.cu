@@ -32,7 +32,7 @@ constexpr int kThreads = 384;
 constexpr int kTileBytes = BQ * HD * 2;       // 32 KB: two 16 KB sub-tiles of 64 columns (one swizzle row each)
 constexpr int kSubBytes = kTileBytes / 2;
 constexpr int kSmemTiles = 2 + 2 * kStages;   // Q_A Q_B | K ring | V ring
-constexpr int kNumBars = 1 + 4 * kStages + 2 + 2 + 1;
+constexpr int kNumBars = 1 + 4 * kStages + 2 + 2 + 2 + 1;
 constexpr int kSmemBytes = kSmemTiles * kTileBytes + kNumBars * 8 + 16 + 1024;
 
 struct AttnParams {
@@ -69,9 +69,30 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(xi) << 23));
 }
 
+// Packed form of the same idea for a PAIR of exponentials (fma.rn.f32x2 / add.f32x2, sm_100): round-to-nearest
+// split x = n + f, f in [-0.5, 0.5], cubic minimax of 2^f (max rel. error 1.3e-4), n added into the exponent field.
+// 10 instructions per pair against 2 MUFU.EX2 - the MUFU unit (16 / clk / SM) is the unit this kernel saturates.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);  // 1.5 * 2^23: the low mantissa bits become round(x)
+  const float2 xi = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(xi, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.0550440177f, 0.0550440177f), make_float2(0.24229379f, 0.24229379f));
+  p = __ffma2_rn(p, f, make_float2(0.69325459f, 0.69325459f));
+  p = __ffma2_rn(p, f, make_float2(0.99994999f, 0.99994999f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(xi.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(xi.y) << 23)));
+}
+
 // kDebug: 0 = product; 1 / 2 / 3 are timing experiments (no exp2 / no row max / neither; wrong results).
-// kPolyEvery: every kPolyEvery-th PAIR of exponentials goes to exp2_poly (0 = none).
-template <int kDebug, int kPolyEvery>
+// kPolyEvery: (scalar form) every kPolyEvery-th PAIR of exponentials goes to exp2_poly (0 = none).
+// kPacked: softmax arithmetic on fp32 pairs, TMEM loads of S pipelined against the running max; kPolyMask8: bit
+// (i % 8) set = pair i takes exp2_poly2 instead of MUFU.  kSplitP: P is handed to the MMA warp in two halves of
+// 64 keys, so that P V can start while the second half is still being exponentiated.
+template <int kDebug, int kPolyEvery, bool kPacked = false, int kPolyMask8 = 0, bool kSplitP = false,
+          bool kElect = false>
 __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_constant__ AttnParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
@@ -87,7 +108,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
   uint64_t* v_empty = v_full + kStages;
   uint64_t* s_full = v_empty + kStages;  // [2]
   uint64_t* p_full = s_full + 2;         // [2]
-  uint64_t* o_full = p_full + 2;         // [1]
+  uint64_t* p_half = p_full + 2;         // [2] first 64 keys of P written (kSplitP)
+  uint64_t* o_full = p_half + 2;         // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,7 +130,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&p_full[i], 128);
+      ptx::mbar_init(&p_full[i], kElect ? 4 : 128);  // kElect: one lane per softmax warp arrives
+      ptx::mbar_init(&p_half[i], kElect ? 4 : 128);
     }
     ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
@@ -163,10 +186,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
         ptx::mma_bf16_ss<1>(tmem + t * 128, qa + off, ka + off, idesc_qk, kk != 0 ? 1u : 0u);
       }
     };
-    auto issue_pv = [&](int t, int st, uint32_t acc) {
+    auto issue_pv = [&](int t, int st, uint32_t acc, int kk0 = 0, int kk1 = BKV / 16) {
       const uint64_t va = v_desc + (uint64_t)(st * kTile16);
 #pragma unroll
-      for (int kk = 0; kk < BKV / 16; ++kk) {
+      for (int kk = kk0; kk < kk1; ++kk) {
         // 16 keys = two 8-row core groups (SBO 1024 B); 128 head-dim columns = two 64-column sub-tiles (LBO 16 KB)
         ptx::mma_bf16_ts(tmem + 256 + t * 128, tmem + t * 128 + kk * 8, va + (uint64_t)(kk * 128), idesc_pv,
                          kk != 0 ? 1u : acc);
@@ -189,21 +212,33 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
       const bool more = j + 1 < n_kv;
       const uint32_t acc = j > 0 ? 1u : 0u;
       ptx::mbar_wait(&v_full[st], ph);
+      if constexpr (kSplitP) {
+        ptx::mbar_wait(&p_half[0], j & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) issue_pv(0, st, acc, 0, 4);
+        __syncwarp();
+      }
       ptx::mbar_wait(&p_full[0], j & 1);
       if (more) ptx::mbar_wait(&k_full[nst], nph);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        issue_pv(0, st, acc);
+        if constexpr (kSplitP) issue_pv(0, st, 1u, 4, 8); else issue_pv(0, st, acc);
         if (more) {
           issue_qk(0, nst);
           ptx::mma_commit(&s_full[0]);
         }
       }
       __syncwarp();
+      if constexpr (kSplitP) {
+        ptx::mbar_wait(&p_half[1], j & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) issue_pv(1, st, acc, 0, 4);
+        __syncwarp();
+      }
       ptx::mbar_wait(&p_full[1], j & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        issue_pv(1, st, acc);
+        if constexpr (kSplitP) issue_pv(1, st, 1u, 4, 8); else issue_pv(1, st, acc);
         ptx::mma_commit(&v_empty[st]);
         if (more) {
           issue_qk(1, nst);
@@ -231,13 +266,110 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
       ptx::mbar_wait(&s_full[t], j & 1);
       ptx::tc_fence_after();
       const int n_valid = P.S - j * BKV;  // < 128 only on the last tile
+      if constexpr (kPacked) {
+        // ---- S -> registers, one chunk in flight while the previous one feeds the running max
+        uint32_t s0[32], s1[32], s2[32], s3[32];
+        auto chunk_max = [&](uint32_t (&sv)[32], int col0) {
+          if (n_valid < BKV) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i >= n_valid) sv[i] = 0xff800000u;  // -inf
+          }
+          float a = -INFINITY, b2 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            a = fmaxf(a, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+            b2 = fmaxf(b2, fmaxf(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])));
+          }
+          return fmaxf(a, b2);
+        };
+        ptx::tmem_ld_32x32b_x32(s_addr, s0);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x32(s_addr + 32, s1);
+        float mx = chunk_max(s0, 0);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x32(s_addr + 64, s2);
+        mx = fmaxf(mx, chunk_max(s1, 32));
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x32(s_addr + 96, s3);
+        mx = fmaxf(mx, chunk_max(s2, 64));
+        ptx::tmem_ld_wait();
+        mx = fmaxf(mx, chunk_max(s3, 96));
+        const float mx_s = mx * c;
+        if (j == 0) {
+          m_ref = mx_s;
+        } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
+          const float m_new = fmaxf(m_ref, mx_s);
+          const float f = ptx::ex2_approx(m_ref - m_new);
+          l *= f;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            uint32_t r[16];
+            ptx::tmem_ld_32x32b_x16(o_addr + ch * 16, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+            ptx::tmem_st_32x32b_x16(o_addr + ch * 16, r);
+          }
+          m_ref = m_new;
+        }
+        // ---- P = 2^(S c - m) on pairs; bf16 P overwrites the first 64 columns of S
+        const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
+        float2 lsum = make_float2(0.f, 0.f);
+        auto exp_chunk = [&](const uint32_t (&sv)[32], int col) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, nm2);
+            float2 e;
+            if ((kPolyMask8 >> (i & 7)) & 1) {
+              e = exp2_poly2(x);
+            } else {
+              e.x = ptx::ex2_approx(x.x);
+              e.y = ptx::ex2_approx(x.y);
+            }
+            lsum = __fadd2_rn(lsum, e);
+            pk[i] = ptx::pack_bf16x2(e.x, e.y);
+          }
+          ptx::tmem_st_32x32b_x16(s_addr + col, pk);
+        };
+        exp_chunk(s0, 0);
+        exp_chunk(s1, 16);
+        if constexpr (kSplitP) {
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          if constexpr (kElect) {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&p_half[t]);
+          } else {
+            ptx::mbar_arrive(&p_half[t]);
+          }
+        }
+        exp_chunk(s2, 32);
+        exp_chunk(s3, 48);
+        l += lsum.x + lsum.y;
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        if constexpr (kElect) {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&p_full[t]);
+        } else {
+          ptx::mbar_arrive(&p_full[t]);
+        }
+        continue;
+      }
       // the whole score row (128 fp32) in registers: ONE TMEM round trip per tile
       uint32_t s0[32], s1[32], s2[32], s3[32];
-      ptx::tmem_ld_32x32b_x32(s_addr, s0);
-      ptx::tmem_ld_32x32b_x32(s_addr + 32, s1);
-      ptx::tmem_ld_32x32b_x32(s_addr + 64, s2);
-      ptx::tmem_ld_32x32b_x32(s_addr + 96, s3);
-      ptx::tmem_ld_wait();
+      if (kDebug & 4) {  // timing experiment: no TMEM read of S at all
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s0[i] = s1[i] = s2[i] = s3[i] = 0x3f000000u + (uint32_t)(i + j);
+      } else {
+        ptx::tmem_ld_32x32b_x32(s_addr, s0);
+        ptx::tmem_ld_32x32b_x32(s_addr + 32, s1);
+        ptx::tmem_ld_32x32b_x32(s_addr + 64, s2);
+        ptx::tmem_ld_32x32b_x32(s_addr + 96, s3);
+        ptx::tmem_ld_wait();
+      }
       if (n_valid < BKV) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -355,6 +487,312 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
   if (warp == 2) ptx::tmem_dealloc<1>(tmem, 512);
 }
 
+
+// =================================================================================================
+// v4: 64-key blocks with a DOUBLE-BUFFERED score tile.
+//
+// In the kernel above P aliases S, so Q K^T of block j+1 cannot be issued before P V of block j: per query tile the
+// chain  Q K^T -> softmax -> P V -> Q K^T  is strictly serial and its latency (two mbarrier hand-offs, TMEM
+// round trips, fences - ~2100 cycles even with the arithmetic removed, r1 timing experiments) bounds the tensor pipe
+// at 1024 / (1024 + latency) per tile pair.  Here a block is 64 keys: S is 64 columns, and each query tile owns TWO S
+// buffers, so Q K^T of block b+2 goes into the buffer that P V of block b has just released while the softmax
+// warps are already working on block b+1.  The tensor pipe always has queued work and the softmax warpgroups run
+// back to back: the kernel is bound by throughput (MUFU / tensor), not by the hand-off latency.
+//
+//   TMEM (512 columns): tile t:  S[t][0] = t*256 + 0, S[t][1] = t*256 + 64, O[t] = t*256 + 128 (128 columns)
+//   K / V still arrive as 128-key TMA tiles (2 stages each); block b uses half b % 2 of tile b / 2.
+//   The lazy rescale of O must not race with P V of the previous block, which may still be running: that (rare)
+//   path first waits on pv_done[t].
+// =================================================================================================
+constexpr int BKB = 64;  // keys per block
+constexpr int kNumBars4 = 1 + 4 * kStages + 4 + 4 + 2 + 1;
+constexpr int kSmemBytes4 = kSmemTiles * kTileBytes + kNumBars4 * 8 + 16 + 1024;
+
+template <int kPolyMask8, int kDebug>
+__global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel_v4(const __grid_constant__ AttnParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint8_t* smem_q = smem;                               // 2 tiles
+  uint8_t* smem_k = smem + 2 * kTileBytes;              // kStages tiles
+  uint8_t* smem_v = smem + (2 + kStages) * kTileBytes;  // kStages tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + kStages;
+  uint64_t* v_full = k_empty + kStages;
+  uint64_t* v_empty = v_full + kStages;
+  uint64_t* s_full = v_empty + kStages;  // [tile][buf]
+  uint64_t* p_full = s_full + 4;         // [tile][buf]
+  uint64_t* pv_done = p_full + 4;        // [tile]
+  uint64_t* o_full = pv_done + 2;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qp = blockIdx.x % P.n_qpairs;
+  const int bh = blockIdx.x / P.n_qpairs;
+  const int h = bh % P.heads, b = bh / P.heads;
+  const int q0 = qp * 2 * BQ;
+  const int n_kv = (P.S + BKV - 1) / BKV;  // 128-key K / V tiles
+  const int nb = (P.S + BKB - 1) / BKB;    // 64-key blocks
+
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&P.tm);
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 4);  // one elected lane per softmax warp
+    }
+    ptx::mbar_init(&pv_done[0], 1);
+    ptx::mbar_init(&pv_done[1], 1);
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer (same tiles as v1) =====================
+      ptx::mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d(&P.tm, q_full, smem_q + t * kTileBytes + sub * kSubBytes, P.q_col0 + h * HD + sub * 64,
+                           q0 + t * BQ, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kStages, ph = (j / kStages) & 1;
+        ptx::mbar_wait(&k_empty[st], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d(&P.tm, &k_full[st], smem_k + st * kTileBytes + sub * kSubBytes,
+                           P.k_col0 + h * HD + sub * 64, j * BKV, b);
+        ptx::mbar_wait(&v_empty[st], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d(&P.tm, &v_full[st], smem_v + st * kTileBytes + sub * kSubBytes,
+                           P.v_col0 + h * HD + sub * 64, j * BKV, b);
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKB, 0, 0);  // 128 x 64, A and B K-major
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, HD, 0, 1);   // A (= P) from TMEM, B (= V) MN-major
+      const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_q), 0, 1024);
+      const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_k), 0, 1024);
+      const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_v), kSubBytes, 1024);
+      constexpr uint32_t kTile16 = kTileBytes >> 4, kSub16 = kSubBytes >> 4;
+      constexpr uint32_t kHalfRows16 = (BKB * 128) >> 4;  // 64 key rows of 128 B inside a sub-tile
+      auto s_col = [&](int t, int blk) { return tmem + t * 256 + (blk & 1) * BKB; };
+      auto issue_qk = [&](int t, int blk) {
+        const int st = (blk >> 1) % kStages;
+        const uint64_t qa = q_desc + (uint64_t)(t * kTile16);
+        const uint64_t ka = k_desc + (uint64_t)(st * kTile16 + (blk & 1) * kHalfRows16);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kSub16 + (kk & 3) * 2;  // (addr >> 4) units
+          ptx::mma_bf16_ss<1>(s_col(t, blk), qa + off, ka + off, idesc_qk, kk != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int blk) {
+        const int st = (blk >> 1) % kStages;
+        const uint64_t va = v_desc + (uint64_t)(st * kTile16);
+#pragma unroll
+        for (int kk = 0; kk < BKB / 16; ++kk) {
+          const int key16 = (blk & 1) * (BKB / 16) + kk;  // 16-key group inside the 128-key V tile
+          ptx::mma_bf16_ts(tmem + t * 256 + 128, s_col(t, blk) + kk * 8, va + (uint64_t)(key16 * 128), idesc_pv,
+                           (kk != 0 || blk > 0) ? 1u : 0u);
+        }
+      };
+      ptx::mbar_wait(q_full, 0);
+      ptx::mbar_wait(&k_full[0], 0);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        issue_qk(0, 0);
+        ptx::mma_commit(&s_full[0]);
+        issue_qk(1, 0);
+        ptx::mma_commit(&s_full[2]);
+        if (nb > 1) {
+          issue_qk(0, 1);
+          ptx::mma_commit(&s_full[1]);
+          issue_qk(1, 1);
+          ptx::mma_commit(&s_full[3]);
+        }
+        ptx::mma_commit(&k_empty[0]);
+      }
+      __syncwarp();
+      for (int blk = 0; blk < nb; ++blk) {
+        const int kt = blk >> 1, st = kt % kStages;
+        if ((blk & 1) == 0) ptx::mbar_wait(&v_full[st], (kt / kStages) & 1);
+        const int nxt = blk + 2;  // the block whose Q K^T reuses this block's S buffer
+        const int kt2 = nxt >> 1, st2 = kt2 % kStages;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          ptx::mbar_wait(&p_full[t * 2 + (blk & 1)], (blk >> 1) & 1);
+          if (nxt < nb && t == 0 && (nxt & 1) == 0) ptx::mbar_wait(&k_full[st2], (kt2 / kStages) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            issue_pv(t, blk);
+            ptx::mma_commit(&pv_done[t]);
+            if (t == 1 && ((blk & 1) == 1 || blk == nb - 1)) ptx::mma_commit(&v_empty[st]);
+            if (nxt < nb) {
+              issue_qk(t, nxt);
+              ptx::mma_commit(&s_full[t * 2 + (nxt & 1)]);
+              if (t == 1 && ((nxt & 1) == 1 || nxt == nb - 1)) ptx::mma_commit(&k_empty[st2]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (ptx::elect_one()) ptx::mma_commit(o_full);
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int t = (warp - 4) >> 2;  // 0: tile A, 1: tile B
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t o_addr = tmem + lane_off + t * 256 + 128;
+    const float c = P.scale_log2;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int blk = 0; blk < nb; ++blk) {
+      const int buf = blk & 1;
+      const uint32_t s_addr = tmem + lane_off + t * 256 + buf * BKB;
+      ptx::mbar_wait(&s_full[t * 2 + buf], (blk >> 1) & 1);
+      ptx::tc_fence_after();
+      const int n_valid = P.S - blk * BKB;  // < 64 only on the last block
+      uint32_t s0[32], s1[32];
+      if (kDebug & 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s0[i] = s1[i] = 0x3f000000u + (uint32_t)(i + blk);
+      } else {
+        ptx::tmem_ld_32x32b_x32(s_addr, s0);
+        ptx::tmem_ld_32x32b_x32(s_addr + 32, s1);
+        ptx::tmem_ld_wait();
+      }
+      if (n_valid < BKB) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= n_valid) s0[i] = 0xff800000u;  // -inf
+          if (32 + i >= n_valid) s1[i] = 0xff800000u;
+        }
+      }
+      float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        mxa = fmaxf(mxa, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 1])));
+        mxb = fmaxf(mxb, fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 1])));
+      }
+      const float mx_s = fmaxf(mxa, mxb) * c;
+      if (blk == 0) {
+        m_ref = mx_s;
+      } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
+        // O[t] may still be receiving P V of the previous block
+        ptx::mbar_wait(&pv_done[t], (blk - 1) & 1);
+        ptx::tc_fence_after();
+        const float m_new = fmaxf(m_ref, mx_s);
+        const float f = ptx::ex2_approx(m_ref - m_new);
+        l *= f;
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(o_addr + ch * 16, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          ptx::tmem_st_32x32b_x16(o_addr + ch * 16, r);
+        }
+        m_ref = m_new;
+      }
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
+      float2 lsum = make_float2(0.f, 0.f);
+      auto exp_chunk = [&](const uint32_t (&sv)[32], int col) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, nm2);
+          float2 e;
+          if (kDebug & 2) {
+            e = x;
+          } else if ((kPolyMask8 >> (i & 7)) & 1) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = ptx::ex2_approx(x.x);
+            e.y = ptx::ex2_approx(x.y);
+          }
+          lsum = __fadd2_rn(lsum, e);
+          pk[i] = ptx::pack_bf16x2(e.x, e.y);
+        }
+        ptx::tmem_st_32x32b_x16(s_addr + col, pk);
+      };
+      exp_chunk(s0, 0);
+      exp_chunk(s1, 16);
+      l += lsum.x + lsum.y;
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[t * 2 + buf]);
+    }
+    // ---- epilogue: O / l -> bf16 -> shared (row-wise) -> global (2 rows x 256 B per warp instruction); see v1
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    constexpr int kPitch = HD * 2 + 16;
+    uint8_t* stage = smem + (warp - 4) * (32 * kPitch);
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      float v[32];
+      tmem_ld32(o_addr + ch * 32, v);
+      uint4* dst = reinterpret_cast<uint4*>(stage + lane * kPitch + ch * 64);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = ptx::pack_bf16x2(v[8 * i + 0] * inv, v[8 * i + 1] * inv);
+        u.y = ptx::pack_bf16x2(v[8 * i + 2] * inv, v[8 * i + 3] * inv);
+        u.z = ptx::pack_bf16x2(v[8 * i + 4] * inv, v[8 * i + 5] * inv);
+        u.w = ptx::pack_bf16x2(v[8 * i + 6] * inv, v[8 * i + 7] * inv);
+        dst[i] = u;
+      }
+    }
+    __syncwarp();
+    const int row0 = q0 + t * BQ + quad * 32;
+    const int rr = lane >> 4, cc = lane & 15;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int r = it * 2 + rr;
+      const int grow = row0 + r;
+      if (grow < P.S) {
+        bf16* orow;
+        if (P.sp_rows > 0) {
+          const int dest = grow / P.sp_rows;
+          orow = P.sp_out[dest] + (long long)b * P.out_bs + (long long)(grow - dest * P.sp_rows) * P.out_ld +
+                 P.out_col0 + h * HD;
+        } else {
+          orow = P.out + (long long)b * P.out_bs + (long long)grow * P.out_ld + P.out_col0 + h * HD;
+        }
+        *reinterpret_cast<uint4*>(orow + cc * 8) = *reinterpret_cast<const uint4*>(stage + r * kPitch + cc * 16);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<1>(tmem, 512);
+}
+
 }  // namespace
 
 bool attention_tc_supported(const AttnArgs& a, std::string* why) {
@@ -395,20 +833,43 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
   P.n_qpairs = (a.S + 2 * BQ - 1) / (2 * BQ);
   P.scale_log2 = 1.4426950408889634f / sqrtf((float)a.hd);
   using KernelFn = void (*)(const AttnParams);
-  // variant 0 = product configuration; 1-3 timing experiments; 4.. = other exp2_poly shares (tuning)
-  static const KernelFn table[] = {attn_tc_kernel<0, 0>, attn_tc_kernel<1, 0>, attn_tc_kernel<2, 0>, attn_tc_kernel<3, 0>,
-                                   attn_tc_kernel<0, 4>, attn_tc_kernel<0, 2>, attn_tc_kernel<0, 3>, attn_tc_kernel<0, 5>,
-                                   attn_tc_kernel<0, 8>};
+  // variant 0 = product configuration.  The rest are kept for A/B timing (tools/attn_sweep.py):
+  //   1-3 timing experiments of the scalar form (wrong results); 4 scalar form, 5 scalar + 25 % polynomial;
+  //   6.. packed form: (poly mask, split P) = (0,0) (0,1) (25%,0) (25%,1) (37.5%,1) (50%,1) (12.5%,1)
+  static const KernelFn table[] = {
+      attn_tc_kernel<0, 0, true, 0x88, true>,
+      attn_tc_kernel<1, 0>, attn_tc_kernel<2, 0>, attn_tc_kernel<3, 0>,
+      attn_tc_kernel<0, 0>, attn_tc_kernel<0, 4>,
+      attn_tc_kernel<0, 0, true, 0x00, false>, attn_tc_kernel<0, 0, true, 0x00, true>,
+      attn_tc_kernel<0, 0, true, 0x88, false>, attn_tc_kernel<0, 0, true, 0x88, true>,
+      attn_tc_kernel<0, 0, true, 0x92, true>, attn_tc_kernel<0, 0, true, 0xAA, true>,
+      attn_tc_kernel<0, 0, true, 0x80, true>,
+      attn_tc_kernel<4, 0>, attn_tc_kernel<7, 0>,  // 13: no TMEM read of S; 14: no read, no max, no exp2
+      attn_tc_kernel<0, 0, true, 0x88, true, true>, attn_tc_kernel<0, 0, true, 0x88, false, true>,  // 15, 16: elected arrive
+      attn_tc_kernel<0, 0, true, 0x00, false, true>};
   constexpr int kNumVariants = sizeof(table) / sizeof(table[0]);
+  // v4 kernels (64-key blocks, double-buffered S): variant 20 + i.  (poly mask, debug) =
+  //   (25%,0) (0,0) (37.5%,0) (50%,0) (12.5%,0) | timing experiments: (0, no S read) (0, no exp2) (0, neither)
+  static const KernelFn table4[] = {attn_tc_kernel_v4<0x88, 0>, attn_tc_kernel_v4<0x00, 0>, attn_tc_kernel_v4<0x92, 0>,
+                                    attn_tc_kernel_v4<0xAA, 0>, attn_tc_kernel_v4<0x80, 0>, attn_tc_kernel_v4<0, 1>,
+                                    attn_tc_kernel_v4<0, 2>,    attn_tc_kernel_v4<0, 3>};
+  constexpr int kNumVariants4 = sizeof(table4) / sizeof(table4[0]);
   static bool attr_set = false;
   if (!attr_set) {
     for (int i = 0; i < kNumVariants; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    for (int i = 0; i < kNumVariants4; ++i)
+      RT_CHECK_CUDA(cudaFuncSetAttribute(table4[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
     attr_set = true;
   }
-  RT_REQUIRE(variant >= 0 && variant < kNumVariants, "attention: unknown variant");
   const long long grid = (long long)P.n_qpairs * a.heads * a.batch;
-  table[variant]<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(P);
+  if (variant >= 20) {
+    RT_REQUIRE(variant - 20 < kNumVariants4, "attention: unknown variant");
+    table4[variant - 20]<<<(unsigned)grid, kThreads, kSmemBytes4, stream>>>(P);
+  } else {
+    RT_REQUIRE(variant >= 0 && variant < kNumVariants, "attention: unknown variant");
+    table[variant]<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(P);
+  }
   RT_POST_LAUNCH();
 }
 
