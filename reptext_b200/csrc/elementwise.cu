@@ -385,11 +385,12 @@ __global__ void __launch_bounds__(256) gemv_grouped_kernel(const float* __restri
                                                            const GemvJob* __restrict__ jobs,
                                                            const int* __restrict__ prefix, int njobs, int total_rows,
                                                            float* __restrict__ out, int out_ld, int silu_out,
-                                                           int accumulate) {
+                                                           int accumulate, int row_base) {
   constexpr int N = VecT<T>::N;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < total_rows; row += gridDim.x * wpb) {
+  for (int row_l = blockIdx.x * wpb + (threadIdx.x >> 5); row_l < total_rows; row_l += gridDim.x * wpb) {
+    const int row = row_l + row_base;  // prefix[] holds absolute row offsets of the model's whole job table
     int lo = 0, hi = njobs - 1;  // last job with prefix[j] <= row
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
@@ -438,11 +439,12 @@ __global__ void __launch_bounds__(256) gemv_grouped_rows_kernel(const float* __r
                                                                 const GemvJob* __restrict__ jobs,
                                                                 const int* __restrict__ prefix, int njobs,
                                                                 int total_rows, float* __restrict__ out, int out_ld,
-                                                                int silu_out, int accumulate) {
+                                                                int silu_out, int accumulate, int row_base) {
   constexpr int N = VecT<T>::N;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (int row = (blockIdx.x * wpb + (threadIdx.x >> 5)) * kR; row < total_rows; row += gridDim.x * wpb * kR) {
+  for (int row_l = (blockIdx.x * wpb + (threadIdx.x >> 5)) * kR; row_l < total_rows; row_l += gridDim.x * wpb * kR) {
+    const int row = row_l + row_base;
     int lo = 0, hi = njobs - 1;  // last job with prefix[j] <= row
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(256) gemv_grouped_rows_kernel(const float* __r
 
 void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
                          const int* prefix_dev, int njobs, int total_rows, float* out, int out_ld, int silu_out,
-                         int accumulate, cudaStream_t stream, bool rows_multiple_of_4) {
+                         int accumulate, cudaStream_t stream, bool rows_multiple_of_4, int row_base) {
   if (batch == 0 || total_rows == 0) return;
   ProfScope ps(PROF_GEMV, (double)total_rows * K * dtype_size(wdtype), stream);
   RT_REQUIRE(x_ld % 4 == 0, "gemv: x_ld must be a multiple of 4");
@@ -514,23 +516,23 @@ void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K,
       int nb = batch - b0;
       if (multi && nb >= 2) {
         gemv_grouped_rows_kernel<T, 2, kR><<<mblocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
-                                                                            total_rows, out, out_ld, silu_out, accumulate);
+                                                                            total_rows, out, out_ld, silu_out, accumulate, row_base);
         b0 += 2;
       } else if (multi) {
         gemv_grouped_rows_kernel<T, 1, kR><<<mblocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
-                                                                            total_rows, out, out_ld, silu_out, accumulate);
+                                                                            total_rows, out, out_ld, silu_out, accumulate, row_base);
         b0 += 1;
       } else if (nb >= 4) {
         gemv_grouped_kernel<T, 4><<<blocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
-                                                                  total_rows, out, out_ld, silu_out, accumulate);
+                                                                  total_rows, out, out_ld, silu_out, accumulate, row_base);
         b0 += 4;
       } else if (nb >= 2) {
         gemv_grouped_kernel<T, 2><<<blocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
-                                                                  total_rows, out, out_ld, silu_out, accumulate);
+                                                                  total_rows, out, out_ld, silu_out, accumulate, row_base);
         b0 += 2;
       } else {
         gemv_grouped_kernel<T, 1><<<blocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
-                                                                  total_rows, out, out_ld, silu_out, accumulate);
+                                                                  total_rows, out, out_ld, silu_out, accumulate, row_base);
         b0 += 1;
       }
       RT_POST_LAUNCH();

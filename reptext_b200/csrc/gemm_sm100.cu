@@ -64,7 +64,8 @@ struct alignas(64) TcParams {
   bf16* sp_out[RT_SP_MAX_RANKS];
   int sp_cols, sp_row0;
   int debug;  // option "gemm_debug": 1 = no epilogue, 2 = every k-block loads k = 0 (timing experiments, wrong
-              // results); 4 = direct row-per-thread epilogue stores instead of the staged ones (A/B, same results)
+              // results); 4 = direct row-per-thread epilogue stores instead of the staged ones, 8 = L2 eviction
+              // hints on the TMA loads (A/B, same results)
 };
 
 template <int BN, int kCtaGroup>
@@ -531,6 +532,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
+    // L2 eviction hints (activations evict_last, weights evict_first) are OFF by default: measured with ncu over the
+    // 188 GEMM launches of a step they RAISE DRAM reads from 52 GB to 74 GB - a weight tile is shared by the 16-18
+    // row tiles of its wave, and evict_first drops it before the neighbours have fetched it.
+    const uint64_t pol_a = (P.debug & 8) ? ptx::kL2EvictLast : ptx::kL2EvictNormal;
+    const uint64_t pol_w = (P.debug & 8) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
     int stage = 0, phase = 0;
     for (int t = cluster_id; t < P.total_tiles; t += num_clusters) {
       const TileCoord tc = decode_tile(P, t, BN, kRowsPerTile);
@@ -547,12 +553,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int k0 = (P.debug & 2) ? 0 : kb * BK;
         if constexpr (kCtaGroup == 1) {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-          ptx::tma_load_3d(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b);
-          ptx::tma_load_2d(&sg.tmW, &full_bar[stage], sb, k0, w_row);
+          ptx::tma_load_3d_hint(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b, pol_a);
+          ptx::tma_load_2d_hint(&sg.tmW, &full_bar[stage], sb, k0, w_row, pol_w);
         } else {
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-          ptx::tma_load_3d_2sm(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b);
-          ptx::tma_load_2d_2sm(&sg.tmW, &full_bar[stage], sb, k0, w_row);
+          ptx::tma_load_3d_2sm_hint(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b, pol_a);
+          ptx::tma_load_2d_2sm_hint(&sg.tmW, &full_bar[stage], sb, k0, w_row, pol_w);
         }
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }

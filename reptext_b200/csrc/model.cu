@@ -68,10 +68,18 @@ struct rt_model {
   GemvJob* jobs_dev = nullptr;  // [0..5] = t1 g1 p1 t2 g2 p2, [6..] = AdaLN linears of every block
   int* prefix_dev = nullptr;    // [0] = 0 (single-job launches), [1..] = row prefix of the AdaLN jobs
   int n_mod_jobs = 0, mod_rows = 0;
+  int first_block_jobs = 0, first_block_rows = 0;  // the AdaLN jobs the first block needs
+  // The AdaLN vectors of blocks 1.. are weight-streaming work (6.5 GB per forward) that nothing needs until the
+  // second block: they are computed on a side stream, under the first block's tensor-core kernels.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   ~rt_model() {
     if (jobs_dev) cudaFree(jobs_dev);
     if (prefix_dev) cudaFree(prefix_dev);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
   }
 };
 
@@ -174,6 +182,7 @@ struct Ctx {
   int P = 1, r = 0, Sg = 0, Dl = 0;
   char* peer_qkv[RT_SP_MAX_RANKS] = {};
   char* peer_cat[RT_SP_MAX_RANKS] = {};
+  bool mod_join_pending = false;  // the AdaLN vectors of blocks 1.. are still being computed on the side stream
   long long sD() const { return (long long)S * D; }
 };
 
@@ -196,7 +205,7 @@ GemmSegment make_qkv_seg(const Ctx& c, const Lin& l, int which /*0 q, 1 k, 2 v*/
 
 // temb = MLP_t(sin(1000 t)) + MLP_g(sin(1000 g)) + MLP_p(pooled)   (controlnet_flux.py:282-291), then the AdaLN
 // vectors of every block: mod = Linear_i(SiLU(temb)).
-void time_text_and_modulation(const Ctx& c, const rt_forward_args& a) {
+void time_text_and_modulation(Ctx& c, const rt_forward_args& a) {
   const rt_model& m = c.m;
   const Workspace& w = c.ws;
   const int D = c.D, B = c.B, P = m.cfg.pooled_projection_dim;
@@ -215,8 +224,29 @@ void time_text_and_modulation(const Ctx& c, const rt_forward_args& a) {
     launch_gemv_grouped(c.dt, w.hid + D, 3 * D, B, D, m.jobs_dev + 4, m.prefix_dev, 1, D, w.temb, D, 0, 1, c.st);
   launch_gemv_grouped(c.dt, w.hid + 2 * D, 3 * D, B, D, m.jobs_dev + 5, m.prefix_dev, 1, D, w.temb, D, 0, 1, c.st);
   launch_silu_f32(w.temb, w.temb_s, (long long)B * D, c.st);
-  launch_gemv_grouped(c.dt, w.temb_s, D, B, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, m.mod_rows, w.mod,
-                      m.mod_total, 0, 0, c.st, /*rows_multiple_of_4=*/D % 4 == 0);  // every AdaLN job has k*D rows
+  const bool r4 = D % 4 == 0;  // every AdaLN job has k * D rows
+  const int n0 = m.first_block_jobs, rows0 = m.first_block_rows;
+  if (m.side && n0 > 0 && n0 < m.n_mod_jobs && !get_option("mod_inline")) {
+    // first block's vectors on the caller's stream, the rest forked onto the side stream (joined before block 1)
+    RT_CHECK_CUDA(cudaEventRecord(m.ev_fork, c.st));
+    RT_CHECK_CUDA(cudaStreamWaitEvent(m.side, m.ev_fork, 0));
+    launch_gemv_grouped(c.dt, w.temb_s, D, B, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, m.mod_rows - rows0,
+                        w.mod, m.mod_total, 0, 0, m.side, r4, rows0);
+    RT_CHECK_CUDA(cudaEventRecord(m.ev_join, m.side));
+    launch_gemv_grouped(c.dt, w.temb_s, D, B, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, rows0, w.mod,
+                        m.mod_total, 0, 0, c.st, r4, 0);
+    c.mod_join_pending = true;
+  } else {
+    launch_gemv_grouped(c.dt, w.temb_s, D, B, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, m.mod_rows, w.mod,
+                        m.mod_total, 0, 0, c.st, r4);
+  }
+}
+
+// every AdaLN vector is needed from here on: join the side stream (no-op when nothing was forked)
+void join_modulation(Ctx& c) {
+  if (!c.mod_join_pending) return;
+  RT_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.m.ev_join, 0));
+  c.mod_join_pending = false;
 }
 
 void embed_inputs(const Ctx& c, const rt_forward_args& a, const void* cond, int cond_batch) {
@@ -461,12 +491,13 @@ void phase_sync(const std::vector<Ctx>& cs) {
   if (cs.size() == 1 && cs[0].P > 1 && !cs[0].sp->lockstep) launch_sp_barrier(*cs[0].sp, cs[0].st);
 }
 template <class Pre, class Post>
-void run_block(const std::vector<Ctx>& cs, Pre pre, Post post) {
+void run_block(std::vector<Ctx>& cs, Pre pre, Post post) {
   for (size_t i = 0; i < cs.size(); ++i) pre(cs[i], i);
   phase_sync(cs);
   for (size_t i = 0; i < cs.size(); ++i) run_attention(cs[i]);
   phase_sync(cs);
   for (size_t i = 0; i < cs.size(); ++i) post(cs[i], i);
+  for (size_t i = 0; i < cs.size(); ++i) join_modulation(cs[i]);  // after the FIRST block (no-op later)
 }
 
 void check_lockstep(int world, size_t ncalls, const rt_forward_args* const* args) {
@@ -551,6 +582,7 @@ void transformer_forward_impl(rt_model* m, const std::vector<const rt_transforme
               });
   // norm_out (AdaLayerNormContinuous: chunk order scale, shift) + proj_out on the image rows
   for (size_t r = 0; r < cs.size(); ++r) {
+    join_modulation(cs[r]);
     const Ctx& c = cs[r];
     const int D = c.D, T = c.T, N = c.N, S = c.S;
     const float* mo = c.ws.mod + m->mod_out;
@@ -693,6 +725,11 @@ int rt_model_finalize(rt_model* m, void* stream) {
     m->mod_total = off > 0 ? off : 4;
     m->mod_rows = rows;
     m->n_mod_jobs = (int)jobs.size() - 6;
+    m->first_block_jobs = c.num_layers > 0 ? 2 : (c.num_single_layers > 0 ? 1 : 0);
+    m->first_block_rows = m->first_block_jobs < m->n_mod_jobs ? prefix[1 + m->first_block_jobs] : rows;
+    RT_CHECK_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+    RT_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    RT_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     RT_CHECK_CUDA(cudaMalloc(&m->jobs_dev, jobs.size() * sizeof(GemvJob)));
     RT_CHECK_CUDA(cudaMalloc(&m->prefix_dev, prefix.size() * sizeof(int)));
     RT_CHECK_CUDA(cudaMemcpyAsync(m->jobs_dev, jobs.data(), jobs.size() * sizeof(GemvJob), cudaMemcpyHostToDevice,

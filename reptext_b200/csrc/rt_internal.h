@@ -99,7 +99,8 @@ struct GemvJob {
 };
 void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
                          const int* job_row_prefix_dev, int njobs, int total_rows, float* out, int out_ld,
-                         int silu_out, int accumulate, cudaStream_t stream, bool rows_multiple_of_4 = false);
+                         int silu_out, int accumulate, cudaStream_t stream, bool rows_multiple_of_4 = false,
+                         int row_base = 0);
 void launch_silu_f32(const float* x, float* out, long long n, cudaStream_t stream);
 
 void launch_time_sinusoid(int dtype, const void* t, int t_batch, int batch, float* out /*[batch,256]*/,

@@ -1,11 +1,8 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python tools/attn_sweep.py 2,10,17,18,19 > gpurun_out/attn_sweep5.log 2>&1; cat gpurun_out/attn_sweep5.log
-for v in 0 15 16; do
-RT_OPTIONS=attn_variant=$v timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench11_v$v.json 2> gpurun_out/bench11_v$v.err
-python - <<EOF
-import json
-d=json.loads([l for l in open('gpurun_out/bench11_v$v.json') if l.startswith('{')][-1])
-print('variant $v', round(d['ms_per_step'],2), {k:(round(v['ms_per_step'],2), round(v['achieved'] or 0)) for k,v in d['breakdown'].items()})
-EOF
-done
+CMD="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
+K='regex:gemm_tc|attn_tc|ln_mod|gemv|euler|rope_table|time_sinusoid|silu_f32|cast_to_f32|gemm_simt|attn_simt'
+$CMD > gpurun_out/plain_r1i.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" --launch-skip 1107 --launch-count 369 --csv --log-file gpurun_out/launches_v2.csv $CMD > gpurun_out/ncu_launches_v2.log 2>&1
+tail -1 gpurun_out/ncu_launches_v2.log | cut -c1-200
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc --launch-skip 700 --launch-count 3 -o gpurun_out/prof_gemm_v2 -f $CMD > gpurun_out/ncu_gemm_v2.log 2>&1
+tail -1 gpurun_out/ncu_gemm_v2.log
