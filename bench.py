@@ -362,10 +362,16 @@ def run_b200(args, wl):
         gpus_per_sample = world if sp is not None else 1
         gem = prof.get("gemm_tcgen05", (0.0, 0.0, 0))
         roof = None
+        traffic = None   # ncu dram__bytes_read + write per GEMM launch, averaged over the 188 launches of one cfg2 step
+        tpath = os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")
+        if args.workload == "cfg2" and os.path.exists(tpath):
+            traffic = json.load(open(tpath))["no_l2_hints"]["bytes_per_launch"]
         if gem[0] > 0:
             ach = gem[1] / (gem[0] / 1000.0) / 1e12
             roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 + TMA, fused epilogues)", achieved=ach,
-                        peak=pk["bf16_sustained"], unit="TFLOP/s", frac=ach / pk["bf16_sustained"], traffic=None,
+                        peak=pk["bf16_sustained"], unit="TFLOP/s", frac=ach / pk["bf16_sustained"], traffic=traffic,
+                        traffic_unit="bytes of DRAM traffic per launch (ncu, profiles/r1_gemm_dram_traffic.json); "
+                                     "algorithmic operand bytes per launch: 203e6",
                         peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)",
                         frac_of_burst=ach / pk["bf16_burst"], launches=gem[2], ms_per_step=gem[0] / args.steps,
                         flops_per_step=gem[1] / args.steps)
