@@ -164,3 +164,46 @@ def test_model_argument_errors():
         cn(**dict(kw, hidden_states=x["latents"]))  # CPU tensor: no CPU path
     with pytest.raises(RuntimeError):
         models.FluxControlNetModel(config.TINY_CONTROLNET, {"x_embedder.weight": torch.zeros(1)}, dtype=torch.float32)
+
+
+def test_one_denoise_step_is_cuda_graph_capturable():
+    """A forward is a straight sequence of launches on the caller's stream (no allocation, no sync inside the library;
+    the AdaLN side stream forks and joins inside the forward), so ControlNet + transformer + Euler capture into ONE
+    CUDA graph; replaying it on new latents must reproduce the eager result bit for bit."""
+    from reptext_b200 import config, models, ops
+    dt, dev = torch.bfloat16, "cuda"
+    TR, CN = config.SMALL128_TRANSFORMER, config.SMALL128_CONTROLNET
+    tr = models.FluxTransformer2DModel.random_init(TR, seed=100, dtype=dt)
+    cn = models.FluxControlNetModel.random_init(CN, seed=101, dtype=dt)
+    x = synth_inputs(TR, CN, 256, 256, 128, seed=9)
+    c = lambda v: v.to(dev, dt)
+    lat, pe, po, cond, mask = c(x["latents"]), c(x["prompt_embeds"]), c(x["pooled"]), c(x["conds"][0]), c(x["masks"][0])
+    ii, ti = x["img_ids"].to(dev), x["txt_ids"].to(dev)
+    t, g = torch.tensor([0.62], device=dev, dtype=dt), torch.tensor([3.5], device=dev, dtype=dt)
+
+    def step(z):
+        kw = dict(hidden_states=z, encoder_hidden_states=pe, pooled_projections=po, timestep=t, guidance=g, img_ids=ii,
+                  txt_ids=ti)
+        bl, _ = cn(controlnet_cond=cond, conditioning_scale=0.9, regional_mask=mask, return_dict=False, **kw)
+        v = tr(controlnet_block_samples=bl, return_dict=False, **kw)[0]
+        return ops.euler_step(v, z, 0.62, 0.55)
+
+    eager1 = step(lat)
+    lat2 = torch.randn_like(lat)
+    eager2 = step(lat2)
+    static_in = lat.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step(static_in)                      # warm-up on the capture stream (workspace, kernel attributes)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        static_out = step(static_in)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, eager1)
+    static_in.copy_(lat2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, eager2)
