@@ -439,7 +439,8 @@ __global__ void __launch_bounds__(256) gemv_grouped_rows_kernel(const float* __r
                                                                 const GemvJob* __restrict__ jobs,
                                                                 const int* __restrict__ prefix, int njobs,
                                                                 int total_rows, float* __restrict__ out, int out_ld,
-                                                                int silu_out, int accumulate, int row_base) {
+                                                                int silu_out, int accumulate, int row_base,
+                                                                const GemvPeers peers) {
   constexpr int N = VecT<T>::N;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -487,8 +488,14 @@ __global__ void __launch_bounds__(256) gemv_grouped_rows_kernel(const float* __r
         for (int b = 0; b < NB; ++b) {
           float v = acc[i][b] + bias;
           if (silu_out) v = v / (1.f + expf(-v));
-          float* o = out + (long long)(b0 + b) * out_ld + J.out_off + r + i;
-          *o = accumulate ? (*o + v) : v;
+          const long long off = (long long)(b0 + b) * out_ld + J.out_off + r + i;
+          if (peers.n > 0) {
+            // sequence-parallel row shard: the result goes to EVERY rank's copy (peer-mapped pointers)
+            for (int d = 0; d < peers.n; ++d) peers.p[d][off] = v;
+          } else {
+            float* o = out + off;
+            *o = accumulate ? (*o + v) : v;
+          }
         }
       }
     }
@@ -497,7 +504,8 @@ __global__ void __launch_bounds__(256) gemv_grouped_rows_kernel(const float* __r
 
 void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
                          const int* prefix_dev, int njobs, int total_rows, float* out, int out_ld, int silu_out,
-                         int accumulate, cudaStream_t stream, bool rows_multiple_of_4, int row_base) {
+                         int accumulate, cudaStream_t stream, bool rows_multiple_of_4, int row_base,
+                         const GemvPeers* peers) {
   if (batch == 0 || total_rows == 0) return;
   ProfScope ps(PROF_GEMV, (double)total_rows * K * dtype_size(wdtype), stream);
   RT_REQUIRE(x_ld % 4 == 0, "gemv: x_ld must be a multiple of 4");
@@ -509,18 +517,20 @@ void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K,
     RT_REQUIRE(K % VecT<T>::N == 0, "gemv: K must be a multiple of the vector width");
     int b0 = 0;
     constexpr int kR = 4;
-    const bool multi = rows_multiple_of_4 && total_rows % kR == 0 && !get_option("gemv_single_row");
+    const bool multi = rows_multiple_of_4 && total_rows % kR == 0 && (!get_option("gemv_single_row") || peers);
+    RT_REQUIRE(!peers || (multi && !accumulate), "gemv: the peer-output form needs 4-row jobs and no accumulation");
+    const GemvPeers pv = peers ? *peers : GemvPeers{};
     int mblocks = (total_rows / kR + wpb - 1) / wpb;
     if (mblocks > cap) mblocks = cap;
     while (b0 < batch) {
       int nb = batch - b0;
       if (multi && nb >= 2) {
         gemv_grouped_rows_kernel<T, 2, kR><<<mblocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
-                                                                            total_rows, out, out_ld, silu_out, accumulate, row_base);
+                                                                            total_rows, out, out_ld, silu_out, accumulate, row_base, pv);
         b0 += 2;
       } else if (multi) {
         gemv_grouped_rows_kernel<T, 1, kR><<<mblocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,
-                                                                            total_rows, out, out_ld, silu_out, accumulate, row_base);
+                                                                            total_rows, out, out_ld, silu_out, accumulate, row_base, pv);
         b0 += 1;
       } else if (nb >= 4) {
         gemv_grouped_kernel<T, 4><<<blocks, threads, 0, stream>>>(x, x_ld, b0, K, jobs_dev, prefix_dev, njobs,

@@ -182,6 +182,8 @@ struct Ctx {
   int P = 1, r = 0, Sg = 0, Dl = 0;
   char* peer_qkv[RT_SP_MAX_RANKS] = {};
   char* peer_cat[RT_SP_MAX_RANKS] = {};
+  float* peer_mod[RT_SP_MAX_RANKS] = {};
+  bool mod_sharded = false;       // this forward computed only its row shard of the AdaLN vectors (peer stores)
   bool mod_join_pending = false;  // the AdaLN vectors of blocks 1.. are still being computed on the side stream
   long long sD() const { return (long long)S * D; }
 };
@@ -228,10 +230,24 @@ void time_text_and_modulation(Ctx& c, const rt_forward_args& a) {
   const int n0 = m.first_block_jobs, rows0 = m.first_block_rows;
   if (m.side && n0 > 0 && n0 < m.n_mod_jobs && !get_option("mod_inline")) {
     // first block's vectors on the caller's stream, the rest forked onto the side stream (joined before block 1)
+    int rest = m.mod_rows - rows0, base = rows0;
+    GemvPeers peers{};
+    const bool shard = c.P > 1 && r4 && rest % (4 * c.P) == 0 && !get_option("sp_replicate_mod");
+    if (shard) {
+      // Sequence-parallel: every rank streams only 1 / P of the AdaLN weights and stores its rows into all ranks'
+      // `mod` buffers.  The peers may still be reading the previous forward's vectors (ControlNet and transformer
+      // share the workspace): a barrier first; the matching barrier after the join is in run_block.
+      if (!c.sp->lockstep) launch_sp_barrier(*c.sp, c.st);
+      rest /= c.P;
+      base += c.r * rest;
+      peers.n = c.P;
+      for (int i = 0; i < c.P; ++i) peers.p[i] = c.peer_mod[i];
+      c.mod_sharded = true;
+    }
     RT_CHECK_CUDA(cudaEventRecord(m.ev_fork, c.st));
     RT_CHECK_CUDA(cudaStreamWaitEvent(m.side, m.ev_fork, 0));
-    launch_gemv_grouped(c.dt, w.temb_s, D, B, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, m.mod_rows - rows0,
-                        w.mod, m.mod_total, 0, 0, m.side, r4, rows0);
+    launch_gemv_grouped(c.dt, w.temb_s, D, B, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, rest, w.mod,
+                        m.mod_total, 0, 0, m.side, r4, base, shard ? &peers : nullptr);
     RT_CHECK_CUDA(cudaEventRecord(m.ev_join, m.side));
     launch_gemv_grouped(c.dt, w.temb_s, D, B, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, rows0, w.mod,
                         m.mod_total, 0, 0, c.st, r4, 0);
@@ -473,6 +489,7 @@ Ctx begin_forward(rt_model* m, const rt_forward_args* a) {
       carve(*m, a->batch, a->n_img, a->n_txt, (char*)g.peer_workspace[i], &pw);  // every rank carves identically
       c.peer_qkv[i] = pw.qkv;
       c.peer_cat[i] = pw.cat;
+      c.peer_mod[i] = pw.mod;
     }
   }
   // FluxPosEmbed over cat(txt_ids, img_ids) (controlnet_flux.py:316-317)
@@ -497,7 +514,13 @@ void run_block(std::vector<Ctx>& cs, Pre pre, Post post) {
   for (size_t i = 0; i < cs.size(); ++i) run_attention(cs[i]);
   phase_sync(cs);
   for (size_t i = 0; i < cs.size(); ++i) post(cs[i], i);
-  for (size_t i = 0; i < cs.size(); ++i) join_modulation(cs[i]);  // after the FIRST block (no-op later)
+  // after the FIRST block (no-op later): the AdaLN vectors of blocks 1.. are needed from here on
+  bool sharded = false;
+  for (size_t i = 0; i < cs.size(); ++i) {
+    sharded = sharded || (cs[i].mod_join_pending && cs[i].mod_sharded);
+    join_modulation(cs[i]);
+  }
+  if (sharded) phase_sync(cs);  // every rank's row shard has landed in every rank's buffer
 }
 
 void check_lockstep(int world, size_t ncalls, const rt_forward_args* const* args) {
@@ -581,8 +604,15 @@ void transformer_forward_impl(rt_model* m, const std::vector<const rt_transforme
                 single_block_post(c, m->sgl[j], nss ? calls[r]->controlnet_single_block_samples[j / iv_s] : nullptr);
               });
   // norm_out (AdaLayerNormContinuous: chunk order scale, shift) + proj_out on the image rows
+  {
+    bool sharded = false;  // (a model without blocks: the join has not happened yet)
+    for (size_t r = 0; r < cs.size(); ++r) {
+      sharded = sharded || (cs[r].mod_join_pending && cs[r].mod_sharded);
+      join_modulation(cs[r]);
+    }
+    if (sharded) phase_sync(cs);
+  }
   for (size_t r = 0; r < cs.size(); ++r) {
-    join_modulation(cs[r]);
     const Ctx& c = cs[r];
     const int D = c.D, T = c.T, N = c.N, S = c.S;
     const float* mo = c.ws.mod + m->mod_out;

@@ -97,10 +97,14 @@ struct GemvJob {
   int rows;
   int out_off;
 };
+struct GemvPeers {  // sequence-parallel row shard: every result is stored to all `n` ranks' output buffers
+  float* p[RT_SP_MAX_RANKS];
+  int n;
+};
 void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
                          const int* job_row_prefix_dev, int njobs, int total_rows, float* out, int out_ld,
                          int silu_out, int accumulate, cudaStream_t stream, bool rows_multiple_of_4 = false,
-                         int row_base = 0);
+                         int row_base = 0, const GemvPeers* peers = nullptr);
 void launch_silu_f32(const float* x, float* out, long long n, cudaStream_t stream);
 
 void launch_time_sinusoid(int dtype, const void* t, int t_batch, int batch, float* out /*[batch,256]*/,
