@@ -793,6 +793,296 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel_v4(const __grid_co
   if (warp == 2) ptx::tmem_dealloc<1>(tmem, 512);
 }
 
+
+// =================================================================================================
+// v5: ONE 128-row query tile per CTA, 128-key blocks, DOUBLE-BUFFERED score tile.
+//
+// The two-tile kernels above are bound by the latency of the chain Q K^T -> softmax -> P V -> Q K^T (P aliases S, so
+// the next Q K^T of a tile cannot be issued before its P V; ~2100 cycles of hand-offs per block even with the
+// arithmetic removed), and v4's 64-key blocks halve the efficiency of the Q K^T instruction.  Here TMEM holds S[0],
+// S[1] (128 columns each) and O (128 columns) for a single tile: Q K^T of block j+2 goes into the buffer P V of block j
+// has just released, Q K^T of block j+1 is already done when the softmax warps finish block j, so they run back to
+// back and the tensor pipe only ever waits for the softmax THROUGHPUT (MUFU / issue), not for a round trip.
+//   warp 0 TMA (K ring of 3, V ring of 2), warp 1 MMA, warp 2 TMEM allocator, warps 4-7 softmax (thread = row).
+// =================================================================================================
+constexpr int kStagesK5 = 2, kStagesV5 = 3;
+constexpr int kThreads5 = 256;
+constexpr int kSmemTiles5 = 1 + kStagesK5 + kStagesV5;
+constexpr int kNumBars5 = 1 + 2 * kStagesK5 + 2 * kStagesV5 + 2 + 2 + 1 + 1;
+constexpr int kSmemBytes5 = kSmemTiles5 * kTileBytes + kNumBars5 * 8 + 16 + 1024;
+
+template <int kPolyMask8, int kDebug>
+__global__ void __launch_bounds__(kThreads5, 1) attn_tc_kernel_v5(const __grid_constant__ AttnParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint8_t* smem_q = smem;                                    // 1 tile
+  uint8_t* smem_k = smem + kTileBytes;                       // kStagesK5 tiles
+  uint8_t* smem_v = smem + (1 + kStagesK5) * kTileBytes;     // kStagesV5 tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemTiles5 * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + kStagesK5;
+  uint64_t* v_full = k_empty + kStagesK5;
+  uint64_t* v_empty = v_full + kStagesV5;
+  uint64_t* s_full = v_empty + kStagesV5;  // [2] score buffer written
+  uint64_t* p_full = s_full + 2;           // [2] P written into the score buffer
+  uint64_t* pv_done = p_full + 2;          // [1] P V of a block completed (lazy-rescale path only)
+  uint64_t* o_full = pv_done + 1;          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_qt = (P.S + BQ - 1) / BQ;
+  const int qt = blockIdx.x % n_qt;
+  const int bh = blockIdx.x / n_qt;
+  const int h = bh % P.heads, b = bh / P.heads;
+  const int q0 = qt * BQ;
+  const int n_kv = (P.S + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&P.tm);
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < kStagesK5; ++i) { ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < kStagesV5; ++i) { ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&p_full[i], 4); }
+    ptx::mbar_init(pv_done, 1);
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t kOCol = 256;  // S[0] = 0, S[1] = 128, O = 256
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      ptx::mbar_arrive_expect_tx(q_full, kTileBytes);
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub)
+        ptx::tma_load_3d(&P.tm, q_full, smem_q + sub * kSubBytes, P.q_col0 + h * HD + sub * 64, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int sk = j % kStagesK5, sv = j % kStagesV5;
+        ptx::mbar_wait(&k_empty[sk], ((j / kStagesK5) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&k_full[sk], kTileBytes);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d(&P.tm, &k_full[sk], smem_k + sk * kTileBytes + sub * kSubBytes, P.k_col0 + h * HD + sub * 64,
+                           j * BKV, b);
+        ptx::mbar_wait(&v_empty[sv], ((j / kStagesV5) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&v_full[sv], kTileBytes);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d(&P.tm, &v_full[sv], smem_v + sv * kTileBytes + sub * kSubBytes, P.v_col0 + h * HD + sub * 64,
+                           j * BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);  // A, B K-major
+    constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, HD, 0, 1);   // A from TMEM, B (= V) MN-major
+    const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_q), 0, 1024);
+    const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_k), 0, 1024);
+    const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_v), kSubBytes, 1024);
+    constexpr uint32_t kTile16 = kTileBytes >> 4, kSub16 = kSubBytes >> 4;
+    auto issue_qk = [&](int j) {
+      const uint64_t ka = k_desc + (uint64_t)((j % kStagesK5) * kTile16);
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        const uint32_t off = (kk >> 2) * kSub16 + (kk & 3) * 2;  // (addr >> 4) units
+        ptx::mma_bf16_ss<1>(tmem + (j & 1) * 128, q_desc + off, ka + off, idesc_qk, kk != 0 ? 1u : 0u);
+      }
+    };
+    auto issue_pv = [&](int j) {
+      const uint64_t va = v_desc + (uint64_t)((j % kStagesV5) * kTile16);
+#pragma unroll
+      for (int kk = 0; kk < BKV / 16; ++kk)
+        ptx::mma_bf16_ts(tmem + kOCol, tmem + (j & 1) * 128 + kk * 8, va + (uint64_t)(kk * 128), idesc_pv,
+                         (kk != 0 || j > 0) ? 1u : 0u);
+    };
+    ptx::mbar_wait(q_full, 0);
+    ptx::mbar_wait(&k_full[0], 0);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
+      issue_qk(0);
+      ptx::mma_commit(&s_full[0]);
+      ptx::mma_commit(&k_empty[0]);
+    }
+    __syncwarp();
+    if (n_kv > 1) {
+      ptx::mbar_wait(&k_full[1], 0);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        issue_qk(1);
+        ptx::mma_commit(&s_full[1]);
+        ptx::mma_commit(&k_empty[1]);
+      }
+      __syncwarp();
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      ptx::mbar_wait(&v_full[j % kStagesV5], (j / kStagesV5) & 1);
+      ptx::mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        issue_pv(j);
+        ptx::mma_commit(&v_empty[j % kStagesV5]);
+        ptx::mma_commit(pv_done);
+      }
+      __syncwarp();
+      const int nx = j + 2;  // its scores reuse the buffer P V of block j has just consumed
+      if (nx < n_kv) {
+        ptx::mbar_wait(&k_full[nx % kStagesK5], (nx / kStagesK5) & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          issue_qk(nx);
+          ptx::mma_commit(&s_full[nx & 1]);
+          ptx::mma_commit(&k_empty[nx % kStagesK5]);
+        }
+        __syncwarp();
+      }
+    }
+    if (ptx::elect_one()) ptx::mma_commit(o_full);
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== softmax warpgroup =====================
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t o_addr = tmem + lane_off + kOCol;
+    const float c = P.scale_log2;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t s_addr = tmem + lane_off + (j & 1) * 128;
+      ptx::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      const int n_valid = P.S - j * BKV;  // < 128 only on the last block
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      if (kDebug & 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s0[i] = s1[i] = s2[i] = s3[i] = 0x3f000000u + (uint32_t)(i + j);
+      } else {
+        ptx::tmem_ld_32x32b_x32(s_addr, s0);
+        ptx::tmem_ld_32x32b_x32(s_addr + 32, s1);
+        ptx::tmem_ld_32x32b_x32(s_addr + 64, s2);
+        ptx::tmem_ld_32x32b_x32(s_addr + 96, s3);
+        ptx::tmem_ld_wait();
+      }
+      if (n_valid < BKV) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= n_valid) s0[i] = 0xff800000u;  // -inf
+          if (32 + i >= n_valid) s1[i] = 0xff800000u;
+          if (64 + i >= n_valid) s2[i] = 0xff800000u;
+          if (96 + i >= n_valid) s3[i] = 0xff800000u;
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+        mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
+        mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+      }
+      const float mx_s = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+      if (j == 0) {
+        m_ref = mx_s;
+      } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
+        ptx::mbar_wait(pv_done, (j - 1) & 1);  // O may still be receiving P V of the previous block
+        ptx::tc_fence_after();
+        const float m_new = fmaxf(m_ref, mx_s);
+        const float f = ptx::ex2_approx(m_ref - m_new);
+        l *= f;
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(o_addr + ch * 16, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          ptx::tmem_st_32x32b_x16(o_addr + ch * 16, r);
+        }
+        m_ref = m_new;
+      }
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
+      float2 lsum = make_float2(0.f, 0.f);
+      auto exp_chunk = [&](const uint32_t (&sv)[32], int col) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, nm2);
+          float2 e;
+          if (kDebug & 2) {
+            e = x;
+          } else if ((kPolyMask8 >> (i & 7)) & 1) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = ptx::ex2_approx(x.x);
+            e.y = ptx::ex2_approx(x.y);
+          }
+          lsum = __fadd2_rn(lsum, e);
+          pk[i] = ptx::pack_bf16x2(e.x, e.y);
+        }
+        ptx::tmem_st_32x32b_x16(s_addr + col, pk);
+      };
+      exp_chunk(s0, 0);
+      exp_chunk(s1, 16);
+      exp_chunk(s2, 32);
+      exp_chunk(s3, 48);
+      l += lsum.x + lsum.y;
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[j & 1]);
+    }
+    // ---- epilogue: O / l -> bf16 -> shared (row-wise) -> global (2 rows x 256 B per warp instruction)
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    constexpr int kPitch = HD * 2 + 16;
+    uint8_t* stage = smem + (warp - 4) * (32 * kPitch);  // Q and K tiles are dead once o_full has fired
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      float v[32];
+      tmem_ld32(o_addr + ch * 32, v);
+      uint4* dst = reinterpret_cast<uint4*>(stage + lane * kPitch + ch * 64);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = ptx::pack_bf16x2(v[8 * i + 0] * inv, v[8 * i + 1] * inv);
+        u.y = ptx::pack_bf16x2(v[8 * i + 2] * inv, v[8 * i + 3] * inv);
+        u.z = ptx::pack_bf16x2(v[8 * i + 4] * inv, v[8 * i + 5] * inv);
+        u.w = ptx::pack_bf16x2(v[8 * i + 6] * inv, v[8 * i + 7] * inv);
+        dst[i] = u;
+      }
+    }
+    __syncwarp();
+    const int row0 = q0 + quad * 32;
+    const int rr = lane >> 4, cc = lane & 15;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int r = it * 2 + rr;
+      const int grow = row0 + r;
+      if (grow < P.S) {
+        bf16* orow;
+        if (P.sp_rows > 0) {
+          const int dest = grow / P.sp_rows;
+          orow = P.sp_out[dest] + (long long)b * P.out_bs + (long long)(grow - dest * P.sp_rows) * P.out_ld +
+                 P.out_col0 + h * HD;
+        } else {
+          orow = P.out + (long long)b * P.out_bs + (long long)grow * P.out_ld + P.out_col0 + h * HD;
+        }
+        *reinterpret_cast<uint4*>(orow + cc * 8) = *reinterpret_cast<const uint4*>(stage + r * kPitch + cc * 16);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<1>(tmem, 512);
+}
+
 }  // namespace
 
 bool attention_tc_supported(const AttnArgs& a, std::string* why) {
@@ -861,6 +1151,24 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
     for (int i = 0; i < kNumVariants4; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(table4[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
     attr_set = true;
+  }
+  // v5 kernels (one query tile per CTA, double-buffered 128-key score tile): variant 30 + i
+  static const KernelFn table5[] = {attn_tc_kernel_v5<0x88, 0>, attn_tc_kernel_v5<0x00, 0>, attn_tc_kernel_v5<0x92, 0>,
+                                    attn_tc_kernel_v5<0xAA, 0>, attn_tc_kernel_v5<0x80, 0>, attn_tc_kernel_v5<0, 1>,
+                                    attn_tc_kernel_v5<0, 2>,    attn_tc_kernel_v5<0, 3>};
+  constexpr int kNumVariants5 = sizeof(table5) / sizeof(table5[0]);
+  static bool attr5_set = false;
+  if (!attr5_set) {
+    for (int i = 0; i < kNumVariants5; ++i)
+      RT_CHECK_CUDA(cudaFuncSetAttribute(table5[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes5));
+    attr5_set = true;
+  }
+  if (variant >= 30) {
+    RT_REQUIRE(variant - 30 < kNumVariants5, "attention: unknown variant");
+    const long long grid5 = (long long)((a.S + BQ - 1) / BQ) * a.heads * a.batch;
+    table5[variant - 30]<<<(unsigned)grid5, kThreads5, kSmemBytes5, stream>>>(P);
+    RT_POST_LAUNCH();
+    return;
   }
   const long long grid = (long long)P.n_qpairs * a.heads * a.batch;
   if (variant >= 20) {

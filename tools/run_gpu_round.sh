@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-RT_OPTIONS=sp_replicate_mod=1 timeout 900 python -m pytest tests/test_sp_gpu.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python tools/mma_shape_probe.py > gpurun_out/mma_shape_probe.log 2>&1; cat gpurun_out/mma_shape_probe.log
