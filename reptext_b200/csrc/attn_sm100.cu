@@ -36,7 +36,8 @@ constexpr int kNumBars = 1 + 4 * kStages + 2 + 2 + 2 + 1;
 constexpr int kSmemBytes = kSmemTiles * kTileBytes + kNumBars * 8 + 16 + 1024;
 
 struct AttnParams {
-  CUtensorMap tm;  // (col, row, batch) over the qkv buffer, box (64, 128, 1), SWIZZLE_128B
+  CUtensorMap tm;   // (col, row, batch) over the qkv buffer, box (64, 128, 1), SWIZZLE_128B
+  CUtensorMap tmh;  // same tensor, box (64, 64, 1): half a K tile per CTA of a pair (v6)
   bf16* out;
   long long out_bs;
   int out_ld, out_col0;
@@ -1083,6 +1084,351 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_tc_kernel_v5(const __grid_c
   if (warp == 2) ptx::tmem_dealloc<1>(tmem, 512);
 }
 
+
+// =================================================================================================
+// v6: v5's structure on a CTA PAIR (tcgen05 cta_group::2).
+//
+// Timing experiments (r1) show every variant above ends at the same ~80 B/clk of shared-memory traffic per SM (MMA
+// operand reads + TMA writes): two query tiles per CTA read Q and K 4 KB each per MMA, one tile per CTA re-loads K / V
+// for half the rows.  With a 2-CTA MMA (M = 256) each CTA still owns ONE query tile (TMEM: S[0], S[1], O, so the
+// score tile is double-buffered and the softmax runs back to back, as in v5), but the B operands are split across the
+// pair: each CTA loads and holds only 64 of the 128 keys of a K tile and 64 of the 128 head-dim columns of a V tile.
+// Per CTA and 128-key block: Q K^T reads 6 KB per MMA instead of 8, P V reads 2 KB instead of 4, TMA writes 32 KB
+// instead of 64 - 96 KB of shared-memory traffic per tile and block against 128 KB (two-tile kernel) / 160 KB (v5).
+//   leader CTA: issues every MMA for the pair; both CTAs: TMA producer for their halves, softmax warpgroup (thread =
+//   row) for their own 128 query rows, P hand-off into the LEADER's barriers (remote arrive from the peer).
+// =================================================================================================
+constexpr int kStagesK6 = 4, kStagesV6 = 4;
+constexpr int kHalfTileBytes = kTileBytes / 2;  // 16 KB: half a K tile (64 keys) or half a V tile (64 columns)
+constexpr int kNumBars6 = 1 + 2 * kStagesK6 + 2 * kStagesV6 + 3 + 3 + 2 + 1 + 2;
+constexpr int kSmemBytes6 = kTileBytes + (kStagesK6 + kStagesV6) * kHalfTileBytes + kNumBars6 * 8 + 16 + 1024;
+
+template <int kPolyMask8, int kDebug, bool kTwoIssuers = false, int kNS = 2>
+__global__ void __launch_bounds__(kThreads5, 1) attn_tc_kernel_v6(const __grid_constant__ AttnParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint8_t* smem_q = smem;                                                  // this CTA's 128 x 128 query tile
+  uint8_t* smem_k = smem + kTileBytes;                                     // kStagesK6 x [64 keys x 128]
+  uint8_t* smem_v = smem + kTileBytes + kStagesK6 * kHalfTileBytes;        // kStagesV6 x [128 keys x 64 columns]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTileBytes + (kStagesK6 + kStagesV6) * kHalfTileBytes);
+  uint64_t* q_full = bars;                 // leader's: both CTAs' TMA bytes
+  uint64_t* k_full = bars + 1;             // leader's
+  uint64_t* k_empty = k_full + kStagesK6;  // each CTA's own (multicast commit)
+  uint64_t* v_full = k_empty + kStagesK6;  // leader's
+  uint64_t* v_empty = v_full + kStagesV6;  // each CTA's own
+  uint64_t* s_full = v_empty + kStagesV6;  // [kNS] each CTA's own (multicast commit)
+  uint64_t* p_full = s_full + 3;           // [kNS] leader's: 4 warps of each CTA
+  uint64_t* pv_done = p_full + 3;          // [2] each CTA's own; P V of block j commits pv_done[j & 1]
+  uint64_t* o_full = pv_done + 2;          // [1] each CTA's own
+  uint64_t* s_free = o_full + 1;           // [2] leader's: P V of a block has consumed the score buffer (kTwoIssuers)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int n_qp = (P.S + 2 * BQ - 1) / (2 * BQ);
+  const int pair = blockIdx.x >> 1;
+  const int qp = pair % n_qp;
+  const int bh = pair / n_qp;
+  const int h = bh % P.heads, b = bh / P.heads;
+  const int q0 = qp * 2 * BQ + (int)cta_rank * BQ;  // this CTA's query rows
+  const int n_kv = (P.S + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&P.tm);
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < kStagesK6; ++i) { ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < kStagesV6; ++i) { ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&p_full[i], 8); }
+    ptx::mbar_init(&pv_done[0], 1);
+    ptx::mbar_init(&pv_done[1], 1);
+    ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(&s_free[0], 1);
+    ptx::mbar_init(&s_free[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<2>(tmem_slot, 512);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t kOCol = kNS * 128;  // S[i] = i * 128, O behind them (kNS = 3 fills all 512 columns)
+  static_assert(kNS == 2 || kNS == 3, "2 or 3 score buffers");
+  static_assert(!kTwoIssuers || kNS == 2, "the two-issuer form is written for 2 score buffers");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs; the bytes land on the leader's full barriers) ==========
+      if (leader) ptx::mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub)
+        ptx::tma_load_3d_2sm(&P.tm, q_full, smem_q + sub * kSubBytes, P.q_col0 + h * HD + sub * 64, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int sk = j % kStagesK6, sv = j % kStagesV6;
+        // K: this CTA's 64 keys (rows) of the tile, both 64-column halves of the head dimension: box (64, 64)
+        ptx::mbar_wait(&k_empty[sk], ((j / kStagesK6) & 1) ^ 1);
+        if (leader) ptx::mbar_arrive_expect_tx(&k_full[sk], 2 * kHalfTileBytes);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d_2sm(&P.tmh, &k_full[sk], smem_k + sk * kHalfTileBytes + sub * (kHalfTileBytes / 2),
+                               P.k_col0 + h * HD + sub * 64, j * BKV + (int)cta_rank * (BKV / 2), b);
+        // V: all 128 keys, this CTA's 64 head-dim columns: box (64, 128)
+        ptx::mbar_wait(&v_empty[sv], ((j / kStagesV6) & 1) ^ 1);
+        if (leader) ptx::mbar_arrive_expect_tx(&v_full[sv], 2 * kHalfTileBytes);
+        ptx::tma_load_3d_2sm(&P.tm, &v_full[sv], smem_v + sv * kHalfTileBytes, P.v_col0 + h * HD + (int)cta_rank * 64,
+                             j * BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer (leader CTA, for the pair) =====================
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(2 * BQ, BKV, 0, 0);  // 256 x 128, A and B K-major
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(2 * BQ, HD, 0, 1);   // A (= P) from TMEM, B (= V) MN-major
+      const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_q), 0, 1024);
+      const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_k), 0, 1024);
+      const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_v), 0, 1024);
+      constexpr uint32_t kHalf16 = kHalfTileBytes >> 4, kQSub16 = kSubBytes >> 4, kKSub16 = (kHalfTileBytes / 2) >> 4;
+      auto issue_qk = [&](int j) {
+        const uint64_t ka = k_desc + (uint64_t)((j % kStagesK6) * kHalf16);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t qoff = (kk >> 2) * kQSub16 + (kk & 3) * 2;  // (addr >> 4) units
+          const uint32_t koff = (kk >> 2) * kKSub16 + (kk & 3) * 2;
+          ptx::mma_bf16_ss<2>(tmem + (j % kNS) * 128, q_desc + qoff, ka + koff, idesc_qk, kk != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int j) {
+        const uint64_t va = v_desc + (uint64_t)((j % kStagesV6) * kHalf16);
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk)
+          ptx::mma_bf16_ts_2sm(tmem + kOCol, tmem + (j % kNS) * 128 + kk * 8, va + (uint64_t)(kk * 128), idesc_pv,
+                               (kk != 0 || j > 0) ? 1u : 0u);
+      };
+      ptx::mbar_wait(q_full, 0);
+      for (int j0 = 0; j0 < kNS && j0 < n_kv; ++j0) {
+        ptx::mbar_wait(&k_full[j0 % kStagesK6], (j0 / kStagesK6) & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          issue_qk(j0);
+          ptx::mma_commit_2sm(&s_full[j0 % kNS], 3);
+          ptx::mma_commit_2sm(&k_empty[j0 % kStagesK6], 3);
+        }
+        __syncwarp();
+      }
+      if constexpr (kTwoIssuers) {
+        // this warp only issues Q K^T; warp 3 issues P V and tells us (s_free) when a score buffer may be overwritten
+        for (int nx = 2; nx < n_kv; ++nx) {
+          ptx::mbar_wait(&k_full[nx % kStagesK6], (nx / kStagesK6) & 1);
+          ptx::mbar_wait(&s_free[nx & 1], ((nx >> 1) - 1) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            issue_qk(nx);
+            ptx::mma_commit_2sm(&s_full[nx & 1], 3);
+            ptx::mma_commit_2sm(&k_empty[nx % kStagesK6], 3);
+          }
+          __syncwarp();
+        }
+      } else {
+      for (int j = 0; j < n_kv; ++j) {
+        ptx::mbar_wait(&v_full[j % kStagesV6], (j / kStagesV6) & 1);
+        ptx::mbar_wait(&p_full[j % kNS], (j / kNS) & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          issue_pv(j);
+          ptx::mma_commit_2sm(&v_empty[j % kStagesV6], 3);
+          ptx::mma_commit_2sm(&pv_done[j & 1], 3);
+        }
+        __syncwarp();
+        const int nx = j + kNS;  // its scores reuse the buffer P V of block j has just consumed
+        if (nx < n_kv) {
+          ptx::mbar_wait(&k_full[nx % kStagesK6], (nx / kStagesK6) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            issue_qk(nx);
+            ptx::mma_commit_2sm(&s_full[nx % kNS], 3);
+            ptx::mma_commit_2sm(&k_empty[nx % kStagesK6], 3);
+          }
+          __syncwarp();
+        }
+      }
+      }
+      if constexpr (!kTwoIssuers) {
+        if (ptx::elect_one()) ptx::mma_commit_2sm(o_full, 3);
+        __syncwarp();
+      }
+    }
+  } else if (warp == 3) {
+    if constexpr (kTwoIssuers) {
+      if (leader) {
+        // ===================== second MMA issuer: P V =====================
+        constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(2 * BQ, HD, 0, 1);
+        const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_v), 0, 1024);
+        constexpr uint32_t kHalf16 = kHalfTileBytes >> 4;
+        for (int j = 0; j < n_kv; ++j) {
+          ptx::mbar_wait(&v_full[j % kStagesV6], (j / kStagesV6) & 1);
+          ptx::mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint64_t va = v_desc + (uint64_t)((j % kStagesV6) * kHalf16);
+#pragma unroll
+            for (int kk = 0; kk < BKV / 16; ++kk)
+              ptx::mma_bf16_ts_2sm(tmem + kOCol, tmem + (j & 1) * 128 + kk * 8, va + (uint64_t)(kk * 128), idesc_pv,
+                                   (kk != 0 || j > 0) ? 1u : 0u);
+            ptx::mma_commit(&s_free[j & 1]);  // leader-local: the Q K^T warp may reuse this score buffer
+            ptx::mma_commit_2sm(&v_empty[j % kStagesV6], 3);
+            ptx::mma_commit_2sm(&pv_done[j & 1], 3);
+          }
+          __syncwarp();
+        }
+        if (ptx::elect_one()) ptx::mma_commit_2sm(o_full, 3);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax warpgroup (this CTA's 128 query rows) =====================
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t o_addr = tmem + lane_off + kOCol;
+    const float c = P.scale_log2;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t s_addr = tmem + lane_off + (j % kNS) * 128;
+      ptx::mbar_wait(&s_full[j % kNS], (j / kNS) & 1);
+      ptx::tc_fence_after();
+      const int n_valid = P.S - j * BKV;  // < 128 only on the last block
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      if (kDebug & 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s0[i] = s1[i] = s2[i] = s3[i] = 0x3f000000u + (uint32_t)(i + j);
+      } else {
+        ptx::tmem_ld_32x32b_x32(s_addr, s0);
+        ptx::tmem_ld_32x32b_x32(s_addr + 32, s1);
+        ptx::tmem_ld_32x32b_x32(s_addr + 64, s2);
+        ptx::tmem_ld_32x32b_x32(s_addr + 96, s3);
+        ptx::tmem_ld_wait();
+      }
+      if (n_valid < BKV) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= n_valid) s0[i] = 0xff800000u;  // -inf
+          if (32 + i >= n_valid) s1[i] = 0xff800000u;
+          if (64 + i >= n_valid) s2[i] = 0xff800000u;
+          if (96 + i >= n_valid) s3[i] = 0xff800000u;
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+        mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
+        mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+      }
+      const float mx_s = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+      if (j == 0) {
+        m_ref = mx_s;
+      } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
+        // O may still be receiving P V of the previous block(s): with kNS score buffers up to kNS - 1 of them are
+        // outstanding.  One barrier per block parity keeps every wait within one phase of its barrier.
+        ptx::mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        if (j >= 2) ptx::mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);
+        ptx::tc_fence_after();
+        const float m_new = fmaxf(m_ref, mx_s);
+        const float f = ptx::ex2_approx(m_ref - m_new);
+        l *= f;
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(o_addr + ch * 16, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          ptx::tmem_st_32x32b_x16(o_addr + ch * 16, r);
+        }
+        m_ref = m_new;
+      }
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
+      float2 lsum = make_float2(0.f, 0.f);
+      auto exp_chunk = [&](const uint32_t (&sv)[32], int col) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, nm2);
+          float2 e;
+          if (kDebug & 2) {
+            e = x;
+          } else if ((kPolyMask8 >> (i & 7)) & 1) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = ptx::ex2_approx(x.x);
+            e.y = ptx::ex2_approx(x.y);
+          }
+          lsum = __fadd2_rn(lsum, e);
+          pk[i] = ptx::pack_bf16x2(e.x, e.y);
+        }
+        ptx::tmem_st_32x32b_x16(s_addr + col, pk);
+      };
+      exp_chunk(s0, 0);
+      exp_chunk(s1, 16);
+      exp_chunk(s2, 32);
+      exp_chunk(s3, 48);
+      l += lsum.x + lsum.y;
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(&p_full[j % kNS]);
+        else ptx::mbar_arrive_cluster_relaxed(&p_full[j % kNS], 0);
+      }
+    }
+    // ---- epilogue: O / l -> bf16 -> shared (row-wise) -> global (2 rows x 256 B per warp instruction)
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    constexpr int kPitch = HD * 2 + 16;
+    uint8_t* stage = smem + (warp - 4) * (32 * kPitch);  // Q and K tiles are dead once o_full has fired
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      float v[32];
+      tmem_ld32(o_addr + ch * 32, v);
+      uint4* dst = reinterpret_cast<uint4*>(stage + lane * kPitch + ch * 64);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = ptx::pack_bf16x2(v[8 * i + 0] * inv, v[8 * i + 1] * inv);
+        u.y = ptx::pack_bf16x2(v[8 * i + 2] * inv, v[8 * i + 3] * inv);
+        u.z = ptx::pack_bf16x2(v[8 * i + 4] * inv, v[8 * i + 5] * inv);
+        u.w = ptx::pack_bf16x2(v[8 * i + 6] * inv, v[8 * i + 7] * inv);
+        dst[i] = u;
+      }
+    }
+    __syncwarp();
+    const int row0 = q0 + quad * 32;
+    const int rr = lane >> 4, cc = lane & 15;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int r = it * 2 + rr;
+      const int grow = row0 + r;
+      if (grow < P.S) {
+        bf16* orow;
+        if (P.sp_rows > 0) {
+          const int dest = grow / P.sp_rows;
+          orow = P.sp_out[dest] + (long long)b * P.out_bs + (long long)(grow - dest * P.sp_rows) * P.out_ld +
+                 P.out_col0 + h * HD;
+        } else {
+          orow = P.out + (long long)b * P.out_bs + (long long)grow * P.out_ld + P.out_col0 + h * HD;
+        }
+        *reinterpret_cast<uint4*>(orow + cc * 8) = *reinterpret_cast<const uint4*>(stage + r * kPitch + cc * 16);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 2) ptx::tmem_dealloc<2>(tmem, 512);
+}
+
 }  // namespace
 
 bool attention_tc_supported(const AttnArgs& a, std::string* why) {
@@ -1114,6 +1460,8 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
   uint64_t strides[2] = {(uint64_t)a.ld * 2, (uint64_t)a.batch_stride * 2};
   uint32_t box[3] = {64, 128, 1};
   encode_tmap_bf16(&P.tm, a.qkv, 3, dims, strides, box);
+  uint32_t box_half[3] = {64, 64, 1};
+  encode_tmap_bf16(&P.tmh, a.qkv, 3, dims, strides, box_half);
   P.out = reinterpret_cast<bf16*>(a.out);
   P.out_bs = a.out_batch_stride; P.out_ld = a.out_ld; P.out_col0 = a.out_col0;
   P.q_col0 = a.q_col0; P.k_col0 = a.k_col0; P.v_col0 = a.v_col0;
@@ -1162,6 +1510,40 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
     for (int i = 0; i < kNumVariants5; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(table5[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes5));
     attr5_set = true;
+  }
+  // v6 kernels (CTA pair, cta_group::2; one query tile per CTA, K / V halves split across the pair): variant 40 + i
+  static const KernelFn table6[] = {attn_tc_kernel_v6<0x88, 0>, attn_tc_kernel_v6<0x00, 0>, attn_tc_kernel_v6<0x92, 0>,
+                                    attn_tc_kernel_v6<0xAA, 0>, attn_tc_kernel_v6<0x80, 0>, attn_tc_kernel_v6<0, 1>,
+                                    attn_tc_kernel_v6<0, 2>,    attn_tc_kernel_v6<0, 3>,
+                                    attn_tc_kernel_v6<0x88, 0, true>, attn_tc_kernel_v6<0x00, 0, true>,  // 48, 49: two MMA issuers
+                                    attn_tc_kernel_v6<0xAA, 0, true>, attn_tc_kernel_v6<0, 3, true>,
+                                    attn_tc_kernel_v6<0x88, 0, false, 3>, attn_tc_kernel_v6<0x00, 0, false, 3>,  // 52.. three score buffers
+                                    attn_tc_kernel_v6<0xAA, 0, false, 3>, attn_tc_kernel_v6<0, 3, false, 3>};
+  constexpr int kNumVariants6 = sizeof(table6) / sizeof(table6[0]);
+  static bool attr6_set = false;
+  if (!attr6_set) {
+    for (int i = 0; i < kNumVariants6; ++i)
+      RT_CHECK_CUDA(cudaFuncSetAttribute(table6[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes6));
+    attr6_set = true;
+  }
+  if (variant >= 40) {
+    RT_REQUIRE(variant - 40 < kNumVariants6, "attention: unknown variant");
+    const long long pairs = (long long)P.n_qpairs * a.heads * a.batch;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kThreads5);
+    cfg.dynamicSmemBytes = kSmemBytes6;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, table6[variant - 40], P));
+    count_launch();
+    return;
   }
   if (variant >= 30) {
     RT_REQUIRE(variant - 30 < kNumVariants5, "attention: unknown variant");
