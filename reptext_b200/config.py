@@ -56,6 +56,7 @@ SMALL128_CONTROLNET = dict(
 # eight heads of 128: the smallest pair whose heads shard over 2, 4 and 8 ranks (sequence-parallel tests)
 SP8_TRANSFORMER = dict(SMALL128_TRANSFORMER, num_attention_heads=8, num_layers=1, num_single_layers=2)
 SP8_CONTROLNET = dict(SMALL128_CONTROLNET, num_attention_heads=8, num_layers=1)
+SP8_INPAINT_CONTROLNET = dict(SP8_CONTROLNET, extra_condition_channels=4)
 
 SMALL128_INPAINT_CONTROLNET = dict(SMALL128_CONTROLNET, extra_condition_channels=4)
 

@@ -53,11 +53,36 @@ def main():
     multi = run()
     multi2 = run()                          # the epoch counters keep growing across calls
     pipe.enable_sequence_parallel(None)
+    # ---- the inpaint pipeline (second ControlNet, true CFG at effective batch 2) the same way
+    from reptext_b200.pipeline_flux_controlnet_inpaint import FluxControlNetPipeline as InpaintPipeline
+    cni = models.FluxControlNetModel.random_init(config.SP8_INPAINT_CONTROLNET, seed=103, dtype=dt, device=dev)
+    ipipe = InpaintPipeline(FlowMatchEulerDiscreteScheduler(), SyntheticVAE(dtype=dt, device=dev),
+                            SyntheticTextEncoders(TR["joint_attention_dim"], TR["pooled_projection_dim"], dt, dev),
+                            None, None, None, tr, cn, cni)
+    npe = torch.randn(1, T, TR["joint_attention_dim"], generator=g).to(dt)
+    npo = torch.randn(1, TR["pooled_projection_dim"], generator=g).to(dt)
+    src = torch.rand(1, 3, H, W, generator=g) * 2 - 1
+
+    def run_inpaint():
+        torch.manual_seed(7)                # the VAE posterior is sampled with the global RNG
+        return ipipe(prompt_embeds=pe, pooled_prompt_embeds=po, negative_prompt_embeds=npe,
+                     negative_pooled_prompt_embeds=npo, height=H, width=W, num_inference_steps=3, guidance_scale=3.5,
+                     true_guidance_scale=3.0, control_image=[canny], control_position=[pos], control_mask=[mask_img],
+                     control_glyph=src, control_image_inpaint=src, control_mask_inpaint=mask_img,
+                     controlnet_conditioning_scale=1.0, controlnet_conditioning_scale_inpaint=0.8,
+                     generator=torch.Generator(device=dev).manual_seed(11), output_type="latent").images
+
+    i_single = run_inpaint()
+    ipipe.enable_sequence_parallel(sp)
+    i_multi = run_inpaint()
+    ipipe.enable_sequence_parallel(None)
+    i_err = rel_l2(i_multi, i_single)
+    print(f"[rank {rank}] inpaint sp world={world} rel_l2 vs single GPU = {i_err:.3e}", flush=True)
     err = rel_l2(multi, single)
     finite, repeat = torch.isfinite(multi.float()).all().item(), torch.equal(multi, multi2)
     print(f"[rank {rank}] sp world={world} rel_l2 vs single GPU = {err:.3e} finite={finite} repeatable={repeat} "
           f"rel_l2(run2, run1)={rel_l2(multi2, multi):.3e}", flush=True)
-    ok = finite and err < 1e-2 and repeat
+    ok = finite and err < 1e-2 and repeat and i_err < 1e-2 and torch.isfinite(i_multi.float()).all().item()
     flag = torch.tensor([int(ok)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     # every rank holds the same gathered latents
