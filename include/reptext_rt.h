@@ -58,6 +58,7 @@ RT_API long long rt_launch_count(void); /* number of this library's kernels laun
 /* options: "force_simt" (0/1), "gemm_cta_group" (0 auto, 1, 2), "attn_variant" (0 auto, ...), "profile" (0/1);
  * A/B and timing aids: "ln_warp_rows" (1 = warp-per-row LayerNorm), "gemv_single_row" (1 = one row per warp), "mod_inline" (1 = AdaLN GEMV on the caller's stream instead of the
  * side stream), "sp_replicate_mod" (1 = sequence-parallel ranks each compute all AdaLN rows instead of a row shard),
+ * "no_pdl" (1 = plain stream-ordered launches instead of programmatic dependent launch),
  * "gemm_debug" (bit 1: no epilogue, bit 2: k-block 0 only - timing experiments with WRONG results;
  * bit 4: direct row-per-thread epilogue stores instead of the staged coalesced ones - same results) */
 RT_API int rt_set_option(const char* name, int value);

@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  ptx::grid_launch_dependents();  // programmatic dependent launch: nothing above reads the previous kernel's output
+  ptx::grid_dependency_wait();
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -1558,7 +1560,19 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
     table4[variant - 20]<<<(unsigned)grid, kThreads, kSmemBytes4, stream>>>(P);
   } else {
     RT_REQUIRE(variant >= 0 && variant < kNumVariants, "attention: unknown variant");
-    table[variant]<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(P);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = get_option("no_pdl") ? 0 : 1;
+    RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, table[variant], P));
+    count_launch();
+    return;
   }
   RT_POST_LAUNCH();
 }

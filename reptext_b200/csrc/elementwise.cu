@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ln_mod_cta_kernel(con
   };
   if (lin_begin >= lin_end) return;
   locate(lin_begin);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // programmatic dependent launch (see ptx_sm100.cuh)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   load_mod();
 
   RawVec<T> cur[kR], nxt[kR];
@@ -344,12 +346,24 @@ void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out
       rpc = (rpc + kR - 1) / kR * kR;
       const long long grid = (total + rpc - 1) / rpc;
       RT_REQUIRE(total < (1ll << 31), "ln_mod: too many rows");
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)grid);
+      cfg.blockDim = dim3(cta_threads);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = get_option("no_pdl") ? 0 : 1;
+      const T* xp = (const T*)x;
+      T* op = (T*)out;
+      const int rpc_i = (int)rpc;
       if (cta_threads <= 384)
-        ln_mod_cta_kernel<T, 384, 2><<<(int)grid, cta_threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld,
-                                                                            batch, rows_total, D, G, (int)rpc);
+        RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_mod_cta_kernel<T, 384, 2>, xp, x_bs, x_ld, op, o_bs, o_ld, batch,
+                                         rows_total, D, G, rpc_i));
       else
-        ln_mod_cta_kernel<T, 1024, 1><<<(int)grid, cta_threads, 0, stream>>>((const T*)x, x_bs, x_ld, (T*)out, o_bs, o_ld,
-                                                                             batch, rows_total, D, G, (int)rpc);
+        RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_mod_cta_kernel<T, 1024, 1>, xp, x_bs, x_ld, op, o_bs, o_ld, batch,
+                                         rows_total, D, G, rpc_i));
       RT_POST_LAUNCH();
       return;
     }

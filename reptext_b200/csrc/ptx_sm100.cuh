@@ -43,6 +43,11 @@ __device__ __forceinline__ void cluster_sync() {
   cluster_arrive();
   cluster_wait();
 }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (prologue: barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the stream is still
+// draining; it must not touch the predecessor's output before grid_dependency_wait().
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -1,4 +1,11 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-RT_OPTIONS=attn_variant=52 timeout 300 python -m pytest tests/test_ops_gpu.py -m gpu -x -q -k attention 2>&1 | tail -5 > gpurun_out/r1m_tests.log; cat gpurun_out/r1m_tests.log
-timeout 200 python tools/attn_sweep.py 2,42,49,54,55,56,57 > gpurun_out/attn_sweep10.log 2>&1; cat gpurun_out/attn_sweep10.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r1n_tests.log; cat gpurun_out/r1n_tests.log
+for o in none no_pdl=1 none no_pdl=1; do
+RT_OPTIONS=$([ $o = none ] && echo "" || echo $o) timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench14_$o.json 2> gpurun_out/bench14_$o.err
+python - <<EOF
+import json
+d=json.loads([l for l in open('gpurun_out/bench14_$o.json') if l.startswith('{')][-1])
+print('$o', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value'],3), d['clocks']['sm_mhz'], {k:(round(v['ms_per_step'],2), round(v['achieved'] or 0)) for k,v in d['breakdown'].items()})
+EOF
+done
