@@ -37,6 +37,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __global__ void sp_barrier_kernel(const BarrierParams p) {
   unsigned long long* mine = p.flags[p.rank];
   const int lane = threadIdx.x;
+  // programmatic dependent launch: this kernel may be resident before its predecessor has finished; the peer
+  // stores it publishes are only complete after this wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   unsigned long long epoch = 0;
   if (lane == 0) {
     epoch = mine[8] + 1;
@@ -70,8 +74,17 @@ void launch_sp_barrier(const rt_sp_group& g, cudaStream_t stream) {
     RT_REQUIRE(g.peer_flags[i], "sp group: null flag pointer");
     p.flags[i] = g.peer_flags[i];
   }
-  sp_barrier_kernel<<<1, 32, 0, stream>>>(p);
-  RT_POST_LAUNCH();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(32);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = get_option("no_pdl") ? 0 : 1;
+  RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sp_barrier_kernel, p));
+  count_launch();
 }
 
 }  // namespace rt
