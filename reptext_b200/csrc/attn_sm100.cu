@@ -262,7 +262,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t s_addr = tmem + lane_off + t * 128;
     const uint32_t o_addr = tmem + lane_off + 256 + t * 128;
-    const int row = q0 + t * BQ + quad * 32 + lane;
     const float c = P.scale_log2;
     float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
@@ -418,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
           float p0 = fmaf(__uint_as_float(SV[2 * i]), c, -m_ref);                            \
           float p1 = fmaf(__uint_as_float(SV[2 * i + 1]), c, -m_ref);                        \
           if (!(kDebug & 1)) {                                                               \
-            if (kPolyEvery > 0 && (i % kPolyEvery) == kPolyEvery - 1) {                      \
+            if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) { \
               p0 = exp2_poly(p0); p1 = exp2_poly(p1);                                        \
             } else {                                                                         \
               p0 = ptx::ex2_approx(p0); p1 = ptx::ex2_approx(p1);                            \

@@ -411,7 +411,7 @@ void double_block_post(const Ctx& c, const DoubleBlk& k, const void* extra) {
 // image rows (problem rows >= T).
 void single_block_pre(const Ctx& c, const SingleBlk& k) {
   const Workspace& w = c.ws;
-  const int D = c.D, T = c.T, N = c.N, S = c.S, ld = c.m.mod_total;
+  const int D = c.D, S = c.S, ld = c.m.mod_total;
   const float* md = w.mod + k.mod;
   const long long sD = c.sD(), s5D = 5 * sD;
   {

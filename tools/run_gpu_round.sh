@@ -1,11 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r1n_tests.log; cat gpurun_out/r1n_tests.log
-for o in none no_pdl=1 none no_pdl=1; do
-RT_OPTIONS=$([ $o = none ] && echo "" || echo $o) timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench14_$o.json 2> gpurun_out/bench14_$o.err
-python - <<EOF
-import json
-d=json.loads([l for l in open('gpurun_out/bench14_$o.json') if l.startswith('{')][-1])
-print('$o', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value'],3), d['clocks']['sm_mhz'], {k:(round(v['ms_per_step'],2), round(v['achieved'] or 0)) for k,v in d['breakdown'].items()})
-EOF
-done
+python __graft_entry__.py --smoke 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; cut -c1-330 gpurun_out/bench_final.json
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_final_ref.json 2> gpurun_out/bench_final_ref.err; cut -c1-330 gpurun_out/bench_final_ref.json
