@@ -133,3 +133,56 @@ def test_full_size_euler_with_zero_velocity_is_identity(full):
     from reptext_b200 import ops
     x = full["x"]
     assert torch.equal(ops.euler_step(torch.zeros_like(x["lat"]), x["lat"], 0.62, 0.57), x["lat"])
+
+
+def test_full_size_pipeline_trajectory_matches_the_oracle_loop(full):
+    """The public T2I __call__ at 1024x1024 with TWO text lines (two ControlNet passes per step, fused mask and sum),
+    6 free-running Euler steps, against the oracle's loop (RepText/pipeline_flux_controlnet.py:1017-1130 restated) on the
+    tensors the pipeline itself prepared: the latents after EVERY step must stay within 1e-2."""
+    import numpy as np
+    from oracle import flux_oracle as O
+    from reptext_b200.pipeline_flux_controlnet import FluxControlNetPipeline
+    from reptext_b200.pipeline_utils import SyntheticTextEncoders, SyntheticVAE
+    from reptext_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    from util import box_mask
+    tr, cn, x, TR, CN = full["tr"], full["cn"], full["x"], full["TR"], full["CN"]
+    dt, dev = torch.bfloat16, torch.device("cuda")
+    pipe = FluxControlNetPipeline(FlowMatchEulerDiscreteScheduler(), SyntheticVAE(dtype=dt, device=dev),
+                                  SyntheticTextEncoders(4096, 768, dt, dev), None, None, None, tr, cn)
+    box = {}
+    inner = pipe._denoise
+
+    def wrapped(**kw):
+        box.update({k: (v.clone() if torch.is_tensor(v) else v) for k, v in kw.items()})
+        return inner(**kw)
+
+    pipe._denoise = wrapped
+    g = torch.Generator().manual_seed(9)
+    cannys = [torch.rand(1, 3, H, W, generator=g) * 2 - 1 for _ in range(2)]
+    masks = [box_mask(H, W, (200, 330, 150, 870)), box_mask(H, W, (520, 640, 220, 800))]
+    poss = [(torch.from_numpy(m)[None, None].float() / 255.0) * 2 - 1 for m in masks]
+    steps, taps = 6, []
+    out = pipe(prompt_embeds=x["pe"], pooled_prompt_embeds=x["po"], height=H, width=W, num_inference_steps=steps,
+               guidance_scale=3.5, control_image=cannys, control_position=poss, control_mask=masks,
+               controlnet_conditioning_scale=0.9, latents=x["lat"].clone(), output_type="latent",
+               callback_on_step_end=lambda p, i, t, k: taps.append(k["latents"].float()) or {})
+    assert out.images.shape == (1, N, 64) and len(taps) == steps
+    f = lambda v: v.float()
+    ts, sg = O.make_sigmas(steps, N)
+    want = []
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            O.denoise_t2i(_F32View(tr.state_dict()), TR, _F32View(cn.state_dict()), CN, latents=f(box["latents"]),
+                          prompt_embeds=f(box["prompt_embeds"]), pooled=f(box["pooled_prompt_embeds"]),
+                          control_image_list=[f(c) for c in box["control_image_list"]],
+                          control_mask_list=[f(m) for m in box["control_mask_list"]], text_ids=f(box["text_ids"]),
+                          img_ids=f(box["latent_image_ids"]), timesteps=ts.to(dev), sigmas=sg.to(dev), guidance_scale=3.5,
+                          conditioning_scale=0.9, conditioning_step=30, callback=lambda i, t, lat: want.append(lat.clone()),
+                          time_dtype=dt)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    errs = [rel_l2(a, b) for a, b in zip(taps, want)]
+    print("full size, 2 text lines, free-running latents rel-L2 per step:", " ".join(f"{e:.2e}" for e in errs))
+    assert max(errs) < 1e-2, errs
