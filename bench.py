@@ -375,10 +375,14 @@ def run_b200(args, wl):
                         peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)",
                         frac_of_burst=ach / pk["bf16_burst"], launches=gem[2], ms_per_step=gem[0] / args.steps,
                         flops_per_step=gem[1] / args.steps)
-        breakdown = {k: dict(ms_per_step=v[0] / args.steps, launches_per_step=v[2] / args.steps,
-                             achieved=(v[1] / (v[0] / 1000.0) / (1e12 if "gemm" in k or "attention" in k else 1e9)) if v[0] else None,
-                             unit="TFLOP/s" if ("gemm" in k or "attention" in k) else "GB/s")
-                     for k, v in prof.items()}
+        def _cls(k, v):
+            tensor = "gemm" in k or "attention" in k
+            ach = (v[1] / (v[0] / 1000.0) / (1e12 if tensor else 1e9)) if v[0] else None
+            peak = pk["bf16_sustained"] if tensor else pk["hbm"]
+            return dict(ms_per_step=v[0] / args.steps, launches_per_step=v[2] / args.steps, achieved=ach,
+                        unit="TFLOP/s" if tensor else "GB/s", bound="tensor" if tensor else "hbm", peak=peak,
+                        frac=(ach / peak) if ach else None)
+        breakdown = {k: _cls(k, v) for k, v in prof.items()}   # every kernel class against its own roofline
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
