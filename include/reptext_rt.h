@@ -56,7 +56,8 @@ RT_API int rt_abi_version(void);
 RT_API int rt_struct_size(int which);
 RT_API long long rt_launch_count(void); /* number of this library's kernels launched so far (process-wide) */
 /* options: "force_simt" (0/1), "gemm_cta_group" (0 auto, 1, 2), "attn_variant" (0 auto, ...), "profile" (0/1);
- * A/B and timing aids: "ln_warp_rows" (1 = warp-per-row LayerNorm), "gemv_single_row" (1 = one row per warp), "mod_inline" (1 = AdaLN GEMV on the caller's stream instead of the
+ * A/B and timing aids: "ln_impl" (0 = warp-per-row-pair LayerNorm, 1 = the CTA form), "ln_warp_rows" (with ln_impl 1: 1 = the first
+ * warp-per-row form), "gemv_single_row" (1 = one row per warp), "mod_inline" (1 = AdaLN GEMV on the caller's stream instead of the
  * side stream), "sp_replicate_mod" (1 = sequence-parallel ranks each compute all AdaLN rows instead of a row shard),
  * "no_pdl" (1 = plain stream-ordered launches instead of programmatic dependent launch),
  * "gemm_debug" (bit 1: no epilogue, bit 2: k-block 0 only - timing experiments with WRONG results;

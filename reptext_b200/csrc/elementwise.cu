@@ -316,6 +316,141 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ln_mod_cta_kernel(con
   }
 }
 
+
+// v3: one warp per PAIR of rows, no block-wide reductions.  The CTA stages (1 + scale) and shift for its (batch, group)
+// in shared memory once (fp32, 8 D bytes), then each of its warps takes two rows: all 2 x kV 16-byte row loads are
+// issued up front, mean and variance are warp-shuffle reductions over registers (two-pass), and the modulation
+// vectors are read from shared memory once for both rows.  ~470 instructions per lane and row, no __syncthreads in
+// the row loop.  bf16, D a multiple of 256 and <= 4096.
+struct LnSeg {  // one (batch, group) segment of rows and the CTAs that process it
+  int batch, row_begin, row_end, cta_begin;
+  const float *scale, *shift;
+};
+constexpr int kLnMaxSegs = 16;
+struct LnSegs {
+  int n, rows_per_cta;
+  LnSeg s[kLnMaxSegs];
+};
+
+template <int kV>
+__global__ void __launch_bounds__(256, 1) ln_mod_rows2_kernel(const bf16* __restrict__ x, long long x_bs, int x_ld,
+                                                              bf16* __restrict__ out, long long o_bs, int o_ld, int D,
+                                                              const LnSegs segs) {
+  extern __shared__ float ln_smem[];  // [D] 1 + scale | [D] shift
+  float* s_sc = ln_smem;
+  float* s_sh = ln_smem + D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // which segment does this CTA belong to?  (static indices: the table stays in the constant bank)
+  int b = 0, r0 = 0, r_end = 0;
+  const float *gsc = nullptr, *gsh = nullptr;
+#pragma unroll
+  for (int i = 0; i < kLnMaxSegs; ++i) {
+    if (i < segs.n && (int)blockIdx.x >= segs.s[i].cta_begin) {
+      b = segs.s[i].batch;
+      r0 = segs.s[i].row_begin + ((int)blockIdx.x - segs.s[i].cta_begin) * segs.rows_per_cta;
+      r_end = segs.s[i].row_end;
+      gsc = segs.s[i].scale;
+      gsh = segs.s[i].shift;
+    }
+  }
+  r_end = min(r_end, r0 + segs.rows_per_cta);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // programmatic dependent launch (see ptx_sm100.cuh)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    const float4 a = *reinterpret_cast<const float4*>(gsc + i);
+    const float4 h = *reinterpret_cast<const float4*>(gsh + i);
+    *reinterpret_cast<float4*>(s_sc + i) = make_float4(1.f + a.x, 1.f + a.y, 1.f + a.z, 1.f + a.w);
+    *reinterpret_cast<float4*>(s_sh + i) = h;
+  }
+  __syncthreads();
+  const float inv_d = 1.f / (float)D;
+  for (int r = r0 + warp * 2; r < r_end; r += (blockDim.x >> 5) * 2) {
+    const bool two = r + 1 < r_end;
+    const bf16* xa = x + (long long)b * x_bs + (long long)r * x_ld + lane * 8;
+    const bf16* xb = xa + (two ? x_ld : 0);
+    uint4 ra[kV], rb[kV];
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      ra[i] = *reinterpret_cast<const uint4*>(xa + i * 256);
+      rb[i] = *reinterpret_cast<const uint4*>(xb + i * 256);
+    }
+    auto lo = [](uint32_t w) { return __uint_as_float(w << 16); };
+    auto hi = [](uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); };
+    float2 sa = f2(0.f, 0.f), sb = f2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const uint32_t wa[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w}, wb[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sa = __fadd2_rn(sa, f2(lo(wa[j]), hi(wa[j])));
+        sb = __fadd2_rn(sb, f2(lo(wb[j]), hi(wb[j])));
+      }
+    }
+    const float mean_a = warp_sum(sa.x + sa.y) * inv_d, mean_b = warp_sum(sb.x + sb.y) * inv_d;
+    const float2 na = f2(-mean_a, -mean_a), nb = f2(-mean_b, -mean_b);
+    float2 qa = f2(0.f, 0.f), qb = f2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const uint32_t wa[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w}, wb[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 da = __fadd2_rn(f2(lo(wa[j]), hi(wa[j])), na), db = __fadd2_rn(f2(lo(wb[j]), hi(wb[j])), nb);
+        qa = __ffma2_rn(da, da, qa);
+        qb = __ffma2_rn(db, db, qb);
+      }
+    }
+    const float rstd_a = rsqrtf(warp_sum(qa.x + qa.y) * inv_d + 1e-6f);
+    const float rstd_b = rsqrtf(warp_sum(qb.x + qb.y) * inv_d + 1e-6f);
+    const float2 rsa = f2(rstd_a, rstd_a), rsb = f2(rstd_b, rstd_b);
+    bf16* oa = out + (long long)b * o_bs + (long long)r * o_ld + lane * 8;
+    bf16* ob = oa + o_ld;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int c = i * 256 + lane * 8;
+      const float4 c0 = *reinterpret_cast<const float4*>(s_sc + c), c1 = *reinterpret_cast<const float4*>(s_sc + c + 4);
+      const float4 h0 = *reinterpret_cast<const float4*>(s_sh + c), h1 = *reinterpret_cast<const float4*>(s_sh + c + 4);
+      const float2 sc[4] = {f2(c0.x, c0.y), f2(c0.z, c0.w), f2(c1.x, c1.y), f2(c1.z, c1.w)};
+      const float2 sh[4] = {f2(h0.x, h0.y), f2(h0.z, h0.w), f2(h1.x, h1.y), f2(h1.z, h1.w)};
+      const uint32_t wa[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w}, wb[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
+      uint32_t pa[4], pb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 da = __fadd2_rn(f2(lo(wa[j]), hi(wa[j])), na), db = __fadd2_rn(f2(lo(wb[j]), hi(wb[j])), nb);
+        const float2 ya = __ffma2_rn(da, __fmul2_rn(rsa, sc[j]), sh[j]);
+        const float2 yb = __ffma2_rn(db, __fmul2_rn(rsb, sc[j]), sh[j]);
+        __nv_bfloat162 ha = __float22bfloat162_rn(ya), hb = __float22bfloat162_rn(yb);
+        pa[j] = *reinterpret_cast<uint32_t*>(&ha);
+        pb[j] = *reinterpret_cast<uint32_t*>(&hb);
+      }
+      *reinterpret_cast<uint4*>(oa + i * 256) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+      if (two) *reinterpret_cast<uint4*>(ob + i * 256) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+    }
+  }
+}
+
+template <int kV>
+static void launch_ln_rows2(const void* x, long long x_bs, int x_ld, void* out, long long o_bs, int o_ld, int D,
+                            const LnSegs& S, int grid, cudaStream_t stream) {
+  const int smem = 2 * D * (int)sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RT_CHECK_CUDA(cudaFuncSetAttribute(ln_mod_rows2_kernel<kV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = get_option("no_pdl") ? 0 : 1;
+  RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_mod_rows2_kernel<kV>, (const bf16*)x, x_bs, x_ld, (bf16*)out, o_bs, o_ld, D, S));
+  count_launch();
+}
+
 void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out, long long o_bs, int o_ld, int batch,
                    int D, int ngroups, const LnModGroup* groups, cudaStream_t stream) {
   RT_REQUIRE(ngroups >= 1 && ngroups <= kLnMaxGroups, "ln_mod: 1..2 row groups");
@@ -330,6 +465,34 @@ void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out
   if (rows_total == 0 || batch == 0) return;
   ProfScope ps(PROF_LN, 2.0 * batch * rows_total * (double)D * dtype_size(dtype), stream);
   const long long total = (long long)batch * rows_total;
+  // bf16, D = kV * 256: the warp-per-row-pair kernel
+  if (dtype == RT_BF16 && D % 256 == 0 && D <= 4096 && (D / 256) % 4 == 0 && batch * ngroups <= kLnMaxSegs &&
+      x_ld % 8 == 0 && o_ld % 8 == 0 && get_option("ln_impl") == 0) {
+    LnSegs S{};
+    // one wave of CTAs (the kernel keeps two whole rows per lane in registers: one CTA per SM)
+    int rpc = (int)((total + sm_count() - 1) / sm_count());
+    rpc = (rpc + 1) / 2 * 2;
+    rpc = rpc < 2 ? 2 : (rpc > 64 ? 64 : rpc);
+    S.rows_per_cta = rpc;
+    int cta = 0;
+    for (int b = 0; b < batch; ++b)
+      for (int g = 0; g < ngroups; ++g) {
+        const int rows = groups[g].row_end - groups[g].row_begin;
+        if (rows <= 0) continue;
+        LnSeg& e = S.s[S.n++];
+        e.batch = b; e.row_begin = groups[g].row_begin; e.row_end = groups[g].row_end; e.cta_begin = cta;
+        e.scale = groups[g].scale + (long long)b * groups[g].ld;
+        e.shift = groups[g].shift + (long long)b * groups[g].ld;
+        cta += (rows + rpc - 1) / rpc;
+      }
+    switch (D / 256) {
+      case 4: launch_ln_rows2<4>(x, x_bs, x_ld, out, o_bs, o_ld, D, S, cta, stream); return;
+      case 8: launch_ln_rows2<8>(x, x_bs, x_ld, out, o_bs, o_ld, D, S, cta, stream); return;
+      case 12: launch_ln_rows2<12>(x, x_bs, x_ld, out, o_bs, o_ld, D, S, cta, stream); return;
+      case 16: launch_ln_rows2<16>(x, x_bs, x_ld, out, o_bs, o_ld, D, S, cta, stream); return;
+      default: break;
+    }
+  }
   const int threads = 256, wpb = threads / 32;
   long long blocks = (total + wpb - 1) / wpb;
   long long cap = (long long)sm_count() * 8;
