@@ -240,6 +240,11 @@ typedef struct rt_gemm_problem {
   float scale;
   const void* mask; /* [m_rows] or NULL */
   int accumulate;
+  /* 3x3 convolution, stride 1, zero padding 1, as an implicit GEMM (tcgen05 path only; the VAE of SURVEY.md 8f):
+   * A is an NHWC image [batch, conv_h, conv_w, a_ld >= conv_c], m_rows = conv_h * conv_w output pixels per image, and
+   * the weights are [n, 9 * ceil(conv_c / 64) * 64] with K index tap * (ceil(conv_c / 64) * 64) + channel
+   * (tap = ky * 3 + kx, zero padded).  conv_w = 0: plain GEMM. */
+  int conv_h, conv_w, conv_c;
 } rt_gemm_problem;
 
 typedef struct rt_gemm_launch {
@@ -288,6 +293,33 @@ RT_API int rt_rope_table(const float* ids, int S, const int* axes_dims /* host, 
 /* In-place per-head RMSNorm * w + RoPE on `heads` heads starting at column col0 (SIMT path's unfused form) */
 RT_API int rt_qknorm_rope(int dtype, void* buf, int64_t batch_stride, int ld, int col0, int batch, int row0, int rows,
                    int heads, int hd, const void* norm_w, const float* rope, int rope_row0, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VAE path: diffusers AutoencoderKL as the pipelines call it
+ * (RepText/pipeline_flux_controlnet.py:705-715 encode, :1136-1140 decode).  Activations are NHWC bf16; the
+ * convolutions run on rt_gemm (conv_h / conv_w / conv_c, or plain GEMMs over pixels / im2col rows).
+ * ------------------------------------------------------------------------------------------------ */
+/* GroupNorm (+ SiLU when silu != 0) over x [batch, hw, C]; stats_ws: batch * groups * 24 bytes of scratch, 8-byte aligned. */
+RT_API int rt_groupnorm_nhwc(const void* x, void* out, int batch, int64_t hw, int C, int groups, const void* gamma,
+                             const void* beta, float eps, int silu, void* stats_ws, void* stream);
+/* Upsample2D's nearest x2: [batch, H, W, C] -> [batch, 2H, 2W, C] */
+RT_API int rt_upsample_nearest2x_nhwc(const void* in, void* out, int batch, int H, int W, int C, void* stream);
+/* In-place softmax of every row of a [rows, cols] matrix (the single-head mid-block attention) */
+RT_API int rt_softmax_rows(void* x, int64_t rows, int cols, int64_t ld, void* stream);
+/* im2col of a 3x3 convolution (stride, leading padding pad_lo) for the convolutions TMA cannot address (stride 2,
+ * 3 input channels): in [batch, H, W, c_ld] -> out [batch, Ho * Wo, Kp], K index tap * C + c, zero beyond 9 * C */
+RT_API int rt_im2col3x3_nhwc(const void* in, void* out, int batch, int H, int W, int C, int c_ld, int Ho, int Wo,
+                             int stride, int pad_lo, int Kp, void* stream);
+
+/* Layout changes at the VAE's edges: NCHW (RT_F32 or RT_BF16) -> NHWC bf16 [batch, hw, c_pad] (channels >= C zero), and
+ * NHWC bf16 [batch, hw, ld] (first C channels) -> NCHW (RT_F32 or RT_BF16) */
+RT_API int rt_nchw_to_nhwc(int src_dtype, const void* in, void* out, int batch, int C, int64_t hw, int c_pad, void* stream);
+RT_API int rt_nhwc_to_nchw(const void* in, int ld, void* out, int dst_dtype, int batch, int C, int64_t hw, void* stream);
+/* DiagonalGaussianDistribution.sample (encode(x).latent_dist.sample(), RepText/pipeline_flux_controlnet.py:705-708) on
+ * NHWC bf16 moments [batch, hw, ld] (mean = channels 0..L, logvar = L..2L): out NCHW [batch, L, hw] =
+ * mean + exp(0.5 * clamp(logvar, -30, 20)) * noise; noise NCHW in `dtype` like out, NULL = the mode */
+RT_API int rt_vae_posterior_sample(const void* moments, int ld, int latent_channels, int batch, int64_t hw,
+                                   const void* noise, void* out, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,8 @@ EXPORTS = [
     "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free", "rt_sp_barrier", "rt_sp_status",
     "rt_euler_step", "rt_cfg_combine", "rt_cfg_euler_step", "rt_mask_scale_add", "rt_glyph_init_blend",
     "rt_gemm", "rt_attention", "rt_layernorm_modulate", "rt_rope_table", "rt_qknorm_rope",
+    "rt_groupnorm_nhwc", "rt_upsample_nearest2x_nhwc", "rt_softmax_rows", "rt_im2col3x3_nhwc",
+    "rt_nchw_to_nhwc", "rt_nhwc_to_nchw", "rt_vae_posterior_sample",
 ]
 
 
@@ -92,7 +94,7 @@ class GemmProblem(C.Structure):
         ("a_rows_total", C.c_int), ("m_rows", C.c_int), ("out_row0", C.c_int), ("K", C.c_int), ("nseg", C.c_int),
         ("seg", GemmSegment * 4), ("gate", C.c_void_p), ("gate_ld", C.c_int), ("extra", C.c_void_p),
         ("extra_batch_stride", C.c_int64), ("extra_ld", C.c_int), ("extra_row0", C.c_int), ("scale", C.c_float),
-        ("mask", C.c_void_p), ("accumulate", C.c_int),
+        ("mask", C.c_void_p), ("accumulate", C.c_int), ("conv_h", C.c_int), ("conv_w", C.c_int), ("conv_c", C.c_int),
     ]
 
 
@@ -167,6 +169,16 @@ def lib() -> C.CDLL:
     L.rt_attention.argtypes = [C.POINTER(AttentionArgs), C.c_int, C.c_void_p]
     L.rt_layernorm_modulate.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.POINTER(LnModGroup), C.c_void_p]
+    L.rt_groupnorm_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    L.rt_upsample_nearest2x_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.rt_softmax_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p]
+    L.rt_im2col3x3_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.rt_nchw_to_nhwc.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]
+    L.rt_nhwc_to_nchw.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+    L.rt_vae_posterior_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_void_p]
     L.rt_rope_table.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     L.rt_qknorm_rope.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

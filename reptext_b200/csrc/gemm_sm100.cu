@@ -54,6 +54,10 @@ struct alignas(64) TcProblem {
   int a_row0, a_bcast, m_rows, out_row0, K, nseg, gate_ld, e_ld, e_row0, accumulate;
   float scale;
   int tiles_m, tiles_n, tile_base, num_tiles;
+  // 3x3 convolution as an implicit GEMM (VAE): A is an NHWC image, tmA is 4-D (C, W, H, B) with a box of
+  // (64 channels, conv_bw, 128 / conv_bw, 1) pixels; k-block kb = tap * conv_kcb + channel block, the tap shifts the
+  // box by (dx, dy) and TMA's out-of-bounds zero fill is the padding.  conv_w == 0: plain GEMM.
+  int conv_w, conv_bw, conv_kcb;
 };
 
 struct alignas(64) TcParams {
@@ -554,7 +558,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         void* sa = smem_a + stage * C::kABytes;
         void* sb = smem_b + stage * C::kBBytes;
         const int k0 = (P.debug & 2) ? 0 : kb * BK;
-        if constexpr (kCtaGroup == 1) {
+        if (pr.conv_w > 0) {
+          // implicit 3x3 convolution: this CTA's 128 pixels start at (x, y) of image a_b
+          const int m_cta = tc.m0 + (int)cta_rank * BM;
+          const int y = m_cta / pr.conv_w, x = m_cta - y * pr.conv_w;
+          const int tap = kb / pr.conv_kcb, cb = kb - tap * pr.conv_kcb;
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          if constexpr (kCtaGroup == 1) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+            ptx::tma_load_4d(&pr.tmA, &full_bar[stage], sa, cb * BK, x + dx, y + dy, a_b);
+            ptx::tma_load_2d(&sg.tmW, &full_bar[stage], sb, k0, w_row);
+          } else {
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+            ptx::tma_load_4d_2sm(&pr.tmA, &full_bar[stage], sa, cb * BK, x + dx, y + dy, a_b);
+            ptx::tma_load_2d_2sm(&sg.tmW, &full_bar[stage], sb, k0, w_row);
+          }
+        } else if constexpr (kCtaGroup == 1) {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
           ptx::tma_load_3d_hint(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b, pol_a);
           ptx::tma_load_2d_hint(&sg.tmW, &full_bar[stage], sb, k0, w_row, pol_w);
@@ -650,19 +669,21 @@ EncodeFn get_encode_fn() {
 
 struct TmapKey {
   const void* base;
-  uint64_t d[3], s[2];
-  uint32_t box[3];
+  uint64_t d[4], s[3];
+  uint32_t box[4];
   int rank;
   bool operator==(const TmapKey& o) const {
-    return base == o.base && rank == o.rank && d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2] && s[0] == o.s[0] &&
-           s[1] == o.s[1] && box[0] == o.box[0] && box[1] == o.box[1] && box[2] == o.box[2];
+    return base == o.base && rank == o.rank && d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2] && d[3] == o.d[3] &&
+           s[0] == o.s[0] && s[1] == o.s[1] && s[2] == o.s[2] && box[0] == o.box[0] && box[1] == o.box[1] &&
+           box[2] == o.box[2] && box[3] == o.box[3];
   }
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.base);
     auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.d[0]); mix(k.d[1]); mix(k.d[2]); mix(k.s[0]); mix(k.s[1]); mix(k.box[1]); mix(k.box[2]); mix(k.rank);
+    mix(k.d[0]); mix(k.d[1]); mix(k.d[2]); mix(k.d[3]); mix(k.s[0]); mix(k.s[1]); mix(k.s[2]); mix(k.box[1]);
+    mix(k.box[2]); mix(k.box[3]); mix(k.rank);
     return h;
   }
 };
@@ -684,8 +705,8 @@ void encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64
     if (it != cache.end()) { *out = it->second; return; }
   }
   RT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
-  cuuint64_t gd[3], gs[2];
-  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) {
     RT_REQUIRE(strides_b[i] % 16 == 0, "TMA strides must be multiples of 16 bytes");
@@ -723,6 +744,15 @@ bool gemm_tc_supported(const GemmLaunch& L, std::string* why) {
   for (int p = 0; p < L.nprob; ++p) {
     const GemmProblem& P = L.prob[p];
     if (P.K % 8 || P.a_ld % 8 || P.a_batch_stride % 8) return fail("K / a_ld / a_batch_stride not multiples of 8");
+    if (P.conv_w > 0) {
+      const int kcb = (P.conv_c + 63) / 64;
+      if (P.conv_h <= 0 || P.conv_c <= 0 || P.conv_c % 8) return fail("conv: bad image shape");
+      if (!(P.conv_w % 128 == 0 || 128 % P.conv_w == 0) || P.conv_w < 8) return fail("conv: width must divide or be a multiple of 128");
+      if (P.conv_w < 128 && P.conv_h % (128 / P.conv_w)) return fail("conv: height must be a multiple of 128 / width");
+      if (P.K != 9 * kcb * 64) return fail("conv: K must be 9 * ceil(C / 64) * 64 (tap-major, zero-padded weights)");
+      if (P.m_rows != P.conv_h * P.conv_w || P.a_row0 != 0) return fail("conv: m_rows must be H * W");
+      if (P.a_batch_stride == 0) return fail("conv: broadcast A is not supported");
+    }
     if (!al16(P.A)) return fail("A not 16-byte aligned");
     if (P.nseg < 1 || P.nseg > kMaxSeg) return fail("nseg");
     if (P.gate && (!al16(P.gate) || P.gate_ld % 4)) return fail("gate alignment");
@@ -820,10 +850,19 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
     const GemmProblem& G = L.prob[p];
     TcProblem& T = P.prob[p];
     const bool bcast = G.a_batch_stride == 0;
-    uint64_t dims[3] = {(uint64_t)G.K, (uint64_t)G.a_rows_total, (uint64_t)(bcast ? 1 : L.batch)};
-    uint64_t strides[2] = {(uint64_t)G.a_ld * 2, (uint64_t)(bcast ? (long long)G.a_rows_total * G.a_ld : G.a_batch_stride) * 2};
-    uint32_t box[3] = {BK, BM, 1};
-    encode_tmap_bf16(&T.tmA, G.A, 3, dims, strides, box);
+    if (G.conv_w > 0) {
+      const uint32_t bw = G.conv_w >= 128 ? 128u : (uint32_t)G.conv_w;
+      uint64_t dims[4] = {(uint64_t)G.conv_c, (uint64_t)G.conv_w, (uint64_t)G.conv_h, (uint64_t)L.batch};
+      uint64_t strides[3] = {(uint64_t)G.a_ld * 2, (uint64_t)G.conv_w * G.a_ld * 2, (uint64_t)G.a_batch_stride * 2};
+      uint32_t box[4] = {BK, bw, 128u / bw, 1};
+      encode_tmap_bf16(&T.tmA, G.A, 4, dims, strides, box);
+      T.conv_w = G.conv_w; T.conv_bw = (int)bw; T.conv_kcb = (G.conv_c + 63) / 64;
+    } else {
+      uint64_t dims[3] = {(uint64_t)G.K, (uint64_t)G.a_rows_total, (uint64_t)(bcast ? 1 : L.batch)};
+      uint64_t strides[2] = {(uint64_t)G.a_ld * 2, (uint64_t)(bcast ? (long long)G.a_rows_total * G.a_ld : G.a_batch_stride) * 2};
+      uint32_t box[3] = {BK, BM, 1};
+      encode_tmap_bf16(&T.tmA, G.A, 3, dims, strides, box);
+    }
     T.a_row0 = G.a_row0; T.a_bcast = bcast; T.m_rows = G.m_rows; T.out_row0 = G.out_row0; T.K = G.K;
     T.nseg = G.nseg;
     T.gate = G.gate; T.gate_ld = G.gate_ld;

@@ -156,6 +156,14 @@ __device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint64_t* bar,
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d_2sm(const void* tmap, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // L2 eviction-priority hints for TMA loads (the values createpolicy.fractional.L2::evict_* produces for fraction
 // 1.0).  Tried on the GEMM (weights evict_first, activations evict_last) and measured WORSE - see gemm_sm100.cu;
 // kept as an option.

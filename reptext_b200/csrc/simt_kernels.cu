@@ -106,6 +106,7 @@ void launch_gemm_simt(const GemmLaunch& L, cudaStream_t stream) {
   for (int pi = 0; pi < L.nprob; ++pi) {
     const GemmProblem& P = L.prob[pi];
     if (P.m_rows == 0 || L.batch == 0) continue;
+    if (P.conv_w > 0) throw Error(RT_ERR_UNSUPPORTED, "the implicit 3x3 convolution exists on the tcgen05 GEMM only");
     for (int si = 0; si < P.nseg; ++si) {
       const GemmSegment& S = P.seg[si];
       if (S.scatter) throw Error(RT_ERR_UNSUPPORTED, "sequence-parallel scatter exists on the tcgen05 GEMM only");

@@ -42,6 +42,8 @@ class Problem:
     mask: Optional[torch.Tensor] = None
     accumulate: bool = False
     broadcast_a: bool = False
+    conv_hw: Optional[Sequence[int]] = None  # (H, W): A is an NHWC image [batch, H * W, C]; 3x3 / stride 1 / pad 1
+    conv_c: Optional[int] = None             # channels used (default A.shape[2])
 
 
 def _fill_problem(dst: L.GemmProblem, p: Problem, keep: list) -> None:
@@ -82,6 +84,10 @@ def _fill_problem(dst: L.GemmProblem, p: Problem, keep: list) -> None:
     dst.scale = p.scale
     dst.mask = L.ptr(p.mask)
     dst.accumulate = int(p.accumulate)
+    if p.conv_hw is not None:
+        dst.conv_h, dst.conv_w = int(p.conv_hw[0]), int(p.conv_hw[1])
+        dst.conv_c = int(p.conv_c if p.conv_c is not None else A.shape[2])
+        assert dst.conv_h * dst.conv_w == A.shape[1] and p.a_row0 == 0
     keep.append(p)
 
 
@@ -222,4 +228,105 @@ def glyph_init_blend(noise: torch.Tensor, glyph_latents: torch.Tensor, mask_u8: 
     L.check(L.lib().rt_glyph_init_blend(L.dtype_code(noise.dtype), L.ptr(noise), L.ptr(glyph_latents),
                                         L.ptr(mask_u8), L.ptr(out), noise.numel(), float(w_glyph), float(w_noise),
                                         L.stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# VAE operators; activations are NHWC bf16 tensors shaped [batch, H * W, C]
+# ------------------------------------------------------------------------------------------------------
+def conv3x3(x: torch.Tensor, hw: Sequence[int], Wk: torch.Tensor, bias: Optional[torch.Tensor],
+            out: Optional[torch.Tensor] = None, residual_into: Optional[torch.Tensor] = None,
+            impl: int = IMPL_AUTO) -> torch.Tensor:
+    """3x3 / stride 1 / padding 1 convolution as ONE implicit-GEMM launch.  ``Wk``: [Cout, 9 * C] tap-major weights
+    (``pack_conv3x3_weight``), C = x.shape[2] a multiple of 64.  ``residual_into``: accumulate ``conv + bias`` into
+    that tensor in place (the ResnetBlock2D skip connection) instead of writing ``out``."""
+    B, HW, Cc = x.shape
+    assert Cc % 64 == 0 and Wk.shape[1] == 9 * Cc and HW == hw[0] * hw[1]
+    if residual_into is not None:
+        seg = Segment(W=Wk, bias=bias, out=residual_into, mode=L.EPI_GATE_RESID)
+        out = residual_into
+    else:
+        if out is None:
+            out = torch.empty(B, HW, Wk.shape[0], dtype=x.dtype, device=x.device)
+        seg = Segment(W=Wk, bias=bias, out=out, mode=L.EPI_BIAS)
+    gemm([Problem(A=x, segs=[seg], K=9 * Cc, conv_hw=hw)], B, x.dtype, impl=impl if impl != IMPL_AUTO else IMPL_AUTO)
+    return out
+
+
+def pack_conv3x3_weight(w: torch.Tensor, c_pad: Optional[int] = None, n_pad: Optional[int] = None) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> [n_pad, 9 * c_pad], K index (ky * 3 + kx) * c_pad + channel, zero padded."""
+    co, ci = w.shape[:2]
+    c_pad = c_pad or (ci + 63) // 64 * 64
+    n_pad = n_pad or (co + 63) // 64 * 64
+    t = torch.zeros(n_pad, 3, 3, c_pad, dtype=w.dtype, device=w.device)
+    t[:co, :, :, :ci] = w.permute(0, 2, 3, 1)
+    return t.reshape(n_pad, 9 * c_pad).contiguous()
+
+
+def groupnorm_nhwc(x: torch.Tensor, groups: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6,
+                   silu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, HW, Cc = x.shape
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty_like(x)
+    ws = torch.empty(B * groups * 3, dtype=torch.float64, device=x.device)
+    L.check(L.lib().rt_groupnorm_nhwc(L.ptr(x), L.ptr(out), B, HW, Cc, groups, L.ptr(gamma), L.ptr(beta), float(eps),
+                                      int(silu), L.ptr(ws), L.stream_ptr()))
+    return out
+
+
+def upsample_nearest2x_nhwc(x: torch.Tensor, hw: Sequence[int]) -> torch.Tensor:
+    B, HW, Cc = x.shape
+    assert x.is_contiguous() and HW == hw[0] * hw[1]
+    out = torch.empty(B, 4 * HW, Cc, dtype=x.dtype, device=x.device)
+    L.check(L.lib().rt_upsample_nearest2x_nhwc(L.ptr(x), L.ptr(out), B, hw[0], hw[1], Cc, L.stream_ptr()))
+    return out
+
+
+def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
+    """In-place softmax over the last dimension of a [rows, cols] (or [B, rows, cols] contiguous) bf16 matrix."""
+    assert x.stride(-1) == 1 and x.dtype == torch.bfloat16
+    rows = x.numel() // x.shape[-1]
+    assert x.is_contiguous()
+    L.check(L.lib().rt_softmax_rows(L.ptr(x), rows, x.shape[-1], x.stride(-2), L.stream_ptr()))
+    return x
+
+
+def im2col3x3_nhwc(x: torch.Tensor, hw: Sequence[int], C_used: int, out_hw: Sequence[int], stride: int, pad_lo: int,
+                   Kp: Optional[int] = None) -> torch.Tensor:
+    B, HW, ld = x.shape
+    assert x.is_contiguous() and HW == hw[0] * hw[1]
+    Kp = Kp or (9 * C_used + 7) // 8 * 8
+    out = torch.empty(B, out_hw[0] * out_hw[1], Kp, dtype=x.dtype, device=x.device)
+    L.check(L.lib().rt_im2col3x3_nhwc(L.ptr(x), L.ptr(out), B, hw[0], hw[1], C_used, ld, out_hw[0], out_hw[1], stride,
+                                      pad_lo, Kp, L.stream_ptr()))
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, c_pad: int) -> torch.Tensor:
+    B, Cc, H, W = x.shape
+    x = x.contiguous()
+    out = torch.empty(B, H * W, c_pad, dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().rt_nchw_to_nhwc(L.dtype_code(x.dtype), L.ptr(x), L.ptr(out), B, Cc, H * W, c_pad, L.stream_ptr()))
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, hw: Sequence[int], C_used: int, dtype: torch.dtype) -> torch.Tensor:
+    B, HW, ld = x.shape
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    out = torch.empty(B, C_used, hw[0], hw[1], dtype=dtype, device=x.device)
+    L.check(L.lib().rt_nhwc_to_nchw(L.ptr(x), ld, L.ptr(out), L.dtype_code(dtype), B, C_used, HW, L.stream_ptr()))
+    return out
+
+
+def vae_posterior_sample(moments: torch.Tensor, hw: Sequence[int], latent_channels: int,
+                         noise: Optional[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
+    B, HW, ld = moments.shape
+    assert moments.is_contiguous() and moments.dtype == torch.bfloat16
+    out = torch.empty(B, latent_channels, hw[0], hw[1], dtype=dtype, device=moments.device)
+    if noise is not None:
+        noise = noise.to(dtype).contiguous()
+        assert noise.shape == out.shape
+    L.check(L.lib().rt_vae_posterior_sample(L.ptr(moments), ld, latent_channels, B, HW, L.ptr(noise), L.ptr(out),
+                                            L.dtype_code(dtype), L.stream_ptr()))
     return out

@@ -1,0 +1,236 @@
+"""VAE path on the GPU, through the C-ABI: every VAE kernel against plain fp32 torch, and the
+``AutoencoderKL`` drop-in (``reptext_b200/vae.py``) against the oracle (``oracle/vae_oracle.py``, fp32, the same
+bf16-rounded weights and inputs).
+
+Tolerances: single kernels 4e-3 rel-L2 (one bf16 output rounding is 2^-9 = 2e-3 relative); the whole encoder / decoder
+(about 25 / 35 bf16 layers deep) 2e-2 on the moments / the image; measured 1.1e-2 / 1.2e-2 at 1024 x 1024, where the
+oracle run by stock torch in bf16 (cuDNN + SDPA) is at 1.6e-2 against its own fp32 run (``profiles/r1_vae.txt``).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import rel_l2
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    """The checker must be fp32: cuDNN / cuBLAS would otherwise run the oracle's convolutions in TF32 (1e-3 error)."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from reptext_b200 import ops as _ops, _lib
+    _lib.lib()
+    return _ops
+
+
+def _rand(shape, seed, scale=1.0, dtype=BF):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda", dtype=torch.float32) * scale).to(dtype)
+
+
+def _nchw(x, hw):           # [B, HW, C] -> [B, C, H, W] fp32
+    B, HW, C = x.shape
+    return x.float().view(B, hw[0], hw[1], C).permute(0, 3, 1, 2).contiguous()
+
+
+def _nhwc(x):               # [B, C, H, W] -> [B, HW, C]
+    B, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B, H * W, C)
+
+
+# ---------------------------------------------------------------------------------------------- kernels
+@pytest.mark.parametrize("H,W,C,Co,B", [(32, 32, 64, 64, 1), (16, 128, 128, 256, 2), (8, 256, 64, 128, 1),
+                                         (64, 16, 192, 64, 2), (48, 64, 512, 512, 1)])
+@pytest.mark.parametrize("impl", [2, 3])
+def test_conv3x3_implicit_gemm(ops, H, W, C, Co, B, impl):
+    """rt_gemm's conv mode (9 shifted 4-D TMA boxes, zero fill = padding) == F.conv2d(padding=1)."""
+    x = _rand((B, H * W, C), 1)
+    w = _rand((Co, C, 3, 3), 2, scale=(9 * C) ** -0.5)
+    b = _rand((Co,), 3, scale=0.1)
+    wk = ops.pack_conv3x3_weight(w)
+    ref = F.conv2d(_nchw(x, (H, W)), w.float(), b.float(), padding=1)
+    out = ops.conv3x3(x, (H, W), wk, b, impl=impl)
+    assert rel_l2(_nchw(out, (H, W)), ref) < 4e-3
+    # skip connection fused into the epilogue, in place
+    skip = _rand((B, H * W, Co), 4)
+    ref2 = ref + _nchw(skip, (H, W))
+    ops.conv3x3(x, (H, W), wk, b, residual_into=skip, impl=impl)
+    assert rel_l2(_nchw(skip, (H, W)), ref2) < 4e-3
+
+
+def test_conv3x3_padded_channels(ops):
+    """16 latent channels zero-padded to 64 (decoder.conv_in) and 3 output channels padded to 64 (decoder.conv_out)."""
+    H, W = 16, 16
+    z = _rand((1, 16, H, W), 5)
+    w = _rand((3, 16, 3, 3), 6, scale=0.1)
+    b = _rand((3,), 7, scale=0.1)
+    x = ops.nchw_to_nhwc(z, 64)
+    assert x.shape == (1, H * W, 64) and float(x[..., 16:].abs().max()) == 0.0
+    wk = ops.pack_conv3x3_weight(w)
+    assert wk.shape == (64, 9 * 64)
+    bp = torch.zeros(64, device="cuda", dtype=BF)
+    bp[:3] = b
+    out = ops.conv3x3(x, (H, W), wk, bp)
+    img = ops.nhwc_to_nchw(out, (H, W), 3, torch.float32)
+    ref = F.conv2d(z.float(), w.float(), b.float(), padding=1)
+    assert rel_l2(img, ref) < 4e-3
+    assert float(out[..., 3:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("H,W,C,stride,pad_lo", [(16, 16, 64, 1, 1), (32, 32, 128, 2, 0), (8, 8, 3, 1, 1)])
+def test_im2col_matches_conv(ops, H, W, C, stride, pad_lo):
+    """im2col + plain GEMM == F.conv2d, for stride 1 / pad 1 and Downsample2D's pad (0, 1, 0, 1) + stride 2."""
+    B, Co = 2, 64
+    c_ld = (C + 7) // 8 * 8
+    x = torch.zeros(B, H * W, c_ld, device="cuda", dtype=BF)
+    x[..., :C] = _rand((B, H * W, C), 8)
+    w = _rand((Co, C, 3, 3), 9, scale=(9 * C) ** -0.5)
+    Ho, Wo = (H, W) if stride == 1 else (H // 2, W // 2)
+    Kp = (9 * C + 7) // 8 * 8
+    col = ops.im2col3x3_nhwc(x, (H, W), C, (Ho, Wo), stride, pad_lo, Kp=Kp)
+    wk = torch.zeros(Co, Kp, device="cuda", dtype=BF)
+    wk[:, :9 * C] = w.permute(0, 2, 3, 1).reshape(Co, 9 * C)
+    out = ops.linear(col, wk)
+    xin = _nchw(x[..., :C].contiguous(), (H, W))
+    if stride == 2:
+        ref = F.conv2d(F.pad(xin, (0, 1, 0, 1)), w.float(), stride=2)
+    else:
+        ref = F.conv2d(xin, w.float(), padding=1)
+    assert rel_l2(_nchw(out, (Ho, Wo)), ref) < 4e-3
+
+
+@pytest.mark.parametrize("C,HW,B,silu", [(64, 256, 1, True), (128, 4096, 2, True), (256, 1000, 1, False),
+                                         (512, 16384, 1, True)])
+def test_groupnorm_nhwc(ops, C, HW, B, silu):
+    x = _rand((B, HW, C), 10, scale=2.0) + 0.5
+    g, b = _rand((C,), 11, 0.2) + 1, _rand((C,), 12, 0.2)
+    out = ops.groupnorm_nhwc(x, 32, g, b, eps=1e-6, silu=silu)
+    ref = F.group_norm(x.float().transpose(1, 2), 32, g.float(), b.float(), eps=1e-6)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_l2(out.float().transpose(1, 2), ref) < 4e-3
+
+
+def test_upsample_softmax_layout_posterior(ops):
+    x = _rand((2, 8 * 16, 64), 13)
+    up = ops.upsample_nearest2x_nhwc(x, (8, 16))
+    ref = F.interpolate(_nchw(x, (8, 16)), scale_factor=2.0, mode="nearest")
+    assert torch.equal(_nchw(up, (16, 32)), ref)
+
+    s = _rand((300, 1024), 14, scale=3.0)
+    ref = torch.softmax(s.float(), dim=-1)
+    ops.softmax_rows_(s)
+    assert rel_l2(s, ref) < 4e-3
+    s = _rand((64, 16384), 15, scale=3.0)
+    ref = torch.softmax(s.float(), dim=-1)
+    ops.softmax_rows_(s)
+    assert rel_l2(s, ref) < 4e-3
+
+    img = _rand((2, 3, 16, 24), 16, dtype=torch.float32)
+    nh = ops.nchw_to_nhwc(img, 8)
+    assert torch.equal(nh[..., :3].float(), _nhwc(img).to(BF).float()) and float(nh[..., 3:].abs().max()) == 0
+    back = ops.nhwc_to_nchw(nh, (16, 24), 3, torch.float32)
+    assert torch.equal(back, img.to(BF).float())
+
+    mom = _rand((2, 16 * 16, 64), 17)
+    noise = _rand((2, 16, 16, 16), 18)
+    z = ops.vae_posterior_sample(mom, (16, 16), 16, noise, BF)
+    m = _nchw(mom, (16, 16))
+    ref = m[:, :16] + torch.exp(0.5 * m[:, 16:32].clamp(-30, 20)) * noise.float()
+    assert rel_l2(z, ref) < 4e-3
+    assert torch.equal(ops.vae_posterior_sample(mom, (16, 16), 16, None, BF).float(), m[:, :16])
+
+
+def test_conv_rejects_unsupported_shapes(ops):
+    x = _rand((1, 24 * 24, 64), 19)
+    wk = ops.pack_conv3x3_weight(_rand((64, 64, 3, 3), 20))
+    with pytest.raises((ValueError, RuntimeError)):
+        ops.conv3x3(x, (24, 24), wk, None)          # width 24 neither divides nor is a multiple of 128
+
+
+# ---------------------------------------------------------------------------------------------- model
+def _vae_pair(cfg_over, seed):
+    from oracle import vae_oracle as V
+    from reptext_b200 import vae
+    cfg = dict(V.FLUX_VAE_CONFIG, **cfg_over)
+    sd = {k: v.to(BF).float() for k, v in V.random_state_dict(cfg, seed=seed).items()}
+    return V, cfg, sd, vae
+
+
+@pytest.mark.parametrize("conv_impl", ["implicit", "im2col"])
+def test_autoencoder_small_vs_oracle(conv_impl):
+    V, cfg, sd, vae = _vae_pair(dict(block_out_channels=(64, 128, 256, 256)), 21)
+    m = vae.AutoencoderKL(cfg, sd, conv_impl=conv_impl)
+    g = torch.Generator().manual_seed(22)
+    img = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).to(BF).float()
+    sdd = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref_mom = V.encode_moments(sdd, cfg, img.cuda())
+    post = m.encode(img.cuda().to(BF)).latent_dist
+    assert rel_l2(post.parameters, ref_mom) < 2e-2
+    noise = torch.randn(2, 16, 16, 16, generator=g).to(BF)
+    z = post.sample_with_noise(noise)
+    assert rel_l2(z, V.sample_posterior(ref_mom, noise.float().cuda())) < 2e-2
+    assert rel_l2(post.mode(), ref_mom[:, :16]) < 2e-2
+
+    zin = torch.randn(2, 16, 16, 16, generator=g).to(BF)
+    with torch.no_grad():
+        ref_img = V.decode(sdd, cfg, zin.float().cuda())
+    out = m.decode(zin.cuda(), return_dict=False)[0]
+    assert out.shape == (2, 3, 128, 128) and out.dtype == BF
+    assert rel_l2(out, ref_img) < 2e-2
+
+
+def test_autoencoder_api_and_errors():
+    V, cfg, sd, vae = _vae_pair(dict(block_out_channels=(64, 128, 256, 256)), 23)
+    m = vae.AutoencoderKL(cfg, sd)
+    assert m.config.scaling_factor == 0.3611 and m.config["shift_factor"] == 0.1159
+    assert len(m.config.block_out_channels) == 4 and m.dtype == BF
+    img = torch.zeros(1, 3, 128, 128, device="cuda")
+    a = m.encode(img).latent_dist.sample(torch.Generator().manual_seed(1))
+    b = m.encode(img, return_dict=False)[0].sample(torch.Generator().manual_seed(1))
+    assert torch.equal(a, b) and a.shape == (1, 16, 16, 16)
+    assert m.decode(a).sample.shape == (1, 3, 128, 128)
+    with pytest.raises(ValueError):
+        m.encode(torch.zeros(1, 4, 128, 128, device="cuda"))
+    with pytest.raises(ValueError):
+        m.decode(torch.zeros(1, 8, 16, 16, device="cuda"))
+    with pytest.raises(ValueError):
+        vae.AutoencoderKL(cfg, sd, device="cpu")
+    bad = dict(sd)
+    del bad["decoder.conv_out.weight"]
+    with pytest.raises(ValueError):
+        vae.AutoencoderKL(cfg, bad).decode(a)
+
+
+def test_autoencoder_fullsize_1024_vs_oracle():
+    """FLUX.1-dev VAE config at the cfg-2 size: one 1024 x 1024 image encoded, one 128 x 128 latent decoded."""
+    V, cfg, sd, vae = _vae_pair({}, 24)
+    m = vae.AutoencoderKL(cfg, sd)
+    g = torch.Generator().manual_seed(25)
+    low = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1          # smooth image + texture, in [-1, 1]
+    img = (F.interpolate(low, size=(1024, 1024), mode="bilinear") * 0.8 +
+           0.2 * (torch.rand(1, 3, 1024, 1024, generator=g) * 2 - 1)).to(BF).float()
+    zin = torch.randn(1, 16, 128, 128, generator=g).to(BF)
+    sdd = {k: v.cuda() for k, v in sd.items()}
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        ref_mom = V.encode_moments(sdd, cfg, img.cuda())
+        ref_img = V.decode(sdd, cfg, zin.float().cuda())
+    post = m.encode(img.cuda().to(BF)).latent_dist
+    e_enc = rel_l2(post.parameters, ref_mom)
+    out = m.decode(zin.cuda(), return_dict=False)[0]
+    e_dec = rel_l2(out, ref_img)
+    print(f"VAE 1024^2: moments rel-L2 {e_enc:.2e}, decoded image rel-L2 {e_dec:.2e}")
+    assert e_enc < 2e-2 and e_dec < 2e-2
