@@ -194,8 +194,9 @@ def run_b200(args, wl):
     import torch.distributed as dist
     from reptext_b200 import _lib, models, ops
     from reptext_b200.pipeline_flux_controlnet import FluxControlNetPipeline
-    from reptext_b200.pipeline_utils import SyntheticTextEncoders, SyntheticVAE
+    from reptext_b200.pipeline_utils import SyntheticTextEncoders
     from reptext_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    from reptext_b200.vae import AutoencoderKL
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from util import box_mask
 
@@ -225,7 +226,8 @@ def run_b200(args, wl):
     h_cond = pin(torch.randn(1, N, CN["in_channels"] + CN["extra_condition_channels"], generator=g).to(dt))
     mask_img = box_mask(H, W, (H // 3, H // 3 + H // 6, W // 5, W - W // 5))
     sch = FlowMatchEulerDiscreteScheduler()
-    pipe = FluxControlNetPipeline(sch, SyntheticVAE(dtype=dt, device=dev),
+    vae = AutoencoderKL.random_init(seed=102, dtype=dt, device=dev)   # FLUX.1-dev VAE architecture, random weights
+    pipe = FluxControlNetPipeline(sch, vae,
                                   SyntheticTextEncoders(TR["joint_attention_dim"], TR["pooled_projection_dim"], dt, dev),
                                   None, None, None, tr, cn)
     mask = pipe._regional_masks([mask_img], dev, dt)[0]
@@ -324,8 +326,8 @@ def run_b200(args, wl):
     def one_image(steps):
         out = pipe(prompt_embeds=h_pe, pooled_prompt_embeds=h_po, height=H, width=W, num_inference_steps=steps,
                    guidance_scale=3.5, control_image=[canny], control_position=[pos], control_mask=[mask_img],
-                   controlnet_conditioning_scale=1.0, latents=h_lat, output_type="latent", callback_on_step_end=tap)
-        res = out.images.to("cpu", non_blocking=False)
+                   controlnet_conditioning_scale=1.0, latents=h_lat, output_type="pt", callback_on_step_end=tap)
+        res = out.images.to("cpu", non_blocking=False)     # the decoded image [1, 3, H, W]
         return res
 
     e2e_value = h2d_step = d2h_step = None
@@ -346,6 +348,28 @@ def run_b200(args, wl):
         h2d_total = sum(t.numel() * t.element_size() for t in (h_pe, h_po, h_lat, canny, pos)) + mask_img.size * 4
         h2d_step = h2d_total / STEPS_PER_IMAGE
         d2h_step = (d2h[0] + res.numel() * res.element_size()) / STEPS_PER_IMAGE
+
+    # ---- the VAE on its own: two encodes per text line + one decode per image, device-timed
+    vae_info = None
+    if rank == 0 and not args.no_e2e:
+        zt = torch.randn(1, 16, H // 8, W // 8, device=dev, dtype=dt)
+        it = canny.to(dev, dt)
+        def _t(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        nl = _lib.launch_count()
+        vae.decode(zt)
+        nl = _lib.launch_count() - nl
+        vae_info = dict(encode_ms=_t(lambda: vae.encode(it)), decode_ms=_t(lambda: vae.decode(zt)), decode_launches=nl,
+                        note="AutoencoderKL drop-in (reptext_b200/vae.py), FLUX.1-dev VAE architecture, random weights; "
+                             "inside the e2e figure: 2 encodes + 1 decode per image")
 
     # ---- the only collective: gather the output latents of all ranks (after the timed regions)
     if sp is not None:
@@ -402,8 +426,10 @@ def run_b200(args, wl):
                                 tensor_util_whole_step=flops / gpus_per_sample / (step_ms / 1000.0) / 1e12 / pk["bf16_sustained"],
                                 finite_output=finite),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_step, d2h_bytes_per_step=d2h_step,
-                             how="FluxControlNetPipeline.__call__, one 28-step image from pinned host inputs, latents "
-                                 "copied to the host after every step"),
+                             how="FluxControlNetPipeline.__call__(output_type='pt'), one 28-step image from pinned host "
+                                 "inputs: VAE encode of the Canny and position images, 28 denoise steps with the latents "
+                                 "copied to the host after every step, VAE decode, image copied to the host"),
+                    vae=vae_info,
                     gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu, breakdown=breakdown)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -23,6 +23,7 @@ def main(argv=None):
     from reptext_b200 import config, glyphs, models
     from reptext_b200.pipeline_flux_controlnet import FluxControlNetPipeline
     from reptext_b200.pipeline_utils import SyntheticTextEncoders, SyntheticVAE
+    from reptext_b200.vae import AutoencoderKL
     from reptext_b200.scheduler import FlowMatchEulerDiscreteScheduler
 
     ap = argparse.ArgumentParser()
@@ -38,6 +39,9 @@ def main(argv=None):
     ap.add_argument("--no-glyph-init", action="store_true", help="control_glyph=None (infer.py:124 'optional')")
     ap.add_argument("--out", default=None)
     ap.add_argument("--output-type", default="pil", choices=["pil", "latent"])
+    ap.add_argument("--vae", default="flux", choices=["flux", "synthetic"],
+                    help="flux: the AutoencoderKL drop-in (FLUX.1-dev VAE architecture, random weights; fp32 'tiny' uses the "
+                         "stand-in); synthetic: the 8x-pooling stand-in")
     a = ap.parse_args(argv)
 
     TR, CN, dt = {"tiny": (config.TINY_TRANSFORMER, config.TINY_CONTROLNET, torch.float32),
@@ -46,7 +50,9 @@ def main(argv=None):
     dev = torch.device("cuda")
     controlnet = models.FluxControlNetModel.random_init(CN, seed=101, dtype=dt, device=dev)
     transformer = models.FluxTransformer2DModel.random_init(TR, seed=100, dtype=dt, device=dev)
-    pipe = FluxControlNetPipeline(FlowMatchEulerDiscreteScheduler(), SyntheticVAE(dtype=dt, device=dev),
+    vae = (AutoencoderKL.random_init(seed=102, dtype=dt, device=dev) if a.vae == "flux" and dt == torch.bfloat16
+           else SyntheticVAE(dtype=dt, device=dev))
+    pipe = FluxControlNetPipeline(FlowMatchEulerDiscreteScheduler(), vae,
                                   SyntheticTextEncoders(TR["joint_attention_dim"], TR["pooled_projection_dim"], dt, dev),
                                   None, None, None, transformer, controlnet)
 

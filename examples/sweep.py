@@ -28,7 +28,8 @@ WORDS = ["مرحبا", "سلام", "القاهرة", "مكتبة", "مقهى", "
 def main(argv=None):
     from reptext_b200 import config, glyphs, models, parallel
     from reptext_b200.pipeline_flux_controlnet import FluxControlNetPipeline
-    from reptext_b200.pipeline_utils import SyntheticTextEncoders, SyntheticVAE
+    from reptext_b200.pipeline_utils import SyntheticTextEncoders
+    from reptext_b200.vae import AutoencoderKL
     from reptext_b200.scheduler import FlowMatchEulerDiscreteScheduler
 
     ap = argparse.ArgumentParser()
@@ -46,7 +47,7 @@ def main(argv=None):
               "flux-dev": (config.FLUX_DEV, config.REPTEXT_CONTROLNET)}[a.config]
     tr = models.FluxTransformer2DModel.random_init(TR, seed=100, dtype=dt, device=dev)
     cn = models.FluxControlNetModel.random_init(CN, seed=101, dtype=dt, device=dev)
-    pipe = FluxControlNetPipeline(FlowMatchEulerDiscreteScheduler(), SyntheticVAE(dtype=dt, device=dev),
+    pipe = FluxControlNetPipeline(FlowMatchEulerDiscreteScheduler(), AutoencoderKL.random_init(seed=102, dtype=dt, device=dev),
                                   SyntheticTextEncoders(TR["joint_attention_dim"], TR["pooled_projection_dim"], dt, dev),
                                   None, None, None, tr, cn)
     font = glyphs.load_font(None, max(a.height // 12, 16))

@@ -38,11 +38,22 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   const bf16* base = x + (long long)b * hw * C + v * 8;
-  for (long long p = p0 + threadIdx.x / vecs; p < p1; p += lanes) {
+  long long p = p0 + threadIdx.x / vecs;
+  for (; p + 3LL * lanes < p1; p += 4LL * lanes) {      // four independent 16-byte loads in flight per thread
+    float t[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ldvec(base + (p + (long long)u * lanes) * C, t[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += t[u][j]; q[j] = fmaf(t[u][j], t[u][j], q[j]); }
+    }
+  }
+  for (; p < p1; p += lanes) {
     float t[8];
     ldvec(base + p * C, t);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] += t[j]; q[j] += t[j] * t[j]; }
+    for (int j = 0; j < 8; ++j) { s[j] += t[j]; q[j] = fmaf(t[j], t[j], q[j]); }
   }
   // block-level fold in shared memory (per channel), then ONE pair of double atomics per (block, group)
   __shared__ float ssum[512], ssq[512];
@@ -72,29 +83,64 @@ __global__ void gn_finalize_kernel(const double* __restrict__ stats, float2* __r
   mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
 }
 
-// y = act((x - mean) * rstd * gamma + beta), act = SiLU or identity
+// y = act((x - mean) * rstd * gamma + beta), act = SiLU or identity.  Like the statistics kernel, a thread owns ONE
+// 16-byte channel vector of a strided set of pixels, so the affine form y = a * x + b (a = rstd * gamma,
+// b = beta - mean * a) is computed once per thread and the pixel loop is load - 8 FMAs - (8 tanh) - store, four pixels
+// in flight per thread.  silu(y) = y * sigmoid(y) = 0.5 * y * (1 + tanh(y / 2)): one MUFU op per element.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool kSilu>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long hw,
                                                        int C, int G, const float2* __restrict__ mr,
                                                        const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
-                                                       int silu, long long total_vecs) {
+                                                       int pixels_per_block) {
+  const int b = blockIdx.y;
   const int vecs = C / 8, cpg = C / G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vecs;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vecs);
-    const long long pix = i / vecs;        // b * hw + p
-    const int b = (int)(pix / hw);
-    float t[8], g[8], be[8], o[8];
-    ldvec(x + pix * C + v * 8, t);
-    ldvec(gamma + v * 8, g);
-    ldvec(beta + v * 8, be);
+  const int v = threadIdx.x % vecs;
+  const int lanes = blockDim.x / vecs;
+  float ga[8], be[8], ca[8], cb[8];
+  ldvec(gamma + v * 8, ga);
+  ldvec(beta + v * 8, be);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 m = __ldg(&mr[(long long)b * G + (v * 8 + j) / cpg]);
+    ca[j] = m.y * ga[j];
+    cb[j] = be[j] - m.x * ca[j];
+  }
+  const long long p0 = (long long)blockIdx.x * pixels_per_block;
+  const long long p1 = min(p0 + pixels_per_block, hw);
+  const bf16* xb = x + (long long)b * hw * C + v * 8;
+  bf16* ob = out + (long long)b * hw * C + v * 8;
+  long long p = p0 + threadIdx.x / vecs;
+  for (; p + 3LL * lanes < p1; p += 4LL * lanes) {
+    float t[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ldvec(xb + (p + (long long)u * lanes) * C, t[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(t[u][j], ca[j], cb[j]);
+        if (kSilu) y = 0.5f * y * (1.f + tanh_approx(0.5f * y));
+        t[u][j] = y;
+      }
+      stvec(ob + (p + (long long)u * lanes) * C, t[u]);
+    }
+  }
+  for (; p < p1; p += lanes) {
+    float t[8];
+    ldvec(xb + p * C, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float2 m = __ldg(&mr[(long long)b * G + (v * 8 + j) / cpg]);
-      float y = (t[j] - m.x) * m.y * g[j] + be[j];
-      if (silu) y = y / (1.f + __expf(-y));
-      o[j] = y;
+      float y = fmaf(t[j], ca[j], cb[j]);
+      if (kSilu) y = 0.5f * y * (1.f + tanh_approx(0.5f * y));
+      t[j] = y;
     }
-    stvec(out + pix * C + v * 8, o);
+    stvec(ob + p * C, t);
   }
 }
 
@@ -235,6 +281,29 @@ __global__ void __launch_bounds__(256) posterior_sample_kernel(const bf16* __res
   }
 }
 
+// the same gather, 8 channels (16 bytes) per thread: C, c_ld multiples of 8 and Kp == 9 * C
+__global__ void __launch_bounds__(256) im2col3x3_vec8_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int H,
+                                                             int W, int C, int c_ld, int Ho, int Wo, int stride,
+                                                             int pad_lo, long long total) {
+  const int vecs = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    long long r = i / vecs;
+    const int tap = (int)(r % 9);
+    long long p = r / 9;                    // (b, yo, xo)
+    const long long pix = p;
+    const int xo = (int)(p % Wo);
+    p /= Wo;
+    const int yo = (int)(p % Ho);
+    const long long b = p / Ho;
+    const int y = yo * stride + tap / 3 - pad_lo, x = xo * stride + tap % 3 - pad_lo;
+    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && x >= 0 && x < W)
+      t = *reinterpret_cast<const uint4*>(in + ((b * H + y) * W + x) * c_ld + v * 8);
+    *reinterpret_cast<uint4*>(out + (pix * 9 + tap) * C + v * 8) = t;
+  }
+}
+
 int grid_for(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   const long long cap = (long long)sm_count_v() * 16;
@@ -272,9 +341,12 @@ int rt_groupnorm_nhwc(const void* x, void* out, int batch, int64_t hw, int C, in
     gn_finalize_kernel<<<(batch * groups + 127) / 128, 128, 0, s>>>((const double*)stats_ws, mr, batch * groups,
                                                                     (double)hw * cpg, eps);
     RT_POST_LAUNCH();
-    const long long total = (long long)batch * hw * vecs;
-    gn_apply_kernel<<<grid_for(total, 256), 256, 0, s>>>((const bf16*)x, (bf16*)out, hw, C, groups, mr,
-                                                         (const bf16*)gamma, (const bf16*)beta, silu, total);
+    if (silu)
+      gn_apply_kernel<true><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)out, hw, C, groups, mr, (const bf16*)gamma,
+                                                 (const bf16*)beta, (int)ppb);
+    else
+      gn_apply_kernel<false><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)out, hw, C, groups, mr, (const bf16*)gamma,
+                                                  (const bf16*)beta, (int)ppb);
     RT_POST_LAUNCH();
   });
 }
@@ -306,8 +378,15 @@ int rt_im2col3x3_nhwc(const void* in, void* out, int batch, int H, int W, int C,
                "im2col: bad argument");
     const long long total = (long long)batch * Ho * Wo * Kp;
     ProfScope ps(PROF_ELEM, (double)total * 2 * 2, (cudaStream_t)stream);
-    im2col3x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in, (bf16*)out, H, W, C, c_ld, Ho,
-                                                                            Wo, stride, pad_lo, Kp, total);
+    if (C % 8 == 0 && c_ld % 8 == 0 && Kp == 9 * C && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      const long long tv = total / 8;
+      im2col3x3_vec8_kernel<<<grid_for(tv, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in, (bf16*)out, H, W, C, c_ld,
+                                                                                Ho, Wo, stride, pad_lo, tv);
+    } else {
+      im2col3x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in, (bf16*)out, H, W, C, c_ld, Ho,
+                                                                              Wo, stride, pad_lo, Kp, total);
+    }
     RT_POST_LAUNCH();
   });
 }

@@ -67,6 +67,75 @@ class DiagonalGaussianDistribution:
         return ops.nhwc_to_nchw(self._m, self._hw, 2 * self._lc, self._dtype)
 
 
+def vae_param_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
+    """Every parameter of a FLUX-style ``AutoencoderKL`` (diffusers names) with its shape: what a checkpoint of
+    ``black-forest-labs/FLUX.1-dev/vae`` holds, used here to draw random weights of that architecture."""
+    boc, lpb, lat = tuple(cfg["block_out_channels"]), cfg["layers_per_block"], cfg["latent_channels"]
+    out: Dict[str, Tuple[int, ...]] = {}
+
+    def wb(name, *shape):
+        out[name + ".weight"] = tuple(shape)
+        out[name + ".bias"] = (shape[0],)
+
+    def resnet(p, cin, cout):
+        wb(p + "norm1", cin)
+        wb(p + "conv1", cout, cin, 3, 3)
+        wb(p + "norm2", cout)
+        wb(p + "conv2", cout, cout, 3, 3)
+        if cin != cout:
+            wb(p + "conv_shortcut", cout, cin, 1, 1)
+
+    def mid(p, c):
+        resnet(p + "mid_block.resnets.0.", c, c)
+        wb(p + "mid_block.attentions.0.group_norm", c)
+        for n in ("to_q", "to_k", "to_v", "to_out.0"):
+            wb(p + "mid_block.attentions.0." + n, c, c)
+        resnet(p + "mid_block.resnets.1.", c, c)
+
+    wb("encoder.conv_in", boc[0], cfg["in_channels"], 3, 3)
+    c = boc[0]
+    for i, co in enumerate(boc):
+        for j in range(lpb):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}.", c, co)
+            c = co
+        if i != len(boc) - 1:
+            wb(f"encoder.down_blocks.{i}.downsamplers.0.conv", c, c, 3, 3)
+    mid("encoder.", c)
+    wb("encoder.conv_norm_out", c)
+    wb("encoder.conv_out", 2 * lat, c, 3, 3)
+    rev = boc[::-1]
+    wb("decoder.conv_in", rev[0], lat, 3, 3)
+    mid("decoder.", rev[0])
+    c = rev[0]
+    for i, co in enumerate(rev):
+        for j in range(lpb + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}.", c, co)
+            c = co
+        if i != len(rev) - 1:
+            wb(f"decoder.up_blocks.{i}.upsamplers.0.conv", c, c, 3, 3)
+    wb("decoder.conv_norm_out", c)
+    wb("decoder.conv_out", cfg["out_channels"], c, 3, 3)
+    return out
+
+
+def random_vae_state_dict(cfg: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded random weights (fan-in scaled, so activations stay O(1) through the stack); CPU fp32."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shape in vae_param_shapes(cfg).items():
+        if k.endswith(".bias"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            t = torch.randn(shape, generator=g) * fan_in ** -0.5
+        sd[k] = t
+    return sd
+
+
 class AutoencoderKL:
     """Drop-in for ``diffusers.AutoencoderKL`` on the calls the RepText pipelines make.
 
@@ -136,6 +205,14 @@ class AutoencoderKL:
                 bo = sd[a + "to_out.0.bias"].detach().to(dev, torch.float32)
                 self._w[a + "to_out.0.bias_folded"] = (wo @ bv + bo).to(dt).contiguous()
 
+    @classmethod
+    def random_init(cls, config: Optional[dict] = None, seed: int = 0, dtype=torch.bfloat16, device="cuda",
+                    conv_impl: str = "implicit") -> "AutoencoderKL":
+        """Random weights of the configured architecture (there is no network for checkpoints; BASELINE.json)."""
+        cfg = dict(FLUX_VAE_CONFIG)
+        cfg.update(config or {})
+        return cls(cfg, random_vae_state_dict(cfg, seed), dtype=dtype, device=device, conv_impl=conv_impl)
+
     def _p(self, name: str) -> torch.Tensor:
         try:
             return self._w[name]
@@ -160,10 +237,19 @@ class AutoencoderKL:
             raise ValueError(f"VAE feature map {h}x{w}: the width must be >= 8 and divide (or be a multiple of) 128, "
                              f"and the height a multiple of 128 / width")
 
+    @staticmethod
+    def _hw_ok(hw: Tuple[int, int]) -> bool:
+        try:
+            AutoencoderKL._check_hw(hw)
+            return True
+        except ValueError:
+            return False
+
     def _conv3(self, x, hw, name, residual_into=None):
+        """3x3 / stride 1 / pad 1.  Feature maps whose 128-pixel tiles are not whole rows or whole-row groups (e.g. 192
+        wide at 1536^2) take the gather + GEMM form - the same arithmetic, one more pass over memory."""
         w, b = self._p(name + ".weight"), self._p(name + ".bias")
-        if self.conv_impl == "implicit":
-            self._check_hw(hw)
+        if self.conv_impl == "implicit" and self._hw_ok(hw):
             return ops.conv3x3(x, hw, w, b, residual_into=residual_into)
         col = ops.im2col3x3_nhwc(x, hw, x.shape[2], hw, 1, 1, Kp=9 * x.shape[2])
         return self._linear(col, w, b, residual_into=residual_into)

@@ -234,3 +234,73 @@ def test_autoencoder_fullsize_1024_vs_oracle():
     e_dec = rel_l2(out, ref_img)
     print(f"VAE 1024^2: moments rel-L2 {e_enc:.2e}, decoded image rel-L2 {e_dec:.2e}")
     assert e_enc < 2e-2 and e_dec < 2e-2
+
+
+def test_autoencoder_sizes_off_the_tma_grid():
+    """Widths that are neither divisors nor multiples of 128 (192 at 1536^2 / 8) take the gather + GEMM form per
+    convolution; the result is the same function."""
+    V, cfg, sd, vae = _vae_pair(dict(block_out_channels=(64, 128, 128, 128)), 26)
+    m = vae.AutoencoderKL(cfg, sd)
+    g = torch.Generator().manual_seed(27)
+    img = (torch.rand(1, 3, 64, 384, generator=g) * 2 - 1).to(BF)      # level widths 384 (TMA), 192, 96, 48 (gather)
+    sdd = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref_mom = V.encode_moments(sdd, cfg, img.float().cuda())
+    assert rel_l2(m.encode(img.cuda()).latent_dist.parameters, ref_mom) < 2e-2
+    z = torch.randn(1, 16, 8, 48, generator=g).to(BF)
+    with torch.no_grad():
+        ref_img = V.decode(sdd, cfg, z.float().cuda())
+    assert rel_l2(m.decode(z.cuda()).sample, ref_img) < 2e-2
+
+
+def test_t2i_call_with_the_real_vae():
+    """The public T2I ``__call__`` from PIL images with the AutoencoderKL drop-in on both ends
+    (RepText/pipeline_flux_controlnet.py:705-715 and :1136-1140): the packed control latents the pipeline prepared
+    against the oracle's encode (same posterior noise: the pipeline draws it from the global CUDA generator), and the
+    returned image against the oracle's decode of the final latents."""
+    import test_pipeline_gpu as TP
+    from oracle import flux_oracle as O
+    from oracle import vae_oracle as V
+    from reptext_b200 import vae
+    cfg = dict(V.FLUX_VAE_CONFIG, block_out_channels=(64, 128, 256, 256))
+    sd = {k: v.to(BF).float() for k, v in V.random_state_dict(cfg, seed=28).items()}
+    H = W = 256
+    pipe, TR, CN, _, _ = TP._tiny_pipe(BF, vae=vae.AutoencoderKL(cfg, sd), TRname="SMALL128_TRANSFORMER",
+                                       CNname="SMALL128_CONTROLNET")
+    box = TP._capture_denoise(pipe)
+    glyph, cannys, poss, masks = TP._glyph_inputs(H, W, 2)
+    torch.cuda.manual_seed(29)
+    out = pipe(prompt="لافتة", height=H, width=W, num_inference_steps=2, guidance_scale=3.5, control_image=cannys,
+               control_position=poss, control_mask=masks, controlnet_conditioning_scale=1.0, max_sequence_length=128,
+               generator=torch.Generator(device="cuda").manual_seed(5), output_type="pt")
+    img = out.images
+    assert img.shape == (1, 3, H, W)
+    sdd = {k: v.cuda() for k, v in sd.items()}
+    # the same draws, in the order prepare_image makes them: per line, Canny then position
+    torch.cuda.manual_seed(29)
+    proc = pipe.image_processor
+    for li in range(2):
+        want = []
+        for im, rep in ((cannys[li], 1), (poss[li], 3)):
+            x = proc.preprocess(im, height=H, width=W).to("cuda", BF)
+            if x.shape[1] == 1:
+                x = x.repeat(1, 3, 1, 1)
+            noise = torch.randn(1, 16, H // 8, W // 8, device="cuda", dtype=BF)
+            with torch.no_grad():
+                want.append(V.encode_for_pipeline(sdd, cfg, x.float(), noise.float()))
+        want = O.pack_latents(torch.cat(want, dim=1))
+        # sample = mean + exp(logvar / 2) * noise: with RANDOM weights the log-variances are O(1), so the noise term is
+        # as large as the mean and exp() doubles the relative error of logvar (a trained VAE has std ~ 1e-3 and the
+        # sample is the mean); the moments themselves are held to 2e-2 above
+        assert rel_l2(box["control_image_list"][li], want) < 4e-2, li
+    # decode: the pipeline's image against the oracle's decode of ITS final latents
+    lat = pipe(prompt="لافتة", height=H, width=W, num_inference_steps=2, guidance_scale=3.5, control_image=cannys,
+               control_position=poss, control_mask=masks, controlnet_conditioning_scale=1.0, max_sequence_length=128,
+               generator=torch.Generator(device="cuda").manual_seed(5), output_type="latent").images
+    z = pipe._unpack_latents(lat, H, W, pipe.vae_scale_factor).float()
+    with torch.no_grad():
+        ref = V.decode_for_pipeline(sdd, cfg, z)
+    got = pipe.vae.decode(pipe._unpack_latents(lat, H, W, pipe.vae_scale_factor) / cfg["scaling_factor"] +
+                          cfg["shift_factor"], return_dict=False)[0]
+    assert rel_l2(got, ref) < 2e-2
+    assert img.dtype in (BF, torch.float32) and bool(torch.isfinite(img.float()).all())
