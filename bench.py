@@ -27,6 +27,7 @@ import torch  # noqa: E402
 METRIC = "1024x1024 RepText denoise steps/s (ControlNet + FLUX.1-dev-arch transformer + Euler; 28 steps = 1 image)"
 UNIT = "steps/s"
 STEPS_PER_IMAGE = 28
+PROMPT = "a street sign in city, with the text 'مرحبا بالعالم', filmfotos, film grain, reversal film photography"
 
 
 def workload(name: str):
@@ -194,7 +195,8 @@ def run_b200(args, wl):
     import torch.distributed as dist
     from reptext_b200 import _lib, models, ops
     from reptext_b200.pipeline_flux_controlnet import FluxControlNetPipeline
-    from reptext_b200.pipeline_utils import SyntheticTextEncoders
+    from reptext_b200.pipeline_utils import SyntheticTokenizer
+    from reptext_b200 import text_encoders as TE
     from reptext_b200.scheduler import FlowMatchEulerDiscreteScheduler
     from reptext_b200.vae import AutoencoderKL
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -227,9 +229,15 @@ def run_b200(args, wl):
     mask_img = box_mask(H, W, (H // 3, H // 3 + H // 6, W // 5, W - W // 5))
     sch = FlowMatchEulerDiscreteScheduler()
     vae = AutoencoderKL.random_init(seed=102, dtype=dt, device=dev)   # FLUX.1-dev VAE architecture, random weights
-    pipe = FluxControlNetPipeline(sch, vae,
-                                  SyntheticTextEncoders(TR["joint_attention_dim"], TR["pooled_projection_dim"], dt, dev),
-                                  None, None, None, tr, cn)
+    # prompt encoders of the named architectures (T5-v1.1-XXL, CLIP ViT-L/14), random weights drawn on the device; the
+    # tokenizers are synthetic (hashing) - their vocabularies are checkpoint files
+    if TR["joint_attention_dim"] == TE.T5_XXL_CONFIG["d_model"] and TR["pooled_projection_dim"] == TE.CLIP_L_CONFIG["hidden_size"]:
+        t5 = TE.T5EncoderModel(None, TE.random_weights(TE.t5_param_shapes(TE.T5_XXL_CONFIG), 103, dev), dtype=dt, device=dev)
+        clip = TE.CLIPTextModel(None, TE.random_weights(TE.clip_param_shapes(TE.CLIP_L_CONFIG), 104, dev), dtype=dt, device=dev)
+        tok, tok2 = SyntheticTokenizer("clip", TE.CLIP_L_CONFIG["vocab_size"], 77), SyntheticTokenizer("t5", TE.T5_XXL_CONFIG["vocab_size"], 512)
+    else:
+        raise SystemExit("bench workloads use the FLUX.1-dev text widths (4096 / 768)")
+    pipe = FluxControlNetPipeline(sch, vae, clip, tok, t5, tok2, tr, cn)
     mask = pipe._regional_masks([mask_img], dev, dt)[0]
     lat, pe, po, cond = [t.to(dev, non_blocking=True) for t in (h_lat, h_pe, h_po, h_cond)]
     img_ids = pipe._prepare_latent_image_ids(1, 2 * (H // 16), 2 * (W // 16), dev, dt)
@@ -324,7 +332,7 @@ def run_b200(args, wl):
         return {}
 
     def one_image(steps):
-        out = pipe(prompt_embeds=h_pe, pooled_prompt_embeds=h_po, height=H, width=W, num_inference_steps=steps,
+        out = pipe(prompt=PROMPT, max_sequence_length=T, height=H, width=W, num_inference_steps=steps,
                    guidance_scale=3.5, control_image=[canny], control_position=[pos], control_mask=[mask_img],
                    controlnet_conditioning_scale=1.0, latents=h_lat, output_type="pt", callback_on_step_end=tap)
         res = out.images.to("cpu", non_blocking=False)     # the decoded image [1, 3, H, W]
@@ -345,9 +353,32 @@ def run_b200(args, wl):
         if world > 1:
             dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         e2e_value = n_samples * STEPS_PER_IMAGE / (float(e2e_ms.item()) / 1000.0)
-        h2d_total = sum(t.numel() * t.element_size() for t in (h_pe, h_po, h_lat, canny, pos)) + mask_img.size * 4
+        h2d_total = sum(t.numel() * t.element_size() for t in (h_lat, canny, pos)) + mask_img.size * 4 + (T + 77) * 8
         h2d_step = h2d_total / STEPS_PER_IMAGE
         d2h_step = (d2h[0] + res.numel() * res.element_size()) / STEPS_PER_IMAGE
+
+    # ---- the prompt encoders on their own: once per image, device-timed
+    text_info = None
+    if rank == 0 and not args.no_e2e:
+        ids5 = tok2([PROMPT], padding="max_length", max_length=T, truncation=True).input_ids.to(dev)
+        idsc = tok([PROMPT], padding="max_length", max_length=77, truncation=True).input_ids.to(dev)
+        def _tt(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        c5 = TE.T5_XXL_CONFIG
+        t5_flop = c5["num_layers"] * (2.0 * T * (4 * c5["d_model"] * c5["d_model"] + 3 * c5["d_model"] * c5["d_ff"])
+                                      + 4.0 * T * T * c5["d_model"])
+        t5_ms, clip_ms = _tt(lambda: t5(ids5)), _tt(lambda: clip(idsc))
+        text_info = dict(t5_xxl_ms=t5_ms, t5_xxl_tflops=t5_flop / t5_ms / 1e9, clip_l_ms=clip_ms, tokens=T,
+                         note="T5EncoderModel / CLIPTextModel drop-ins (reptext_b200/text_encoders.py), random weights, "
+                              "synthetic tokenizer; inside the e2e figure once per image")
 
     # ---- the VAE on its own: two encodes per text line + one decode per image, device-timed
     vae_info = None
@@ -426,10 +457,11 @@ def run_b200(args, wl):
                                 tensor_util_whole_step=flops / gpus_per_sample / (step_ms / 1000.0) / 1e12 / pk["bf16_sustained"],
                                 finite_output=finite),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_step, d2h_bytes_per_step=d2h_step,
-                             how="FluxControlNetPipeline.__call__(output_type='pt'), one 28-step image from pinned host "
-                                 "inputs: VAE encode of the Canny and position images, 28 denoise steps with the latents "
-                                 "copied to the host after every step, VAE decode, image copied to the host"),
-                    vae=vae_info,
+                             how="FluxControlNetPipeline.__call__(prompt=str, output_type='pt'), one 28-step image from "
+                                 "host inputs: tokenise, CLIP-L + T5-XXL prompt encode, VAE encode of the Canny and position "
+                                 "images, 28 denoise steps with the latents copied to the host after every step, VAE "
+                                 "decode, image copied to the host"),
+                    vae=vae_info, text_encoders=text_info,
                     gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu, breakdown=breakdown)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -321,6 +321,27 @@ RT_API int rt_nhwc_to_nchw(const void* in, int ld, void* out, int dst_dtype, int
 RT_API int rt_vae_posterior_sample(const void* moments, int ld, int latent_channels, int batch, int64_t hw,
                                    const void* noise, void* out, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Prompt-encoder path: transformers' T5EncoderModel and CLIPTextModel as the pipelines call
+ * them (RepText/pipeline_flux_controlnet.py:232-347).  bf16 only; the projections / MLPs run on rt_gemm.
+ * ------------------------------------------------------------------------------------------------ */
+/* out[r, :] = (x[r, :] - mean?) * rsqrt(var + eps) * weight (+ bias): subtract_mean = 0 is T5LayerNorm (RMS, bias NULL),
+ * 1 is nn.LayerNorm.  D <= 4096, multiple of 8. */
+RT_API int rt_norm_rows(const void* x, int64_t x_ld, void* out, int64_t out_ld, int64_t rows, int D, const void* weight,
+                        const void* bias, float eps, int subtract_mean, void* stream);
+/* softmax(scale * q k^T + rel_bias[h][key - query + S - 1], keys <= query if causal) v for head_dim 64;
+ * q / k / v at column offsets of one [batch, S, ld] buffer, head-major; rel_bias [heads, 2 S - 1] fp32 or NULL */
+RT_API int rt_text_attention(const void* qkv, int64_t batch_stride, int ld, int q_col0, int k_col0, int v_col0, void* out,
+                             int64_t out_batch_stride, int out_ld, int out_col0, int batch, int S, int heads, int hd,
+                             float scale, const float* rel_bias, int causal, void* stream);
+/* kind 0: out[r, :F] = in[r, :F] * in[r, F:2F] (T5's gated-GELU; the GELU is the GEMM epilogue's);
+ * kind 1: out[r, :F] = quick_gelu(in[r, :F]) (CLIP) */
+RT_API int rt_glu_act(int kind, const void* in, int64_t in_ld, void* out, int64_t out_ld, int64_t rows, int F, void* stream);
+/* out[i, :] = table[ids[i], :] (+ pos_table[i % S, :]); ids: int64 on the device; *bad_flag (device int, zeroed by the
+ * caller) is set when an id is outside [0, vocab) */
+RT_API int rt_embedding(const void* table, int64_t vocab, int D, const int64_t* ids, int64_t n, const void* pos_table, int S,
+                        void* out, int* bad_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@ EXPORTS = [
     "rt_gemm", "rt_attention", "rt_layernorm_modulate", "rt_rope_table", "rt_qknorm_rope",
     "rt_groupnorm_nhwc", "rt_upsample_nearest2x_nhwc", "rt_softmax_rows", "rt_im2col3x3_nhwc",
     "rt_nchw_to_nhwc", "rt_nhwc_to_nchw", "rt_vae_posterior_sample",
+    "rt_norm_rows", "rt_text_attention", "rt_glu_act", "rt_embedding",
 ]
 
 
@@ -179,6 +180,14 @@ def lib() -> C.CDLL:
     L.rt_nhwc_to_nchw.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p]
     L.rt_vae_posterior_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_void_p]
+    L.rt_norm_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_float, C.c_int, C.c_void_p]
+    L.rt_text_attention.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int,
+                                    C.c_void_p]
+    L.rt_glu_act.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+    L.rt_embedding.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
+                               C.c_void_p, C.c_void_p]
     L.rt_rope_table.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     L.rt_qknorm_rope.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -235,7 +244,7 @@ def set_option(name: str, value: int) -> None:
 
 
 PROF_CLASSES = ["gemm_tcgen05", "gemm_simt", "attention_tcgen05", "attention_simt", "layernorm_modulate", "gemv",
-                "elementwise"]
+                "elementwise", "attention_text_mma"]
 
 
 def profile_reset() -> None:

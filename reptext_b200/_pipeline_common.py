@@ -15,6 +15,7 @@ true-CFG step 0 predicts zero; inpaint residuals are dropped when no text-line r
 """
 from __future__ import annotations
 
+import warnings
 from typing import Any, Callable, Dict, List, Optional, Union
 
 import numpy as np
@@ -119,11 +120,53 @@ class RepTextPipelineBase(DiffusionPipeline):
         if max_sequence_length is not None and max_sequence_length > 512:
             raise ValueError(f"`max_sequence_length` cannot be greater than 512 but is {max_sequence_length}")
 
-    def _encode_text(self, prompt, num_images_per_prompt, max_sequence_length):
+    def _get_t5_prompt_embeds(self, prompt, num_images_per_prompt: int = 1, max_sequence_length: int = 512, device=None,
+                              dtype=None):
+        """``:232-304``: tokenizer_2 (padding to ``max_sequence_length``, truncation) -> ``text_encoder_2(ids)[0]``; no
+        attention mask is passed, as upstream."""
+        device = device or self._execution_device
+        prompt = [prompt] if isinstance(prompt, str) else list(prompt)
+        batch_size = len(prompt)
+        text_inputs = self.tokenizer_2(prompt, padding="max_length", max_length=max_sequence_length, truncation=True,
+                                       return_length=False, return_overflowing_tokens=False, return_tensors="pt")
+        text_input_ids = text_inputs.input_ids
+        untruncated_ids = self.tokenizer_2(prompt, padding="longest", return_tensors="pt").input_ids
+        if untruncated_ids.shape[-1] >= text_input_ids.shape[-1] and not torch.equal(text_input_ids, untruncated_ids):
+            warnings.warn(f"part of the prompt was truncated: `max_sequence_length` is {max_sequence_length} tokens")
+        prompt_embeds = self.text_encoder_2(text_input_ids.to(device), output_hidden_states=False)[0]
+        prompt_embeds = prompt_embeds.to(dtype=self.text_encoder_2.dtype, device=device)
+        _, seq_len, _ = prompt_embeds.shape
+        prompt_embeds = prompt_embeds.repeat(1, num_images_per_prompt, 1)
+        return prompt_embeds.view(batch_size * num_images_per_prompt, seq_len, -1)
+
+    def _get_clip_prompt_embeds(self, prompt, num_images_per_prompt: int = 1, device=None):
+        """``:307-347``: tokenizer (77 tokens) -> ``text_encoder(ids).pooler_output``."""
+        device = device or self._execution_device
+        prompt = [prompt] if isinstance(prompt, str) else list(prompt)
+        batch_size = len(prompt)
+        text_inputs = self.tokenizer(prompt, padding="max_length", max_length=self.tokenizer_max_length, truncation=True,
+                                     return_overflowing_tokens=False, return_length=False, return_tensors="pt")
+        text_input_ids = text_inputs.input_ids
+        untruncated_ids = self.tokenizer(prompt, padding="longest", return_tensors="pt").input_ids
+        if untruncated_ids.shape[-1] >= text_input_ids.shape[-1] and not torch.equal(text_input_ids, untruncated_ids):
+            warnings.warn(f"part of the prompt was truncated: CLIP takes {self.tokenizer_max_length} tokens")
+        pooled = self.text_encoder(text_input_ids.to(device), output_hidden_states=False).pooler_output
+        pooled = pooled.to(dtype=self.text_encoder.dtype, device=device)
+        pooled = pooled.repeat(1, num_images_per_prompt)
+        return pooled.view(batch_size * num_images_per_prompt, -1)
+
+    def _encode_text(self, prompt, num_images_per_prompt, max_sequence_length, clip_prompt=None):
+        """Prompt(s) -> (T5 embeddings [B, L, 4096], CLIP pooled [B, 768]).  With tokenizers and both encoders attached
+        this is the reference's path (``:349-456``: CLIP on ``prompt``, T5 on ``prompt_2``); a single object with an
+        ``encode(prompts, L)`` method in the ``text_encoder`` slot is the synthetic stand-in."""
         enc = getattr(self, "text_encoder", None)
+        if all(getattr(self, n, None) is not None for n in ("tokenizer", "tokenizer_2", "text_encoder_2")) and enc is not None:
+            pooled = self._get_clip_prompt_embeds(clip_prompt if clip_prompt is not None else prompt, num_images_per_prompt)
+            pe = self._get_t5_prompt_embeds(prompt, num_images_per_prompt, max_sequence_length)
+            return pe, pooled
         if enc is None or not hasattr(enc, "encode"):
             raise ValueError("no text encoder is attached to this pipeline: pass `prompt_embeds` and "
-                             "`pooled_prompt_embeds` (the T5 / CLIP encoders are outside the accelerated path)")
+                             "`pooled_prompt_embeds`, or attach tokenizer / tokenizer_2 / text_encoder / text_encoder_2")
         prompts = [prompt] if isinstance(prompt, str) else list(prompt)
         pe, po = enc.encode(prompts, max_sequence_length)
         pe = pe.repeat_interleave(num_images_per_prompt, dim=0)

@@ -132,7 +132,7 @@ void launch_sp_barrier(const rt_sp_group& g, cudaStream_t stream);
 // When the option is on, every launch of a class is bracketed by CUDA events on ITS stream; bench.py reads
 // the per-class sums (rt_profile_read) for the roofline line.  Off by default (zero overhead).
 enum ProfClass : int { PROF_GEMM_TC = 0, PROF_GEMM_SIMT, PROF_ATTN_TC, PROF_ATTN_SIMT, PROF_LN, PROF_GEMV, PROF_ELEM,
-                       PROF_NCLS };
+                       PROF_ATTN_TEXT, PROF_NCLS };
 struct ProfScope {
   ProfScope(int cls, double work, cudaStream_t s);
   ~ProfScope();

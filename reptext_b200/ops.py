@@ -330,3 +330,55 @@ def vae_posterior_sample(moments: torch.Tensor, hw: Sequence[int], latent_channe
     L.check(L.lib().rt_vae_posterior_sample(L.ptr(moments), ld, latent_channels, B, HW, L.ptr(noise), L.ptr(out),
                                             L.dtype_code(dtype), L.stream_ptr()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# Prompt-encoder operators; bf16 tensors shaped [batch, S, D]
+# ------------------------------------------------------------------------------------------------------
+def norm_rows(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float,
+              subtract_mean: bool) -> torch.Tensor:
+    """T5LayerNorm (``subtract_mean=False``, no bias) or nn.LayerNorm over the last dimension."""
+    assert x.stride(-1) == 1 and x.is_contiguous() and x.dtype == torch.bfloat16
+    D = x.shape[-1]
+    out = torch.empty_like(x)
+    L.check(L.lib().rt_norm_rows(L.ptr(x), D, L.ptr(out), D, x.numel() // D, D, L.ptr(weight), L.ptr(bias), float(eps),
+                                 int(subtract_mean), L.stream_ptr()))
+    return out
+
+
+def text_attention(qkv: torch.Tensor, heads: int, scale: float, rel_bias: Optional[torch.Tensor] = None,
+                   causal: bool = False) -> torch.Tensor:
+    """qkv [B, S, 3 * heads * 64] (q | k | v, head-major) -> [B, S, heads * 64]."""
+    B, S, W3 = qkv.shape
+    D = heads * 64
+    assert W3 == 3 * D and qkv.is_contiguous() and qkv.dtype == torch.bfloat16
+    if rel_bias is not None:
+        assert rel_bias.dtype == torch.float32 and rel_bias.is_contiguous() and tuple(rel_bias.shape) == (heads, 2 * S - 1)
+    out = torch.empty(B, S, D, dtype=qkv.dtype, device=qkv.device)
+    L.check(L.lib().rt_text_attention(L.ptr(qkv), qkv.stride(0), qkv.stride(1), 0, D, 2 * D, L.ptr(out), out.stride(0),
+                                      out.stride(1), 0, B, S, heads, 64, float(scale), L.ptr(rel_bias), int(causal),
+                                      L.stream_ptr()))
+    return out
+
+
+def glu_act(x: torch.Tensor, F_out: int, kind: int) -> torch.Tensor:
+    """kind 0: x[..., :F] * x[..., F:2F]; kind 1: quick_gelu(x[..., :F])."""
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    rows = x.numel() // x.shape[-1]
+    out = torch.empty(*x.shape[:-1], F_out, dtype=x.dtype, device=x.device)
+    L.check(L.lib().rt_glu_act(kind, L.ptr(x), x.shape[-1], L.ptr(out), F_out, rows, F_out, L.stream_ptr()))
+    return out
+
+
+def embedding(table: torch.Tensor, ids: torch.Tensor, pos_table: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """table[ids] (+ pos_table[position]) for ids [B, S] (int64); raises IndexError on ids outside the table."""
+    assert table.is_contiguous() and table.dtype == torch.bfloat16 and ids.dim() == 2
+    ids = ids.to(device=table.device, dtype=torch.int64).contiguous()
+    B, S = ids.shape
+    out = torch.empty(B, S, table.shape[1], dtype=table.dtype, device=table.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=table.device)
+    L.check(L.lib().rt_embedding(L.ptr(table), table.shape[0], table.shape[1], L.ptr(ids), B * S, L.ptr(pos_table), S,
+                                 L.ptr(out), L.ptr(bad), L.stream_ptr()))
+    if int(bad.item()):
+        raise IndexError("token id outside the embedding table")
+    return out

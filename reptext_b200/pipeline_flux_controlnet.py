@@ -36,7 +36,7 @@ class FluxControlNetPipeline(RepTextPipelineBase):
         device = device or self._execution_device
         if prompt_embeds is None:
             prompt_embeds, pooled_prompt_embeds = self._encode_text(prompt_2 or prompt, num_images_per_prompt,
-                                                                    max_sequence_length)
+                                                                    max_sequence_length, clip_prompt=prompt)
         return prompt_embeds, pooled_prompt_embeds, self._text_ids(prompt_embeds.shape[1], device)
 
     @torch.no_grad()

@@ -45,7 +45,7 @@ class FluxControlNetPipeline(RepTextPipelineBase):
         device = device or self._execution_device
         if prompt_embeds is None:
             prompt_embeds, pooled_prompt_embeds = self._encode_text(prompt_2 or prompt, num_images_per_prompt,
-                                                                    max_sequence_length)
+                                                                    max_sequence_length, clip_prompt=prompt)
         if do_classifier_free_guidance:
             if negative_prompt_embeds is None:
                 negative_prompt = negative_prompt or DEFAULT_NEGATIVE_PROMPT

@@ -234,6 +234,54 @@ class SyntheticTextEncoders:
         return (torch.stack(pe).to(self.device, self.dtype), torch.stack(po).to(self.device, self.dtype))
 
 
+class _TokenizerOutput(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k) from None
+
+
+class SyntheticTokenizer:
+    """Stand-in for the CLIP BPE / T5 sentencepiece tokenizers (their vocabulary files are checkpoints; there is no
+    network): whitespace-split words hashed into the id range, with the framing of the real ones - ``kind="clip"``:
+    BOS, words, EOS (the LARGEST id, as in CLIP's vocabulary, which ``pooler_output`` relies on), padded with the
+    EOS / pad id; ``kind="t5"``: words, EOS = 1, padded with 0.  Same call signature and ``.input_ids`` result as a
+    transformers tokenizer.  NOT a language tokenizer."""
+
+    def __init__(self, kind: str, vocab_size: int, model_max_length: int):
+        assert kind in ("clip", "t5")
+        self.kind, self.vocab_size, self.model_max_length = kind, vocab_size, model_max_length
+        if kind == "clip":
+            self.bos_token_id, self.eos_token_id, self.pad_token_id = vocab_size - 2, vocab_size - 1, vocab_size - 1
+        else:
+            self.bos_token_id, self.eos_token_id, self.pad_token_id = None, 1, 0
+
+    def _words(self, text: str) -> List[int]:
+        lo, hi = (0, self.vocab_size - 2) if self.kind == "clip" else (2, self.vocab_size)
+        out = []
+        for w in text.split():
+            h = int.from_bytes(hashlib.sha256(w.encode("utf-8")).digest()[:6], "little")
+            out.append(lo + h % (hi - lo))
+        return out
+
+    def __call__(self, text, padding="longest", max_length=None, truncation=False, return_tensors="pt", **kw):
+        texts = [text] if isinstance(text, str) else list(text)
+        rows = []
+        for t in texts:
+            ids = self._words(t)
+            ids = ([self.bos_token_id] if self.kind == "clip" else []) + ids + [self.eos_token_id]
+            if truncation and max_length is not None and len(ids) > max_length:
+                ids = ids[:max_length - 1] + [self.eos_token_id]
+            rows.append(ids)
+        width = max_length if padding == "max_length" and max_length is not None else max(len(r) for r in rows)
+        rows = [r + [self.pad_token_id] * (width - len(r)) for r in rows]
+        return _TokenizerOutput(input_ids=torch.tensor(rows, dtype=torch.long))
+
+    def batch_decode(self, ids, **kw):
+        return ["<%d tokens>" % len(r) for r in ids]
+
+
 @contextlib.contextmanager
 def no_grad():
     with torch.no_grad():

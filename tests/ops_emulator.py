@@ -51,6 +51,8 @@ def gemm(problems, batch, dtype, rope=None, head_dim=0, impl=0, sp_out=None, sp_
             view = s.out[:, p.out_row0:p.out_row0 + m, s.out_col0:s.out_col0 + n]
             if s.mode == L.EPI_BIAS:
                 r = acc
+            elif s.mode == L.EPI_GELU:
+                r = F.gelu(acc, approximate="tanh")
             elif s.mode == L.EPI_GATE_RESID:
                 g = p.gate.double()[:, None, :] if p.gate is not None else 1.0
                 r = view.double() + g * acc
@@ -108,7 +110,45 @@ def vae_posterior_sample(moments, hw, latent_channels, noise, dtype):
     return z.to(dtype)
 
 
+def norm_rows(x, weight, bias, eps, subtract_mean):
+    t = x.double()
+    if subtract_mean:
+        t = t - t.mean(-1, keepdim=True)
+    y = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + eps) * weight.double()
+    if bias is not None:
+        y = y + bias.double()
+    return y.to(x.dtype)
+
+
+def text_attention(qkv, heads, scale, rel_bias=None, causal=False):
+    B, S, W3 = qkv.shape
+    D = W3 // 3
+    q, k, v = [t.double().view(B, S, heads, 64).transpose(1, 2) for t in qkv.split(D, dim=-1)]
+    s = scale * (q @ k.transpose(-1, -2))
+    i = torch.arange(S)
+    if rel_bias is not None:
+        s = s + rel_bias.double()[:, (i[None, :] - i[:, None]) + S - 1][None]
+    if causal:
+        s = s + torch.full((S, S), float("-inf"), dtype=torch.float64).triu(1)
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, S, D).to(qkv.dtype)
+
+
+def glu_act(x, F_out, kind):
+    a = x[..., :F_out].double()
+    r = a * x[..., F_out:2 * F_out].double() if kind == 0 else a * torch.sigmoid(1.702 * a)
+    return r.to(x.dtype)
+
+
+def embedding(table, ids, pos_table=None):
+    if int(ids.min()) < 0 or int(ids.max()) >= table.shape[0]:
+        raise IndexError("token id outside the embedding table")
+    out = table[ids]
+    if pos_table is not None:
+        out = out + pos_table[: ids.shape[1]]
+    return out
+
+
 def install(monkeypatch, ops_module):
     for name in ("gemm", "groupnorm_nhwc", "upsample_nearest2x_nhwc", "softmax_rows_", "im2col3x3_nhwc", "nchw_to_nhwc",
-                 "nhwc_to_nchw", "vae_posterior_sample"):
+                 "nhwc_to_nchw", "vae_posterior_sample", "norm_rows", "text_attention", "glu_act", "embedding"):
         monkeypatch.setattr(ops_module, name, globals()[name])
