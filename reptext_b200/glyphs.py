@@ -7,8 +7,9 @@ ControlNet image; the sum of all glyph images is the optional ``control_glyph`` 
 loop as functions so that the drop-in pipelines can be driven exactly like ``infer.py`` drives the reference.
 
 Arabic (and other right-to-left, contextually shaped) text must be reshaped and reordered BEFORE PIL draws it unless PIL
-was built with libraqm: ``shape_text`` uses ``arabic_reshaper`` + ``python-bidi`` when they are installed, PIL's own
-raqm layout when it is available, and otherwise draws the string as given (isolated forms, logical order) and says so.
+was built with libraqm: ``shape_text`` leaves the string alone when raqm is available, uses ``arabic_reshaper`` +
+``python-bidi`` when they are installed, and otherwise the built-in shaper of ``reptext_b200/arabic.py`` (presentation
+forms from the Unicode Character Database, lam-alef ligatures, UBA reordering for mixed Arabic / digits / Latin lines).
 """
 from __future__ import annotations
 
@@ -49,9 +50,8 @@ def shape_text(text: str) -> str:
         from bidi.algorithm import get_display
         return get_display(arabic_reshaper.reshape(text))
     except Exception:
-        warnings.warn("right-to-left text without libraqm, arabic_reshaper or python-bidi: glyphs are drawn in "
-                      "logical order and isolated forms", RuntimeWarning, stacklevel=2)
-        return text
+        from . import arabic
+        return arabic.shape(text)
 
 
 def canny(img_bgr: np.ndarray, low_threshold: int = 50, high_threshold: int = 100) -> np.ndarray:
