@@ -12,7 +12,8 @@ from typing import Optional, Sequence
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "librt_reptext.so")
+# RT_LIB: A/B aid - load another BUILD of this same library (e.g. the previous commit's) instead of the in-tree one
+LIB_PATH = os.environ.get("RT_LIB") or os.path.join(HERE, "csrc", "librt_reptext.so")
 
 RT_F32, RT_BF16 = 0, 1
 RT_TRANSFORMER, RT_CONTROLNET = 0, 1

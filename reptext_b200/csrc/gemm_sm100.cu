@@ -500,9 +500,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   uint64_t* tempty_bar = bars + 2 * C::kStages + C::kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 2 * C::kAccStages);
 
-  const int warp = threadIdx.x >> 5;
+  // warp / CTA-rank values go through a shuffle so that the compiler can PROVE them warp-uniform: the producer and
+  // MMA-issuer loops below are then compiled onto the uniform datapath (descriptors in uniform registers) instead of
+  // per-instruction R2UR + waterfall loops (115 SASS instructions per k-block for 4 MMAs, measured with ncu: the
+  // issuing thread was busy 82 % of the time and the tensor pipe starved behind it).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (kCtaGroup == 2) ? ptx::cluster_ctarank() : 0u;
+  const uint32_t cta_rank = (kCtaGroup == 2) ? (uint32_t)__shfl_sync(0xffffffffu, (int)ptx::cluster_ctarank(), 0) : 0u;
   const bool leader = cta_rank == 0;
   const int cluster_id = blockIdx.x / kCtaGroup;
   const int num_clusters = gridDim.x / kCtaGroup;
@@ -537,8 +541,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   ptx::grid_launch_dependents();
   ptx::grid_dependency_wait();
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
     // L2 eviction hints (activations evict_last, weights evict_first) are OFF by default: measured with ncu over the
     // 188 GEMM launches of a step they RAISE DRAM reads from 52 GB to 74 GB - a weight tile is shared by the 16-18
     // row tiles of its wave, and evict_first drops it before the neighbours have fetched it.
@@ -558,36 +562,42 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         void* sa = smem_a + stage * C::kABytes;
         void* sb = smem_b + stage * C::kBBytes;
         const int k0 = (P.debug & 2) ? 0 : kb * BK;
-        if (pr.conv_w > 0) {
-          // implicit 3x3 convolution: this CTA's 128 pixels start at (x, y) of image a_b
-          const int m_cta = tc.m0 + (int)cta_rank * BM;
-          const int y = m_cta / pr.conv_w, x = m_cta - y * pr.conv_w;
-          const int tap = kb / pr.conv_kcb, cb = kb - tap * pr.conv_kcb;
-          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-          if constexpr (kCtaGroup == 1) {
+        if (ptx::elect_one()) {
+          if (pr.conv_w > 0) {
+            // implicit 3x3 convolution: this CTA's 128 pixels start at (x, y) of image a_b
+            const int m_cta = tc.m0 + (int)cta_rank * BM;
+            const int y = m_cta / pr.conv_w, x = m_cta - y * pr.conv_w;
+            const int tap = kb / pr.conv_kcb, cb = kb - tap * pr.conv_kcb;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            if constexpr (kCtaGroup == 1) {
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+              ptx::tma_load_4d(&pr.tmA, &full_bar[stage], sa, cb * BK, x + dx, y + dy, a_b);
+              ptx::tma_load_2d(&sg.tmW, &full_bar[stage], sb, k0, w_row);
+            } else {
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+              ptx::tma_load_4d_2sm(&pr.tmA, &full_bar[stage], sa, cb * BK, x + dx, y + dy, a_b);
+              ptx::tma_load_2d_2sm(&sg.tmW, &full_bar[stage], sb, k0, w_row);
+            }
+          } else if constexpr (kCtaGroup == 1) {
             ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-            ptx::tma_load_4d(&pr.tmA, &full_bar[stage], sa, cb * BK, x + dx, y + dy, a_b);
-            ptx::tma_load_2d(&sg.tmW, &full_bar[stage], sb, k0, w_row);
+            ptx::tma_load_3d_hint(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b, pol_a);
+            ptx::tma_load_2d_hint(&sg.tmW, &full_bar[stage], sb, k0, w_row, pol_w);
           } else {
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-            ptx::tma_load_4d_2sm(&pr.tmA, &full_bar[stage], sa, cb * BK, x + dx, y + dy, a_b);
-            ptx::tma_load_2d_2sm(&sg.tmW, &full_bar[stage], sb, k0, w_row);
+            ptx::tma_load_3d_2sm_hint(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b, pol_a);
+            ptx::tma_load_2d_2sm_hint(&sg.tmW, &full_bar[stage], sb, k0, w_row, pol_w);
           }
-        } else if constexpr (kCtaGroup == 1) {
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-          ptx::tma_load_3d_hint(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b, pol_a);
-          ptx::tma_load_2d_hint(&sg.tmW, &full_bar[stage], sb, k0, w_row, pol_w);
-        } else {
-          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-          ptx::tma_load_3d_2sm_hint(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b, pol_a);
-          ptx::tma_load_2d_2sm_hint(&sg.tmW, &full_bar[stage], sb, k0, w_row, pol_w);
         }
+        __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
-    // ===================== MMA issuer (leader CTA only) =====================
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader CTA only; whole warp runs the loop, one elected lane issues) =====
     constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * kCtaGroup, BN, 0, 0);
+    // stage 0 descriptors; a stage advances the 14-bit (addr >> 4) field (the ring is < 256 KB: no carry out of it)
+    const uint64_t adesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a), 0, 1024);
+    const uint64_t bdesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b), 0, 1024);
     int stage = 0, phase = 0, iter = 0;
     for (int t = cluster_id; t < P.total_tiles; t += num_clusters, ++iter) {
       const TileCoord tc = decode_tile(P, t, BN, kRowsPerTile);
@@ -599,20 +609,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint64_t adesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * C::kABytes), 0, 1024);
-        const uint64_t bdesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * C::kBBytes), 0, 1024);
+        const uint64_t adesc = adesc0 + (uint64_t)(stage * (C::kABytes >> 4));
+        const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (C::kBBytes >> 4));
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          ptx::mma_bf16_ss<kCtaGroup>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            ptx::mma_bf16_ss<kCtaGroup>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (kCtaGroup == 1) {
+            ptx::mma_commit(&empty_bar[stage]);
+            if (kb == nkb - 1) ptx::mma_commit(&tfull_bar[as]);
+          } else {
+            ptx::mma_commit_2sm(&empty_bar[stage], 3);
+            if (kb == nkb - 1) ptx::mma_commit_2sm(&tfull_bar[as], 3);
+          }
         }
-        if constexpr (kCtaGroup == 1) {
-          ptx::mma_commit(&empty_bar[stage]);
-          if (kb == nkb - 1) ptx::mma_commit(&tfull_bar[as]);
-        } else {
-          ptx::mma_commit_2sm(&empty_bar[stage], 3);
-          if (kb == nkb - 1) ptx::mma_commit_2sm(&tfull_bar[as], 3);
-        }
+        __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -637,8 +650,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                  smem + C::kEpiStageOff + quad * kStageWarpBytes);
       }
       ptx::tc_fence_before();
+      // The hand-off's payload is TMEM (tcgen05.ld completed by tcgen05.wait::ld, ordered by the fence above), so the
+      // remote arrive needs no release: .release.cluster costs MEMBAR.ALL.GPU + ERRBAR per thread and tile, i.e. every
+      // epilogue thread would wait for its global stores to be acknowledged before freeing the accumulator.
       if constexpr (kCtaGroup == 1) ptx::mbar_arrive(&tempty_bar[as]);
-      else ptx::mbar_arrive_cluster(&tempty_bar[as], 0);
+      else ptx::mbar_arrive_cluster_relaxed(&tempty_bar[as], 0);
     }
   }
 
