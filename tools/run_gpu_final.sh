@@ -9,3 +9,5 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/f
 echo "ref rc=$?"; cut -c1-400 gpurun_out/final_bench_ref.json
 timeout 900 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err
 echo "bench rc=$?"; tail -3 gpurun_out/final_bench.err | cut -c1-300; cut -c1-1500 gpurun_out/final_bench.json
+timeout 600 python tools/bench_inpaint.py > gpurun_out/final_inpaint.json 2> gpurun_out/final_inpaint.err; echo "inpaint rc=$?"; tail -1 gpurun_out/final_inpaint.json | cut -c1-400
+timeout 600 python bench.py --workload cfg5 --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/final_cfg5_1gpu.json 2> gpurun_out/final_cfg5_1gpu.err; echo "cfg5 rc=$?"; cut -c1-300 gpurun_out/final_cfg5_1gpu.json
