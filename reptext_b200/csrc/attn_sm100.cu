@@ -34,6 +34,11 @@ constexpr int kSubBytes = kTileBytes / 2;
 constexpr int kSmemTiles = 2 + 2 * kStages;   // Q_A Q_B | K ring | V ring
 constexpr int kNumBars = 1 + 4 * kStages + 2 + 2 + 2 + 1;
 constexpr int kSmemBytes = kSmemTiles * kTileBytes + kNumBars * 8 + 16 + 1024;
+constexpr int kThreadsHalfRow = 640;                              // kHalfRow: 4 + 16 warps
+constexpr int kXchOff = kSmemTiles * kTileBytes + 256;            // kHalfRow: exchange area behind the barriers
+constexpr int kXchFloats = 3 * 512;                               // [2 parities + 1 for the row sums][tile][half][128 rows]
+constexpr int kSmemBytesHalfRow = kXchOff + kXchFloats * 4 + 1024;
+static_assert(kNumBars * 8 + 16 <= 256, "barrier block");
 
 struct AttnParams {
   CUtensorMap tm;   // (col, row, batch) over the qkv buffer, box (64, 128, 1), SWIZZLE_128B
@@ -92,9 +97,16 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // kPacked: softmax arithmetic on fp32 pairs, TMEM loads of S pipelined against the running max; kPolyMask8: bit
 // (i % 8) set = pair i takes exp2_poly2 instead of MUFU.  kSplitP: P is handed to the MMA warp in two halves of
 // 64 keys, so that P V can start while the second half is still being exponentiated.
+// kHalfRow: TWO threads per query row (640 threads: warps 4-7 / 8-11 = tile A keys 0-63 / 64-127 of the block, warps
+// 12-15 / 16-19 = tile B) - two softmax warps per tile on every scheduler instead of one, so that the fixed-latency
+// dependencies of one warp (IPC 0.38 in the ncu sampling of the one-thread-per-row form) are covered by the other.  The
+// two halves of a row exchange their maxima through shared memory (a 64-thread named barrier per tile and lane
+// quadrant), keep partial row sums until the epilogue, and hand P over separately: the first half arrives on p_half,
+// the second on p_full (needs kPacked and kSplitP).
 template <int kDebug, int kPolyEvery, bool kPacked = false, int kPolyMask8 = 0, bool kSplitP = false,
-          bool kElect = false>
-__global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_constant__ AttnParams P) {
+          bool kElect = false, bool kHalfRow = false>
+__global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
+    attn_tc_kernel(const __grid_constant__ AttnParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
@@ -254,6 +266,142 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel(const __grid_const
     if (ptx::elect_one()) ptx::mma_commit(o_full);
     __syncwarp();
   }
+  } else if constexpr (kHalfRow) {
+    // ===================== softmax, two threads per row =====================
+    static_assert(!kHalfRow || (kPacked && kSplitP && !kElect), "kHalfRow needs the packed, split-P, all-threads-arrive form");
+    // register budget: 640 x 96 at launch = 4 x 32 x 64 (after the dec above) + 16 x 32 x 104; the inc can only draw on what the
+    // CTA itself released, a larger request blocks for ever
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int idx = warp - 4;
+    const int quad = idx & 3;        // TMEM lane quadrant (= warp % 4)
+    const int hf = (idx >> 2) & 1;   // keys hf * 64 .. hf * 64 + 63 of every block
+    const int t = idx >> 3;          // 0: tile A, 1: tile B
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t s_addr = tmem + lane_off + t * 128;
+    const uint32_t o_addr = tmem + lane_off + 256 + t * 128;
+    const int bar_id = 1 + t * 4 + quad;  // named barrier of the two warps that share these 32 rows
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
+    float* xch = reinterpret_cast<float*>(smem + kXchOff);
+    float* x_mine = xch + (t * 2 + hf) * 128 + quad * 32 + lane;
+    const float* x_other = xch + (t * 2 + (hf ^ 1)) * 128 + quad * 32 + lane;
+    const float c = P.scale_log2;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      ptx::mbar_wait(&s_full[t], j & 1);
+      ptx::tc_fence_after();
+      const int n_valid = P.S - j * BKV - hf * 64;  // valid keys of this half (<= 0: none) - only short on the last block
+      uint32_t s0[32], s1[32];
+      auto chunk_max = [&](uint32_t (&sv)[32], int col0) {
+        if (n_valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i >= n_valid) sv[i] = 0xff800000u;  // -inf
+        }
+        float a = -INFINITY, b2 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          a = fmaxf(a, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+          b2 = fmaxf(b2, fmaxf(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])));
+        }
+        return fmaxf(a, b2);
+      };
+      ptx::tmem_ld_32x32b_x32(s_addr + hf * 64, s0);
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32b_x32(s_addr + hf * 64 + 32, s1);
+      float mx = chunk_max(s0, 0);
+      ptx::tmem_ld_wait();
+      mx = fmaxf(mx, chunk_max(s1, 32));
+      // the other half of the row: both threads now hold their scores in registers, so after this barrier the second
+      // half may overwrite columns 32..63 (P) that the first half has just read as scores
+      x_mine[(j & 1) * 512] = mx;
+      pair_sync();
+      mx = fmaxf(mx, x_other[(j & 1) * 512]);
+      const float mx_s = mx * c;
+      if (j == 0) {
+        m_ref = mx_s;
+      } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {  // same rows, same values: both halves decide alike
+        const float m_new = fmaxf(m_ref, mx_s);
+        const float f = ptx::ex2_approx(m_ref - m_new);
+        l *= f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {  // this half's 64 columns of O
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(o_addr + hf * 64 + ch * 16, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          ptx::tmem_st_32x32b_x16(o_addr + hf * 64 + ch * 16, r);
+        }
+        m_ref = m_new;
+      }
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
+      float2 lsum = make_float2(0.f, 0.f);
+      auto exp_chunk = [&](const uint32_t (&sv)[32], int col) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, nm2);
+          float2 e;
+          if ((kPolyMask8 >> (i & 7)) & 1) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = ptx::ex2_approx(x.x);
+            e.y = ptx::ex2_approx(x.y);
+          }
+          lsum = __fadd2_rn(lsum, e);
+          pk[i] = ptx::pack_bf16x2(e.x, e.y);
+        }
+        ptx::tmem_st_32x32b_x16(s_addr + col, pk);
+      };
+      exp_chunk(s0, hf * 32);
+      exp_chunk(s1, hf * 32 + 16);
+      l += lsum.x + lsum.y;
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(hf == 0 ? &p_half[t] : &p_full[t]);
+    }
+    // ---- epilogue: as below, the two halves of a row share one staging tile and split the copy-out
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    x_mine[2 * 512] = l;
+    pair_sync();
+    const float inv = 1.f / (l + x_other[2 * 512]);
+    constexpr int kPitch = HD * 2 + 16;
+    uint8_t* stage = smem + (t * 4 + quad) * (32 * kPitch);  // Q / K tiles are dead (o_full)
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      float v[32];
+      tmem_ld32(o_addr + hf * 64 + ch * 32, v);
+      uint4* dst = reinterpret_cast<uint4*>(stage + lane * kPitch + (hf * 2 + ch) * 64);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = ptx::pack_bf16x2(v[8 * i + 0] * inv, v[8 * i + 1] * inv);
+        u.y = ptx::pack_bf16x2(v[8 * i + 2] * inv, v[8 * i + 3] * inv);
+        u.z = ptx::pack_bf16x2(v[8 * i + 4] * inv, v[8 * i + 5] * inv);
+        u.w = ptx::pack_bf16x2(v[8 * i + 6] * inv, v[8 * i + 7] * inv);
+        dst[i] = u;
+      }
+    }
+    pair_sync();
+    const int row0 = q0 + t * BQ + quad * 32;
+    const int rr = lane >> 4, cc = lane & 15;
+#pragma unroll 4
+    for (int it = hf * 8; it < hf * 8 + 8; ++it) {
+      const int r = it * 2 + rr;
+      const int grow = row0 + r;
+      if (grow < P.S) {
+        bf16* orow;
+        if (P.sp_rows > 0) {
+          const int dest = grow / P.sp_rows;
+          orow = P.sp_out[dest] + (long long)b * P.out_bs + (long long)(grow - dest * P.sp_rows) * P.out_ld +
+                 P.out_col0 + h * HD;
+        } else {
+          orow = P.out + (long long)b * P.out_bs + (long long)grow * P.out_ld + P.out_col0 + h * HD;
+        }
+        *reinterpret_cast<uint4*>(orow + cc * 8) = *reinterpret_cast<const uint4*>(stage + r * kPitch + cc * 16);
+      }
+    }
   } else {
     // ===================== softmax warpgroups =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
@@ -1526,6 +1674,34 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
     for (int i = 0; i < kNumVariants6; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(table6[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes6));
     attr6_set = true;
+  }
+  // half-row kernels (two softmax threads per query row, 640 threads): variant 60 + i; poly share 25 / 0 / 50 / 37.5 %
+  static const KernelFn tableH[] = {attn_tc_kernel<0, 0, true, 0x88, true, false, true>,
+                                    attn_tc_kernel<0, 0, true, 0x00, true, false, true>,
+                                    attn_tc_kernel<0, 0, true, 0xAA, true, false, true>,
+                                    attn_tc_kernel<0, 0, true, 0x92, true, false, true>};
+  constexpr int kNumVariantsH = sizeof(tableH) / sizeof(tableH[0]);
+  static bool attrH_set = false;
+  if (!attrH_set) {
+    for (int i = 0; i < kNumVariantsH; ++i)
+      RT_CHECK_CUDA(cudaFuncSetAttribute(tableH[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesHalfRow));
+    attrH_set = true;
+  }
+  if (variant >= 60) {
+    RT_REQUIRE(variant - 60 < kNumVariantsH, "attention: unknown variant");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((long long)P.n_qpairs * a.heads * a.batch));
+    cfg.blockDim = dim3(kThreadsHalfRow);
+    cfg.dynamicSmemBytes = kSmemBytesHalfRow;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = get_option("no_pdl") ? 0 : 1;
+    RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tableH[variant - 60], P));
+    count_launch();
+    return;
   }
   if (variant >= 40) {
     RT_REQUIRE(variant - 40 < kNumVariants6, "attention: unknown variant");

@@ -188,6 +188,12 @@ def test_attention_tcgen05(ops, S, B, H):
     _attention_case(ops, torch.bfloat16, 128, S, 2, B, H)
 
 
+@pytest.mark.parametrize("impl", [62, 63, 64])  # two softmax threads per row (variants 60..62 = 25 / 0 / 50 % polynomial exp2)
+@pytest.mark.parametrize("S,B,H", [(256, 1, 1), (384, 2, 3), (40, 1, 1), (100, 1, 2), (4608, 1, 2), (1111, 2, 2)])
+def test_attention_tcgen05_half_row(ops, S, B, H, impl):
+    _attention_case(ops, torch.bfloat16, 128, S, impl, B, H)
+
+
 def _attention_case(ops, dtype, hd, S, impl, B, H):
     qkv = _rand((B, S, 3 * H * hd + 8), dtype, 1)
     out = ops.attention(qkv, H, hd, 0, H * hd, 2 * H * hd, impl=impl)
