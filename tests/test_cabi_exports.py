@@ -52,6 +52,24 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     assert "HGMMA" not in sass
 
 
+def test_gemm_issue_loops_stay_on_the_uniform_datapath():
+    """Regression guard for a silent 8 % slowdown: when the TMA-producer / MMA-issuer loops of gemm_tc_kernel are compiled as
+    single-lane (divergent) code, every tcgen05.mma / TMA operand goes through R2UR + a BRA.U.ANY waterfall loop (115 SASS
+    instructions per k-block, ncu: issuing thread busy 82 %, tensor pipe 80 % active); warp-uniform loops with one elected
+    lane have none (52 instructions, tensor pipe 94 %; profiles/r1_ncu_gemm_vs_cublas_probe.txt)."""
+    import subprocess
+    obj = os.path.join(ROOT, "reptext_b200", "csrc", "build", "gemm_sm100.o")
+    from reptext_b200 import build
+    build.build(force=False, verbose=False)
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    funcs = [f for f in re.split(r"\n\s*Function : ", sass)[1:] if "gemm_tc_kernel" in f.split("\n")[0]]
+    assert len(funcs) >= 5
+    for f in funcs:
+        assert f.count("UTCHMMA") == 4 and "UTMALDG" in f
+        assert "BRA.U.ANY" not in f, f.split("\n")[0]
+        assert f.count("R2UR") <= 48, (f.split("\n")[0], f.count("R2UR"))
+
+
 def test_no_product_module_imports_the_oracle():
     pkg = os.path.join(ROOT, "reptext_b200")
     for dirpath, _, files in os.walk(pkg):
