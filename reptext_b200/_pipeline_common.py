@@ -15,6 +15,7 @@ true-CFG step 0 predicts zero; inpaint residuals are dropped when no text-line r
 """
 from __future__ import annotations
 
+import os
 import warnings
 from typing import Any, Callable, Dict, List, Optional, Union
 
@@ -57,9 +58,67 @@ def retrieve_latents(encoder_output, generator=None, sample_mode: str = "sample"
     raise AttributeError("Could not access latents of provided encoder_output")
 
 
+def _load_tokenizer(dirpath: str, class_name: Optional[str]):
+    """Tokenizers stay upstream's and host-side: transformers' ``CLIPTokenizer`` / ``T5TokenizerFast`` read from the
+    pipeline directory's ``tokenizer/`` and ``tokenizer_2/`` (never from the hub)."""
+    if not os.path.isdir(dirpath):
+        raise OSError(f"{dirpath!r} is missing")
+    try:
+        import transformers
+    except ImportError as e:  # pragma: no cover - transformers is part of the reference's own requirements
+        raise ImportError("loading a tokenizer directory needs the `transformers` package (RepText/requirements.txt)") from e
+    tok_cls = getattr(transformers, class_name or "", None) or transformers.AutoTokenizer
+    return tok_cls.from_pretrained(dirpath, local_files_only=True)
+
+
 class RepTextPipelineBase(DiffusionPipeline):
     _callback_tensor_inputs = ["latents", "prompt_embeds"]
     _inpaint = False
+
+    # ---- RepText/infer.py:31-33: FluxControlNetPipeline.from_pretrained(base_model, controlnet=..., torch_dtype=...) --
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, torch_dtype: torch.dtype = torch.bfloat16,
+                        device: Union[str, torch.device] = "cuda", variant: Optional[str] = None, **components):
+        """Build the pipeline from a LOCAL copy of a diffusers pipeline repository (``model_index.json`` + one
+        sub-directory per component; ``black-forest-labs/FLUX.1-dev``).  As in diffusers, any component passed as a
+        keyword (``controlnet=``, ``controlnet_inpaint=``, ``vae=``, ``tokenizer=`` ...) is used as it is and not loaded;
+        ``controlnet`` (and ``controlnet_inpaint`` for the inpaint pipeline) are not part of the base repository and must
+        be passed, like in the reference.  Models land on ``device`` (there is no CPU path), so the reference's trailing
+        ``.to("cuda")`` is a no-op."""
+        import inspect
+        from . import checkpoint as ck
+        from .models import FluxTransformer2DModel
+        from .scheduler import FlowMatchEulerDiscreteScheduler
+        from .text_encoders import CLIPTextModel, T5EncoderModel
+        from .vae import AutoencoderKL
+        d = ck.resolve_dir(pretrained_model_name_or_path)
+        index = ck.read_model_index(d)
+        wanted = [n for n in inspect.signature(cls.__init__).parameters if n != "self"]
+        loaders = {"transformer": FluxTransformer2DModel, "vae": AutoencoderKL, "text_encoder": CLIPTextModel,
+                   "text_encoder_2": T5EncoderModel, "scheduler": FlowMatchEulerDiscreteScheduler}
+        unknown = [k for k in components if k not in wanted]
+        if unknown:
+            raise TypeError(f"{cls.__name__}.from_pretrained got unexpected components {unknown}; it takes {wanted}")
+        for name in wanted:                      # everything that can be refused is refused before any weight is read
+            if name in components:
+                continue
+            if name in ("controlnet", "controlnet_inpaint"):
+                raise ValueError(f"pass `{name}=FluxControlNetModel.from_pretrained(...)`: it is not part of {d!r} "
+                                 "(RepText/infer.py:30-33)")
+            if name not in index:
+                raise OSError(f"{d!r}: model_index.json has no component {name!r}")
+        built = {}
+        for name in wanted:
+            if name in components:
+                built[name] = components[name]
+            elif name in ("tokenizer", "tokenizer_2"):
+                built[name] = _load_tokenizer(os.path.join(d, name), index[name][1])
+            elif name == "scheduler":
+                built[name] = loaders[name].from_pretrained(d, subfolder=name)
+            else:
+                built[name] = loaders[name].from_pretrained(d, subfolder=name, torch_dtype=torch_dtype, device=device,
+                                                            variant=variant)
+        return cls(**built)
 
     def _setup(self):
         vae = getattr(self, "vae", None)

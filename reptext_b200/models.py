@@ -104,6 +104,35 @@ class _RuntimeModel:
     def from_config(cls, config: dict, **kw):
         return cls(config, **kw)
 
+    # ---- checkpoints in the reference's directory layout (RepText/infer.py:27-33) --------------------
+    _class_name = "FluxTransformer2DModel"
+    _config_defaults: Dict[str, Any] = {}
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None,
+                        torch_dtype: torch.dtype = torch.bfloat16, device: Union[str, torch.device] = "cuda",
+                        variant: Optional[str] = None, **unused):
+        """``<dir>/config.json`` + ``<dir>/diffusion_pytorch_model.safetensors`` (single file, or the shards of
+        ``...safetensors.index.json``), as ``ModelMixin.from_pretrained`` reads them - from a LOCAL directory only
+        (:mod:`reptext_b200.checkpoint`).  Keys missing from ``config.json`` take the constructor defaults of the class
+        the directory was saved from (``RepText/controlnet_flux.py:44-60`` / diffusers' ``FluxTransformer2DModel``)."""
+        from . import checkpoint as ck
+        d = ck.resolve_dir(pretrained_model_name_or_path, subfolder)
+        raw, stored_cls = ck.read_config(d)
+        if stored_cls not in (None, cls._class_name):
+            raise ValueError(f"{d!r} holds a {stored_cls}, not a {cls._class_name}")
+        cfg = dict(cls._config_defaults)
+        cfg.update(raw)
+        cfg["axes_dims_rope"] = tuple(cfg["axes_dims_rope"])
+        return cls(cfg, ck.load_state_dict(d, (ck.DIFFUSERS_STEM,), variant), dtype=torch_dtype, device=device)
+
+    def save_pretrained(self, save_directory, max_shard_size: int = 10 * 2 ** 30) -> None:
+        """Write ``config.json`` and the weights (sharded above ``max_shard_size`` bytes) so that
+        :meth:`from_pretrained` - and diffusers' own loader, the key names are its - reads them back."""
+        from . import checkpoint as ck
+        ck.write_config(save_directory, self._cfg, self._class_name)
+        ck.save_state_dict(save_directory, self.state_dict(), ck.DIFFUSERS_STEM, max_shard_size)
+
     @classmethod
     def random_init(cls, config: dict, seed: int = 0, dtype: torch.dtype = torch.bfloat16, device="cuda",
                     zero_init: bool = False):
@@ -240,6 +269,12 @@ class FluxControlNetModel(_RuntimeModel):
     """Drop-in for ``RepText/controlnet_flux.py:41`` (inference path)."""
 
     _kind = "controlnet"
+    _class_name = "FluxControlNetModel"
+    # constructor defaults of RepText/controlnet_flux.py:44-60 (a config.json only stores what was passed)
+    _config_defaults = dict(patch_size=1, in_channels=64, num_layers=19, num_single_layers=38, attention_head_dim=128,
+                            num_attention_heads=24, joint_attention_dim=4096, pooled_projection_dim=768,
+                            guidance_embeds=False, axes_dims_rope=(16, 56, 56), num_mode=None,
+                            extra_conditioning_channels=0, extra_condition_channels=0)
 
     def __init__(self, config: dict, state_dict=None, dtype=torch.bfloat16, device="cuda"):
         if config.get("num_mode") is not None:
@@ -370,6 +405,11 @@ class FluxTransformer2DModel(_RuntimeModel):
     """Drop-in for diffusers' ``FluxTransformer2DModel`` as the reference pipelines call it."""
 
     _kind = "transformer"
+    _class_name = "FluxTransformer2DModel"
+    # constructor defaults of diffusers' FluxTransformer2DModel (FLUX.1-dev's config.json has no axes_dims_rope)
+    _config_defaults = dict(patch_size=1, in_channels=64, out_channels=None, num_layers=19, num_single_layers=38,
+                            attention_head_dim=128, num_attention_heads=24, joint_attention_dim=4096,
+                            pooled_projection_dim=768, guidance_embeds=False, axes_dims_rope=(16, 56, 56))
 
     @torch.no_grad()
     def forward(

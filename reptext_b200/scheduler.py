@@ -39,6 +39,24 @@ class FlowMatchEulerDiscreteScheduler:
         self._begin_index: Optional[int] = None
         self.num_inference_steps: Optional[int] = None
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None, **unused):
+        """``<dir>[/subfolder]/scheduler_config.json`` (``black-forest-labs/FLUX.1-dev``'s ``scheduler/``), local only."""
+        from . import checkpoint as ck
+        d = ck.resolve_dir(pretrained_model_name_or_path, subfolder)
+        raw, stored_cls = ck.read_config(d, ("scheduler_config.json", "config.json"))
+        if stored_cls not in (None, "FlowMatchEulerDiscreteScheduler"):
+            raise ValueError(f"{d!r} holds a {stored_cls}; the RepText pipelines step with FlowMatchEulerDiscreteScheduler")
+        unknown = [k for k in raw if k not in SCHEDULER and raw[k] not in (None, False)]
+        if unknown:
+            raise ValueError(f"scheduler options {unknown} are not implemented (FLUX.1-dev's scheduler_config.json uses none)")
+        return cls(**{k: v for k, v in raw.items() if k in SCHEDULER})
+
+    def save_pretrained(self, save_directory) -> None:
+        from . import checkpoint as ck
+        ck.write_config(save_directory, {k: getattr(self.config, k) for k in SCHEDULER},
+                        "FlowMatchEulerDiscreteScheduler", name="scheduler_config.json")
+
     @property
     def step_index(self):
         return self._step_index

@@ -45,6 +45,37 @@ class _Encoder:
         for k, v in state_dict.items():
             self._w[k] = v.detach().to(self.device, self.dtype).contiguous()
 
+    _class_name = ""
+    _shapes = staticmethod(lambda cfg: {})
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None, torch_dtype=torch.bfloat16,
+                        device="cuda", variant: Optional[str] = None, **unused):
+        """transformers' layout (``config.json`` + ``model.safetensors`` or its shards; ``black-forest-labs/FLUX.1-dev``'s
+        ``text_encoder/`` and ``text_encoder_2/``) from a LOCAL directory (:mod:`reptext_b200.checkpoint`).  Every parameter
+        the encoder reads must be there with its shape; extra tensors (a T5 decoder, a CLIP vision tower) are ignored."""
+        from . import checkpoint as ck
+        d = ck.resolve_dir(pretrained_model_name_or_path, subfolder)
+        raw, stored_cls = ck.read_config(d)
+        if stored_cls is not None and cls._class_name not in stored_cls and stored_cls not in cls._also:
+            raise ValueError(f"{d!r} holds a {stored_cls}, not a {cls._class_name}")
+        sd = ck.load_state_dict(d, (ck.TRANSFORMERS_STEM,), variant)
+        if "shared.weight" not in sd and "encoder.embed_tokens.weight" in sd:
+            sd["shared.weight"] = sd["encoder.embed_tokens.weight"]
+        cfg = dict(cls._defaults)
+        cfg.update({k: v for k, v in raw.items() if k in cls._defaults})
+        want = cls._shapes(cfg)
+        bad = [k for k in want if k not in sd or tuple(sd[k].shape) != tuple(want[k])]
+        if bad:
+            raise RuntimeError(f"{d!r}: parameters missing or of the wrong shape for this config: {bad[:4]}")
+        return cls(cfg, {k: sd[k] for k in want}, dtype=torch_dtype, device=device)
+
+    def save_pretrained(self, save_directory) -> None:
+        from . import checkpoint as ck
+        cfg = {k: getattr(self.config, k) for k in self._defaults}
+        ck.write_config(save_directory, cfg, self._class_name, transformers=True)
+        ck.save_state_dict(save_directory, {k: v for k, v in self._w.items() if k in self._shapes(cfg)}, ck.TRANSFORMERS_STEM)
+
     def _p(self, name: str) -> torch.Tensor:
         try:
             return self._w[name]
@@ -89,6 +120,9 @@ def t5_relative_buckets(S: int, num_buckets: int, max_distance: int) -> torch.Te
 
 class T5EncoderModel(_Encoder):
     """``transformers.T5EncoderModel`` (v1.1: gated-GELU, no biases, RMS norms, unscaled scores + relative bias)."""
+    _class_name, _also = "T5EncoderModel", ("T5ForConditionalGeneration", "T5Model")
+    _defaults = T5_XXL_CONFIG
+    _shapes = staticmethod(lambda cfg: t5_param_shapes(cfg))
 
     def __init__(self, config: Optional[dict], state_dict: Dict[str, torch.Tensor], dtype=torch.bfloat16, device="cuda"):
         super().__init__(config, T5_XXL_CONFIG, state_dict, dtype, device)
@@ -144,6 +178,9 @@ class T5EncoderModel(_Encoder):
 
 class CLIPTextModel(_Encoder):
     """``transformers.CLIPTextModel``: pre-LN blocks, causal mask, quick-GELU; ``pooler_output`` = state at the EOS token."""
+    _class_name, _also = "CLIPTextModel", ("CLIPModel", "CLIPTextModelWithProjection")
+    _defaults = CLIP_L_CONFIG
+    _shapes = staticmethod(lambda cfg: clip_param_shapes(cfg))
 
     def __init__(self, config: Optional[dict], state_dict: Dict[str, torch.Tensor], dtype=torch.bfloat16, device="cuda"):
         super().__init__(config, CLIP_L_CONFIG, state_dict, dtype, device)

@@ -206,6 +206,37 @@ class AutoencoderKL:
                 self._w[a + "to_out.0.bias_folded"] = (wo @ bv + bo).to(dt).contiguous()
 
     @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None, torch_dtype=torch.bfloat16,
+                        device="cuda", variant: Optional[str] = None, conv_impl: str = "implicit", **unused) -> "AutoencoderKL":
+        """``<dir>[/subfolder]/config.json`` + ``diffusion_pytorch_model.safetensors`` of a diffusers ``AutoencoderKL``
+        (e.g. ``black-forest-labs/FLUX.1-dev``'s ``vae/``) from a LOCAL directory (:mod:`reptext_b200.checkpoint`).  The
+        architecture must be the FLUX one this path implements: every parameter of :func:`vae_param_shapes` present with
+        its shape, nothing else (no quant / post-quant convolutions)."""
+        from . import checkpoint as ck
+        d = ck.resolve_dir(pretrained_model_name_or_path, subfolder)
+        raw, stored_cls = ck.read_config(d)
+        if stored_cls not in (None, "AutoencoderKL"):
+            raise ValueError(f"{d!r} holds a {stored_cls}, not an AutoencoderKL")
+        cfg = dict(FLUX_VAE_CONFIG)
+        cfg.update(raw)
+        if cfg.get("use_quant_conv") or cfg.get("use_post_quant_conv"):
+            raise ValueError("AutoencoderKL with quant_conv / post_quant_conv is not the FLUX VAE this path implements")
+        sd = ck.load_state_dict(d, (ck.DIFFUSERS_STEM,), variant)
+        want = vae_param_shapes(cfg)
+        missing = [k for k in want if k not in sd]
+        unexpected = [k for k in sd if k not in want]
+        wrong = [k for k in want if k in sd and tuple(sd[k].shape) != want[k]]
+        if missing or unexpected or wrong:
+            raise RuntimeError(f"{d!r} is not a FLUX-architecture AutoencoderKL: missing {missing[:3]}, unexpected "
+                               f"{unexpected[:3]}, wrong shape {wrong[:3]}")
+        return cls(cfg, sd, dtype=torch_dtype, device=device, conv_impl=conv_impl)
+
+    def save_pretrained(self, save_directory) -> None:
+        """Not available: the constructor re-packs the convolution kernels for the implicit GEMM and drops the originals;
+        keep the directory the model was loaded from."""
+        raise NotImplementedError(self.save_pretrained.__doc__)
+
+    @classmethod
     def random_init(cls, config: Optional[dict] = None, seed: int = 0, dtype=torch.bfloat16, device="cuda",
                     conv_impl: str = "implicit") -> "AutoencoderKL":
         """Random weights of the configured architecture (there is no network for checkpoints; BASELINE.json)."""

@@ -73,7 +73,7 @@ def param_table(cfg: dict, kind: str) -> Iterator[Tuple[str, Tuple[int, ...], st
     if kind == "transformer":
         yield "norm_out.linear.weight", (2 * D, D), "w"
         yield "norm_out.linear.bias", (2 * D,), "b"
-        cout = cfg.get("out_channels", cin) * cfg.get("patch_size", 1) ** 2
+        cout = (cfg.get("out_channels") or cin) * cfg.get("patch_size", 1) ** 2
         yield "proj_out.weight", (cout, D), "w"
         yield "proj_out.bias", (cout,), "b"
     elif kind == "controlnet":
