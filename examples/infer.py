@@ -1,11 +1,14 @@
 #!/usr/bin/env python
 """``RepText/infer.py`` on the B200 runtime: the same flow (font -> per-line glyph / position / mask / Canny ->
 ``pipe(prompt, control_image=..., control_position=..., control_mask=..., control_glyph=...)``), with two differences
-forced by the offline box: the modules are random-init (no Hub access; pass --transformer / --controlnet state dicts
-to use real weights) and the VAE / text encoders are the synthetic stand-ins of ``reptext_b200.pipeline_utils``.
+forced by the offline box: without checkpoints the modules are random-init and the text encoders are the synthetic
+stand-ins of ``reptext_b200.pipeline_utils``; with LOCAL copies of the two repositories the reference's own two loading
+lines (``RepText/infer.py:30-33``) run as they are.
 
     python examples/infer.py --config small --text "مرحبا" --text "RepText" --steps 4 --out results/result.png
     python examples/infer.py --config flux-dev --height 1024 --width 1024 --steps 30          # FLUX.1-dev shapes
+    python examples/infer.py --base-model /models/FLUX.1-dev --controlnet-model /models/RepText --height 1024 \
+        --width 1024 --steps 30 --font-size 80 --out results/result.png                       # real checkpoints
 """
 from __future__ import annotations
 
@@ -42,12 +45,23 @@ def main(argv=None):
     ap.add_argument("--vae", default="flux", choices=["flux", "synthetic"],
                     help="flux: the AutoencoderKL drop-in (FLUX.1-dev VAE architecture, random weights; fp32 'tiny' uses the "
                          "stand-in); synthetic: the 8x-pooling stand-in")
+    ap.add_argument("--base-model", default=None, help="local copy of black-forest-labs/FLUX.1-dev (infer.py:27)")
+    ap.add_argument("--controlnet-model", default=None, help="local copy of Shakker-Labs/RepText (infer.py:28)")
     a = ap.parse_args(argv)
+    if bool(a.base_model) != bool(a.controlnet_model):
+        ap.error("--base-model and --controlnet-model go together")
 
     TR, CN, dt = {"tiny": (config.TINY_TRANSFORMER, config.TINY_CONTROLNET, torch.float32),
                   "small": (config.SMALL128_TRANSFORMER, config.SMALL128_CONTROLNET, torch.bfloat16),
                   "flux-dev": (config.FLUX_DEV, config.REPTEXT_CONTROLNET, torch.bfloat16)}[a.config]
     dev = torch.device("cuda")
+    if a.base_model:
+        # RepText/infer.py:30-33, unchanged
+        controlnet = models.FluxControlNetModel.from_pretrained(a.controlnet_model, torch_dtype=torch.bfloat16)
+        pipe = FluxControlNetPipeline.from_pretrained(
+            a.base_model, controlnet=controlnet, torch_dtype=torch.bfloat16
+        ).to("cuda")
+        return _run(a, pipe, glyphs)
     controlnet = models.FluxControlNetModel.random_init(CN, seed=101, dtype=dt, device=dev)
     transformer = models.FluxTransformer2DModel.random_init(TR, seed=100, dtype=dt, device=dev)
     vae = (AutoencoderKL.random_init(seed=102, dtype=dt, device=dev) if a.vae == "flux" and dt == torch.bfloat16
@@ -55,7 +69,10 @@ def main(argv=None):
     pipe = FluxControlNetPipeline(FlowMatchEulerDiscreteScheduler(), vae,
                                   SyntheticTextEncoders(TR["joint_attention_dim"], TR["pooled_projection_dim"], dt, dev),
                                   None, None, None, transformer, controlnet)
+    return _run(a, pipe, glyphs)
 
+
+def _run(a, pipe, glyphs):
     text_list = a.text or ["مرحبا بالعالم", "RepText"]
     font = glyphs.load_font(a.font, a.font_size)
     line_h = int(a.font_size * 1.6)

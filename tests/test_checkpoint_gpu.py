@@ -129,3 +129,11 @@ def test_pipeline_from_pretrained_matches_the_hand_built_pipeline(tmp_path):
                                                    text_encoder=pipe.text_encoder, text_encoder_2=pipe.text_encoder_2,
                                                    transformer=pipe.transformer)
     assert pipe2.scheduler is sch and pipe2.transformer is pipe.transformer
+    # examples/infer.py --base-model / --controlnet-model: the reference's script flow on the loaded pipeline
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("infer_example", os.path.join(os.path.dirname(__file__), "..", "examples", "infer.py"))
+    infer = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(infer)
+    lat = infer.main(["--base-model", root, "--controlnet-model", str(tmp_path / "RepText"), "--steps", "2",
+                      "--output-type", "latent", "--text", "مرحبا"])
+    assert lat.shape == (1, 256, 64) and torch.isfinite(lat.float()).all()
