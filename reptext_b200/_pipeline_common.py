@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import os
 import warnings
-from typing import Any, Callable, Dict, List, Optional, Union
+from typing import List, Optional, Union
 
 import numpy as np
 import torch

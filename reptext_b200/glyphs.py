@@ -14,7 +14,6 @@ forms from the Unicode Character Database, lam-alef ligatures, UBA reordering fo
 from __future__ import annotations
 
 import re
-import warnings
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
