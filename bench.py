@@ -420,7 +420,8 @@ def run_b200(args, wl):
         traffic = None   # ncu dram__bytes_read + write per GEMM launch, averaged over the 188 launches of one cfg2 step
         tpath = os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")
         if args.workload == "cfg2" and os.path.exists(tpath):
-            traffic = json.load(open(tpath))["no_l2_hints"]["bytes_per_launch"]
+            tj = json.load(open(tpath))
+            traffic = (tj.get("banded_long_k") or tj["no_l2_hints"])["bytes_per_launch"]
         if gem[0] > 0:
             ach = gem[1] / (gem[0] / 1000.0) / 1e12
             roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 + TMA, fused epilogues)", achieved=ach,

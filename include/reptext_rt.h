@@ -60,6 +60,8 @@ RT_API long long rt_launch_count(void); /* number of this library's kernels laun
  * warp-per-row form), "gemv_single_row" (1 = one row per warp), "mod_inline" (1 = AdaLN GEMV on the caller's stream instead of the
  * side stream), "sp_replicate_mod" (1 = sequence-parallel ranks each compute all AdaLN rows instead of a row shard),
  * "no_pdl" (1 = plain stream-ordered launches instead of programmatic dependent launch),
+ * "gemm_band" (tile order of the tcgen05 GEMM: 0 = auto - row tiles fastest unless A is too large to stay in L2 between
+ * waves, then bands of row tiles swept over all column tiles; -1 = always row tiles fastest; n > 0 = bands of n row tiles),
  * "gemm_debug" (bit 1: no epilogue, bit 2: k-block 0 only - timing experiments with WRONG results;
  * bit 4: direct row-per-thread epilogue stores instead of the staged coalesced ones - same results) */
 RT_API int rt_set_option(const char* name, int value);

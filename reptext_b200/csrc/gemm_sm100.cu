@@ -58,6 +58,11 @@ struct alignas(64) TcProblem {
   // (64 channels, conv_bw, 128 / conv_bw, 1) pixels; k-block kb = tap * conv_kcb + channel block, the tap shifts the
   // box by (dx, dy) and TMA's out-of-bounds zero fill is the padding.  conv_w == 0: plain GEMM.
   int conv_w, conv_bw, conv_kcb;
+  // Tile order.  band == 0: row tiles fastest (a wave = every row tile x a few column tiles: right when A stays in L2 and
+  // W is streamed once).  band > 0: the row tiles are cut into bands of `band` tiles and a band is swept over ALL column
+  // tiles before the next one starts: a wave then reads `band` row blocks of A and all of W - the order for long-K problems whose A operand (141 MB for the single blocks' proj_out) does not survive in L2
+  // from one wave to the next and would otherwise be re-read once per wave.
+  int band;
 };
 
 struct alignas(64) TcParams {
@@ -96,10 +101,24 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int t, int b
   c.p = (P.nprob > 1 && t >= P.prob[1].tile_base) ? 1 : 0;
   const TcProblem& pr = P.prob[c.p];
   int tl = t - pr.tile_base;
-  int mt = tl % pr.tiles_m;
-  int rest = tl / pr.tiles_m;
-  c.b = rest % P.batch;
-  int nt = rest / P.batch;
+  int mt, nt;
+  if (pr.band > 0) {
+    const int per_batch = pr.tiles_m * pr.tiles_n;
+    c.b = tl / per_batch;
+    const int r = tl - c.b * per_batch;
+    // column tiles fastest inside a band: the few tiles of the NEXT band that a wave picks up early (a band is rarely
+    // exactly one wave) then share one row block of A instead of touching several
+    const int full = pr.band * pr.tiles_n;             // tiles of a full band
+    const int bi = r / full, rem = r - bi * full;
+    const int mi = rem / pr.tiles_n;
+    nt = rem - mi * pr.tiles_n;
+    mt = bi * pr.band + mi;
+  } else {
+    mt = tl % pr.tiles_m;
+    const int rest = tl / pr.tiles_m;
+    c.b = rest % P.batch;
+    nt = rest / P.batch;
+  }
   c.m0 = mt * rows_per_tile;
   c.n0 = nt * bn;
   c.seg = 0;
@@ -903,6 +922,19 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
     T.tiles_n = gemm_total_n(G) / bn;
     T.tile_base = tile_base;
     T.num_tiles = T.tiles_m * T.tiles_n * L.batch;
+    // option "gemm_band": 0 = auto, -1 = never, n > 0 = bands of n row tiles for every problem (tests, A/B)
+    const int band_opt = get_option("gemm_band");
+    const int slots = num_sms / cg;  // tiles in flight
+    T.band = 0;
+    if (band_opt > 0) {
+      T.band = band_opt;
+    } else if (band_opt == 0 && G.conv_w == 0) {
+      // A is re-read once per wave when it cannot stay in L2 (126 MB, shared with W and the output): band it when it is
+      // large, there is more than one wave, and a band of at least two row tiles fills the machine
+      const double a_bytes = (double)G.m_rows * G.K * 2.0 * (bcast ? 1 : L.batch);
+      const int band = slots / T.tiles_n;
+      if (a_bytes > 64e6 && T.num_tiles > slots && band >= 2 && band < T.tiles_m) T.band = band;
+    }
     tile_base += T.num_tiles;
   }
   P.total_tiles = tile_base;

@@ -133,6 +133,39 @@ def test_gemm(ops, case):
     assert torch.equal(keep, out0), name
 
 
+@pytest.mark.parametrize("band", [1, 2, 3, 5])
+@pytest.mark.parametrize("case", [c for c in GEMM_CASES if c[0] in ("tc1_bn128", "tc1_gate", "tc2_gate", "tc1_qkvm", "tc2_big",
+                                                                    "auto_big_k_long")], ids=lambda c: c[0])
+def test_gemm_banded_tile_order(ops, case, band):
+    """Option gemm_band: the row tiles in bands swept over all column tiles (the order long-K problems take on their
+    own) - same results for every band height, batch, ragged last band, several segments."""
+    from reptext_b200 import _lib as L
+    L.set_option("gemm_band", band)
+    try:
+        test_gemm(ops, case)
+        test_gemm_two_problems_joint_rows(ops, 3)
+    finally:
+        L.set_option("gemm_band", 0)
+
+
+def test_gemm_auto_band_on_the_long_k_shape(ops):
+    """(4608, 3072, 15360): A is 141 MB, three waves - the launch bands itself (6 row tiles); bit-identical to the
+    row-tiles-fastest order (the order changes which CTA computes a tile, not the arithmetic of a tile)."""
+    from reptext_b200 import _lib as L
+    dt = torch.bfloat16
+    A, W = _rand((1, 4608, 15360), dt, 1), _rand((3072, 15360), dt, 2, 15360 ** -0.5)
+    b = _rand((3072,), dt, 3, 0.1)
+    outs = []
+    for band in (0, -1, 4):
+        L.set_option("gemm_band", band)
+        out = torch.zeros(1, 4608, 3072, dtype=dt, device="cuda")
+        ops.gemm([ops.Problem(A=A, segs=[ops.Segment(W=W, bias=b, out=out)])], 1, dt, impl=3)
+        outs.append(out)
+    L.set_option("gemm_band", 0)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert rel_l2(outs[0][:, :512].float(), A[:, :512].float() @ W.float().t() + b.float()) < 4e-3
+
+
 @pytest.mark.parametrize("impl", [1, 2, 3], ids=["simt", "tc1", "tc2"])
 def test_gemm_two_problems_joint_rows(ops, impl):
     """Text rows and image rows of one joint buffer, each with its own weights, in ONE launch; the
