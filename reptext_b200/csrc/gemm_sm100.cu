@@ -851,7 +851,7 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
   std::string why;
   if (!gemm_tc_supported(L, &why)) throw Error(RT_ERR_UNSUPPORTED, "tcgen05 GEMM: " + why);
   if (L.batch == 0) return;
-  const int bn = pick_bn(L);
+  int bn = pick_bn(L);
   int cg = force_cta_group;
   if (cg == 0) {
     // auto: pair two SMs on 256-row tiles (each CTA then stages only half of the W tile: less shared-memory
@@ -870,6 +870,26 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
     int dev = 0;
     RT_CHECK_CUDA(cudaGetDevice(&dev));
     RT_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // Small launches (the prompt encoders at 512 tokens: 32-160 tiles of 256 x 256 for 74 CTA pairs): when 128-wide
+  // single-CTA tiles fill clearly more of the machine, take them - a 128-wide tile runs at ~85 % of the 256-wide rate
+  // (profiles/r1_gemm_after_uniform_issue.txt), so the fill has to win by more than that.  Same arithmetic per element.
+  if (force_cta_group == 0 && bn == 256) {
+    auto tiles = [&](int rows_per_tile, int cols) {
+      long long t = 0;
+      for (int p = 0; p < L.nprob; ++p)
+        t += (long long)((L.prob[p].m_rows + rows_per_tile - 1) / rows_per_tile) * (gemm_total_n(L.prob[p]) / cols) * L.batch;
+      return t;
+    };
+    auto fill = [](long long t, int slots) { return t <= 0 ? 0.0 : (double)t / (double)(((t + slots - 1) / slots) * slots); };
+    bool conv = false;
+    for (int p = 0; p < L.nprob; ++p) conv |= L.prob[p].conv_w > 0;
+    const int slots = num_sms / cg;
+    const long long t_now = tiles(BM * cg, 256);
+    if (!conv && t_now < 2 * slots) {
+      const double eff_now = fill(t_now, slots), eff_alt = 0.85 * fill(tiles(BM, 128), num_sms);
+      if (eff_alt > 1.10 * eff_now) { bn = 128; cg = 1; }
+    }
   }
 
   TcParams P{};
