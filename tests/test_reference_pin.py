@@ -1,0 +1,212 @@
+"""Parity PINNED TO THE REFERENCE'S OWN CODE (CPU; no GPU needed).
+
+``/root/reference/RepText/{controlnet_flux,pipeline_flux_controlnet,pipeline_flux_controlnet_inpaint}.py`` are imported by
+path, unmodified, over the stand-in ``diffusers`` of ``tests/ref_shim`` (BFL block arithmetic from torchtitan, the real
+transformers CLIP / T5) and RUN.  Three links are checked:
+
+  reference run  ==  committed golden (tests/golden/ref_*.npz)        [needs /root/reference; skipped on the GPU box]
+  reference ``FluxControlNetModel.forward``  ==  ``oracle.controlnet_forward``   [needs /root/reference]
+  oracle (loops AND preparation, from the same PIL images / prompts)  ==  committed golden    [runs anywhere]
+
+The GPU tests (tests/test_reference_gpu.py) then compare the product pipelines with the same golden files.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ref_fixture as F
+import ref_run
+from oracle import flux_oracle as O
+from util import rel_l2, synth_inputs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+needs_ref = pytest.mark.skipif(not ref_run.available(), reason="the reference (/root/reference) is not on this box")
+needs_shim = pytest.mark.skipif(not ref_run.shim_importable(), reason="torchtitan's BFL modules are not importable")
+
+
+def golden(name):
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def _ls(cfg):
+    return {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}
+
+
+# ------------------------------------------------------------------------------------------ reference == oracle (models)
+@needs_ref
+@pytest.mark.parametrize("single_layers", [0, 2])
+@pytest.mark.parametrize("guidance_embeds", [True, False])
+def test_reference_controlnet_forward_equals_oracle(single_layers, guidance_embeds):
+    """RepText/controlnet_flux.py:216-413, executed, against oracle.controlnet_forward: fp32, batch 2, <= 1e-6
+    (rows a1-a9; ``single_layers=2`` runs the loop at :354-381 and the zero-linears at :390-392 - row a7)."""
+    from reptext_b200 import config, weights
+    R = ref_run.load()
+    TR = config.TINY_TRANSFORMER
+    CN = dict(config.TINY_CONTROLNET, num_single_layers=single_layers, guidance_embeds=guidance_embeds)
+    m = R.controlnet_flux.FluxControlNetModel(**_ls(CN)).eval()
+    sd = weights.random_state_dict(CN, "controlnet", seed=101)
+    m.load_state_dict(sd, strict=True)
+    x = synth_inputs(TR, CN, 256, 192, 64, seed=3, batch=2)
+    t = torch.tensor([0.75, 0.3])
+    g = torch.tensor([3.5, 2.0]) if guidance_embeds else None
+    with torch.no_grad():
+        out = m(hidden_states=x["latents"], controlnet_cond=x["conds"][0], conditioning_scale=0.7,
+                encoder_hidden_states=x["prompt_embeds"], pooled_projections=x["pooled"], timestep=t,
+                img_ids=x["img_ids"], txt_ids=x["txt_ids"], guidance=g, return_dict=True)
+        rb, rs = out.controlnet_block_samples, out.controlnet_single_block_samples
+        ob, os_ = O.controlnet_forward(sd, CN, x["latents"], x["conds"][0], 0.7, x["prompt_embeds"], x["pooled"], t,
+                                       x["img_ids"], x["txt_ids"], g)
+    assert len(rb) == len(ob) == CN["num_layers"]
+    for a, b in zip(ob, rb):
+        assert float(b.norm()) > 1.0 and rel_l2(a, b) < 1e-6
+    if single_layers:
+        assert len(rs) == len(os_) == single_layers
+        for a, b in zip(os_, rs):
+            assert b.shape == x["latents"].shape[:2] + (256,) and rel_l2(a, b) < 1e-6
+    else:
+        assert rs is None and os_ is None
+
+
+@needs_shim
+def test_shim_transformer_equals_oracle():
+    """The stand-in FluxTransformer2DModel (BFL blocks + diffusers 0.36's loop: guidance embedder, residual injection
+    ``i // ceil(L / len)`` for both block families) against oracle.transformer_forward."""
+    from reptext_b200 import config, weights
+    ref_run.shim()
+    from diffusers.models.transformers.transformer_flux import FluxTransformer2DModel
+    TR, CN = config.TINY_TRANSFORMER, config.TINY_CONTROLNET
+    sd = weights.random_state_dict(TR, "transformer", seed=100)
+    m = FluxTransformer2DModel(**_ls(TR)).eval()
+    m.load_state_dict(sd, strict=True)
+    x = synth_inputs(TR, CN, 256, 192, 64, seed=4, batch=2)
+    g = torch.Generator().manual_seed(9)
+    D = TR["num_attention_heads"] * TR["attention_head_dim"]
+    blocks = [0.1 * torch.randn(2, x["N"], D, generator=g) for _ in range(2)]
+    singles = [0.1 * torch.randn(2, x["N"], D, generator=g) for _ in range(3)]
+    t, gd = torch.tensor([0.6, 0.2]), torch.tensor([3.5, 1.0])
+    with torch.no_grad():
+        got = m(hidden_states=x["latents"], timestep=t, guidance=gd, pooled_projections=x["pooled"],
+                encoder_hidden_states=x["prompt_embeds"], controlnet_block_samples=blocks,
+                controlnet_single_block_samples=singles, txt_ids=x["txt_ids"], img_ids=x["img_ids"], return_dict=False)[0]
+        want = O.transformer_forward(sd, TR, x["latents"], x["prompt_embeds"], x["pooled"], t, x["img_ids"], x["txt_ids"],
+                                     gd, blocks, singles)
+    assert rel_l2(want, got) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ reference run == golden
+@needs_ref
+@pytest.mark.parametrize("name", sorted(F.CASES))
+def test_reference_run_reproduces_committed_golden(name):
+    """The committed tests/golden/ref_*.npz ARE what the reference's own ``__call__`` produces here."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden_ref
+    torch.set_num_threads(8)
+    rec = make_golden_ref.run_case(name)
+    want = golden(name)
+    assert set(rec) == set(want)
+    tol = 1e-6 if F.CASES[name]["dtype"] == "fp32" else 1e-3       # bf16 on the CPU: reduction order may differ by box
+    for k in want:
+        assert rec[k].shape == tuple(want[k].shape), k
+        assert rel_l2(torch.from_numpy(rec[k]), want[k]) <= tol, (k, rel_l2(torch.from_numpy(rec[k]), want[k]))
+
+
+# ------------------------------------------------------------------------------------------ oracle == golden (anywhere)
+def _oracle_loop(name, z, dtype):
+    case = F.CASES[name]
+    sds = F.state_dicts(case)
+    TR, CN, CNI = F.model_configs(case)
+    c = lambda t: t.to(dtype)
+    cs = lambda sd: {k: v.to(dtype) for k, v in sd.items()}
+    _, _, _, masks = F.glyph_inputs(case["H"], case["W"], case["lines"])
+    taps = []
+    args = dict(latents=c(z["init_latents"]), prompt_embeds=c(z["prompt_embeds"]), pooled=c(z["pooled"]),
+                control_image_list=[c(x) for x in z["conds"]],
+                control_mask_list=[O.regional_mask(np.array(m), dtype) for m in masks], text_ids=c(z["txt_ids"]),
+                img_ids=c(z["img_ids"]), timesteps=z["timesteps"], sigmas=z["sigmas"], guidance_scale=case["guidance"],
+                conditioning_scale=case["scale"], conditioning_step=case["cond_step"],
+                callback=lambda i, t, lat: taps.append(lat.float().clone()))
+    with torch.no_grad():
+        if case["kind"] == "inpaint":
+            O.denoise_inpaint(cs(sds["tr"]), TR, cs(sds["cn"]), CN, cs(sds["cni"]), CNI,
+                              control_image_inpaint=c(z["cond_inpaint"]), true_guidance_scale=case["true_cfg"],
+                              conditioning_scale_inpaint=case["scale_inpaint"], **args)
+        else:
+            O.denoise_t2i(cs(sds["tr"]), TR, cs(sds["cn"]), CN, **args)
+    return torch.stack(taps)
+
+
+@pytest.mark.parametrize("name", sorted(F.CASES))
+def test_oracle_loop_equals_reference_run(name):
+    """oracle.denoise_t2i / denoise_inpaint on the tensors the reference prepared == the reference's per-step latents
+    (pipeline_flux_controlnet.py:1017-1130, pipeline_flux_controlnet_inpaint.py:1140-1295): fp32 <= 1e-5 at every step;
+    the bf16 cases run the oracle in bf16 on the CPU like the reference did."""
+    torch.set_num_threads(8)
+    z = golden(name)
+    fp32 = F.CASES[name]["dtype"] == "fp32"
+    got = _oracle_loop(name, z, torch.float32 if fp32 else torch.bfloat16)
+    want = z["latents_per_step"]
+    assert got.shape == want.shape
+    for i in range(want.shape[0]):
+        e = rel_l2(got[i], want[i])
+        assert e < (1e-5 if fp32 else 1e-2), (name, i, e)
+    if F.CASES[name]["kind"] == "inpaint":          # true-CFG step 0 predicts zero: latents unchanged
+        assert torch.equal(want[0], z["init_latents"])
+
+
+@pytest.mark.parametrize("name", ["ref_tiny_t2i", "ref_tiny_t2i_offgrid", "ref_tiny_inpaint"])
+def test_oracle_preparation_equals_reference_run(name):
+    """Rows a14-a18 restated in the oracle, from the same PIL images and prompt strings: ``prepare_image``
+    (pipeline_flux_controlnet.py:663-731), ``prepare_image_with_mask`` (pipeline_flux_controlnet_inpaint.py:761-826),
+    ``prepare_latents_reptext`` (:608-660; dead in T2I, live in inpaint), the sigma schedule, ids and the prompt encoders
+    == what the reference's own preparation code built (recorded by hooks on its modules during the golden run)."""
+    from oracle import text_oracle as TO
+    from oracle import vae_oracle as V
+    torch.set_num_threads(8)
+    case = F.CASES[name]
+    z = golden(name)
+    sds = F.state_dicts(case)
+    vcfg = F.vae_config(case)
+    kw = F.call_kwargs(case)
+    H, W = case["H"], case["W"]
+    inpaint = case["kind"] == "inpaint"
+    gen = kw["generator"]
+
+    def encode(x, generator=None):
+        with torch.no_grad():
+            return V.sample_posterior(V.encode_moments(sds["vae"], vcfg, x), generator=generator)
+
+    # prompt encoders (the reference calls CLIP on `prompt`, T5 on `prompt_2`; negative prompt first when CFG is on)
+    tcfg, ccfg = F.text_configs(case)
+    tok, tok2 = F.tokenizers()
+    prompts = ([F.NEGATIVE] if inpaint else []) + [F.PROMPT]
+    prompts2 = ([F.NEGATIVE] if inpaint else []) + [F.PROMPT_2]
+    with torch.no_grad():
+        pe = torch.cat([TO.t5_encoder(sds["t5"], tcfg, tok2([p], padding="max_length", max_length=case["T"],
+                                                             truncation=True).input_ids) for p in prompts2])
+        po = torch.cat([TO.clip_text(sds["clip"], ccfg, tok([p], padding="max_length", max_length=77,
+                                                            truncation=True).input_ids)[1] for p in prompts])
+    assert rel_l2(pe, z["prompt_embeds"]) < 1e-5 and rel_l2(po, z["pooled"]) < 1e-5
+
+    # control conditions
+    for li in range(case["lines"]):
+        cond = O.prepare_image(encode, kw["control_image"][li], kw["control_position"][li], H, W, 1, torch.float32,
+                               do_classifier_free_guidance=inpaint)
+        assert cond.shape == z["conds"][li].shape and rel_l2(cond, z["conds"][li]) < 1e-5, (li, rel_l2(cond, z["conds"][li]))
+    if inpaint:
+        ci = O.prepare_image_with_mask(encode, kw["control_image_inpaint"], kw["control_mask_inpaint"], H, W, 1,
+                                       torch.float32, do_classifier_free_guidance=True)
+        assert ci.shape == z["cond_inpaint"].shape == (2, (H // 16) * (W // 16), 68)
+        assert rel_l2(ci, z["cond_inpaint"]) < 1e-5
+
+    # initial latents, schedule, ids
+    lat = O.prepare_latents_reptext(encode, kw["control_glyph"], 1, H, W, torch.float32, gen, live=inpaint)
+    # live (inpaint): 0.10 * glyph latents enter inside the mask, VAE oracle vs BFL autoencoder ~1e-5; dead (T2I): the noise
+    assert rel_l2(lat, z["init_latents"]) < (5e-5 if inpaint else 1e-7)
+    ts, sg = O.make_sigmas(case["steps"], (H // 16) * (W // 16))
+    assert torch.allclose(ts, z["timesteps"], rtol=1e-6) and torch.allclose(sg, z["sigmas"], rtol=1e-6, atol=1e-7)
+    assert torch.equal(O.prepare_latent_image_ids(2 * (H // 16), 2 * (W // 16)), z["img_ids"])
+    assert torch.equal(torch.zeros(case["T"], 3), z["txt_ids"])
