@@ -50,17 +50,20 @@ def workload(name: str):
     raise SystemExit(f"unknown workload {name}")
 
 
-def step_flops(TR, CN, N, T, lines=1):
-    """2*M*N*K per GEMM, 4*S^2*D per attention; norms / softmax / elementwise not counted."""
+def step_flops(TR, CN, N, T, lines=1, cn_live_layers=None):
+    """2*M*N*K per GEMM, 4*S^2*D per attention; norms / softmax / elementwise not counted.
+    ``cn_live_layers``: ControlNet double blocks actually run (the pipelines skip blocks whose sample the transformer
+    never reads - 5 of 6 for FLUX.1-dev + RepText); None = all of them (the reference's count: 82.69 TFLOP at cfg 2)."""
     def model(c, kind):
         D = c["num_attention_heads"] * c["attention_head_dim"]
         S = N + T
         dbl = 24 * S * D * D + 4 * S * S * D
-        f = c["num_layers"] * dbl + c["num_single_layers"] * dbl
+        nl = c["num_layers"] if (kind != "cn" or cn_live_layers is None) else cn_live_layers
+        f = nl * dbl + c["num_single_layers"] * dbl
         f += 2 * N * D * c["in_channels"] + 2 * T * D * c["joint_attention_dim"]
         if kind == "cn":
             f += 2 * N * D * (c["in_channels"] + c["extra_condition_channels"])
-            f += (c["num_layers"] + c["num_single_layers"]) * 2 * N * D * D
+            f += (nl + c["num_single_layers"]) * 2 * N * D * D
         else:
             f += 2 * N * D * c["out_channels"]
         return f
@@ -127,66 +130,312 @@ def peaks():
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (a port of the reference path; diffusers itself is not installable here) on host cores
 # ---------------------------------------------------------------------------------------------------------
-def cpu_oracle_steps_per_s(wl, repeats=1):
-    """Times ONE double-stream and ONE single-stream block of the oracle at the full sequence length in fp32 on all
-    host threads and extrapolates to the step: (L_tr + L_cn) doubles + L_single singles (+ ControlNet zero-linears).
-    A full step is 82.7 TFLOP - minutes on host cores - so the sample is bounded (task statement, section 4)."""
+_CPU_STATE = {}
+
+
+def cpu_oracle_sample(wl):
+    """ONE bounded sample of the step on the host cores, through the oracle (the reference path restated; the reference
+    itself is Python over diffusers and cannot travel to this box): the reference's own ``FluxControlNetModel.forward`` at
+    the full size (controlnet_flux.py:216-413: embedders, 6 double-stream blocks, 6 zero-linears, x scale) plus ONE
+    single-stream block of the transformer, fp32, all host threads.  That is 9.6 of the step's 82.7 TFLOP; the step rate is
+    the sample rate scaled by the FLOP ratio (both kinds of block run at the same FLOP rate on the CPU).
+    -> (seconds for the sample, FLOPs of the sample, FLOPs of a step, description)."""
     from oracle import flux_oracle as O
     from reptext_b200 import weights
     TR, CN = wl["TR"], wl["CN"]
     N, T = (wl["H"] // 16) * (wl["W"] // 16), wl["T"]
     D = TR["num_attention_heads"] * TR["attention_head_dim"]
-    one = dict(TR, num_layers=1, num_single_layers=1)
-    sd = {k: v for k, v in weights.random_state_dict(one, "transformer", seed=0).items()
-          if k.startswith(("transformer_blocks.0.", "single_transformer_blocks.0."))}
-    g = torch.Generator().manual_seed(0)
-    x, c = torch.randn(1, N, D, generator=g), torch.randn(1, T, D, generator=g)
-    temb = torch.randn(1, D, generator=g)
-    ids = torch.cat([torch.zeros(T, 3), O.prepare_latent_image_ids(2 * (wl["H"] // 16), 2 * (wl["W"] // 16))])
-    rope = O.rope_table(ids, TR["axes_dims_rope"])
-    Wz = torch.randn(D, D, generator=g) * D ** -0.5
+    st = _CPU_STATE
+    if "cn_sd" not in st:
+        g = torch.Generator().manual_seed(0)
+        st["cn_sd"] = weights.random_state_dict(CN, "controlnet", seed=0)
+        one = dict(TR, num_layers=0, num_single_layers=1)
+        st["sg_sd"] = {k: v for k, v in weights.random_state_dict(one, "transformer", seed=1).items()
+                       if k.startswith("single_transformer_blocks.0.")}
+        st["lat"] = torch.randn(1, N, TR["in_channels"], generator=g)
+        st["cond"] = torch.randn(1, N, CN["in_channels"] + CN["extra_condition_channels"], generator=g)
+        st["pe"] = torch.randn(1, T, TR["joint_attention_dim"], generator=g)
+        st["po"] = torch.randn(1, TR["pooled_projection_dim"], generator=g)
+        st["x"], st["c"], st["temb"] = torch.randn(1, N, D, generator=g), torch.randn(1, T, D, generator=g), torch.randn(1, D, generator=g)
+        st["img_ids"] = O.prepare_latent_image_ids(2 * (wl["H"] // 16), 2 * (wl["W"] // 16))
+        st["txt_ids"] = torch.zeros(T, 3)
+        st["rope"] = O.rope_table(torch.cat([st["txt_ids"], st["img_ids"]]), TR["axes_dims_rope"])
     with torch.no_grad():
-        td = ts = tz = 1e30
-        for _ in range(repeats):
-            t0 = time.perf_counter(); O.double_block(sd, "transformer_blocks.0.", x, c, temb, rope, TR["num_attention_heads"])
-            t1 = time.perf_counter(); O.single_block(sd, "single_transformer_blocks.0.", x, c, temb, rope, TR["num_attention_heads"])
-            t2 = time.perf_counter(); torch.nn.functional.linear(x, Wz)
-            t3 = time.perf_counter()
-            td, ts, tz = min(td, t1 - t0), min(ts, t2 - t1), min(tz, t3 - t2)
-    n_d = TR["num_layers"] + CN["num_layers"]
-    n_s = TR["num_single_layers"] + CN["num_single_layers"]
-    step_s = n_d * td + n_s * ts + (CN["num_layers"] + CN["num_single_layers"]) * tz
-    sample = (f"oracle (fp32 torch CPU port of the diffusers path) timed on 1 double block ({td:.2f} s) + 1 single block "
-              f"({ts:.2f} s) + 1 zero-linear ({tz:.2f} s) at S={N + T}, D={D}; step = {n_d} doubles + {n_s} singles "
-              f"+ {CN['num_layers']} zero-linears, extrapolated")
-    return 1.0 / step_s, sample
+        t0 = time.perf_counter()
+        O.controlnet_forward(st["cn_sd"], CN, st["lat"], st["cond"], 1.0, st["pe"], st["po"], torch.tensor([0.7]),
+                             st["img_ids"], st["txt_ids"], torch.tensor([3.5]))
+        t1 = time.perf_counter()
+        O.single_block(st["sg_sd"], "single_transformer_blocks.0.", st["x"], st["c"], st["temb"], st["rope"],
+                       TR["num_attention_heads"])
+        t2 = time.perf_counter()
+    S = N + T
+    f_block = 24 * S * D * D + 4 * S * S * D
+    f_cn = step_flops(dict(TR, num_layers=0, num_single_layers=0, in_channels=0, joint_attention_dim=0, out_channels=0),
+                      CN, N, T)
+    f_sample = f_cn + f_block
+    f_step = step_flops(TR, CN, N, T)
+    desc = (f"oracle (fp32 torch CPU restatement of the reference path) - one full-size FluxControlNetModel.forward "
+            f"({t1 - t0:.2f} s, {f_cn / 1e12:.2f} TFLOP) + one single-stream block ({t2 - t1:.2f} s, {f_block / 1e12:.2f} TFLOP) "
+            f"at S={S}, D={D}; step = {f_step / 1e12:.2f} TFLOP, rate scaled by the FLOP ratio {f_step / f_sample:.2f}")
+    return t2 - t0, f_sample, f_step, desc
+
+
+def cpu_oracle_steps_per_s(wl, repeats=1):
+    best = None
+    for _ in range(repeats):
+        sec, f_sample, f_step, desc = cpu_oracle_sample(wl)
+        if best is None or sec < best[0]:
+            best = (sec, f_sample, f_step, desc)
+    sec, f_sample, f_step, desc = best
+    return 1.0 / (sec * f_step / f_sample), desc
 
 
 def run_reference(args, wl):
+    """The reference arm: the reference's own CPU path for this step on the box's host cores.  The reference is Python over
+    diffusers and cannot travel to (or be installed on) the GPU box, so the thing timed is the oracle - the restatement that
+    tests/test_reference_pin.py pins to the reference's own files (bit-identical ControlNet forward).  Every "step" of this
+    arm is ONE bounded sample (cpu_oracle_sample: 11.6 % of a step's FLOPs, ~4-6 s): --steps K --warmup W really runs K + W
+    samples and `timed_region_s` is their wall time; `value` is the step rate those samples imply."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    vals = []
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_oracle_steps_per_s(wl)
-    sample = ""
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_oracle_sample(wl)
+    secs, desc, f_sample, f_step = [], "", 1.0, 1.0
     t_begin = time.perf_counter()
     for _ in range(max(1, args.steps)):
-        v, sample = cpu_oracle_steps_per_s(wl)
-        vals.append(v)
-        if time.perf_counter() - t_begin > 150:
+        sec, f_sample, f_step, desc = cpu_oracle_sample(wl)
+        secs.append(sec)
+        if time.perf_counter() - t_begin > 170:      # keep the whole run within a few minutes
             break
-    v = sum(vals) / len(vals)
+    timed = time.perf_counter() - t_begin
+    mean = sum(secs) / len(secs)
+    v = 1.0 / (mean * f_step / f_sample)
     cores = torch.get_num_threads()
-    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=len(vals), warmup=args.warmup,
+    sample = desc + f"; {len(secs)} samples timed in {timed:.1f} s, min {min(secs):.2f} / mean {mean:.2f} / max {max(secs):.2f} s"
+    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=len(secs), warmup=args.warmup,
                 ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", config=dict(workload=wl["name"], note="CPU arm does not scale with --gpus"),
+                data="synthetic", config=dict(workload=wl["name"], note="CPU arm does not scale with --gpus",
+                                              sample_fraction_of_step=f_sample / f_step, timed_region_s=timed,
+                                              samples_timed=len(secs)),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 images_per_s=v / STEPS_PER_IMAGE)
     print(json.dumps(line), flush=True)
 
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU baseline leg: the SAME step through stock torch on the same B200 (BASELINE.md section 4 / SURVEY.md 2a: "the kernel
+# to beat is torch 2.11's cuBLASLt / SDPA bf16 path running the oracle on the B200").  A baseline, like cpu_baseline: the
+# oracle is the thing measured HERE, never the product.
+# ---------------------------------------------------------------------------------------------------------
+def gpu_baseline_leg(tr, cn, TR, CN, lat, pe, po, cond, mask, img_ids, txt_ids, sigmas, tsd, steps, ours_first):
+    from oracle import flux_oracle as O
+    dt = torch.bfloat16
+    tr_sd, cn_sd = tr.state_dict(), cn.state_dict()      # the product's own device tensors (diffusers names), no copy
+    g = torch.tensor([3.5], device=lat.device)
+    sig = sigmas.to(lat.device)
+    m3 = mask.reshape(1, -1, 1)
+
+    def step(i, latents):
+        j = i % STEPS_PER_IMAGE
+        timestep = tsd[j].expand(1).to(dt)
+        b, _ = O.controlnet_forward(cn_sd, CN, latents, cond, 1.0, pe, po, timestep / 1000, img_ids, txt_ids, g, dt)
+        b = [m3 * x for x in b]
+        v = O.transformer_forward(tr_sd, TR, latents, pe, po, timestep / 1000, img_ids, txt_ids, g, b, None, dt)
+        return O.euler_step(v, sig[j], sig[j + 1], latents)
+
+    with torch.no_grad():
+        x = lat
+        x = step(0, x)
+        first = x
+        x = step(1, x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x = lat
+        for i in range(steps):
+            x = step(i, x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    d = (first.float() - ours_first.float()).norm() / ours_first.float().norm()
+    return dict(value=1000.0 / ms, unit=UNIT, ms_per_step=ms, steps=steps, dtype="bf16",
+                kind="oracle/flux_oracle.py (the reference path restated) run by stock torch 2.11: F.linear -> cuBLASLt, "
+                     "F.scaled_dot_product_attention -> cuDNN / flash, ATen LayerNorm / RMSNorm / elementwise; same "
+                     "weights (shared device tensors), same inputs, device-timed after 2 warm-up steps; runs all 6 "
+                     "ControlNet blocks like the reference",
+                latents_rel_l2_vs_b200_kernels_step0=float(d))
+
+
+def elementwise_leg(dev, pk):
+    """The HBM-class kernels of the path (north_star: 'achieved HBM GB/s for the elementwise kernels'; SURVEY.md 8d:
+    report at the batched cfg-3 size too): Euler, CFG + Euler, mask * scale (+ add), glyph blend at B = 1 and B = 8
+    samples of 1024^2.  Every call is timed alone between CUDA events after a 512 MB write that evicts L2."""
+    from reptext_b200 import ops
+    dt = torch.bfloat16
+    flush = torch.empty(128 << 20, dtype=torch.float32, device=dev)
+    out = {}
+
+    def t(fn, nbytes, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(reps):
+            flush.fill_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        us = tot / reps * 1000.0
+        gbs = nbytes / (us * 1e-6) / 1e9
+        return dict(us=round(us, 2), bytes=nbytes, gbs=round(gbs, 1), frac_of_hbm=round(gbs / pk["hbm"], 3))
+
+    for B in (1, 8):
+        N, C, D = 4096, 64, 3072
+        v, x = torch.randn(B, N, C, device=dev, dtype=dt), torch.randn(B, N, C, device=dev, dtype=dt)
+        v2 = torch.randn(2 * B, N, C, device=dev, dtype=dt)
+        s6 = torch.randn(B, N, D, device=dev, dtype=dt)
+        acc = torch.randn(B, N, D, device=dev, dtype=dt)
+        m = torch.rand(N, device=dev).to(dt)
+        nz, gl = torch.randn(B, 16, 128, 128, device=dev, dtype=dt), torch.randn(B, 16, 128, 128, device=dev, dtype=dt)
+        gm = (torch.rand(B, 16, 128, 128, device=dev) > 0.5).to(torch.uint8)
+        e = 2
+        out[f"B{B}"] = dict(
+            euler_step=t(lambda: ops.euler_step(v, x, 0.9, 0.85), 3 * v.numel() * e),
+            cfg_euler_step=t(lambda: ops.cfg_euler_step(v2, x, 3.5, False, 0.9, 0.85), (v2.numel() + 2 * x.numel()) * e),
+            mask_scale_add=t(lambda: ops.mask_scale_add(s6, m, acc, 0.9), 3 * s6.numel() * e),
+            glyph_init_blend=t(lambda: ops.glyph_init_blend(nz, gl, gm, 0.10, 1.00), 3 * nz.numel() * e + gm.numel()))
+    out["note"] = ("bytes = algorithmic reads + writes; at B = 1 the Euler / CFG tensors are 0.5 MB each: the figure is launch "
+                   "latency (~2-3 us), not bandwidth; mask_scale_add is the UNFUSED form of the regional-mask multiply and "
+                   "multi-line sum (the product fuses both into the zero-linear GEMM epilogue)")
+    return out
+
+
+def make_step(tr, cn, ops, pe, po, cond, mask, img_ids, txt_ids, guidance, sig, tsd, sp_kw):
+    dt = torch.bfloat16
+
+    def one_step(i, latents):
+        j = i % STEPS_PER_IMAGE
+        kw = dict(hidden_states=latents, encoder_hidden_states=pe, pooled_projections=po,
+                  timestep=(tsd[j].expand(1).to(dt)) / 1000, guidance=guidance, img_ids=img_ids, txt_ids=txt_ids)
+        bl, sl = cn(controlnet_cond=cond, conditioning_scale=1.0, regional_mask=mask, return_dict=False, **kw, **sp_kw)
+        v = tr(controlnet_block_samples=bl, controlnet_single_block_samples=sl, return_dict=False, **kw, **sp_kw)[0]
+        return ops.euler_step(v, latents, sig[j], sig[j + 1])
+    return one_step
+
+
+def sp_leg(args, tr, cn, TR, CN, pipe, dev, rank, world, pk, barrier):
+    """BASELINE.json configs[4] inside the default multi-GPU run: ONE 1536x1536 sample (N = 9216 image + 512 text tokens),
+    tokens and attention heads sharded over all `world` ranks (strong scaling).  Measures, with the SAME weights and inputs:
+    the one-GPU step (every rank runs the whole sample itself, max over ranks), the sequence-parallel step, the latents of 2
+    free-running steps against the one-GPU result, and the flag barrier alone."""
+    import numpy as np
+    import torch.distributed as dist
+    from reptext_b200 import _lib, ops, parallel
+    from reptext_b200._pipeline_common import calculate_shift
+    from reptext_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import box_mask
+    wl = workload("cfg5")
+    dt = torch.bfloat16
+    H, W, T = wl["H"], wl["W"], wl["T"]
+    N = (H // 16) * (W // 16)
+    g = torch.Generator().manual_seed(1000)
+    lat = torch.randn(1, N, TR["in_channels"], generator=g).to(dt).to(dev)
+    pe = torch.randn(1, T, TR["joint_attention_dim"], generator=g).to(dt).to(dev)
+    po = torch.randn(1, TR["pooled_projection_dim"], generator=g).to(dt).to(dev)
+    cond = torch.randn(1, N, CN["in_channels"] + CN["extra_condition_channels"], generator=g).to(dt).to(dev)
+    mask = pipe._regional_masks([box_mask(H, W, (H // 3, H // 3 + H // 6, W // 5, W - W // 5))], dev, dt)[0]
+    img_ids = pipe._prepare_latent_image_ids(1, 2 * (H // 16), 2 * (W // 16), dev, dt)
+    txt_ids = torch.zeros(T, 3, device=dev, dtype=dt)
+    guidance = torch.tensor([3.5], device=dev)
+    sch = FlowMatchEulerDiscreteScheduler()
+    sc = sch.config
+    sch.set_timesteps(sigmas=np.linspace(1.0, 1 / STEPS_PER_IMAGE, STEPS_PER_IMAGE), device=dev,
+                      mu=calculate_shift(N, sc.base_image_seq_len, sc.max_image_seq_len, sc.base_shift, sc.max_shift))
+    sig, tsd = sch.sigmas.tolist(), sch.timesteps
+    K = max(2, min(args.steps, 8))
+
+    def timed(step, x0, prof=False):
+        x = x0
+        for i in range(3):
+            x = step(i, x)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if prof:
+            _lib.set_option("profile", 1)
+            _lib.profile_reset()
+        barrier()
+        e0.record()
+        x = x0
+        for i in range(K):
+            x = step(i, x)
+            if i == 1:
+                two = x
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pr = None
+        if prof:
+            torch.cuda.synchronize()
+            pr = _lib.profile_read()
+            _lib.set_option("profile", 0)
+            _lib.profile_reset()
+        return float(t.item()) / K, two, pr
+
+    one = make_step(tr, cn, ops, pe, po, cond, mask, img_ids, txt_ids, guidance, sig, tsd, {})
+    ms1, two1, _ = timed(one, lat)
+    sp = parallel.SequenceParallelGroup()
+    sh = lambda t, d=1: parallel.shard_tokens(t, rank, world, d)
+    stepN = make_step(tr, cn, ops, sh(pe), po, sh(cond), sh(mask.reshape(1, -1, 1)), sh(img_ids, 0), sh(txt_ids, 0),
+                      guidance, sig, tsd, dict(sp=sp))
+    msN, twoN, _ = timed(stepN, sh(lat))
+    sp.check()
+    _, _, prof = timed(stepN, sh(lat), prof=True)      # separate pass: events around every launch
+    sp.check()
+    twoN = parallel.gather_tokens(twoN)
+    err = float((twoN.float() - two1.float()).norm() / two1.float().norm())
+    # the flag barrier alone
+    for _ in range(10):
+        sp.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        sp.barrier()
+    e1.record()
+    torch.cuda.synchronize()
+    bar_us = e0.elapsed_time(e1) / 200 * 1000.0
+    sp.close()
+    flops = step_flops(TR, CN, N, T, cn_live_layers=cn_live(TR, CN))
+    n_bar = 2 * (cn_live(TR, CN) + TR["num_layers"] + TR["num_single_layers"]) + 6
+    breakdown = {}
+    for k, v in (prof or {}).items():
+        tensor = "gemm" in k or "attention" in k
+        ach = (v[1] / (v[0] / 1000.0) / (1e12 if tensor else 1e9)) if v[0] else None
+        breakdown[k] = dict(ms_per_step=v[0] / K, launches_per_step=v[2] / K, achieved=ach,
+                            unit="TFLOP/s" if tensor else "GB/s")
+    return dict(workload=wl["name"], n_gpus=world, steps=K, ms_per_step=msN, steps_per_s=1000.0 / msN,
+                one_gpu_ms_per_step=ms1, speedup=ms1 / msN, strong_scaling_efficiency=ms1 / msN / world,
+                target_ms_per_step=27.1 if world == 8 else None, flops_per_step=flops,
+                tensor_util_per_gpu=flops / world / (msN / 1000.0) / 1e12 / pk["bf16_sustained"],
+                latents_rel_l2_vs_one_gpu_after_2_steps=err, barrier_us=bar_us, barriers_per_step=n_bar,
+                barrier_ms_per_step=bar_us * n_bar / 1000.0, breakdown=breakdown,
+                how="same weights, same inputs, same process group as the headline run; one-GPU figure = every rank runs "
+                    "the whole sample itself (max over ranks); device-timed, 3 warm-up steps, barrier + synchronize on "
+                    "both sides")
+
+
+def cn_live(TR, CN):
+    from reptext_b200.models import FluxControlNetModel
+    if CN["num_single_layers"]:
+        return CN["num_layers"]
+    return FluxControlNetModel.consumed_samples(CN["num_layers"], TR["num_layers"])
 
 # ---------------------------------------------------------------------------------------------------------
 # B200 arm
@@ -238,6 +487,7 @@ def run_b200(args, wl):
     else:
         raise SystemExit("bench workloads use the FLUX.1-dev text widths (4096 / 768)")
     pipe = FluxControlNetPipeline(sch, vae, clip, tok, t5, tok2, tr, cn)
+    pipe.skip_unconsumed_controlnet_blocks = not args.full_controlnet
     mask = pipe._regional_masks([mask_img], dev, dt)[0]
     lat, pe, po, cond = [t.to(dev, non_blocking=True) for t in (h_lat, h_pe, h_po, h_cond)]
     img_ids = pipe._prepare_latent_image_ids(1, 2 * (H // 16), 2 * (W // 16), dev, dt)
@@ -266,14 +516,10 @@ def run_b200(args, wl):
     sig = sch.sigmas.tolist()
     tsd = sch.timesteps
 
-    def one_step(i, latents):
-        t = tsd[i % STEPS_PER_IMAGE]
-        kw = dict(hidden_states=latents, encoder_hidden_states=pe, pooled_projections=po,
-                  timestep=(t.expand(1).to(dt)) / 1000, guidance=guidance, img_ids=img_ids, txt_ids=txt_ids)
-        bl, sl = cn(controlnet_cond=cond, conditioning_scale=1.0, regional_mask=mask, return_dict=False, **kw, **sp_kw)
-        v = tr(controlnet_block_samples=bl, controlnet_single_block_samples=sl, return_dict=False, **kw, **sp_kw)[0]
-        j = i % STEPS_PER_IMAGE
-        return ops.euler_step(v, latents, sig[j], sig[j + 1])
+    if not args.full_controlnet:
+        # what the pipelines do by default: ControlNet blocks whose sample the transformer never reads are not run
+        cn.set_consumer(TR["num_layers"], TR["num_single_layers"])
+    one_step = make_step(tr, cn, ops, pe, po, cond, mask, img_ids, txt_ids, guidance, sig, tsd, sp_kw)
 
     def barrier():
         if world > 1:
@@ -411,9 +657,29 @@ def run_b200(args, wl):
         outs = [torch.empty_like(x) for _ in range(world)]
         dist.all_gather(outs, x)
 
+    pk = peaks()
+    # ---- the kernel to beat, same box, same inputs: the reference path through stock torch in bf16
+    gpu_base = None
+    if world == 1 and sp is None and not args.no_gpu_baseline:
+        try:
+            gpu_base = gpu_baseline_leg(tr, cn, TR, CN, lat, pe, po, cond, mask, img_ids, txt_ids, sch.sigmas, tsd,
+                                        max(2, min(args.steps, 6)), one_step(0, lat))
+        except Exception as e:  # a baseline that cannot run must not take the product's line with it
+            gpu_base = dict(unavailable=repr(e)[:300])
+        torch.cuda.empty_cache()
+    elementwise = elementwise_leg(dev, pk) if (rank == 0 and not args.no_e2e) else None
+    # ---- BASELINE.json configs[4] next to the headline: one 1536^2 sample sequence-parallel over all ranks
+    sp_rec = None
+    if world > 1 and sp is None and not args.no_sp and args.workload == "cfg2":
+        try:
+            sp_rec = sp_leg(args, tr, cn, TR, CN, pipe, dev, rank, world, pk, barrier)
+        except Exception as e:
+            sp_rec = dict(unavailable=repr(e)[:300])
+
     if rank == 0:
-        pk = peaks()
-        flops = step_flops(TR, CN, N, T)
+        live = None if args.full_controlnet else cn_live(TR, CN)
+        flops = step_flops(TR, CN, N, T, cn_live_layers=live)
+        flops_reference = step_flops(TR, CN, N, T)
         gpus_per_sample = world if sp is not None else 1
         gem = prof.get("gemm_tcgen05", (0.0, 0.0, 0))
         roof = None
@@ -454,7 +720,13 @@ def run_b200(args, wl):
                                              "barriers, NCCL only gathers the final latents)" if sp is not None else
                                              f"dp{world} (independent samples, no data-path collective)"),
                                 l2="not flushed: each step streams 32 GB of weights, far larger than the 126 MB L2",
-                                flops_per_step=flops, images_per_s=value / STEPS_PER_IMAGE,
+                                flops_per_step=flops, flops_per_step_reference=flops_reference,
+                                controlnet_blocks_run=(CN["num_layers"] if live is None else live),
+                                controlnet_note=("the pipelines' default: ControlNet blocks whose sample the transformer "
+                                                 "never reads (i // ceil(19 / 6): sample 5) are not run; latents are "
+                                                 "bit-identical (tests/test_fullsize_gpu.py); --full-controlnet runs all 6; "
+                                                 "utilisation figures count only the FLOPs executed"),
+                                images_per_s=value / STEPS_PER_IMAGE,
                                 tensor_util_whole_step=flops / gpus_per_sample / (step_ms / 1000.0) / 1e12 / pk["bf16_sustained"],
                                 finite_output=finite),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_step, d2h_bytes_per_step=d2h_step,
@@ -463,7 +735,10 @@ def run_b200(args, wl):
                                  "images, 28 denoise steps with the latents copied to the host after every step, VAE "
                                  "decode, image copied to the host"),
                     vae=vae_info, text_encoders=text_info,
-                    gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu, breakdown=breakdown)
+                    gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu, gpu_baseline=gpu_base,
+                    breakdown=breakdown, elementwise=elementwise, sp=sp_rec)
+        if gpu_base and gpu_base.get("value"):
+            line["gpu_baseline"]["b200_kernels_over_stock_torch"] = value / gpu_base["value"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -478,6 +753,9 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the pipeline end-to-end leg (profiling runs only)")
+    ap.add_argument("--full-controlnet", action="store_true", help="run every ControlNet block like the reference (A/B of the unconsumed-block skip)")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-sp", action="store_true", help="skip the cfg5 sequence-parallel record of multi-GPU runs")
     args = ap.parse_args()
     wl = workload(args.workload)
     if args.impl == "reference":

@@ -144,6 +144,16 @@ RT_API int rt_controlnet_forward(rt_model* m, const rt_forward_args* a, const vo
                           float conditioning_scale, const void* mask, int accumulate, void* block_samples,
                           void* single_block_samples);
 
+/* Tell a ControlNet how many of its samples have a consumer.  diffusers' FluxTransformer2DModel.forward adds
+ * controlnet_block_samples[i // ceil(L / n)] after block i (L = 19, n = 6 -> interval 4 -> samples 0..4; sample 5 is
+ * never read), so the pair FLUX.1-dev + RepText pays for a sixth ControlNet block and zero-linear
+ * (RepText/controlnet_flux.py:320-349, :385-388) whose output nobody uses: 1.38 TFLOP of an 82.7 TFLOP step.
+ * With live_layers / live_single_layers set (>= 0) rt_controlnet_forward only runs the blocks that feed a consumed sample
+ * and leaves the other samples of the output stack UNTOUCHED (the caller zero-fills them once).  -1 = run everything
+ * (the default: a C-ABI caller that reads every sample gets every sample).  The Python pipelines, which only ever hand
+ * the lists to `transformer(...)`, set it from the transformer's layer counts. */
+RT_API int rt_controlnet_set_live(rt_model* m, int live_layers, int live_single_layers);
+
 /* FluxTransformer2DModel.forward (diffusers 0.36.0) as called at
  * RepText/pipeline_flux_controlnet.py:1092-1104.  controlnet_*_samples are host arrays of device
  * pointers to [batch, n_img, D] tensors (or NULL / 0); sample i//ceil(L/n) is added after block i,

@@ -332,10 +332,13 @@ def make_sigmas(num_inference_steps: int, image_seq_len: int, cfg: dict = SCHEDU
 
 
 def euler_step(model_output: Tensor, sigma: Tensor, sigma_next: Tensor, sample: Tensor) -> Tensor:
-    """scheduler.step (pipeline_flux_controlnet.py:1109).  NB torch type promotion: the product of the
-    0-dim fp32 ``dt`` and a bf16 ``model_output`` is a bf16 tensor (rounded before the fp32 add).  On
-    CPU torch also rounds ``dt`` itself to bf16 first; on CUDA (sigmas live on the CPU in diffusers, so
-    ``dt`` is a host scalar) it stays fp32.  In fp32 all forms coincide."""
+    """scheduler.step (pipeline_flux_controlnet.py:1109).  NB torch type promotion: the product of the 0-dim fp32
+    ``dt`` and a bf16 ``model_output`` is a bf16 tensor (rounded before the fp32 add), and ``dt`` itself is cast to
+    bf16 by the multiply whenever it is a 0-dim TENSOR on the same device as ``model_output`` - which is the case in
+    diffusers 0.36 (``set_timesteps(device=)`` leaves ``sigmas`` on the device) and in this function on the CPU.
+    Measured with torch 2.11 on a B200 (profiles/r2_euler_dt_probe.txt); ``rt_euler_step`` follows it
+    (tests/test_ops_gpu.py::test_euler_cfg_mask_blend_match_oracle compares with torch's own evaluation).  In fp32
+    all forms coincide."""
     sample = sample.to(torch.float32)
     prev = sample + (sigma_next - sigma) * model_output
     return prev.to(model_output.dtype)

@@ -74,6 +74,7 @@ def _load_tokenizer(dirpath: str, class_name: Optional[str]):
 class RepTextPipelineBase(DiffusionPipeline):
     _callback_tensor_inputs = ["latents", "prompt_embeds"]
     _inpaint = False
+    skip_unconsumed_controlnet_blocks = True
 
     # ---- RepText/infer.py:31-33: FluxControlNetPipeline.from_pretrained(base_model, controlnet=..., torch_dtype=...) --
     @classmethod
@@ -228,6 +229,10 @@ class RepTextPipelineBase(DiffusionPipeline):
                              "`pooled_prompt_embeds`, or attach tokenizer / tokenizer_2 / text_encoder / text_encoder_2")
         prompts = [prompt] if isinstance(prompt, str) else list(prompt)
         pe, po = enc.encode(prompts, max_sequence_length)
+        if clip_prompt is not None:              # the pooled vector follows `prompt`, the sequence `prompt_2`
+            clips = [clip_prompt] if isinstance(clip_prompt, str) else list(clip_prompt)
+            if clips != prompts:
+                po = enc.encode(clips, max_sequence_length)[1]
         pe = pe.repeat_interleave(num_images_per_prompt, dim=0)
         po = po.repeat_interleave(num_images_per_prompt, dim=0)
         return pe, po
@@ -352,6 +357,14 @@ class RepTextPipelineBase(DiffusionPipeline):
                  controlnet_conditioning_scale_inpaint=1.0, true_guidance_scale=3.5):
         device = latents.device
         num_warmup_steps = max(len(timesteps) - num_inference_steps * self.scheduler.order, 0)
+        # the pipelines only ever hand the ControlNet samples to `self.transformer`, which reads sample i // ceil(L / n):
+        # blocks that produce samples it never reads are not run (FLUX.1-dev + RepText: the sixth block; latents are
+        # bit-identical).  `pipe.skip_unconsumed_controlnet_blocks = False` restores the reference's full ControlNet.
+        tc = self.transformer.config
+        consumer = (tc.num_layers, tc.num_single_layers) if self.skip_unconsumed_controlnet_blocks else (None, None)
+        for net in (self.controlnet, getattr(self, "controlnet_inpaint", None)):
+            if net is not None and hasattr(net, "set_consumer"):
+                net.set_consumer(*consumer)
         do_cfg = self._inpaint and self.do_classifier_free_guidance
         guidance_const = None
         if self.transformer.config.guidance_embeds:

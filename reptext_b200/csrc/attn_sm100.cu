@@ -1578,6 +1578,342 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_tc_kernel_v6(const __grid_c
   if (warp == 2) ptx::tmem_dealloc<2>(tmem, 512);
 }
 
+
+// =================================================================================================
+// PAIR kernel: the two-tile ping-pong of attn_tc_kernel on a CTA PAIR (tcgen05 cta_group::2).
+//
+// Why.  With one CTA per SM every Q K^T instruction (128 x 128 x 16, both operands from shared memory) reads 8 KB per 64
+// tensor cycles = 128 B/clk - the whole bandwidth of the shared-memory crossbar - while TMA keeps writing the next K / V
+// tiles into the same memory: the r1 timing experiments found every single-CTA variant, arithmetic removed, pinned at
+// 1320-1460 TFLOP/s for exactly that reason, and cuDNN's Blackwell kernel measures 1510-1540 on the same box and shapes
+// (profiles/r2_attn_lib_compare.txt).  A 2-CTA MMA (M = 256: 128 query rows in each CTA) takes its B operand HALF from
+// each CTA: per CTA a Q K^T instruction reads 4 KB of Q + 2 KB of K, a P V instruction (P from TMEM) 2 KB of V, and TMA
+// writes 16 + 16 KB per 128-key block instead of 32 + 32.  Shared-memory traffic per CTA and block: 160 KB instead of
+// 256 KB (78 B/clk at full tensor rate instead of 125).
+// v6 (above, A/B only) had the pair but ONE query tile per CTA, which leaves the chain Q K^T -> softmax -> P V of a tile
+// exposed; here each CTA keeps the product's two tiles (A, B) and the tensor pipe ping-pongs between MMA-tile A (= tile
+// A of both CTAs, 256 rows) and MMA-tile B.
+//
+//   cluster = 2 CTAs = 4 query tiles (512 rows) of one (batch, head); the LEADER (cluster rank 0) issues every MMA
+//   both CTAs: warp 0 TMA producer for their halves - Q: own two tiles; K: 64 of the block's 128 keys; V: 64 of the
+//              128 head-dim columns - with the bytes counted on the LEADER's full barriers (cta_group::2 loads);
+//              warps 4-7 / 8-11 softmax warpgroups of their own tiles A / B (thread = query row), P handed over by
+//              one elected lane per warp arriving on the LEADER's p_half / p_full barriers (remote arrive from the peer)
+//   TMEM (both CTAs, same columns): S_A | S_B | O_A | O_B, 128 fp32 columns each; bf16 P overwrites S
+//   tcgen05.commit multicasts to both CTAs: each CTA's own k_empty / v_empty / s_full / o_full barriers
+// =================================================================================================
+constexpr int kStagesK7 = 4, kStagesV7 = 4;
+constexpr int kHalfBytes7 = kTileBytes / 2;  // 16 KB: 64 keys x 128 (K half) or 128 keys x 64 columns (V half)
+constexpr int kNumBars7 = 1 + 2 * kStagesK7 + 2 * kStagesV7 + 2 + 2 + 2 + 1;
+constexpr int kSmemBytes7 = 2 * kTileBytes + (kStagesK7 + kStagesV7) * kHalfBytes7 + kNumBars7 * 8 + 16 + 1024;
+static_assert(kNumBars7 * 8 + 16 <= 256, "barrier block");
+static_assert(8 * 32 * (HD * 2 + 16) <= 2 * kTileBytes + kStagesK7 * kHalfBytes7, "epilogue staging fits in Q + K");
+
+template <int kPolyMask8>
+__global__ void __launch_bounds__(kThreads, 1) attn_tc_pair_kernel(const __grid_constant__ AttnParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint8_t* smem_q = smem;                                              // this CTA's tiles A, B
+  uint8_t* smem_k = smem + 2 * kTileBytes;                             // kStagesK7 x [64 keys x 128]
+  uint8_t* smem_v = smem_k + kStagesK7 * kHalfBytes7;                  // kStagesV7 x [128 keys x 64 columns]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kStagesV7 * kHalfBytes7);
+  uint64_t* q_full = bars;                 // leader's: both CTAs' TMA bytes
+  uint64_t* k_full = bars + 1;             // leader's
+  uint64_t* k_empty = k_full + kStagesK7;  // each CTA's own (multicast commit)
+  uint64_t* v_full = k_empty + kStagesK7;  // leader's
+  uint64_t* v_empty = v_full + kStagesV7;  // each CTA's own
+  uint64_t* s_full = v_empty + kStagesV7;  // [2] each CTA's own
+  uint64_t* p_full = s_full + 2;           // [2] leader's: one lane of each of the 8 softmax warps of an MMA tile
+  uint64_t* p_half = p_full + 2;           // [2] leader's: first 64 keys of P written
+  uint64_t* o_full = p_half + 2;           // [1] each CTA's own
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int n_qq = (P.S + 4 * BQ - 1) / (4 * BQ);  // clusters per (batch, head)
+  const int cl = blockIdx.x >> 1;
+  const int qq = cl % n_qq;
+  const int bh = cl / n_qq;
+  const int h = bh % P.heads, b = bh / P.heads;
+  const int q0 = qq * 4 * BQ + (int)cta_rank * 2 * BQ;  // this CTA's 256 query rows
+  const int n_kv = (P.S + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&P.tm);
+    ptx::prefetch_tmap(&P.tmh);
+  }
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < kStagesK7; ++i) { ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < kStagesV7; ++i) { ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 8);
+      ptx::mbar_init(&p_half[i], 8);
+    }
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<2>(tmem_slot, 512);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  ptx::grid_launch_dependents();  // programmatic dependent launch: nothing above reads the previous kernel's output
+  ptx::grid_dependency_wait();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer (both CTAs; the bytes land on the leader's full barriers) ==========
+      if (leader) ptx::mbar_arrive_expect_tx(q_full, 4 * kTileBytes);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d_2sm(&P.tm, q_full, smem_q + t * kTileBytes + sub * kSubBytes,
+                               P.q_col0 + h * HD + sub * 64, q0 + t * BQ, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int sk = j % kStagesK7, sv = j % kStagesV7;
+        // K: this CTA's 64 keys of the block, both 64-column halves of the head dimension: box (64, 64)
+        ptx::mbar_wait(&k_empty[sk], ((j / kStagesK7) & 1) ^ 1);
+        if (leader) ptx::mbar_arrive_expect_tx(&k_full[sk], 2 * kHalfBytes7);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d_2sm(&P.tmh, &k_full[sk], smem_k + sk * kHalfBytes7 + sub * (kHalfBytes7 / 2),
+                               P.k_col0 + h * HD + sub * 64, j * BKV + (int)cta_rank * (BKV / 2), b);
+        // V: all 128 keys, this CTA's 64 head-dim columns: box (64, 128)
+        ptx::mbar_wait(&v_empty[sv], ((j / kStagesV7) & 1) ^ 1);
+        if (leader) ptx::mbar_arrive_expect_tx(&v_full[sv], 2 * kHalfBytes7);
+        ptx::tma_load_3d_2sm(&P.tm, &v_full[sv], smem_v + sv * kHalfBytes7, P.v_col0 + h * HD + (int)cta_rank * 64,
+                             j * BKV, b);
+      }
+    } else if (warp == 1 && leader) {
+      // ===================== MMA issuer (leader CTA, for the pair) =====================
+      // The whole warp runs the loop (descriptor arithmetic stays on the uniform datapath); one elected lane issues.
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(2 * BQ, BKV, 0, 0);  // 256 x 128, A and B K-major
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(2 * BQ, HD, 0, 1);   // A (= P) from TMEM, B (= V) MN-major
+      const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_q), 0, 1024);
+      const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_k), 0, 1024);
+      const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_v), 0, 1024);
+      constexpr uint32_t kTile16 = kTileBytes >> 4, kHalf16 = kHalfBytes7 >> 4;
+      constexpr uint32_t kQSub16 = kSubBytes >> 4, kKSub16 = (kHalfBytes7 / 2) >> 4;
+      auto issue_qk = [&](int t, int sk) {
+        const uint64_t qa = q_desc + (uint64_t)(t * kTile16), ka = k_desc + (uint64_t)(sk * kHalf16);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t qoff = (kk >> 2) * kQSub16 + (kk & 3) * 2;  // (addr >> 4) units
+          const uint32_t koff = (kk >> 2) * kKSub16 + (kk & 3) * 2;
+          ptx::mma_bf16_ss<2>(tmem + t * 128, qa + qoff, ka + koff, idesc_qk, kk != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int sv, uint32_t acc, int kk0, int kk1) {
+        const uint64_t va = v_desc + (uint64_t)(sv * kHalf16);
+#pragma unroll
+        for (int kk = kk0; kk < kk1; ++kk)  // 16 keys = 16 rows of 128 B in this CTA's 64-column half
+          ptx::mma_bf16_ts_2sm(tmem + 256 + t * 128, tmem + t * 128 + kk * 8, va + (uint64_t)(kk * 128), idesc_pv,
+                               kk != 0 ? 1u : acc);
+      };
+      ptx::mbar_wait(q_full, 0);
+      ptx::mbar_wait(&k_full[0], 0);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        issue_qk(0, 0);
+        ptx::mma_commit_2sm(&s_full[0], 3);
+        issue_qk(1, 0);
+        ptx::mma_commit_2sm(&s_full[1], 3);
+        ptx::mma_commit_2sm(&k_empty[0], 3);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kv; ++j) {
+        const int sv = j % kStagesV7, phv = (j / kStagesV7) & 1;
+        const int nsk = (j + 1) % kStagesK7, nphk = ((j + 1) / kStagesK7) & 1;
+        const bool more = j + 1 < n_kv;
+        const uint32_t acc = j > 0 ? 1u : 0u;
+        ptx::mbar_wait(&v_full[sv], phv);
+        ptx::mbar_wait(&p_half[0], j & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) issue_pv(0, sv, acc, 0, 4);
+        __syncwarp();
+        ptx::mbar_wait(&p_full[0], j & 1);
+        if (more) ptx::mbar_wait(&k_full[nsk], nphk);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          issue_pv(0, sv, 1u, 4, 8);
+          if (more) {
+            issue_qk(0, nsk);
+            ptx::mma_commit_2sm(&s_full[0], 3);
+          }
+        }
+        __syncwarp();
+        ptx::mbar_wait(&p_half[1], j & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) issue_pv(1, sv, acc, 0, 4);
+        __syncwarp();
+        ptx::mbar_wait(&p_full[1], j & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          issue_pv(1, sv, 1u, 4, 8);
+          ptx::mma_commit_2sm(&v_empty[sv], 3);
+          if (more) {
+            issue_qk(1, nsk);
+            ptx::mma_commit_2sm(&s_full[1], 3);
+            ptx::mma_commit_2sm(&k_empty[nsk], 3);
+          }
+        }
+        __syncwarp();
+      }
+      if (ptx::elect_one()) ptx::mma_commit_2sm(o_full, 3);
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax warpgroups (this CTA's tiles A, B) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int t = (warp - 4) >> 2;  // 0: tile A, 1: tile B
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t s_addr = tmem + lane_off + t * 128;
+    const uint32_t o_addr = tmem + lane_off + 256 + t * 128;
+    const float c = P.scale_log2;
+    float m_ref = -INFINITY, l = 0.f;
+    auto hand_over = [&](uint64_t* bar) {  // P (or its first half) is in TMEM: tell the leader's MMA warp
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(bar);
+        else ptx::mbar_arrive_cluster_relaxed(bar, 0);
+      }
+    };
+    for (int j = 0; j < n_kv; ++j) {
+      ptx::mbar_wait(&s_full[t], j & 1);
+      ptx::tc_fence_after();
+      const int n_valid = P.S - j * BKV;  // < 128 only on the last block
+      // ---- S -> registers, one chunk in flight while the previous one feeds the running max
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      auto chunk_max = [&](uint32_t (&sv)[32], int col0) {
+        if (n_valid < BKV) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i >= n_valid) sv[i] = 0xff800000u;  // -inf
+        }
+        float a = -INFINITY, b2 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          a = fmaxf(a, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+          b2 = fmaxf(b2, fmaxf(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])));
+        }
+        return fmaxf(a, b2);
+      };
+      ptx::tmem_ld_32x32b_x32(s_addr, s0);
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32b_x32(s_addr + 32, s1);
+      float mx = chunk_max(s0, 0);
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32b_x32(s_addr + 64, s2);
+      mx = fmaxf(mx, chunk_max(s1, 32));
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32b_x32(s_addr + 96, s3);
+      mx = fmaxf(mx, chunk_max(s2, 64));
+      ptx::tmem_ld_wait();
+      mx = fmaxf(mx, chunk_max(s3, 96));
+      const float mx_s = mx * c;
+      if (j == 0) {
+        m_ref = mx_s;
+      } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
+        // lazy rescale: s_full[t] of block j was committed after P V of block j - 1 (in-order pipe), so O is quiescent
+        const float m_new = fmaxf(m_ref, mx_s);
+        const float f = ptx::ex2_approx(m_ref - m_new);
+        l *= f;
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(o_addr + ch * 16, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          ptx::tmem_st_32x32b_x16(o_addr + ch * 16, r);
+        }
+        m_ref = m_new;
+      }
+      // ---- P = 2^(S c - m) on pairs; bf16 P overwrites the first 64 columns of S
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
+      float2 lsum = make_float2(0.f, 0.f);
+      auto exp_chunk = [&](const uint32_t (&sv)[32], int col) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, nm2);
+          float2 e;
+          if ((kPolyMask8 >> (i & 7)) & 1) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = ptx::ex2_approx(x.x);
+            e.y = ptx::ex2_approx(x.y);
+          }
+          lsum = __fadd2_rn(lsum, e);
+          pk[i] = ptx::pack_bf16x2(e.x, e.y);
+        }
+        ptx::tmem_st_32x32b_x16(s_addr + col, pk);
+      };
+      exp_chunk(s0, 0);
+      exp_chunk(s1, 16);
+      hand_over(&p_half[t]);
+      exp_chunk(s2, 32);
+      exp_chunk(s3, 48);
+      l += lsum.x + lsum.y;
+      hand_over(&p_full[t]);
+    }
+    // ---- epilogue: O / l -> bf16 -> shared (row-wise) -> global (2 rows x 256 B per warp instruction); all MMAs of
+    // the pair have completed (o_full), so this CTA's Q tiles and K ring are dead
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    constexpr int kPitch = HD * 2 + 16;  // 272 B: conflict-free row-wise writes and transposed reads
+    uint8_t* stage = smem + (warp - 4) * (32 * kPitch);
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      float v[32];
+      tmem_ld32(o_addr + ch * 32, v);
+      uint4* dst = reinterpret_cast<uint4*>(stage + lane * kPitch + ch * 64);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = ptx::pack_bf16x2(v[8 * i + 0] * inv, v[8 * i + 1] * inv);
+        u.y = ptx::pack_bf16x2(v[8 * i + 2] * inv, v[8 * i + 3] * inv);
+        u.z = ptx::pack_bf16x2(v[8 * i + 4] * inv, v[8 * i + 5] * inv);
+        u.w = ptx::pack_bf16x2(v[8 * i + 6] * inv, v[8 * i + 7] * inv);
+        dst[i] = u;
+      }
+    }
+    __syncwarp();
+    const int row0 = q0 + t * BQ + quad * 32;  // first row of this warp
+    const int rr = lane >> 4, cc = lane & 15;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int r = it * 2 + rr;
+      const int grow = row0 + r;
+      if (grow < P.S) {
+        bf16* orow;
+        if (P.sp_rows > 0) {
+          const int dest = grow / P.sp_rows;
+          orow = P.sp_out[dest] + (long long)b * P.out_bs + (long long)(grow - dest * P.sp_rows) * P.out_ld +
+                 P.out_col0 + h * HD;
+        } else {
+          orow = P.out + (long long)b * P.out_bs + (long long)grow * P.out_ld + P.out_col0 + h * HD;
+        }
+        *reinterpret_cast<uint4*>(orow + cc * 8) = *reinterpret_cast<const uint4*>(stage + r * kPitch + cc * 16);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 2) ptx::tmem_dealloc<2>(tmem, 512);
+}
+
 }  // namespace
 
 bool attention_tc_supported(const AttnArgs& a, std::string* why) {
@@ -1686,6 +2022,37 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
     for (int i = 0; i < kNumVariantsH; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(tableH[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesHalfRow));
     attrH_set = true;
+  }
+  if (variant >= 70) {
+    // pair kernel (CTA pair, cta_group::2, two query tiles per CTA): variant 70 + i; polynomial share 25 / 0 / 37.5 / 50 %
+    static const KernelFn table7[] = {attn_tc_pair_kernel<0x88>, attn_tc_pair_kernel<0x00>, attn_tc_pair_kernel<0x92>,
+                                      attn_tc_pair_kernel<0xAA>};
+    constexpr int kNumVariants7 = sizeof(table7) / sizeof(table7[0]);
+    RT_REQUIRE(variant - 70 < kNumVariants7, "attention: unknown variant");
+    static bool attr7_set = false;
+    if (!attr7_set) {
+      for (int i = 0; i < kNumVariants7; ++i)
+        RT_CHECK_CUDA(cudaFuncSetAttribute(table7[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes7));
+      attr7_set = true;
+    }
+    const long long clusters = (long long)((a.S + 4 * BQ - 1) / (4 * BQ)) * a.heads * a.batch;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes7;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = get_option("no_pdl") ? 1 : 2;
+    RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, table7[variant - 70], P));
+    count_launch();
+    return;
   }
   if (variant >= 60) {
     RT_REQUIRE(variant - 60 < kNumVariantsH, "attention: unknown variant");

@@ -872,8 +872,19 @@ void launch_qknorm_rope(int dtype, void* buf, long long bs, int ld, int col0, in
 // ------------------------------------------------------------------------------------------------
 // FlowMatch Euler step (scheduler.step at RepText/pipeline_flux_controlnet.py:1109) and true-CFG
 // (pipeline_flux_controlnet_inpaint.py:1264-1270).  16 bytes per thread per tensor, grid-stride.
-//   out = T( float(x) + float(T(dt * float(v))) )       (dt stays fp32: CUDA form, see oracle note)
+//   out = T( float(x) + float(T(float(T(dt)) * float(v))) )
+// diffusers 0.36 keeps scheduler.sigmas ON THE DEVICE (set_timesteps(..., device=)), so `dt = sigma_next - sigma` is a
+// 0-dim fp32 CUDA tensor; torch's type promotion ignores 0-dim tensors of the same category, the multiply runs in the
+// dtype of model_output and its fetch casts dt to that dtype first: dt is ROUNDED TO bf16 in a bf16 run.  Measured on
+// a B200 with torch 2.11 (tools/euler_dt_probe.py, profiles/r2_euler_dt_probe.txt): that form matches bit for bit, the
+// host-scalar form (sigmas on the CPU, as EulerDiscreteScheduler keeps them: dt stays fp32) differs in 12608 of
+// 262144 elements.  Option euler_dt_host=1 selects the host-scalar form.
 // ------------------------------------------------------------------------------------------------
+static float euler_dt(int dtype, float sigma, float sigma_next) {
+  const float dt = sigma_next - sigma;
+  if (dtype == RT_BF16 && !get_option("euler_dt_host")) return __bfloat162float(__float2bfloat16_rn(dt));
+  return dt;
+}
 template <typename T>
 __global__ void __launch_bounds__(256) euler_kernel(const T* __restrict__ v, const T* __restrict__ x,
                                                     T* __restrict__ out, long long n, float dt) {
@@ -902,7 +913,7 @@ static int ew_blocks(long long nvec) {
 void launch_euler_step(int dtype, const void* v, const void* x, void* out, long long n, float sigma,
                        float sigma_next, cudaStream_t stream) {
   if (n == 0) return;
-  const float dt = sigma_next - sigma;
+  const float dt = euler_dt(dtype, sigma, sigma_next);
   RT_DISPATCH_DTYPE(dtype, T, (euler_kernel<T><<<ew_blocks(n / VecT<T>::N), 256, 0, stream>>>(
                                   (const T*)v, (const T*)x, (T*)out, n, dt)));
   RT_POST_LAUNCH();
@@ -957,7 +968,7 @@ void launch_cfg_euler(int dtype, const void* v2, const void* x, void* out, long 
   if (n == 0) return;
   RT_REQUIRE((n * (long long)dtype_size(dtype)) % 16 == 0, "cfg: n*sizeof(T) must be a multiple of 16");
   RT_DISPATCH_DTYPE(dtype, T, (cfg_kernel<T, true><<<ew_blocks(n / VecT<T>::N), 256, 0, stream>>>(
-                                  (const T*)v2, (const T*)x, (T*)out, n, s, zero_pred, sigma_next - sigma)));
+                                  (const T*)v2, (const T*)x, (T*)out, n, s, zero_pred, euler_dt(dtype, sigma, sigma_next))));
   RT_POST_LAUNCH();
 }
 

@@ -69,6 +69,8 @@ struct rt_model {
   int* prefix_dev = nullptr;    // [0] = 0 (single-job launches), [1..] = row prefix of the AdaLN jobs
   int n_mod_jobs = 0, mod_rows = 0;
   int first_block_jobs = 0, first_block_rows = 0;  // the AdaLN jobs the first block needs
+  // ControlNet only: how many of the double / single blocks have a CONSUMER (rt_controlnet_set_live; -1 = all of them)
+  int live_layers = -1, live_single = -1;
   // The AdaLN vectors of blocks 1.. are weight-streaming work (6.5 GB per forward) that nothing needs until the
   // second block: they are computed on a side stream, under the first block's tensor-core kernels.
   cudaStream_t side = nullptr;
@@ -561,13 +563,20 @@ void controlnet_forward_impl(rt_model* m, const std::vector<const rt_controlnet_
     p.accumulate = k.accumulate;
     launch_gemm(L, c.st);
   };
-  for (int i = 0; i < m->cfg.num_layers; ++i)
+  // Blocks whose sample nobody consumes are not run (rt_controlnet_set_live): a single block's sample only feeds later
+  // single blocks, a double block's sample feeds every later block - so trailing singles can always be dropped, trailing
+  // doubles only when no single block runs after them.  The skipped samples are left untouched.
+  const int ns_live = (m->live_single >= 0 && m->live_single < m->cfg.num_single_layers) ? m->live_single
+                                                                                        : m->cfg.num_single_layers;
+  const int nl_live = (ns_live == 0 && m->live_layers >= 0 && m->live_layers < m->cfg.num_layers) ? m->live_layers
+                                                                                                  : m->cfg.num_layers;
+  for (int i = 0; i < nl_live; ++i)
     run_block(cs, [&](const Ctx& c, size_t) { double_block_pre(c, m->dbl[i]); },
               [&](const Ctx& c, size_t r) {
                 double_block_post(c, m->dbl[i], nullptr);
                 zero_linear(c, *calls[r], m->cn_blk[i], calls[r]->block_samples, i);
               });
-  for (int j = 0; j < m->cfg.num_single_layers; ++j)
+  for (int j = 0; j < ns_live; ++j)
     run_block(cs, [&](const Ctx& c, size_t) { single_block_pre(c, m->sgl[j]); },
               [&](const Ctx& c, size_t r) {
                 single_block_post(c, m->sgl[j], nullptr);
@@ -768,6 +777,14 @@ int rt_model_finalize(rt_model* m, void* stream) {
                                   (cudaStream_t)stream));
     RT_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // the host vectors die here
     m->finalized = true;
+  });
+}
+
+int rt_controlnet_set_live(rt_model* m, int live_layers, int live_single_layers) {
+  return guarded([&] {
+    RT_REQUIRE(m && m->cfg.kind == RT_CONTROLNET, "set_live: not a ControlNet model");
+    m->live_layers = live_layers;
+    m->live_single = live_single_layers;
   });
 }
 

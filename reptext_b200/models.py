@@ -279,8 +279,45 @@ class FluxControlNetModel(_RuntimeModel):
     def __init__(self, config: dict, state_dict=None, dtype=torch.bfloat16, device="cuda"):
         if config.get("num_mode") is not None:
             raise NotImplementedError("ControlNet-Union (num_mode) is outside the RepText hot path")
+        self._live = (-1, -1)
         super().__init__(config, state_dict, dtype, device)
         self.union = False
+
+    def load_state_dict(self, sd, strict: bool = True) -> None:
+        super().load_state_dict(sd, strict)
+        self._apply_live()
+
+    # ---- samples nobody consumes are not computed -----------------------------------------------------
+    @staticmethod
+    def consumed_samples(n_samples: int, consumer_layers: int) -> int:
+        """How many of ``n_samples`` ControlNet samples ``FluxTransformer2DModel.forward`` reads: sample
+        ``i // ceil(L / n)`` after block ``i`` (diffusers 0.36; SURVEY.md A.6): 6 samples, 19 blocks -> 5."""
+        if n_samples == 0 or consumer_layers <= 0:
+            return 0
+        interval = -(-consumer_layers // n_samples)
+        return min(n_samples, (consumer_layers - 1) // interval + 1)
+
+    def set_consumer(self, num_layers: Optional[int], num_single_layers: Optional[int] = None) -> None:
+        """Declare the transformer whose ``controlnet_block_samples`` / ``controlnet_single_block_samples`` this model
+        feeds (``None, None`` = unknown consumer: compute every sample, the default).  Blocks that only produce samples
+        the consumer never reads are then skipped (``rt_controlnet_set_live``); those samples come back as ZEROS.  The
+        RepText pipelines call this with their transformer's layer counts (``skip_unconsumed_controlnet_blocks``);
+        with FLUX.1-dev + RepText that removes the sixth ControlNet block and zero-linear - 1.7 % of a step - and the
+        latents are bit-identical because sample 5 is never added anywhere."""
+        c = self._cfg
+        if num_layers is None:
+            self._live = (-1, -1)
+        else:
+            live_d = self.consumed_samples(c["num_layers"], num_layers)
+            live_s = self.consumed_samples(c["num_single_layers"], num_single_layers or 0)
+            if live_s > 0:               # the single blocks run after ALL double blocks
+                live_d = c["num_layers"]
+            self._live = (live_d, live_s)
+        self._apply_live()
+
+    def _apply_live(self) -> None:
+        if self._handle is not None:
+            L.check(L.lib().rt_controlnet_set_live(self._handle, self._live[0], self._live[1]))
 
     @property
     def inner_dim(self) -> int:
@@ -362,16 +399,21 @@ class FluxControlNetModel(_RuntimeModel):
         nl, ns = c["num_layers"], c["num_single_layers"]
         acc_b, acc_s = accumulate_into if accumulate_into is not None else (None, None)
 
-        def out_buf(n, acc):
+        def out_buf(n, acc, live):
             if n == 0:
                 return None
             if acc is not None:
                 if tuple(acc.shape) != (n, B, N, D) or acc.dtype != self._dtype or not acc.is_contiguous():
                     raise ValueError("accumulate_into must be the stacked [layers, B, N, D] output of a previous call")
                 return acc
-            return torch.empty(n, B, N, D, dtype=self._dtype, device=cond.device)
+            out = torch.empty(n, B, N, D, dtype=self._dtype, device=cond.device)
+            if 0 <= live < n:            # samples no block writes (set_consumer): defined, and zero
+                out[live:].zero_()
+            return out
 
-        blocks, singles = out_buf(nl, acc_b), out_buf(ns, acc_s)
+        live_d, live_s = self._live
+        blocks = out_buf(nl, acc_b, live_d if live_s <= 0 else -1)
+        singles = out_buf(ns, acc_s, live_s)
         mask = None
         if regional_mask is not None:
             mask = self._check("regional_mask", regional_mask.reshape(-1))

@@ -36,12 +36,14 @@ class FluxControlNetPipeline(RepTextPipelineBase):
         self.mask_processor = VaeImageProcessor(vae_scale_factor=self.vae_scale_factor, do_resize=True,
                                                 do_convert_grayscale=True, do_normalize=False, do_binarize=True)
 
-    def encode_prompt(self, prompt, prompt_2, do_classifier_free_guidance: bool = True, negative_prompt=None,
-                      negative_prompt_2=None, device=None, num_images_per_prompt: int = 1, prompt_embeds=None,
-                      pooled_prompt_embeds=None, max_sequence_length: int = 512, lora_scale=None,
+    def encode_prompt(self, prompt, prompt_2, device=None, num_images_per_prompt: int = 1,
+                      do_classifier_free_guidance: bool = True, negative_prompt=None, negative_prompt_2=None,
+                      prompt_embeds=None, pooled_prompt_embeds=None, max_sequence_length: int = 512, lora_scale=None,
                       negative_prompt_embeds=None, negative_pooled_prompt_embeds=None):
-        """``:336-448``.  ``negative_prompt_embeds`` / ``negative_pooled_prompt_embeds`` are an extension so that the
-        pipeline also runs without text encoders."""
+        """``:333-448``, same positional order.  CLIP encodes ``prompt`` / ``negative_prompt`` (pooled), T5 encodes
+        ``prompt_2`` / ``negative_prompt_2`` (``:403-429``).  ``negative_prompt_embeds`` / ``negative_pooled_prompt_embeds``
+        (keyword only in practice: they come after every upstream parameter) are an extension so that the pipeline also
+        runs without text encoders."""
         device = device or self._execution_device
         if prompt_embeds is None:
             prompt_embeds, pooled_prompt_embeds = self._encode_text(prompt_2 or prompt, num_images_per_prompt,
@@ -51,9 +53,10 @@ class FluxControlNetPipeline(RepTextPipelineBase):
                 negative_prompt = negative_prompt or DEFAULT_NEGATIVE_PROMPT
                 negative_prompt_2 = negative_prompt_2 or negative_prompt
                 n = prompt_embeds.shape[0] // num_images_per_prompt
-                neg = [negative_prompt_2] * n if isinstance(negative_prompt_2, str) else list(negative_prompt_2)
+                rep = lambda p: [p] * n if isinstance(p, str) else list(p)
                 negative_prompt_embeds, negative_pooled_prompt_embeds = self._encode_text(
-                    neg, num_images_per_prompt, prompt_embeds.shape[1])
+                    rep(negative_prompt_2), num_images_per_prompt, prompt_embeds.shape[1],
+                    clip_prompt=rep(negative_prompt))
         else:
             negative_prompt_embeds = negative_pooled_prompt_embeds = None
         return (prompt_embeds, pooled_prompt_embeds, negative_prompt_embeds, negative_pooled_prompt_embeds,

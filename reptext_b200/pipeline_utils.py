@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import contextlib
 import hashlib
+import warnings
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Union
 
@@ -105,49 +106,79 @@ class DiffusionPipeline:
 
 
 class VaeImageProcessor:
-    """PIL / numpy / tensor -> float NCHW in [-1, 1] (or [0, 1] masks), resized to (height, width)."""
+    """diffusers' ``VaeImageProcessor`` on the calls the RepText pipelines make (``image_processor``: RGB in [-1, 1];
+    ``mask_processor``: grayscale, binarised, not normalised).  Semantics kept from diffusers 0.36:
+
+    * the target size is rounded DOWN to a multiple of ``vae_scale_factor`` (16 here, so 1000 x 760 -> 992 x 752);
+    * PIL inputs are resized with PIL's Lanczos filter, tensors and numpy arrays with ``F.interpolate`` (nearest);
+    * numpy arrays are taken as HWC (or NHWC) floats ALREADY in [0, 1]; tensors as CHW (or NCHW) in [0, 1]; a tensor
+      with 4 channels is taken for latents and returned untouched; an input that already has negative values is not
+      normalised again."""
 
     def __init__(self, vae_scale_factor: int = 8, do_resize: bool = True, do_normalize: bool = True,
-                 do_binarize: bool = False, do_convert_grayscale: bool = False, do_convert_rgb: bool = False):
+                 do_binarize: bool = False, do_convert_grayscale: bool = False, do_convert_rgb: bool = False,
+                 vae_latent_channels: int = 4):
+        if do_convert_rgb and do_convert_grayscale:
+            raise ValueError("`do_convert_rgb` and `do_convert_grayscale` can not both be set to `True`")
         self.config = FrozenConfig(vae_scale_factor=vae_scale_factor, do_resize=do_resize, do_normalize=do_normalize,
                                    do_binarize=do_binarize, do_convert_grayscale=do_convert_grayscale,
-                                   do_convert_rgb=do_convert_rgb)
+                                   do_convert_rgb=do_convert_rgb, vae_latent_channels=vae_latent_channels,
+                                   resample="lanczos")
 
-    def _one(self, img) -> torch.Tensor:
+    def _target(self, height, width, default_h, default_w):
+        f = self.config.vae_scale_factor
+        height = default_h if height is None else height
+        width = default_w if width is None else width
+        return height - height % f, width - width % f
+
+    def _from_pil(self, imgs, height, width) -> torch.Tensor:
         c = self.config
-        if PIL is not None and isinstance(img, PIL.Image.Image):
-            if c.do_convert_grayscale:
-                img = img.convert("L")
-            elif c.do_convert_rgb:
-                img = img.convert("RGB")
-            arr = np.array(img).astype(np.float32) / 255.0
-        elif isinstance(img, np.ndarray):
-            arr = img.astype(np.float32)
-            if arr.max() > 1.0:
-                arr = arr / 255.0
-        elif isinstance(img, torch.Tensor):
-            t = img.float()
-            if t.dim() == 2:
-                t = t[None]
-            return t if t.dim() == 3 else t[0]
-        else:
-            raise ValueError(f"unsupported image type {type(img)}")
-        if arr.ndim == 2:
+        if c.do_resize:
+            height, width = self._target(height, width, imgs[0].height, imgs[0].width)
+            imgs = [im.resize((width, height), resample=PIL.Image.Resampling.LANCZOS) for im in imgs]
+        if c.do_convert_rgb:
+            imgs = [im.convert("RGB") for im in imgs]
+        elif c.do_convert_grayscale:
+            imgs = [im.convert("L") for im in imgs]
+        arr = np.stack([np.array(im).astype(np.float32) / 255.0 for im in imgs], axis=0)
+        if arr.ndim == 3:
             arr = arr[..., None]
-        if c.do_convert_grayscale and arr.shape[-1] == 3:
-            arr = arr.mean(-1, keepdims=True)
-        return torch.from_numpy(arr).permute(2, 0, 1)
+        return torch.from_numpy(arr.transpose(0, 3, 1, 2))
 
     def preprocess(self, image, height: Optional[int] = None, width: Optional[int] = None) -> torch.Tensor:
         c = self.config
-        imgs = image if isinstance(image, (list, tuple)) else [image]
-        if isinstance(image, torch.Tensor) and image.dim() == 4:
-            x = image.float()
+        kinds = (np.ndarray, torch.Tensor) if PIL is None else (PIL.Image.Image, np.ndarray, torch.Tensor)
+        if c.do_convert_grayscale and isinstance(image, (torch.Tensor, np.ndarray)) and image.ndim == 3:
+            image = image.unsqueeze(1) if isinstance(image, torch.Tensor) else np.expand_dims(image, axis=-1)
+        imgs = [image] if isinstance(image, kinds) else image
+        if not (isinstance(imgs, (list, tuple)) and len(imgs) > 0 and all(isinstance(i, kinds) for i in imgs)):
+            raise ValueError(f"unsupported image input {type(image)}: expected PIL images, numpy arrays or tensors")
+        imgs = list(imgs)
+        first = imgs[0]
+        if PIL is not None and isinstance(first, PIL.Image.Image):
+            x = self._from_pil(imgs, height, width)
         else:
-            x = torch.stack([self._one(i) for i in imgs])
-        if c.do_resize and height is not None and width is not None and tuple(x.shape[-2:]) != (height, width):
-            x = F.interpolate(x, size=(height, width), mode="bilinear", align_corners=False)
-        if c.do_normalize:
+            if isinstance(first, np.ndarray):
+                arr = np.concatenate(imgs, axis=0) if first.ndim == 4 else np.stack(imgs, axis=0)
+                if arr.ndim == 3:
+                    arr = arr[..., None]
+                x = torch.from_numpy(np.ascontiguousarray(arr.transpose(0, 3, 1, 2)))
+            else:
+                x = torch.cat(imgs, dim=0) if first.ndim == 4 else torch.stack(imgs, dim=0)
+                if c.do_convert_grayscale and x.ndim == 3:
+                    x = x.unsqueeze(1)
+                if x.ndim == 4 and x.shape[1] == c.vae_latent_channels:          # latents: nothing to do
+                    return x
+            if x.ndim != 4:
+                raise ValueError(f"image tensors must be CHW or NCHW (HWC / NHWC for numpy), got {x.ndim} dimensions")
+            if c.do_resize:
+                height, width = self._target(height, width, x.shape[2], x.shape[3])
+                x = F.interpolate(x, size=(height, width))
+        normalize = c.do_normalize
+        if normalize and x.min() < 0:
+            warnings.warn("image values are already in [-1, 1]; expected [0, 1] - not normalising again", FutureWarning)
+            normalize = False
+        if normalize:
             x = 2.0 * x - 1.0
         if c.do_binarize:
             x = (x >= 0.5).to(x.dtype)

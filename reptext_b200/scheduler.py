@@ -4,7 +4,9 @@ device=, mu=)``, ``timesteps``, ``sigmas``, ``order``, ``step(model_output, t, s
 
 Semantics follow diffusers 0.36.0 ``scheduling_flow_match_euler_discrete.py`` with FLUX.1-dev's
 ``scheduler_config.json`` (dynamic exponential shifting).  ``step`` runs the hand-written Euler kernel
-(``rt_euler_step``); the sigma table stays on the host like in diffusers, so a step never syncs.
+(``rt_euler_step``).  diffusers keeps ``sigmas`` on the DEVICE and indexes it per step (plus a device -> host sync to
+find the step index); here a host copy of the table feeds the kernel's scalar arguments, so a step never syncs, and the
+kernel reproduces the rounding of the device-tensor form (``dt`` rounded to the model dtype; csrc/elementwise.cu).
 """
 from __future__ import annotations
 
@@ -95,7 +97,7 @@ class FlowMatchEulerDiscreteScheduler:
         self._host_timesteps = ts.tolist()
         self._host_sigmas = torch.cat([sig, torch.zeros(1)]).tolist()
         self.timesteps = ts.to(device=device)
-        self.sigmas = torch.cat([sig, torch.zeros(1)])      # host, fp32 (diffusers keeps them on the CPU)
+        self.sigmas = torch.cat([sig, torch.zeros(1)])      # host copy, fp32 (see the module docstring)
         self._step_index = None
         self._begin_index = None
 

@@ -37,6 +37,11 @@ def run_case(name):
     rec["latents_per_step"] = taps
     rec["timesteps"] = pipe.scheduler.timesteps.float().cpu()
     rec["sigmas"] = pipe.scheduler.sigmas.float().cpu()
+    if case["dtype"] == "bf16":
+        # fp32 truth for the bf16 cases: the oracle's loop (== the reference's to 1e-5, tests/test_reference_pin.py) in
+        # fp32 on the SAME prepared tensors, timesteps rounded to bf16 like the bf16 run rounds them.  (Re-running the
+        # reference's __call__ in fp32 would draw different noise: randn in bf16 is not rounded fp32 randn.)
+        rec["latents_per_step_fp32"] = F.oracle_loop(name, rec, torch.float32, torch.bfloat16)
     return {k: v.numpy().astype(np.float32) for k, v in rec.items()}
 
 

@@ -337,3 +337,32 @@ def prepared_from_capture(box):
     if t.get("controlnet_single_block_samples") is not None:
         out["single_block_samples0"] = torch.stack([f(s) for s in t["controlnet_single_block_samples"]])
     return out
+
+
+def oracle_loop(name, z, dtype, time_dtype=None):
+    """oracle.denoise_t2i / denoise_inpaint on the tensors the reference prepared (``z`` = a golden record) in ``dtype``;
+    ``time_dtype`` = the dtype the reference held ``timestep`` in (bf16 runs round it: controlnet_flux.py:282).
+    -> per-step latents [steps, B, N, 64] float32."""
+    from oracle import flux_oracle as O
+    case = CASES[name]
+    sds = state_dicts(case)
+    TR, CN, CNI = model_configs(case)
+    c = lambda t: t.to(dtype)
+    cs = lambda sd: {k: v.to(dtype) for k, v in sd.items()}
+    _, _, _, masks = glyph_inputs(case["H"], case["W"], case["lines"])
+    mask_dtype = torch_dtype(case)               # the reference casts the mask to latents.dtype
+    taps = []
+    args = dict(latents=c(z["init_latents"]), prompt_embeds=c(z["prompt_embeds"]), pooled=c(z["pooled"]),
+                control_image_list=[c(x) for x in z["conds"]],
+                control_mask_list=[O.regional_mask(np.array(m), mask_dtype).to(dtype) for m in masks], text_ids=c(z["txt_ids"]),
+                img_ids=c(z["img_ids"]), timesteps=z["timesteps"], sigmas=z["sigmas"], guidance_scale=case["guidance"],
+                conditioning_scale=case["scale"], conditioning_step=case["cond_step"],
+                callback=lambda i, t, lat: taps.append(lat.float().clone()), time_dtype=time_dtype)
+    with torch.no_grad():
+        if case["kind"] == "inpaint":
+            O.denoise_inpaint(cs(sds["tr"]), TR, cs(sds["cn"]), CN, cs(sds["cni"]), CNI,
+                              control_image_inpaint=c(z["cond_inpaint"]), true_guidance_scale=case["true_cfg"],
+                              conditioning_scale_inpaint=case["scale_inpaint"], **args)
+        else:
+            O.denoise_t2i(cs(sds["tr"]), TR, cs(sds["cn"]), CN, **args)
+    return torch.stack(taps)

@@ -207,3 +207,104 @@ def test_one_denoise_step_is_cuda_graph_capturable():
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(static_out, eager2)
+
+
+@pytest.mark.parametrize("dtype,trn,cnn,H,Wd,T,tol", [
+    (torch.float32, "TINY_TRANSFORMER", "TINY_CONTROLNET", 256, 192, 64, 1e-4),
+    (torch.bfloat16, "SMALL128_TRANSFORMER", "SMALL128_CONTROLNET", 256, 256, 128, 1e-2)])
+def test_controlnet_with_single_layers_and_single_sample_injection(dtype, trn, cnn, H, Wd, T, tol):
+    """Row a7: a ControlNet WITH single-stream blocks (RepText/controlnet_flux.py:351-381: concatenated tokens through
+    FluxSingleTransformerBlock, image rows collected; :390-392 zero-linears on them) and the transformer consuming
+    ``controlnet_single_block_samples`` (diffusers: sample ``j // ceil(38 / n)`` added to the image rows after single
+    block j).  The oracle's controlnet_forward is bit-identical to the reference's own forward for this configuration
+    (tests/test_reference_pin.py::test_reference_controlnet_forward_equals_oracle[single_layers=2])."""
+    from oracle import flux_oracle as O
+    from reptext_b200 import config
+    TR = getattr(config, trn)
+    CN = dict(getattr(config, cnn), num_single_layers=2)
+    tr, cn, tr_sd, cn_sd = _build(TR, CN, dtype)
+    x = synth_inputs(TR, CN, H, Wd, T, seed=17, batch=2, n_lines=2)
+    if dtype == torch.bfloat16:
+        x = {k: ([t.to(dtype).float() for t in v] if isinstance(v, list) else (v.to(dtype).float() if torch.is_tensor(v) else v))
+             for k, v in x.items()}
+    dev = "cuda"
+    t, g = torch.tensor([0.41, 0.41]), torch.tensor([3.5, 3.5])
+    to, go = _oracle_time(t, dtype).to(dev), _oracle_time(g, dtype).to(dev)
+    xg = {k: ([t_.to(dev) for t_ in v] if isinstance(v, list) else (v.to(dev) if torch.is_tensor(v) else v)) for k, v in x.items()}
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        osd_tr, osd_cn = _oracle_on(dev, tr_sd), _oracle_on(dev, cn_sd)
+        with torch.no_grad():
+            ob, os_ = O.controlnet_forward(osd_cn, CN, xg["latents"], xg["conds"][0], 0.8, xg["prompt_embeds"],
+                                           xg["pooled"], to, xg["img_ids"], xg["txt_ids"], go)
+            ob1, os1 = O.controlnet_forward(osd_cn, CN, xg["latents"], xg["conds"][1], 0.8, xg["prompt_embeds"],
+                                            xg["pooled"], to, xg["img_ids"], xg["txt_ids"], go)
+            onp = O.transformer_forward(osd_tr, TR, xg["latents"], xg["prompt_embeds"], xg["pooled"], to,
+                                        xg["img_ids"], xg["txt_ids"], go, ob, os_)
+            onp_b = O.transformer_forward(osd_tr, TR, xg["latents"], xg["prompt_embeds"], xg["pooled"], to,
+                                          xg["img_ids"], xg["txt_ids"], go, ob, None)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert len(os_) == 2
+    c = lambda v: v.to(dev, dtype)
+    kw = dict(encoder_hidden_states=c(xg["prompt_embeds"]), pooled_projections=c(xg["pooled"]), timestep=c(t),
+              img_ids=c(xg["img_ids"]), txt_ids=c(xg["txt_ids"]), guidance=g.to(dev))
+    m0, m1 = c(xg["masks"][0]), c(xg["masks"][1])
+    blocks, singles = cn(hidden_states=c(xg["latents"]), controlnet_cond=c(xg["conds"][0]), conditioning_scale=0.8,
+                         return_dict=False, **kw)
+    assert len(blocks) == CN["num_layers"] and len(singles) == 2
+    for i, (got, want) in enumerate(zip(list(blocks) + list(singles), list(ob) + list(os_))):
+        assert got.shape == want.shape and rel_l2(got.float(), want) < tol, (i, rel_l2(got.float(), want))
+    # the transformer consumes both lists (the oracle's, so that its own error is what is measured)
+    np1 = tr(hidden_states=c(xg["latents"]), controlnet_block_samples=[c(s) for s in ob],
+             controlnet_single_block_samples=[c(s) for s in os_], return_dict=False, **kw)[0]
+    assert rel_l2(np1.float(), onp) < tol, rel_l2(np1.float(), onp)
+    assert rel_l2(onp, onp_b) > 10 * tol          # the single-sample injection is visible at this tolerance
+    # mask + multi-line sum on the single samples too (pipeline_flux_controlnet.py:1065-1069, :1080-1087)
+    b0, s0 = cn(hidden_states=c(xg["latents"]), controlnet_cond=c(xg["conds"][0]), conditioning_scale=0.8,
+                return_dict=False, regional_mask=m0, **kw)
+    b01, s01 = cn(hidden_states=c(xg["latents"]), controlnet_cond=c(xg["conds"][1]), conditioning_scale=0.8,
+                  return_dict=False, regional_mask=m1, accumulate_into=(b0[0]._rt_stacked, s0[0]._rt_stacked), **kw)
+    for i in range(2):
+        want = xg["masks"][0] * os_[i] + xg["masks"][1] * os1[i]
+        assert rel_l2(s01[i].float(), want) < tol, ("single mask+sum", i, rel_l2(s01[i].float(), want))
+
+
+def test_unconsumed_controlnet_blocks_are_skipped_bit_identically():
+    """with 6 ControlNet samples and a 19-block consumer only samples 0..4 are ever read.  Scaled down:
+    3 ControlNet blocks feeding a 2-block transformer -> interval 1... use 4 CN blocks / 3 consumer blocks (interval 1,
+    samples 0..2).  set_consumer() must (a) leave every consumed sample bit-identical, (b) return zeros for the rest,
+    (c) launch fewer kernels, (d) give a bit-identical noise prediction."""
+    from reptext_b200 import _lib, config, models
+    TR = dict(config.SMALL128_TRANSFORMER, num_layers=3)
+    CN = dict(config.SMALL128_CONTROLNET, num_layers=5)       # ceil(3 / 5) = 1 -> samples 0, 1, 2 are read; 3, 4 are not
+    assert models.FluxControlNetModel.consumed_samples(6, 19) == 5          # the FLUX.1-dev + RepText pairing
+    assert models.FluxControlNetModel.consumed_samples(5, 3) == 3
+    assert models.FluxControlNetModel.consumed_samples(2, 4) == 2 and models.FluxControlNetModel.consumed_samples(0, 4) == 0
+    dtype, dev = torch.bfloat16, "cuda"
+    tr, cn, _, _ = _build(TR, CN, dtype)
+    x = synth_inputs(TR, CN, 256, 256, 128, seed=23, batch=1)
+    c = lambda v: v.to(dev, dtype)
+    kw = dict(hidden_states=c(x["latents"]), encoder_hidden_states=c(x["prompt_embeds"]), pooled_projections=c(x["pooled"]),
+              timestep=c(torch.tensor([0.5])), img_ids=c(x["img_ids"]), txt_ids=c(x["txt_ids"]),
+              guidance=torch.tensor([3.5], device=dev))
+    n0 = _lib.launch_count()
+    full, _ = cn(controlnet_cond=c(x["conds"][0]), conditioning_scale=0.9, regional_mask=c(x["masks"][0]), return_dict=False, **kw)
+    torch.cuda.synchronize()
+    n_full = _lib.launch_count() - n0
+    v_full = tr(controlnet_block_samples=full, return_dict=False, **kw)[0]
+    cn.set_consumer(TR["num_layers"], TR["num_single_layers"])
+    n0 = _lib.launch_count()
+    live, _ = cn(controlnet_cond=c(x["conds"][0]), conditioning_scale=0.9, regional_mask=c(x["masks"][0]), return_dict=False, **kw)
+    torch.cuda.synchronize()
+    n_live = _lib.launch_count() - n0
+    v_live = tr(controlnet_block_samples=live, return_dict=False, **kw)[0]
+    for i in range(3):
+        assert torch.equal(live[i], full[i]), i
+    for i in (3, 4):
+        assert float(full[i].float().abs().max()) > 0 and float(live[i].float().abs().max()) == 0.0
+    assert n_live < n_full and torch.equal(v_live, v_full)
+    cn.set_consumer(None)
+    again, _ = cn(controlnet_cond=c(x["conds"][0]), conditioning_scale=0.9, regional_mask=c(x["masks"][0]), return_dict=False, **kw)
+    assert torch.equal(again[4], full[4])

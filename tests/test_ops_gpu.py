@@ -227,6 +227,13 @@ def test_attention_tcgen05_half_row(ops, S, B, H, impl):
     _attention_case(ops, torch.bfloat16, 128, S, impl, B, H)
 
 
+@pytest.mark.parametrize("impl", [72, 73])  # CTA-pair kernel (cta_group::2, two query tiles per CTA): 25 % / 0 % polynomial exp2
+@pytest.mark.parametrize("S,B,H", [(256, 1, 1), (512, 1, 2), (384, 2, 3), (40, 1, 1), (100, 1, 2), (700, 1, 1), (4608, 1, 2),
+                                   (1111, 2, 2), (1216, 1, 3)])
+def test_attention_tcgen05_pair(ops, S, B, H, impl):
+    _attention_case(ops, torch.bfloat16, 128, S, impl, B, H)
+
+
 def _attention_case(ops, dtype, hd, S, impl, B, H):
     qkv = _rand((B, S, 3 * H * hd + 8), dtype, 1)
     out = ops.attention(qkv, H, hd, 0, H * hd, 2 * H * hd, impl=impl)
@@ -279,11 +286,24 @@ def test_euler_cfg_mask_blend_match_oracle(ops, dtype):
     n = (2, 1000, 64)
     v, x = _rand(n, dtype, 1), _rand(n, dtype, 2)
     s0, s1 = 0.8731, 0.8012
-    dt = (torch.tensor(s1) - torch.tensor(s0)).item()   # sigmas are fp32 tensors in the scheduler
+    from reptext_b200 import _lib
+    # The expectation is TORCH'S OWN evaluation of FlowMatchEulerDiscreteScheduler.step's expression
+    #     prev = sample.to(float32) + (sigmas[i + 1] - sigmas[i]) * model_output ; prev.to(model_output.dtype)
+    # with `sigmas` a float32 tensor ON THE DEVICE, which is where diffusers 0.36's set_timesteps(device=) leaves it: dt is
+    # a 0-dim CUDA tensor, torch multiplies in model_output's dtype and rounds dt to it first.  The kernel follows that;
+    # option euler_dt_host=1 follows the other form (sigmas on the CPU: dt stays fp32).
+    for where, opt in (("cuda", 0), ("cpu", 1)):
+        sig = torch.tensor([s0, s1], dtype=torch.float32, device=where)
+        want = (x.to(torch.float32) + (sig[1] - sig[0]) * v).to(v.dtype)
+        _lib.set_option("euler_dt_host", opt)
+        try:
+            got = ops.euler_step(v, x, s0, s1)
+        finally:
+            _lib.set_option("euler_dt_host", 0)
+        assert torch.equal(got, want), (where, int((got != want).sum()))
+    dt = (torch.tensor(s1) - torch.tensor(s0))
+    dt = dt.to(dtype).float().item()                    # the device-sigmas form rounds dt to the model dtype
     got = ops.euler_step(v, x, s0, s1)
-    # CUDA form of scheduler.step: dt is an fp32 host scalar; dt * v is rounded to the model dtype
-    want = (x.float() + (dt * v.float()).to(dtype).float()).to(dtype)
-    assert torch.equal(got, want)
     if dtype == torch.float32:  # and the oracle's own function agrees in fp32
         assert torch.allclose(got.cpu(), O.euler_step(v.cpu(), torch.tensor(s0), torch.tensor(s1), x.cpu()), atol=1e-6)
 
