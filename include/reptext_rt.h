@@ -128,10 +128,14 @@ RT_API int rt_ipc_open(const unsigned char* handle64, void** dev_ptr);
 RT_API int rt_ipc_close(void* dev_ptr);
 RT_API int rt_ipc_free(void* dev_ptr);
 /* All-ranks barrier on `stream` (one tiny kernel: release-store of this rank's epoch into every peer's flag
- * block, acquire-spin on its own).  A rank that waits longer than ~10 s sets its time-out flag and moves on;
- * rt_sp_status synchronises the stream and reports it. */
+ * block, acquire-spin on its own).  A rank that waits longer than ~10 s sets the ABORT word of EVERY rank's flag
+ * block and moves on; the abort is sticky - every later barrier of the group returns at once - so a failed group
+ * costs one time-out, not one per barrier.  rt_sp_status synchronises the stream and reports it (the pipelines
+ * call it once per denoising step); rt_sp_reset zeroes this rank's flag block (epochs + abort word) and must be
+ * bracketed by host-side barriers over all ranks (parallel.SequenceParallelGroup.reset). */
 RT_API int rt_sp_barrier(const rt_sp_group* g, void* stream);
 RT_API int rt_sp_status(const rt_sp_group* g, void* stream, int* timed_out);
+RT_API int rt_sp_reset(const rt_sp_group* g, void* stream);
 
 /* FluxControlNetModel.forward — RepText/controlnet_flux.py:216-413, called at
  * RepText/pipeline_flux_controlnet.py:1043-1056 and pipeline_flux_controlnet_inpaint.py:1167, :1214.

@@ -26,7 +26,7 @@ EXPORTS = [
     "rt_model_create", "rt_model_set_weight", "rt_model_finalize", "rt_model_destroy", "rt_model_workspace_bytes",
     "rt_controlnet_forward", "rt_transformer_forward", "rt_controlnet_set_live",
     "rt_controlnet_forward_lockstep", "rt_transformer_forward_lockstep",
-    "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free", "rt_sp_barrier", "rt_sp_status",
+    "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free", "rt_sp_barrier", "rt_sp_status", "rt_sp_reset",
     "rt_euler_step", "rt_cfg_combine", "rt_cfg_euler_step", "rt_mask_scale_add", "rt_glyph_init_blend",
     "rt_gemm", "rt_attention", "rt_layernorm_modulate", "rt_rope_table", "rt_qknorm_rope",
     "rt_groupnorm_nhwc", "rt_upsample_nearest2x_nhwc", "rt_softmax_rows", "rt_im2col3x3_nhwc",
@@ -230,6 +230,10 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
         return None
     if not t.is_cuda:
         raise ValueError("reptext_b200 needs CUDA tensors (there is no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # the library launches on the CURRENT device's stream; a tensor elsewhere would be read from the wrong GPU
+        raise ValueError(f"tensor on {t.device} but the current device is cuda:{torch.cuda.current_device()}: "
+                         f"enter torch.cuda.device({t.device.index}) around the call")
     return t.data_ptr()
 
 

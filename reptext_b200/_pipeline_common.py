@@ -427,11 +427,12 @@ class RepTextPipelineBase(DiffusionPipeline):
                     outs = outs or {}
                     latents = outs.pop("latents", latents)
                     prompt_embeds = outs.pop("prompt_embeds", prompt_embeds)
+                if sp is not None:
+                    sp.check()       # a timed-out barrier surfaces within the step (the abort is sticky on the device)
                 if i == len(timesteps) - 1 or ((i + 1) > num_warmup_steps and (i + 1) % self.scheduler.order == 0):
                     progress_bar.update()
         if sp is not None:
             from .parallel import gather_tokens
-            sp.check()
             latents = gather_tokens(latents, sp.group)
         return latents
 

@@ -18,6 +18,17 @@ static std::map<std::string, int>& options() {
                                          {"profile", 0}, {"ln_warp_rows", 0}, {"gemv_single_row", 0}, {"gemm_debug", 0}, {"mod_inline", 0}, {"sp_replicate_mod", 0}, {"no_pdl", 0}, {"ln_impl", 0}, {"text_attn_simt", 0}, {"gemm_band", 0}, {"euler_dt_host", 0}};
   return o;
 }
+int device_sm_count() {
+  static int n[64] = {0};
+  const int dev = current_device();
+  RT_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  if (!n[dev]) {
+    RT_CHECK_CUDA(cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev));
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
+
 int get_option(const char* name) {
   auto it = options().find(name);
   return it == options().end() ? 0 : it->second;

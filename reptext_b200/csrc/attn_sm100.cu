@@ -1977,24 +1977,22 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
                                     attn_tc_kernel_v4<0xAA, 0>, attn_tc_kernel_v4<0x80, 0>, attn_tc_kernel_v4<0, 1>,
                                     attn_tc_kernel_v4<0, 2>,    attn_tc_kernel_v4<0, 3>};
   constexpr int kNumVariants4 = sizeof(table4) / sizeof(table4[0]);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     for (int i = 0; i < kNumVariants; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     for (int i = 0; i < kNumVariants4; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(table4[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
-    attr_set = true;
   }
   // v5 kernels (one query tile per CTA, double-buffered 128-key score tile): variant 30 + i
   static const KernelFn table5[] = {attn_tc_kernel_v5<0x88, 0>, attn_tc_kernel_v5<0x00, 0>, attn_tc_kernel_v5<0x92, 0>,
                                     attn_tc_kernel_v5<0xAA, 0>, attn_tc_kernel_v5<0x80, 0>, attn_tc_kernel_v5<0, 1>,
                                     attn_tc_kernel_v5<0, 2>,    attn_tc_kernel_v5<0, 3>};
   constexpr int kNumVariants5 = sizeof(table5) / sizeof(table5[0]);
-  static bool attr5_set = false;
-  if (!attr5_set) {
+  static PerDeviceOnce attr5_set;
+  if (attr5_set.first()) {
     for (int i = 0; i < kNumVariants5; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(table5[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes5));
-    attr5_set = true;
   }
   // v6 kernels (CTA pair, cta_group::2; one query tile per CTA, K / V halves split across the pair): variant 40 + i
   static const KernelFn table6[] = {attn_tc_kernel_v6<0x88, 0>, attn_tc_kernel_v6<0x00, 0>, attn_tc_kernel_v6<0x92, 0>,
@@ -2005,11 +2003,10 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
                                     attn_tc_kernel_v6<0x88, 0, false, 3>, attn_tc_kernel_v6<0x00, 0, false, 3>,  // 52.. three score buffers
                                     attn_tc_kernel_v6<0xAA, 0, false, 3>, attn_tc_kernel_v6<0, 3, false, 3>};
   constexpr int kNumVariants6 = sizeof(table6) / sizeof(table6[0]);
-  static bool attr6_set = false;
-  if (!attr6_set) {
+  static PerDeviceOnce attr6_set;
+  if (attr6_set.first()) {
     for (int i = 0; i < kNumVariants6; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(table6[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes6));
-    attr6_set = true;
   }
   // half-row kernels (two softmax threads per query row, 640 threads): variant 60 + i; poly share 25 / 0 / 50 / 37.5 %
   static const KernelFn tableH[] = {attn_tc_kernel<0, 0, true, 0x88, true, false, true>,
@@ -2017,11 +2014,10 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
                                     attn_tc_kernel<0, 0, true, 0xAA, true, false, true>,
                                     attn_tc_kernel<0, 0, true, 0x92, true, false, true>};
   constexpr int kNumVariantsH = sizeof(tableH) / sizeof(tableH[0]);
-  static bool attrH_set = false;
-  if (!attrH_set) {
+  static PerDeviceOnce attrH_set;
+  if (attrH_set.first()) {
     for (int i = 0; i < kNumVariantsH; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(tableH[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesHalfRow));
-    attrH_set = true;
   }
   if (variant >= 70) {
     // pair kernel (CTA pair, cta_group::2, two query tiles per CTA): variant 70 + i; polynomial share 25 / 0 / 37.5 / 50 %
@@ -2029,11 +2025,10 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
                                       attn_tc_pair_kernel<0xAA>};
     constexpr int kNumVariants7 = sizeof(table7) / sizeof(table7[0]);
     RT_REQUIRE(variant - 70 < kNumVariants7, "attention: unknown variant");
-    static bool attr7_set = false;
-    if (!attr7_set) {
+    static PerDeviceOnce attr7_set;
+    if (attr7_set.first()) {
       for (int i = 0; i < kNumVariants7; ++i)
         RT_CHECK_CUDA(cudaFuncSetAttribute(table7[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes7));
-      attr7_set = true;
     }
     const long long clusters = (long long)((a.S + 4 * BQ - 1) / (4 * BQ)) * a.heads * a.batch;
     cudaLaunchConfig_t cfg{};

@@ -10,16 +10,7 @@ namespace rt {
 
 long long g_launch_count = 0;
 
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int sm_count() { return device_sm_count(); }
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm (eps 1e-6, no affine) + (1 + scale) * xn + shift.  One warp per row, row cached in
@@ -432,10 +423,9 @@ template <int kV>
 static void launch_ln_rows2(const void* x, long long x_bs, int x_ld, void* out, long long o_bs, int o_ld, int D,
                             const LnSegs& S, int grid, cudaStream_t stream) {
   const int smem = 2 * D * (int)sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     RT_CHECK_CUDA(cudaFuncSetAttribute(ln_mod_rows2_kernel<kV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);

@@ -821,11 +821,10 @@ bool gemm_tc_supported(const GemmLaunch& L, std::string* why) {
 template <int BN, int CG>
 static void launch_cfg(const TcParams& P, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN, CG>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     RT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::kSmemBytes));
-    attr_set = true;
   }
   int clusters = num_sms / CG;
   if (clusters > P.total_tiles) clusters = P.total_tiles;
@@ -865,12 +864,7 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
   RT_REQUIRE(cg == 1 || cg == 2, "cta_group must be 1 or 2");
   if (cg == 2 && bn < 128) cg = 1;  // each CTA must hold at least 64 rows of W
 
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    RT_CHECK_CUDA(cudaGetDevice(&dev));
-    RT_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = device_sm_count();
   // Small launches (the prompt encoders at 512 tokens: 32-160 tiles of 256 x 256 for 74 CTA pairs): when 128-wide
   // single-CTA tiles fill clearly more of the machine, take them - a 128-wide tile runs at ~85 % of the 256-wide rate
   // (profiles/r1_gemm_after_uniform_issue.txt), so the fill has to win by more than that.  Same arithmetic per element.

@@ -32,6 +32,26 @@ struct Error : std::runtime_error {
   } while (0)
 
 inline size_t dtype_size(int dt) { return dt == RT_BF16 ? 2 : 4; }
+
+// ------------------------------------------------------------------ per-device state
+// cudaFuncSetAttribute and the SM count belong to ONE device; a process may place models on several
+// (from_pretrained(device=...)), so one-time set-up is remembered per device, keyed by the device that is
+// current at the launch (the Python layer makes the tensors' device current around every native call).
+inline int current_device() {
+  int dev = 0;
+  RT_CHECK_CUDA(cudaGetDevice(&dev));
+  return dev;
+}
+struct PerDeviceOnce {  // if (once.first()) { ...set attributes...; }  - true once per device
+  unsigned long long done = 0;
+  bool first() {
+    const int dev = current_device();
+    if (done >> dev & 1) return false;
+    done |= 1ull << dev;
+    return true;
+  }
+};
+int device_sm_count();  // of the current device (api.cu)
 int get_option(const char* name);
 
 // run f, translating exceptions into a status code + rt_last_error()

@@ -33,7 +33,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // One warp.  Every earlier kernel of this stream has completed (stream order), so its peer stores are performed;
 // the system-scope fence + release stores publish them, the acquire loads on the other side make them visible
 // to every later kernel of the waiting rank's stream.  Epochs only grow, so there is nothing to reset and a
-// barrier can never be satisfied by a stale value.
+// barrier can never be satisfied by a stale value.  Flag block: words 0..7 the peers' epochs, 8 this rank's epoch
+// counter, 9 the ABORT word - sticky: once a wait timed out, every later barrier of every rank returns at once (the
+// forward then finishes on garbage, quickly) until the host notices (rt_sp_status, once per step) and the group
+// is re-synchronised (rt_sp_reset under a host barrier).
 __global__ void sp_barrier_kernel(const BarrierParams p) {
   unsigned long long* mine = p.flags[p.rank];
   const int lane = threadIdx.x;
@@ -41,20 +44,26 @@ __global__ void sp_barrier_kernel(const BarrierParams p) {
   // stores it publishes are only complete after this wait
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  unsigned long long epoch = 0;
+  unsigned long long epoch = 0, aborted = 0;
   if (lane == 0) {
     epoch = mine[8] + 1;
     mine[8] = epoch;
+    aborted = ld_acquire_sys(mine + 9);  // sticky: set by an earlier time-out here, or published by a peer's
   }
   epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  aborted = __shfl_sync(0xffffffffu, aborted, 0);
   __threadfence_system();
   if (lane < p.world && lane != p.rank) st_release_sys(p.flags[lane] + p.rank, epoch);
-  if (lane < p.world && lane != p.rank) {
+  if (!aborted && lane < p.world && lane != p.rank) {
     const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
     while (ld_acquire_sys(mine + lane) < epoch) {
       __nanosleep(64);
+      // a peer that gave up tells everybody (word 9 of every flag block), so the group fails within one time-out
+      // instead of one time-out per barrier and rank
+      if ((++spins & 255) == 0 && ld_acquire_sys(mine + 9)) break;
       if (globaltimer_ns() - t0 > 10000000000ull) {  // 10 s: a peer died; flag it instead of hanging the GPU
-        mine[9] = 1;
+        for (int r = 0; r < p.world; ++r) st_release_sys(p.flags[r] + 9, 1ull);
         break;
       }
     }
@@ -108,6 +117,16 @@ int rt_sp_status(const rt_sp_group* g, void* stream, int* timed_out) {
     RT_CHECK_CUDA(cudaMemcpyAsync(&v, g->peer_flags[g->rank] + 9, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     RT_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     *timed_out = v != 0;
+  });
+}
+
+int rt_sp_reset(const rt_sp_group* g, void* stream) {
+  // zero this rank's flag block (epochs, counter, abort word).  The caller brackets it with host barriers over
+  // ALL ranks: nobody may be inside a forward, and nobody may start one before every rank has reset.
+  return guarded([&] {
+    RT_REQUIRE(g && g->rank >= 0 && g->rank < RT_SP_MAX_RANKS && g->peer_flags[g->rank], "sp_reset: bad argument");
+    RT_CHECK_CUDA(cudaMemsetAsync(g->peer_flags[g->rank], 0, 16 * sizeof(unsigned long long), (cudaStream_t)stream));
+    RT_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   });
 }
 

@@ -350,16 +350,7 @@ __global__ void __launch_bounds__(128) embedding_kernel(const bf16* __restrict__
   }
 }
 
-int sm_count_t() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int sm_count_t() { return rt::device_sm_count(); }
 
 }  // namespace
 }  // namespace rt
@@ -405,20 +396,16 @@ int rt_text_attention(const void* qkv, int64_t batch_stride, int ld, int q_col0,
     if (!get_option("text_attn_simt")) {
       RT_REQUIRE(aligned, "text_attention: pointers / strides / column offsets must be multiples of 8 elements");
       const size_t smem = kTA_SmemFixed + (size_t)(rel_bias ? 2 * S - 1 : 0) * sizeof(float);
-      static bool attr = false;
-      if (!attr) {
+      static PerDeviceOnce attr;
+      if (attr.first())
         RT_CHECK_CUDA(cudaFuncSetAttribute(text_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        attr = true;
-      }
       dim3 grid((S + kTA_QT - 1) / kTA_QT, heads, batch);
       text_attn_mma_kernel<<<grid, 128, smem, s>>>(a);
     } else {
       const size_t smem = (size_t)(32 * 65 + 32 * 64 + 32 * 64 + (rel_bias ? 2 * S - 1 : 0)) * sizeof(float);
-      static bool attr = false;
-      if (!attr) {
+      static PerDeviceOnce attr;
+      if (attr.first())
         RT_CHECK_CUDA(cudaFuncSetAttribute(text_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
-      }
       dim3 grid((S + 31) / 32, heads, batch);
       text_attn_kernel<<<grid, 256, smem, s>>>(a);
     }

@@ -11,16 +11,7 @@
 namespace rt {
 namespace {
 
-int sm_count_v() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int sm_count_v() { return device_sm_count(); }
 
 // ---- GroupNorm statistics: x [B, HW, C] bf16, stats [B, G, 2] double (sum, sum of squares), zeroed by the launcher.
 // A thread owns 8 consecutive channels (one 16-byte vector) of a strided set of pixels; C / G is a multiple of ... 1:

@@ -348,13 +348,14 @@ class FluxControlNetModel(_RuntimeModel):
         ``pipeline_flux_controlnet.py:1060-1069``) and ``accumulate_into`` (the stacked outputs of a previous
         text line; the sum at ``:1072-1087``).  ``sp``: sequence-parallel group (every tensor is then this rank's
         token shard; BASELINE.json configs[4])."""
-        call, keep, (blocks, singles) = self._marshal(
-            hidden_states, controlnet_cond, controlnet_mode, conditioning_scale, encoder_hidden_states,
-            pooled_projections, timestep, img_ids, txt_ids, guidance, joint_attention_kwargs, regional_mask,
-            accumulate_into, sp, None)
-        L.check(L.lib().rt_controlnet_forward(self._handle, C.byref(call.a), call.controlnet_cond, call.cond_batch,
-                                              call.conditioning_scale, call.mask, call.accumulate,
-                                              call.block_samples, call.single_block_samples))
+        with torch.cuda.device(self._device):  # the library launches on the current device's stream
+            call, keep, (blocks, singles) = self._marshal(
+                hidden_states, controlnet_cond, controlnet_mode, conditioning_scale, encoder_hidden_states,
+                pooled_projections, timestep, img_ids, txt_ids, guidance, joint_attention_kwargs, regional_mask,
+                accumulate_into, sp, None)
+            L.check(L.lib().rt_controlnet_forward(self._handle, C.byref(call.a), call.controlnet_cond,
+                                                  call.cond_batch, call.conditioning_scale, call.mask,
+                                                  call.accumulate, call.block_samples, call.single_block_samples))
         return self._wrap(blocks, singles, return_dict)
 
     def forward_lockstep(self, group, per_rank: List[dict], return_dict: bool = False):
@@ -471,12 +472,14 @@ class FluxTransformer2DModel(_RuntimeModel):
         *,
         sp=None,
     ):
-        call, keep, out = self._marshal(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids,
-                                        txt_ids, guidance, joint_attention_kwargs, controlnet_block_samples,
-                                        controlnet_single_block_samples, controlnet_blocks_repeat, sp, None)
-        L.check(L.lib().rt_transformer_forward(self._handle, C.byref(call.a), call.controlnet_block_samples,
-                                               call.n_block_samples, call.controlnet_single_block_samples,
-                                               call.n_single_block_samples, call.out))
+        with torch.cuda.device(self._device):
+            call, keep, out = self._marshal(hidden_states, encoder_hidden_states, pooled_projections, timestep,
+                                            img_ids, txt_ids, guidance, joint_attention_kwargs,
+                                            controlnet_block_samples, controlnet_single_block_samples,
+                                            controlnet_blocks_repeat, sp, None)
+            L.check(L.lib().rt_transformer_forward(self._handle, C.byref(call.a), call.controlnet_block_samples,
+                                                   call.n_block_samples, call.controlnet_single_block_samples,
+                                                   call.n_single_block_samples, call.out))
         if not return_dict:
             return (out,)
         return Transformer2DModelOutput(sample=out)

@@ -222,7 +222,19 @@ class SequenceParallelGroup(_SpBase):
         bad = C.c_int(0)
         L.check(L.lib().rt_sp_status(C.byref(self.struct()), L.stream_ptr(), C.byref(bad)))
         if bad.value:
-            raise RuntimeError("sequence-parallel barrier timed out: a peer rank is not making progress")
+            raise RuntimeError("sequence-parallel barrier timed out: a peer rank is not making progress "
+                               "(the group stays aborted until every rank calls reset())")
+
+    def reset(self) -> None:
+        """COLLECTIVE.  Re-synchronise the group after a failed forward (a rank raised mid-forward, or a barrier timed
+        out): every rank drains its stream, then zeroes its own flag block - epochs, epoch counter and the sticky
+        abort word - between two host barriers, so that no peer store can land in a block that is being cleared."""
+        import ctypes as C
+        from . import _lib as L
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        L.check(L.lib().rt_sp_reset(C.byref(self.struct()), L.stream_ptr()))
+        dist.barrier(group=self.group)
 
     def close(self) -> None:
         if self._own is not None:
