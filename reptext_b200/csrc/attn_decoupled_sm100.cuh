@@ -1,0 +1,374 @@
+// Decoupled joint attention (included by attn_sm100.cu; same problem, same AttnParams, same results contract).
+//
+// What the measurements of round 2 say about the ping-pong kernel (profiles/r2_attn_handoff_trace.txt,
+// r2_mma_rate_probe.txt, r2_softmax_rate_probe.txt):
+//   * a 128 x 128 x 16 tcgen05.mma takes 64 cycles in SS and in TS mode, back to back, with the K / V stream and a
+//     P stream into shared memory running beside it - the tensor pipe and its operand fetch are NOT the bound;
+//   * one softmax warp needs ~10 cycles per key (MUFU 8 cycles per warp instruction, its FMA / ALU work hardly
+//     overlapping it with one or two warps on a scheduler; four warps reach ~7), so a tile's 128 keys take ~1300
+//     cycles; with P aliasing S in tensor memory the chain  Q K^T -> softmax -> P V -> Q K^T  of a tile is serial and
+//     the other tile has only 1024 cycles of MMA work to cover it: 2900-3350 cycles per key block for 2048 of MMAs.
+// This form breaks the chain and doubles the warps:
+//   * P goes through SHARED memory (bf16, K-major SWIZZLE_128B, written by the softmax threads, fence.proxy.async),
+//     P V is an SS-mode MMA: S is free as soon as the softmax threads have it in registers (s_free), so Q K^T of
+//     block j+1 is issued a whole softmax ahead and the softmax warps never wait for the tensor pipe;
+//   * TWO threads per query row (keys 0-63 / 64-127 of the block): 16 softmax warps, four per scheduler; the halves
+//     exchange their row maxima (16 bits, rounded up - both halves then use the same reference) through shared memory
+//     under a 64-thread named barrier and keep partial row sums until the epilogue;
+//   * shared memory: Q_A Q_B | K ring of 2 | V ring of 2 | one 16 KB P HALF tile (128 rows x 64 keys) per query tile,
+//     used by the tile's two key halves in turn: the threads of keys 64-127 write when P V of keys 0-63 has been read
+//     (pv_lo_done), so they settle ~800 cycles behind the threads of keys 0-63 and stay there.  224 KB: a whole P tile
+//     per query tile would leave room for one K stage only, and a K tile takes ~2400 cycles from the TMA request to
+//     shared memory when every SM streams K / V (measured: the single-stage form stalled on it; so did ONE P tile
+//     shared by the two query tiles - it chains their softmax phases through the MMA issue order);
+//   * TWO MMA-issuing warps: Q K^T is issued the moment a tile's scores are free, P V the moment a P half lands -
+//     one in-order issuer made each wait behind the other's barrier.
+//
+//   warp 0 TMA producer, warp 1 Q K^T issuer, warp 2 TMEM allocator (pipe observer of the trace build), warp 3 P V
+//   issuer, warps 4-7 / 8-11 tile A keys 0-63 / 64-127, warps 12-15 / 16-19 tile B.
+#pragma once
+
+constexpr int kThreads8 = 640;
+constexpr int kSmemTiles8 = 7;                      // Q_A Q_B K0 K1 V0 V1 (P_A half, P_B half)
+constexpr int kBarOff8 = kSmemTiles8 * kTileBytes;  // 256 B of barriers
+constexpr int kXchOff8 = kBarOff8 + 256;            // [parity][tile][half][128 rows] x 16 bit
+constexpr int kXchBytes8 = 2 * 2 * 2 * 128 * 2;
+constexpr int kSmemPad8 = 768;                      // the dynamic window must be 256-byte aligned (checked)
+constexpr int kSmemBytes8 = kXchOff8 + kXchBytes8 + kSmemPad8;
+static_assert(kSmemBytes8 <= 232448, "227 KB of shared memory per CTA");
+
+template <int kPolyMask8, bool kTrace = false>
+__global__ void __launch_bounds__(kThreads8, 1) attn_tc_kernel_v8(const __grid_constant__ AttnParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  const uint32_t pad = ((raw_u32 + 1023u) & ~1023u) - raw_u32;
+  if (pad > kSmemPad8) __trap();
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* smem_q = smem;                     // 2 tiles
+  uint8_t* smem_k = smem + 2 * kTileBytes;    // 2 tiles
+  uint8_t* smem_v = smem + 4 * kTileBytes;    // 2 tiles
+  uint8_t* smem_p = smem + 6 * kTileBytes;    // 2 half tiles: one per query tile, used by its two key halves in turn
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff8);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2] Q K^T of the tile's next block has completed
+  uint64_t* s_free = bars + 11;   // [2] every softmax warp of the tile holds its scores in registers (8 arrivals)
+  uint64_t* p_lo = bars + 13;     // [2] keys 0-63 of P written (4 arrivals)
+  uint64_t* p_hi = bars + 15;     // [2] keys 64-127
+  uint64_t* pvl_done = bars + 17;  // [2] P V over keys 0-63 of the tile's block has completed: the P half tile is free
+  uint64_t* pv_done = bars + 19;   // [2] ... over keys 64-127 too: the P half tile is free, O may be rescaled
+  uint64_t* o_full = bars + 21;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint16_t* xch = reinterpret_cast<uint16_t*>(smem + kXchOff8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qp = blockIdx.x % P.n_qpairs;
+  const int bh = blockIdx.x / P.n_qpairs;
+  const int h = bh % P.heads, b = bh / P.heads;
+  const int q0 = qp * 2 * BQ;
+  const int n_kv = (P.S + BKV - 1) / BKV;
+  auto trace = [&](int j, int slot) {
+    if constexpr (kTrace) {
+      if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && j < 128) RT_ATTN_TRACE_STORE(j, slot);
+    }
+  };
+
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&P.tm);
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&s_free[i], 8);
+      ptx::mbar_init(&p_lo[i], 4);
+      ptx::mbar_init(&p_hi[i], 4);
+      ptx::mbar_init(&pvl_done[i], 1);
+      ptx::mbar_init(&pv_done[i], 1);
+    }
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  ptx::grid_launch_dependents();
+  ptx::grid_dependency_wait();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (kTrace && warp == 2) {
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) { ptx::mbar_wait(&s_full[0], (j + 1) & 1); trace(j, 22); }
+        if (j + 1 < n_kv) { ptx::mbar_wait(&s_full[1], (j + 1) & 1); trace(j, 25); }
+        ptx::mbar_wait(&pv_done[0], j & 1); trace(j, 21);
+        ptx::mbar_wait(&pv_done[1], j & 1); trace(j, 24);
+      }
+    }
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      ptx::mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d(&P.tm, q_full, smem_q + t * kTileBytes + sub * kSubBytes, P.q_col0 + h * HD + sub * 64,
+                           q0 + t * BQ, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1, ph = (j >> 1) & 1;
+        ptx::mbar_wait(&k_empty[st], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d(&P.tm, &k_full[st], smem_k + st * kTileBytes + sub * kSubBytes,
+                           P.k_col0 + h * HD + sub * 64, j * BKV, b);
+        ptx::mbar_wait(&v_empty[st], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          ptx::tma_load_3d(&P.tm, &v_full[st], smem_v + st * kTileBytes + sub * kSubBytes,
+                           P.v_col0 + h * HD + sub * 64, j * BKV, b);
+      }
+    } else if (warp == 1) {
+      // ===================== Q K^T issuer =====================
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV, 0, 0);  // A, B K-major
+      const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_q), 0, 1024);
+      const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_k), 0, 1024);
+      constexpr uint32_t kTile16 = kTileBytes >> 4, kSub16 = kSubBytes >> 4;
+      auto issue_qk = [&](int t, int kst) {
+        const uint64_t qa = q_desc + (uint64_t)(t * kTile16), ka = k_desc + (uint64_t)(kst * kTile16);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kSub16 + (kk & 3) * 2;
+          ptx::mma_bf16_ss<1>(tmem + t * 128, qa + off, ka + off, idesc_qk, kk != 0 ? 1u : 0u);
+        }
+      };
+      ptx::mbar_wait(q_full, 0);
+      for (int j = 0; j < n_kv; ++j) {  // scores of block j: as soon as the softmax threads have block j-1 in registers
+        const int st = j & 1, ph = (j >> 1) & 1;
+        ptx::mbar_wait(&k_full[st], ph);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (j > 0) ptx::mbar_wait(&s_free[t], (j - 1) & 1);
+          trace(j, 30 + t);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            issue_qk(t, st);
+            ptx::mma_commit(&s_full[t]);
+            if (t == 1) ptx::mma_commit(&k_empty[st]);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (warp == 3) {
+      // ===================== P V issuer =====================
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, HD, 0, 1);   // A (= P) K-major, B (= V) MN-major
+      const uint64_t p_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_p), 0, 1024);
+      const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_v), kSubBytes, 1024);
+      constexpr uint32_t kTile16 = kTileBytes >> 4, kSub16 = kSubBytes >> 4;
+      auto issue_pv = [&](int t, int st, uint32_t acc, int kk0) {  // 64 keys: k-steps kk0 .. kk0 + 3
+        const uint64_t pa = p_desc + (uint64_t)(t * kSub16), va = v_desc + (uint64_t)(st * kTile16);
+#pragma unroll
+        for (int kk = kk0; kk < kk0 + 4; ++kk)
+          ptx::mma_bf16_ss<1>(tmem + 256 + t * 128, pa + (uint64_t)((kk & 3) * 2), va + (uint64_t)(kk * 128), idesc_pv,
+                              kk != kk0 ? 1u : acc);
+      };
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1, ph = (j >> 1) & 1;
+        ptx::mbar_wait(&v_full[st], ph);
+        trace(j, 0);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          ptx::mbar_wait(&p_lo[t], j & 1);
+          trace(j, 1 + t * 3);
+          ptx::tc_fence_after();  // a (rare) rescale of O by the softmax threads precedes their arrival
+          if (ptx::elect_one()) {
+            issue_pv(t, st, j > 0 ? 1u : 0u, 0);
+            ptx::mma_commit(&pvl_done[t]);
+          }
+          __syncwarp();
+          ptx::mbar_wait(&p_hi[t], j & 1);
+          trace(j, 2 + t * 3);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            issue_pv(t, st, 1u, 4);
+            ptx::mma_commit(&pv_done[t]);
+            if (t == 1) ptx::mma_commit(&v_empty[st]);
+          }
+          __syncwarp();
+        }
+      }
+      if (ptx::elect_one()) ptx::mma_commit(o_full);
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax: two threads per query row =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int idx = warp - 4;
+    const int quad = idx & 3;        // TMEM lane quadrant (= warp % 4)
+    const int hf = (idx >> 2) & 1;   // keys hf * 64 .. hf * 64 + 63 of every block
+    const int t = idx >> 3;          // 0: tile A, 1: tile B
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t s_addr = tmem + lane_off + t * 128 + hf * 64;
+    const uint32_t o_addr = tmem + lane_off + 256 + t * 128 + hf * 64;
+    const int bar_id = 1 + t * 4 + quad;  // named barrier of the two warps that share these 32 rows
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
+    uint16_t* x_mine = xch + (t * 2 + hf) * 128 + row;
+    const uint16_t* x_other = xch + (t * 2 + (hf ^ 1)) * 128 + row;
+    uint8_t* p_row = smem_p + t * kSubBytes + row * 128;  // the tile's P half tile: keys hf * 64 .. + 63 of the block
+    const int sw = row & 7;
+    uint64_t* p_bar = hf == 0 ? &p_lo[t] : &p_hi[t];
+    const float c = P.scale_log2;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      ptx::mbar_wait(&s_full[t], j & 1);
+      if (quad == 0 && hf == 0) trace(j, 8 + t * 4);
+      ptx::tc_fence_after();
+      const int n_valid = P.S - j * BKV - hf * 64;  // valid keys of this half (<= 0: none) - only short on the last block
+      uint32_t s0[32], s1[32];
+      auto chunk_max = [&](uint32_t (&sv)[32], int col0) {
+        if (n_valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i >= n_valid) sv[i] = 0xff800000u;  // -inf
+        }
+        float a = -INFINITY, b2 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          a = fmaxf(a, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+          b2 = fmaxf(b2, fmaxf(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])));
+        }
+        return fmaxf(a, b2);
+      };
+      ptx::tmem_ld_32x32b_x32(s_addr, s0);
+      ptx::tmem_ld_32x32b_x32(s_addr + 32, s1);
+      ptx::tmem_ld_wait();
+      // the scores are in registers: the tensor pipe may overwrite S with the next block's
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_free[t]);
+      float mx = fmaxf(chunk_max(s0, 0), chunk_max(s1, 32));
+      // both halves of a row must use the SAME reference: exchange 16-bit values rounded towards +inf and take the
+      // larger of the two ROUNDED values on both sides (the reference only has to bound the row from above)
+      uint32_t mb = __float_as_uint(mx);
+      uint32_t mh = mb >> 16;
+      if (!(mb >> 31) && (mb & 0xffffu) && mh < 0x7f80u) mh += 1;
+      x_mine[(j & 1) * 512] = (uint16_t)mh;
+      if (quad == 0 && hf == 0) trace(j, 9 + t * 4);
+      pair_sync();
+      mx = fmaxf(__uint_as_float(mh << 16), __uint_as_float((uint32_t)x_other[(j & 1) * 512] << 16));
+      const float mx_s = mx * c;
+      if (j == 0) {
+        m_ref = mx_s;
+      } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {  // same rows, same values: both halves decide alike
+        const float m_new = fmaxf(m_ref, mx_s);
+        const float f = ptx::ex2_approx(m_ref - m_new);
+        l *= f;
+        ptx::mbar_wait(&pv_done[t], (j - 1) & 1);  // O += P V of the previous block has completed
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {  // this half's 64 columns of O
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(o_addr + ch * 16, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          ptx::tmem_st_32x32b_x16(o_addr + ch * 16, r);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        m_ref = m_new;
+      }
+      // P = 2^(S c - m) on pairs, kept in registers (they replace the scores) until the whole half row is done
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
+      float2 lsum0 = make_float2(0.f, 0.f), lsum1 = make_float2(0.f, 0.f);
+      uint32_t pk[32];
+      auto exp_chunk = [&](const uint32_t (&sv)[32], int base, float2& lsum) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, nm2);
+          float2 e;
+          if ((kPolyMask8 >> (i & 7)) & 1) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = ptx::ex2_approx(x.x);
+            e.y = ptx::ex2_approx(x.y);
+          }
+          lsum = __fadd2_rn(lsum, e);
+          pk[base + i] = ptx::pack_bf16x2(e.x, e.y);
+        }
+      };
+      exp_chunk(s0, 0, lsum0);
+      exp_chunk(s1, 16, lsum1);
+      l += (lsum0.x + lsum0.y) + (lsum1.x + lsum1.y);
+      if (quad == 0 && hf == 0) trace(j, 16 + t);
+      // the tile's P half tile is free when the P V over the OTHER key half has read it
+      if (hf == 1) ptx::mbar_wait(&pvl_done[t], j & 1);
+      else if (j > 0) ptx::mbar_wait(&pv_done[t], (j - 1) & 1);
+      if (quad == 0 && hf == 0) trace(j, 18 + t);
+#pragma unroll
+      for (int ck = 0; ck < 8; ++ck)  // 8 keys = 16 bytes; chunk position swizzled by the row (SWIZZLE_128B)
+        *reinterpret_cast<uint4*>(p_row + ((ck ^ sw) << 4)) =
+            make_uint4(pk[4 * ck], pk[4 * ck + 1], pk[4 * ck + 2], pk[4 * ck + 3]);
+      ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_bar);
+      if (quad == 0) trace(j, 10 + t * 4 + hf);
+    }
+    // ---- epilogue: O / l -> bf16 -> shared (row-wise) -> global; the two halves of a row share one staging tile
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    float* xsum = reinterpret_cast<float*>(smem_p);  // every MMA has completed: the P tile is dead
+    xsum[(t * 2 + hf) * 128 + row] = l;
+    pair_sync();
+    const float inv = 1.f / (l + xsum[(t * 2 + (hf ^ 1)) * 128 + row]);
+    constexpr int kPitch = HD * 2 + 16;
+    uint8_t* stage = smem + (t * 4 + quad) * (32 * kPitch);  // Q / K / V tiles are dead (o_full)
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      float v[32];
+      tmem_ld32(o_addr + ch * 32, v);
+      uint4* dst = reinterpret_cast<uint4*>(stage + lane * kPitch + (hf * 2 + ch) * 64);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = ptx::pack_bf16x2(v[8 * i + 0] * inv, v[8 * i + 1] * inv);
+        u.y = ptx::pack_bf16x2(v[8 * i + 2] * inv, v[8 * i + 3] * inv);
+        u.z = ptx::pack_bf16x2(v[8 * i + 4] * inv, v[8 * i + 5] * inv);
+        u.w = ptx::pack_bf16x2(v[8 * i + 6] * inv, v[8 * i + 7] * inv);
+        dst[i] = u;
+      }
+    }
+    pair_sync();
+    const int row0 = q0 + t * BQ + quad * 32;
+    const int rr = lane >> 4, cc = lane & 15;
+#pragma unroll 4
+    for (int it = hf * 8; it < hf * 8 + 8; ++it) {
+      const int r = it * 2 + rr;
+      const int grow = row0 + r;
+      if (grow < P.S) {
+        bf16* orow;
+        if (P.sp_rows > 0) {
+          const int dest = grow / P.sp_rows;
+          orow = P.sp_out[dest] + (long long)b * P.out_bs + (long long)(grow - dest * P.sp_rows) * P.out_ld +
+                 P.out_col0 + h * HD;
+        } else {
+          orow = P.out + (long long)b * P.out_bs + (long long)grow * P.out_ld + P.out_col0 + h * HD;
+        }
+        *reinterpret_cast<uint4*>(orow + cc * 8) = *reinterpret_cast<const uint4*>(stage + r * kPitch + cc * 16);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<1>(tmem, 512);
+}

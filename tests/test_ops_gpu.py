@@ -221,17 +221,15 @@ def test_attention_tcgen05(ops, S, B, H):
     _attention_case(ops, torch.bfloat16, 128, S, 2, B, H)
 
 
-@pytest.mark.parametrize("impl", [62, 63, 64])  # two softmax threads per row (variants 60..62 = 25 / 0 / 50 % polynomial exp2)
-@pytest.mark.parametrize("S,B,H", [(256, 1, 1), (384, 2, 3), (40, 1, 1), (100, 1, 2), (4608, 1, 2), (1111, 2, 2)])
-def test_attention_tcgen05_half_row(ops, S, B, H, impl):
-    _attention_case(ops, torch.bfloat16, 128, S, impl, B, H)
-
-
-@pytest.mark.parametrize("impl", [72, 73])  # CTA-pair kernel (cta_group::2, two query tiles per CTA): 25 % / 0 % polynomial exp2
-@pytest.mark.parametrize("S,B,H", [(256, 1, 1), (512, 1, 2), (384, 2, 3), (40, 1, 1), (100, 1, 2), (700, 1, 1), (4608, 1, 2),
-                                   (1111, 2, 2), (1216, 1, 3)])
-def test_attention_tcgen05_pair(ops, S, B, H, impl):
-    _attention_case(ops, torch.bfloat16, 128, S, impl, B, H)
+def test_attention_variants_are_not_in_the_product_library(ops):
+    """The shipped library holds ONE attention kernel; the measured A/B forms (half-row, CTA pair, decoupled, ...) live
+    in the -DRT_AB_VARIANTS build (python -m reptext_b200.build --ab) and are exercised by tools/attn_check.py."""
+    from reptext_b200 import _lib as L
+    if hasattr(L.lib(), "rt_debug_attn_trace"):
+        pytest.skip("RT_LIB points at the A/B build")
+    qkv = _rand((1, 256, 3 * 128), torch.bfloat16, 1)
+    with pytest.raises(RuntimeError, match="product kernel only"):
+        ops.attention(qkv, 1, 128, 0, 128, 256, impl=62)
 
 
 def _attention_case(ops, dtype, hd, S, impl, B, H):

@@ -3,6 +3,9 @@
 cudaProfilerStart/Stop window (ncu --profile-from-start off --set full --import-source on)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the A/B kernels live in the -DRT_AB_VARIANTS build (python -m reptext_b200.build --ab)
+os.environ.setdefault("RT_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "reptext_b200", "csrc",
+                                           "librt_reptext_ab.so"))
 import torch
 from reptext_b200 import ops
 S, H = 4608, 24

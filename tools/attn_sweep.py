@@ -2,6 +2,9 @@
 """Isolated timing of the tcgen05 attention kernel (and its debug variants) at the step's shape."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the A/B kernels live in the -DRT_AB_VARIANTS build (python -m reptext_b200.build --ab)
+os.environ.setdefault("RT_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "reptext_b200", "csrc",
+                                           "librt_reptext_ab.so"))
 import torch
 from reptext_b200 import ops
 
