@@ -290,6 +290,11 @@ typedef struct rt_attention_args {
   int batch, S, heads, hd;
   int sp_rows; /* > 0 (tcgen05 path): output row r goes to sp_out[r / sp_rows] at row r % sp_rows (same out_ld,
                   out_col0, out_batch_stride); `out` is ignored */
+  int sp_txt_rows; /* with sp_rows > 0: the first sp_txt_rows rows of every rank's sp_rows-row shard are its TEXT rows.
+                  When sp_txt_rows % 64 == 0, (S / sp_rows * sp_txt_rows) % 128 == 0 and (sp_rows - sp_txt_rows) % 128
+                  == 0 the keys are walked in the UNSHARDED order (every rank's text rows, then every rank's image
+                  rows): same key blocks, same summation order, bit-identical rows to the single-GPU launch.
+                  0 = walk the buffer as it lies (rank-major) */
   void* sp_out[8];
 } rt_attention_args;
 /* impl: 0 auto, 1 SIMT, >= 2 tcgen05 variant (impl - 2) */

@@ -113,7 +113,7 @@ class AttentionArgs(C.Structure):
         ("dtype", C.c_int), ("qkv", C.c_void_p), ("batch_stride", C.c_int64), ("ld", C.c_int), ("q_col0", C.c_int),
         ("k_col0", C.c_int), ("v_col0", C.c_int), ("out", C.c_void_p), ("out_batch_stride", C.c_int64),
         ("out_ld", C.c_int), ("out_col0", C.c_int), ("batch", C.c_int), ("S", C.c_int), ("heads", C.c_int),
-        ("hd", C.c_int), ("sp_rows", C.c_int), ("sp_out", C.c_void_p * SP_MAX_RANKS),
+        ("hd", C.c_int), ("sp_rows", C.c_int), ("sp_txt_rows", C.c_int), ("sp_out", C.c_void_p * SP_MAX_RANKS),
     ]
 
 

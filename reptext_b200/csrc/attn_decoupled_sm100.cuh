@@ -267,9 +267,9 @@ __global__ void __launch_bounds__(kThreads8, 1) attn_tc_kernel_v8(const __grid_c
       mx = fmaxf(__uint_as_float(mh << 16), __uint_as_float((uint32_t)x_other[(j & 1) * 512] << 16));
       const float mx_s = mx * c;
       if (j == 0) {
-        m_ref = mx_s;
+        m_ref = ceilf(mx_s);
       } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {  // same rows, same values: both halves decide alike
-        const float m_new = fmaxf(m_ref, mx_s);
+        const float m_new = ceilf(fmaxf(m_ref, mx_s));
         const float f = ptx::ex2_approx(m_ref - m_new);
         l *= f;
         ptx::mbar_wait(&pv_done[t], (j - 1) & 1);  // O += P V of the previous block has completed

@@ -16,7 +16,11 @@
 // The tensor pipe ping-pongs between the two tiles: while warpgroup A runs exp2 on S_A[j+1] the MMA warp
 // issues P_B V and Q_B K^T.  P (bf16) overwrites the first 64 columns of its own S buffer; the in-order
 // execution of tcgen05.mma makes "P V(j) then Q K^T(j+1) into the same columns" safe.  The running max
-// is only raised when it grows by more than 2^8 (lazy rescale), so O is almost never read back.
+// is only raised when it grows by more than 2^8 (lazy rescale), so O is almost never read back.  The reference
+// exponent is kept INTEGER (ceil of the maximum, in log2 units): P = 2^(x - m) is then the same bf16 mantissa whatever
+// m a row happens to carry, so the result does not depend on the ORDER or the split of the key blocks beyond fp32
+// summation order - the sequence-parallel mode (keys arrive rank-major) agrees with the single-GPU run to ~1e-5
+// where a fractional reference made the two differ by a bf16 rounding of every P (1e-2 after 57 blocks).
 #include "dtype_utils.cuh"
 #include "ptx_sm100.cuh"
 #include "rt_internal.h"
@@ -52,7 +56,23 @@ struct AttnParams {
   // sequence-parallel mode: output row r belongs to rank r / sp_rows and is stored straight into that rank's buffer
   int sp_rows;
   bf16* sp_out[RT_SP_MAX_RANKS];
+  // sequence-parallel mode, keys in the unsharded order (0 = off): text rows per shard, text key blocks in total
+  int sp_txt, sp_txt_blocks;
 };
+
+// Row coordinate(s) of key block j in the (rank-major) buffer.  Plain launches and sp_txt == 0: rows j*128 .. +127 as
+// they lie.  Unsharded order: block j < sp_txt_blocks holds 128 text rows = two 64-row pieces of (possibly) different
+// ranks' shards; the other blocks are 128 image rows inside one rank's shard.  `half`: 0 / 1 = rows 0-63 / 64-127.
+__device__ __forceinline__ int kv_block_row(const AttnParams& P, int j, int half) {
+  if (P.sp_txt == 0) return j * BKV + half * 64;
+  if (j < P.sp_txt_blocks) {
+    const int t = j * BKV + half * 64;  // text row in the unsharded order
+    return (t / P.sp_txt) * P.sp_rows + t % P.sp_txt;
+  }
+  const int n_loc = P.sp_rows - P.sp_txt;
+  const int i = (j - P.sp_txt_blocks) * BKV + half * 64;  // image row in the unsharded order
+  return (i / n_loc) * P.sp_rows + P.sp_txt + i % n_loc;
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -196,18 +216,26 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
                          q0 + t * BQ, b);
     for (int j = 0; j < n_kv; ++j) {
       const int st = j % kStages, ph = (j / kStages) & 1;
+      // a text block of the unsharded order is two 64-row pieces (box 64 x 64); every other block one 128-row box
+      const bool split = P.sp_txt != 0 && j < P.sp_txt_blocks;
+      const int r0 = kv_block_row(P, j, 0), r1 = kv_block_row(P, j, 1);
+      auto load_tile = [&](uint64_t* bar, uint8_t* dst, int col0) {
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          if (split) {
+            ptx::tma_load_3d(&P.tmh, bar, dst + sub * kSubBytes, col0 + sub * 64, r0, b);
+            ptx::tma_load_3d(&P.tmh, bar, dst + sub * kSubBytes + 64 * 128, col0 + sub * 64, r1, b);
+          } else {
+            ptx::tma_load_3d(&P.tm, bar, dst + sub * kSubBytes, col0 + sub * 64, r0, b);
+          }
+        }
+      };
       ptx::mbar_wait(&k_empty[st], ph ^ 1);
       ptx::mbar_arrive_expect_tx(&k_full[st], kTileBytes);
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub)
-        ptx::tma_load_3d(&P.tm, &k_full[st], smem_k + st * kTileBytes + sub * kSubBytes, P.k_col0 + h * HD + sub * 64,
-                         j * BKV, b);
+      load_tile(&k_full[st], smem_k + st * kTileBytes, P.k_col0 + h * HD);
       ptx::mbar_wait(&v_empty[st], ph ^ 1);
       ptx::mbar_arrive_expect_tx(&v_full[st], kTileBytes);
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub)
-        ptx::tma_load_3d(&P.tm, &v_full[st], smem_v + st * kTileBytes + sub * kSubBytes, P.v_col0 + h * HD + sub * 64,
-                         j * BKV, b);
+      load_tile(&v_full[st], smem_v + st * kTileBytes, P.v_col0 + h * HD);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -362,9 +390,9 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
       mx = fmaxf(mx, x_other[(j & 1) * 512]);
       const float mx_s = mx * c;
       if (j == 0) {
-        m_ref = mx_s;
+        m_ref = ceilf(mx_s);
       } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {  // same rows, same values: both halves decide alike
-        const float m_new = fmaxf(m_ref, mx_s);
+        const float m_new = ceilf(fmaxf(m_ref, mx_s));
         const float f = ptx::ex2_approx(m_ref - m_new);
         l *= f;
 #pragma unroll 1
@@ -535,11 +563,11 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
         const float mx_s = mx * c;
         if (quad == 0) trace(j, 9 + t * 4);
         if (j == 0) {
-          m_ref = mx_s;
+          m_ref = ceilf(mx_s);
         } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
           redo0 = true;
           if (quad == 0) trace(j, 16 + t);
-          const float m_new = fmaxf(m_ref, mx_s);
+          const float m_new = ceilf(fmaxf(m_ref, mx_s));
           const float f = ptx::ex2_approx(m_ref - m_new);
           l *= f;
 #pragma unroll 1
@@ -645,9 +673,9 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
       float mx_s = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
       if (kDebug & 2) mx_s = 0.f;
       if (j == 0) {
-        m_ref = mx_s;
+        m_ref = ceilf(mx_s);
       } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
-        const float m_new = fmaxf(m_ref, mx_s);
+        const float m_new = ceilf(fmaxf(m_ref, mx_s));
         const float f = ptx::ex2_approx(m_ref - m_new);
         l *= f;
 #pragma unroll 1
@@ -977,6 +1005,13 @@ void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
   P.q_col0 = a.q_col0; P.k_col0 = a.k_col0; P.v_col0 = a.v_col0;
   P.S = a.S; P.heads = a.heads;
   P.sp_rows = a.sp_rows > 0 ? a.sp_rows : 0;
+  if (P.sp_rows > 0 && a.sp_txt_rows > 0 && a.sp_txt_rows < a.sp_rows && a.S % a.sp_rows == 0) {
+    const int world = a.S / a.sp_rows, n_loc = a.sp_rows - a.sp_txt_rows;
+    if (a.sp_txt_rows % 64 == 0 && (world * a.sp_txt_rows) % BKV == 0 && n_loc % BKV == 0) {
+      P.sp_txt = a.sp_txt_rows;
+      P.sp_txt_blocks = world * a.sp_txt_rows / BKV;
+    }
+  }
   for (int i = 0; i < RT_SP_MAX_RANKS; ++i) P.sp_out[i] = reinterpret_cast<bf16*>(a.sp_out[i]);
   P.n_qpairs = (a.S + 2 * BQ - 1) / (2 * BQ);
   P.scale_log2 = 1.4426950408889634f / sqrtf((float)a.hd);

@@ -215,12 +215,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_kernel_v4(const __grid_co
       }
       const float mx_s = fmaxf(mxa, mxb) * c;
       if (blk == 0) {
-        m_ref = mx_s;
+        m_ref = ceilf(mx_s);
       } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
         // O[t] may still be receiving P V of the previous block
         ptx::mbar_wait(&pv_done[t], (blk - 1) & 1);
         ptx::tc_fence_after();
-        const float m_new = fmaxf(m_ref, mx_s);
+        const float m_new = ceilf(fmaxf(m_ref, mx_s));
         const float f = ptx::ex2_approx(m_ref - m_new);
         l *= f;
 #pragma unroll 1
@@ -504,11 +504,11 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_tc_kernel_v5(const __grid_c
       }
       const float mx_s = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
       if (j == 0) {
-        m_ref = mx_s;
+        m_ref = ceilf(mx_s);
       } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
         ptx::mbar_wait(pv_done, (j - 1) & 1);  // O may still be receiving P V of the previous block
         ptx::tc_fence_after();
-        const float m_new = fmaxf(m_ref, mx_s);
+        const float m_new = ceilf(fmaxf(m_ref, mx_s));
         const float f = ptx::ex2_approx(m_ref - m_new);
         l *= f;
 #pragma unroll 1
@@ -843,14 +843,14 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_tc_kernel_v6(const __grid_c
       }
       const float mx_s = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
       if (j == 0) {
-        m_ref = mx_s;
+        m_ref = ceilf(mx_s);
       } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
         // O may still be receiving P V of the previous block(s): with kNS score buffers up to kNS - 1 of them are
         // outstanding.  One barrier per block parity keeps every wait within one phase of its barrier.
         ptx::mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
         if (j >= 2) ptx::mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);
         ptx::tc_fence_after();
-        const float m_new = fmaxf(m_ref, mx_s);
+        const float m_new = ceilf(fmaxf(m_ref, mx_s));
         const float f = ptx::ex2_approx(m_ref - m_new);
         l *= f;
 #pragma unroll 1
@@ -1188,10 +1188,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc_pair_kernel(const __grid_
       mx = fmaxf(mx, chunk_max(s3, 96));
       const float mx_s = mx * c;
       if (j == 0) {
-        m_ref = mx_s;
+        m_ref = ceilf(mx_s);
       } else if (__any_sync(0xffffffffu, mx_s > m_ref + 8.f)) {
         // lazy rescale: s_full[t] of block j was committed after P V of block j - 1 (in-order pipe), so O is quiescent
-        const float m_new = fmaxf(m_ref, mx_s);
+        const float m_new = ceilf(fmaxf(m_ref, mx_s));
         const float f = ptx::ex2_approx(m_ref - m_new);
         l *= f;
 #pragma unroll 1

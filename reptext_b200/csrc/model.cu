@@ -318,6 +318,7 @@ void run_attention(const Ctx& c) {
     t.out = nullptr; t.out_col0 = c.r * c.Dl;
     t.S = c.Sg; t.heads = c.m.H / c.P;
     t.sp_rows = c.S;
+    t.sp_txt_rows = c.T;  // keys in the unsharded order when the shard sizes allow it: same bits as on one GPU
     for (int i = 0; i < c.P; ++i) t.sp_out[i] = c.peer_cat[i];
   }
   launch_attention(t, c.st);

@@ -141,6 +141,39 @@ def test_lockstep_forward_matches_unsharded_and_oracle(world, batch):
     assert rel_l2(got, onp) < 1e-2, rel_l2(got, onp)
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_lockstep_forward_is_bit_identical_when_the_shards_align(world):
+    """When every rank's text rows are a multiple of 64 and its image rows a multiple of 128, the attention kernel walks
+    the keys in the UNSHARDED order (rt_attention_args.sp_txt_rows): same key blocks, same exp2 path per key, same fp32
+    summation order.  Every other kernel computes a row independently of its neighbours, so the sharded forward is the
+    single-GPU forward bit for bit (ControlNet samples and noise prediction) - BASELINE.json configs[4]'s shapes
+    (64 + 1152 rows per rank at 8 ranks) are of this kind; tests/test_fullsize_gpu.py checks them at full size."""
+    from reptext_b200.parallel import LockstepGroup
+    dt, dev = torch.bfloat16, "cuda"
+    TR, CN, tr, cn, tr_sd, cn_sd = _models()
+    H, Wd, T = 1024, 512, 512                      # N = 2048 image + 512 text tokens: 64 + 256 rows per rank at world 8
+    x = synth_inputs(TR, CN, H, Wd, T, seed=12, batch=1, n_lines=1)
+    xg = {k: ([t.to(dev, dt) for t in v] if isinstance(v, list) else (v.to(dev, dt) if torch.is_tensor(v) else v)) for k, v in x.items()}
+    t = torch.full((1,), 0.62, device=dev, dtype=dt)
+    g = torch.full((1,), 3.5, device=dev, dtype=dt)
+    mask = xg["masks"][0]
+    kw = dict(hidden_states=xg["latents"], encoder_hidden_states=xg["prompt_embeds"], pooled_projections=xg["pooled"],
+              timestep=t, guidance=g, img_ids=xg["img_ids"], txt_ids=xg["txt_ids"])
+    bl, _ = cn(controlnet_cond=xg["conds"][0], conditioning_scale=0.8, regional_mask=mask, return_dict=False, **kw)
+    ref = tr(controlnet_block_samples=bl, return_dict=False, **kw)[0]
+    grp = LockstepGroup(world, dev)
+    per_rank = [dict(hidden_states=_shard(xg["latents"], r, world), encoder_hidden_states=_shard(xg["prompt_embeds"], r, world),
+                     pooled_projections=xg["pooled"], timestep=t, guidance=g, img_ids=_shard(xg["img_ids"], r, world, 0),
+                     txt_ids=_shard(xg["txt_ids"], r, world, 0)) for r in range(world)]
+    cn_out = cn.forward_lockstep(grp, [dict(p, controlnet_cond=_shard(xg["conds"][0], r, world), conditioning_scale=0.8,
+                                            regional_mask=_shard(mask.reshape(1, -1, 1), r, world))
+                                       for r, p in enumerate(per_rank)])
+    for i in range(len(bl)):
+        assert torch.equal(torch.cat([cn_out[r][0][i] for r in range(world)], dim=1), bl[i]), i
+    outs = tr.forward_lockstep(grp, [dict(p, controlnet_block_samples=cn_out[r][0]) for r, p in enumerate(per_rank)])
+    assert torch.equal(torch.cat(outs, dim=1), ref)
+
+
 def test_sequence_parallel_needs_the_tensor_core_path():
     from reptext_b200 import config, models
     from reptext_b200.parallel import LockstepGroup
