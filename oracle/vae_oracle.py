@@ -14,7 +14,7 @@ state dict with diffusers' parameter names:
     decoder.up_blocks.{i}.resnets.{j}..., .upsamplers.0.conv
     {encoder,decoder}.mid_block.resnets.{0,1}..., .mid_block.attentions.0.{group_norm,to_q,to_k,to_v,to_out.0}
 
-FLUX.1-dev ``vae/config.json`` (from memory, parity unpinned upstream): block_out_channels (128, 256, 512, 512),
+FLUX.1-dev ``vae/config.json`` (from memory; the oracle itself is pinned against the BFL autoencoder, tests/test_vae_oracle.py): block_out_channels (128, 256, 512, 512),
 layers_per_block 2, latent_channels 16, norm_num_groups 32, eps 1e-6, mid-block attention, no quant / post-quant
 conv, scaling_factor 0.3611, shift_factor 0.1159.  PINNED against the independent Black-Forest-Labs autoencoder that
 torchtitan ships on this box (``tests/test_vae_oracle.py``, weight remap BFL <-> diffusers names).

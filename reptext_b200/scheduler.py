@@ -49,7 +49,12 @@ class FlowMatchEulerDiscreteScheduler:
         raw, stored_cls = ck.read_config(d, ("scheduler_config.json", "config.json"))
         if stored_cls not in (None, "FlowMatchEulerDiscreteScheduler"):
             raise ValueError(f"{d!r} holds a {stored_cls}; the RepText pipelines step with FlowMatchEulerDiscreteScheduler")
-        unknown = [k for k in raw if k not in SCHEDULER and raw[k] not in (None, False)]
+        # diffusers >= 0.31 writes every constructor default when it re-saves a scheduler: keys that sit at their diffusers
+        # default (an option that is OFF, or the formula this class implements) are accepted and ignored
+        at_default = dict(time_shift_type="exponential", stochastic_sampling=False, invert_sigmas=False,
+                          use_karras_sigmas=False, use_exponential_sigmas=False, use_beta_sigmas=False, shift_terminal=None)
+        unknown = [k for k in raw if k not in SCHEDULER and raw[k] not in (None, False)
+                   and not (k in at_default and raw[k] == at_default[k])]
         if unknown:
             raise ValueError(f"scheduler options {unknown} are not implemented (FLUX.1-dev's scheduler_config.json uses none)")
         return cls(**{k: v for k, v in raw.items() if k in SCHEDULER})

@@ -109,6 +109,16 @@ def test_scheduler_round_trip(tmp_path):
     assert raw["_class_name"] == "FlowMatchEulerDiscreteScheduler" and raw["max_shift"] == 1.2
     back = FlowMatchEulerDiscreteScheduler.from_pretrained(str(tmp_path), subfolder="scheduler")
     assert back.config.max_shift == 1.2 and back.config.base_image_seq_len == 256 and back.config.use_dynamic_shifting
+    # a config re-saved by diffusers >= 0.31 carries every constructor default: accepted while they sit at the default
+    raw.update(time_shift_type="exponential", stochastic_sampling=False, invert_sigmas=False, use_karras_sigmas=False,
+               use_exponential_sigmas=False, use_beta_sigmas=False, shift_terminal=None)
+    json.dump(raw, open(tmp_path / "scheduler" / "scheduler_config.json", "w"))
+    assert FlowMatchEulerDiscreteScheduler.from_pretrained(str(tmp_path / "scheduler")).config.max_shift == 1.2
+    raw["time_shift_type"] = "linear"
+    json.dump(raw, open(tmp_path / "scheduler" / "scheduler_config.json", "w"))
+    with pytest.raises(ValueError, match="time_shift_type"):
+        FlowMatchEulerDiscreteScheduler.from_pretrained(str(tmp_path / "scheduler"))
+    raw["time_shift_type"] = "exponential"
     raw["use_karras_sigmas"] = True
     json.dump(raw, open(tmp_path / "scheduler" / "scheduler_config.json", "w"))
     with pytest.raises(ValueError, match="use_karras_sigmas"):
