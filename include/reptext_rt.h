@@ -234,6 +234,10 @@ typedef struct rt_gemm_segment {
   int scatter; /* 1 (tcgen05 path, BIAS / QKNORM_ROPE only): column block c = (n - n_begin) / sp_cols of this segment
                   goes to launch.sp_out[c] at row sp_row0 + out_row0 + m, column out_col0 + (n - n_begin) % sp_cols;
                   `out` is ignored, out_batch_stride / out_ld describe the destination buffers */
+  int out_f32; /* 1 (tcgen05 path; RT_EPI_BIAS, or RT_EPI_SCALE_MASK without mask / accumulate): `out` is FP32 - the
+                  accumulator leaves without a bf16 rounding (out_batch_stride / out_ld / out_col0 count fp32 elements).
+                  Used for the VAE mid-block's attention scores, whose softmax is taken over fp32 logits like the
+                  reference's (diffusers AutoencoderKL -> SDPA) */
 } rt_gemm_segment;
 
 typedef struct rt_gemm_problem {
@@ -327,6 +331,10 @@ RT_API int rt_groupnorm_nhwc(const void* x, void* out, int batch, int64_t hw, in
 RT_API int rt_upsample_nearest2x_nhwc(const void* in, void* out, int batch, int H, int W, int C, void* stream);
 /* In-place softmax of every row of a [rows, cols] matrix (the single-head mid-block attention) */
 RT_API int rt_softmax_rows(void* x, int64_t rows, int cols, int64_t ld, void* stream);
+/* softmax over each row of an FP32 [rows, cols] matrix (row stride ld_in), written as bf16 to `out` (row stride
+ * ld_out); the row is held in registers: one read, one write.  cols % 4 == 0, cols <= 65536 */
+RT_API int rt_softmax_rows_f32(const void* x, int64_t rows, int cols, int64_t ld_in, void* out, int64_t ld_out,
+                               void* stream);
 /* im2col of a 3x3 convolution (stride, leading padding pad_lo) for the convolutions TMA cannot address (stride 2,
  * 3 input channels): in [batch, H, W, c_ld] -> out [batch, Ho * Wo, Kp], K index tap * C + c, zero beyond 9 * C */
 RT_API int rt_im2col3x3_nhwc(const void* in, void* out, int batch, int H, int W, int C, int c_ld, int Ho, int Wo,

@@ -29,7 +29,7 @@ EXPORTS = [
     "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free", "rt_sp_barrier", "rt_sp_status", "rt_sp_reset",
     "rt_euler_step", "rt_cfg_combine", "rt_cfg_euler_step", "rt_mask_scale_add", "rt_glyph_init_blend",
     "rt_gemm", "rt_attention", "rt_layernorm_modulate", "rt_rope_table", "rt_qknorm_rope",
-    "rt_groupnorm_nhwc", "rt_upsample_nearest2x_nhwc", "rt_softmax_rows", "rt_im2col3x3_nhwc",
+    "rt_groupnorm_nhwc", "rt_upsample_nearest2x_nhwc", "rt_softmax_rows", "rt_softmax_rows_f32", "rt_im2col3x3_nhwc",
     "rt_nchw_to_nhwc", "rt_nhwc_to_nchw", "rt_vae_posterior_sample",
     "rt_norm_rows", "rt_text_attention", "rt_glu_act", "rt_embedding",
 ]
@@ -86,7 +86,7 @@ class GemmSegment(C.Structure):
     _fields_ = [
         ("W", C.c_void_p), ("bias", C.c_void_p), ("n_begin", C.c_int), ("n_end", C.c_int), ("mode", C.c_int),
         ("out", C.c_void_p), ("out_batch_stride", C.c_int64), ("out_ld", C.c_int), ("out_col0", C.c_int),
-        ("norm_w", C.c_void_p), ("scatter", C.c_int),
+        ("norm_w", C.c_void_p), ("scatter", C.c_int), ("out_f32", C.c_int),
     ]
 
 
@@ -176,6 +176,7 @@ def lib() -> C.CDLL:
                                     C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     L.rt_upsample_nearest2x_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.rt_softmax_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p]
+    L.rt_softmax_rows_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     L.rt_im2col3x3_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.rt_nchw_to_nhwc.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]

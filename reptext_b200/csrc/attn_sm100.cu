@@ -134,6 +134,7 @@ template <int kDebug, int kPolyEvery, bool kPacked = false, int kPolyMask8 = 0, 
           bool kElect = false, bool kHalfRow = false, bool kTrace = false, bool kEarly = false>
 __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
     attn_tc_kernel(const __grid_constant__ AttnParams P) {
+  constexpr int kBackoff = (kDebug & 8) ? 20 : (kDebug & 16) ? 100 : 0;  // A/B: sleep between barrier polls
   auto trace = [&](int j, int slot) {
     if constexpr (kTrace) {
       if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && j < 128) RT_ATTN_TRACE_STORE(j, slot);
@@ -197,12 +198,12 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
   if (kTrace && warp == 3) {
     // observer: tensor-pipe completion times (tcgen05.commit arrivals), in the order the MMA warp issues them
     for (int j = 0; j < n_kv; ++j) {
-      ptx::mbar_wait(&t_bar[0], j & 1); trace(j, 20);
-      ptx::mbar_wait(&t_bar[1], j & 1); trace(j, 21);
-      if (j + 1 < n_kv) { ptx::mbar_wait(&s_full[0], (j + 1) & 1); trace(j, 22); }
-      ptx::mbar_wait(&t_bar[2], j & 1); trace(j, 23);
-      ptx::mbar_wait(&t_bar[3], j & 1); trace(j, 24);
-      if (j + 1 < n_kv) { ptx::mbar_wait(&s_full[1], (j + 1) & 1); trace(j, 25); }
+      ptx::mbar_wait<kBackoff>(&t_bar[0], j & 1); trace(j, 20);
+      ptx::mbar_wait<kBackoff>(&t_bar[1], j & 1); trace(j, 21);
+      if (j + 1 < n_kv) { ptx::mbar_wait<kBackoff>(&s_full[0], (j + 1) & 1); trace(j, 22); }
+      ptx::mbar_wait<kBackoff>(&t_bar[2], j & 1); trace(j, 23);
+      ptx::mbar_wait<kBackoff>(&t_bar[3], j & 1); trace(j, 24);
+      if (j + 1 < n_kv) { ptx::mbar_wait<kBackoff>(&s_full[1], (j + 1) & 1); trace(j, 25); }
     }
   }
   if (warp == 0 && lane == 0) {
@@ -230,10 +231,10 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
           }
         }
       };
-      ptx::mbar_wait(&k_empty[st], ph ^ 1);
+      ptx::mbar_wait<kBackoff>(&k_empty[st], ph ^ 1);
       ptx::mbar_arrive_expect_tx(&k_full[st], kTileBytes);
       load_tile(&k_full[st], smem_k + st * kTileBytes, P.k_col0 + h * HD);
-      ptx::mbar_wait(&v_empty[st], ph ^ 1);
+      ptx::mbar_wait<kBackoff>(&v_empty[st], ph ^ 1);
       ptx::mbar_arrive_expect_tx(&v_full[st], kTileBytes);
       load_tile(&v_full[st], smem_v + st * kTileBytes, P.v_col0 + h * HD);
     }
@@ -264,8 +265,8 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
                          kk != 0 ? 1u : acc);
       }
     };
-    ptx::mbar_wait(q_full, 0);
-    ptx::mbar_wait(&k_full[0], 0);
+    ptx::mbar_wait<kBackoff>(q_full, 0);
+    ptx::mbar_wait<kBackoff>(&k_full[0], 0);
     ptx::tc_fence_after();
     if (ptx::elect_one()) {
       issue_qk(0, 0);
@@ -280,10 +281,10 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
       const int nst = (j + 1) % kStages, nph = ((j + 1) / kStages) & 1;
       const bool more = j + 1 < n_kv;
       const uint32_t acc = j > 0 ? 1u : 0u;
-      ptx::mbar_wait(&v_full[st], ph);
+      ptx::mbar_wait<kBackoff>(&v_full[st], ph);
       trace(j, 0);
       if constexpr (kSplitP) {
-        ptx::mbar_wait(&p_half[0], j & 1);
+        ptx::mbar_wait<kBackoff>(&p_half[0], j & 1);
         trace(j, 1);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -292,9 +293,9 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
         }
         __syncwarp();
       }
-      ptx::mbar_wait(&p_full[0], j & 1);
+      ptx::mbar_wait<kBackoff>(&p_full[0], j & 1);
       trace(j, 2);
-      if (more) ptx::mbar_wait(&k_full[nst], nph);
+      if (more) ptx::mbar_wait<kBackoff>(&k_full[nst], nph);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         if constexpr (kSplitP) issue_pv(0, st, 1u, 4, 8); else issue_pv(0, st, acc);
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
       __syncwarp();
       trace(j, 3);
       if constexpr (kSplitP) {
-        ptx::mbar_wait(&p_half[1], j & 1);
+        ptx::mbar_wait<kBackoff>(&p_half[1], j & 1);
         trace(j, 4);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
         }
         __syncwarp();
       }
-      ptx::mbar_wait(&p_full[1], j & 1);
+      ptx::mbar_wait<kBackoff>(&p_full[1], j & 1);
       trace(j, 5);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
     const float c = P.scale_log2;
     float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      ptx::mbar_wait(&s_full[t], j & 1);
+      ptx::mbar_wait<kBackoff>(&s_full[t], j & 1);
       if (quad == 0 && hf == 0) trace(j, 8 + t * 4);
       ptx::tc_fence_after();
       const int n_valid = P.S - j * BKV - hf * 64;  // valid keys of this half (<= 0: none) - only short on the last block
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
       if (quad == 0) trace(j, 10 + t * 4 + hf);
     }
     // ---- epilogue: as below, the two halves of a row share one staging tile and split the copy-out
-    ptx::mbar_wait(o_full, 0);
+    ptx::mbar_wait<kBackoff>(o_full, 0);
     ptx::tc_fence_after();
     x_mine[2 * 512] = l;
     pair_sync();
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
     const float c = P.scale_log2;
     float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      ptx::mbar_wait(&s_full[t], j & 1);
+      ptx::mbar_wait<kBackoff>(&s_full[t], j & 1);
       if (quad == 0) trace(j, 8 + t * 4);
       ptx::tc_fence_after();
       const int n_valid = P.S - j * BKV;  // < 128 only on the last tile
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
     // TMEM gives each thread one ROW; storing it directly would write 32 rows x 16 B per instruction - 32 lines for
     // the LSU and, when the destination is a peer GPU (sequence-parallel mode), 16-byte NVLink packets.  All MMAs
     // have completed (o_full), so the Q / K tiles are dead: each softmax warp stages its 32 x 128 block there.
-    ptx::mbar_wait(o_full, 0);
+    ptx::mbar_wait<kBackoff>(o_full, 0);
     ptx::tc_fence_after();
     const float inv = 1.f / l;
     constexpr int kPitch = HD * 2 + 16;  // 272 B: conflict-free row-wise writes and transposed reads
@@ -786,7 +787,8 @@ static void launch_attention_variant(const AttnParams& P, const AttnArgs& a, cud
   //   6.. packed form: (poly mask, split P) = (0,0) (0,1) (25%,0) (25%,1) (37.5%,1) (50%,1) (12.5%,1)
   static const KernelFn table[] = {
       attn_tc_kernel<0, 0, true, 0x88, true>,
-      attn_tc_kernel<1, 0>, attn_tc_kernel<2, 0>, attn_tc_kernel<3, 0>,
+      attn_tc_kernel<8, 0, true, 0x88, true>, attn_tc_kernel<16, 0, true, 0x88, true>,  // 1, 2: barrier polls with 20 / 100 ns sleeps
+      attn_tc_kernel<3, 0>,
       attn_tc_kernel<0, 0>, attn_tc_kernel<0, 4>,
       attn_tc_kernel<0, 0, true, 0x00, false>, attn_tc_kernel<0, 0, true, 0x00, true>,
       attn_tc_kernel<0, 0, true, 0x88, false>, attn_tc_kernel<0, 0, true, 0x88, true>,

@@ -41,7 +41,7 @@ struct alignas(64) TcSegment {
   bf16* out;
   const bf16* norm_w;
   long long out_bs;
-  int n_begin, n_end, mode, out_ld, out_col0, scatter;
+  int n_begin, n_end, mode, out_ld, out_col0, scatter, out_f32;
 };
 
 struct alignas(64) TcProblem {
@@ -196,6 +196,30 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const TcProblem
            sg.out_col0 + (col - dest * P.sp_cols);
   };
 
+  if (sg.out_f32) {
+    // fp32 destination (rt_gemm_segment::out_f32): (acc + bias) [* scale], no bf16 rounding; a thread owns one row and
+    // writes it as 16-byte stores (128 contiguous bytes per 32 columns)
+    float* frow = reinterpret_cast<float*>(sg.out) + (long long)b * sg.out_bs + (long long)(pr.out_row0 + m) * sg.out_ld +
+                  sg.out_col0 + nl0;
+    const float sc = sg.mode == EPI_SCALE_MASK ? pr.scale : 1.f;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_load_f32x32(tacc + c * 32, v);
+      if (bias) {
+        float bv[32];
+        load_bf16x32(bias + c * 32, bv);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += bv[i];
+      }
+      if (row_ok) {
+        float4* dst = reinterpret_cast<float4*>(frow + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i] * sc, v[4 * i + 1] * sc, v[4 * i + 2] * sc, v[4 * i + 3] * sc);
+      }
+    }
+    return;
+  }
   if (sg.mode == EPI_QKNORM_ROPE) {
     // one head = 128 columns; two passes over TMEM (reads are cheap) instead of 128 live registers
     const float2* rp = P.rope ? P.rope + (long long)(pr.out_row0 + m) * 64 : nullptr;
@@ -662,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const int m0w = tc.m0 + (int)cta_rank * BM + quad * 32;
       if (P.debug & 1) {
         // timing experiment: accumulators are dropped
-      } else if (P.debug & 4) {
+      } else if ((P.debug & 4) || pr.seg[tc.seg].out_f32) {
         epilogue_tile<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w + lane, tc.n0);
       } else {
         epilogue_tile_staged<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w, lane, tc.n0,
@@ -800,6 +824,10 @@ bool gemm_tc_supported(const GemmLaunch& L, std::string* why) {
       if (!al16(S.W) || (!S.scatter && (!S.out || !al16(S.out))) || (S.bias && !al16(S.bias)))
         return fail("W / out / bias alignment");
       if (S.out_ld % 8 || S.out_col0 % 8 || S.out_batch_stride % 8) return fail("out ld / col0 / stride alignment");
+      if (S.out_f32) {
+        if (S.scatter || (S.mode != EPI_BIAS && S.mode != EPI_SCALE_MASK)) return fail("out_f32 needs a BIAS or SCALE_MASK segment");
+        if (S.mode == EPI_SCALE_MASK && (P.mask || P.accumulate)) return fail("out_f32: no mask / accumulate");
+      }
       if (S.scatter) {
         if (S.mode != EPI_BIAS && S.mode != EPI_QKNORM_ROPE) return fail("scatter needs a BIAS or QKNORM_ROPE segment");
         if (L.sp_cols <= 0 || L.sp_cols % 128) return fail("sp_cols must be a positive multiple of 128");
@@ -929,7 +957,7 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
       D.out = reinterpret_cast<bf16*>(S.out);
       D.norm_w = reinterpret_cast<const bf16*>(S.norm_w);
       D.out_bs = S.out_batch_stride; D.n_begin = S.n_begin; D.n_end = S.n_end; D.mode = S.mode;
-      D.out_ld = S.out_ld; D.out_col0 = S.out_col0; D.scatter = S.scatter;
+      D.out_ld = S.out_ld; D.out_col0 = S.out_col0; D.scatter = S.scatter; D.out_f32 = S.out_f32;
     }
     const int rows_per_tile = BM * cg;
     T.tiles_m = (G.m_rows + rows_per_tile - 1) / rows_per_tile;

@@ -102,9 +102,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef RT_MBAR_SPIN_LIMIT
 #define RT_MBAR_SPIN_LIMIT (1u << 26)
 #endif
+// kBackoffNs > 0: sleep between polls, so that a waiting warp does not spend its scheduler's issue slots on the poll loop
+template <int kBackoffNs = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if constexpr (kBackoffNs > 0) __nanosleep(kBackoffNs);
     if (++spins > RT_MBAR_SPIN_LIMIT) __trap();
   }
 }

@@ -110,6 +110,7 @@ void launch_gemm_simt(const GemmLaunch& L, cudaStream_t stream) {
     for (int si = 0; si < P.nseg; ++si) {
       const GemmSegment& S = P.seg[si];
       if (S.scatter) throw Error(RT_ERR_UNSUPPORTED, "sequence-parallel scatter exists on the tcgen05 GEMM only");
+      if (S.out_f32) throw Error(RT_ERR_UNSUPPORTED, "fp32 output of bf16 operands (out_f32) exists on the tcgen05 GEMM only");
       SimtGemmArgs g;
       g.A = P.A; g.a_bs = P.a_batch_stride; g.a_ld = P.a_ld; g.a_row0 = P.a_row0;
       g.W = S.W; g.bias = S.bias;

@@ -192,6 +192,55 @@ __global__ void __launch_bounds__(1024) softmax_rows_kernel(bf16* __restrict__ x
   }
 }
 
+// softmax over each row of an fp32 [rows, cols] matrix -> bf16; one CTA per row, the row lives in registers (kV float4
+// per thread): ONE read of the logits, which never see a bf16 rounding (the reference's SDPA keeps them in fp32)
+template <int kV>
+__global__ void __launch_bounds__(1024) softmax_rows_f32_kernel(const float* __restrict__ x, long long ld_in,
+                                                                bf16* __restrict__ out, long long ld_out, int cols) {
+  __shared__ float red[32];
+  const float4* row = reinterpret_cast<const float4*>(x + (long long)blockIdx.x * ld_in);
+  bf16* orow = out + (long long)blockIdx.x * ld_out;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nvec = cols >> 2;
+  float4 v[kV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    v[i] = c < nvec ? row[c] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    mx = fmaxf(fmaxf(mx, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < nw; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    v[i].x = __expf(v[i].x - mx); v[i].y = __expf(v[i].y - mx); v[i].z = __expf(v[i].z - mx); v[i].w = __expf(v[i].w - mx);
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < nw; ++w) sum += red[w];
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c < nvec) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x * inv, v[i].y * inv), hi = __floats2bfloat162_rn(v[i].z * inv, v[i].w * inv);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(orow + 4 * c) = u;
+    }
+  }
+}
+
 // im2col for a 3x3 convolution with stride `stride` and padding (top / left = pad_lo, bottom / right as needed):
 // in [B, H, W, Cin_ld] (first C channels used) -> out [B, Ho * Wo, Kp], K index = tap * C + c, zero beyond 9 * C
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int H, int W,
@@ -348,6 +397,26 @@ int rt_upsample_nearest2x_nhwc(const void* in, void* out, int batch, int H, int 
     const long long total = (long long)batch * 4 * H * W * (C / 8);
     ProfScope ps(PROF_ELEM, (double)total * 16 * 1.25, (cudaStream_t)stream);
     upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in, (bf16*)out, H, W, C, total);
+    RT_POST_LAUNCH();
+  });
+}
+
+int rt_softmax_rows_f32(const void* x, int64_t rows, int cols, int64_t ld_in, void* out, int64_t ld_out, void* stream) {
+  return guarded([&] {
+    RT_REQUIRE(x && out && rows >= 1 && cols >= 4 && cols % 4 == 0 && cols <= 65536 && ld_in % 4 == 0 && ld_out % 4 == 0,
+               "softmax_rows_f32: bad argument");
+    RT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "softmax_rows_f32: alignment");
+    const int nvec = cols / 4;
+    const int threads = nvec >= 1024 ? 1024 : (nvec + 31) / 32 * 32;
+    const int per = (nvec + threads - 1) / threads;  // float4 per thread
+    cudaStream_t s = (cudaStream_t)stream;
+    const float* xf = (const float*)x;
+    bf16* ob = (bf16*)out;
+    if (per <= 1) softmax_rows_f32_kernel<1><<<(unsigned)rows, threads, 0, s>>>(xf, ld_in, ob, ld_out, cols);
+    else if (per <= 2) softmax_rows_f32_kernel<2><<<(unsigned)rows, threads, 0, s>>>(xf, ld_in, ob, ld_out, cols);
+    else if (per <= 4) softmax_rows_f32_kernel<4><<<(unsigned)rows, threads, 0, s>>>(xf, ld_in, ob, ld_out, cols);
+    else if (per <= 8) softmax_rows_f32_kernel<8><<<(unsigned)rows, threads, 0, s>>>(xf, ld_in, ob, ld_out, cols);
+    else softmax_rows_f32_kernel<16><<<(unsigned)rows, threads, 0, s>>>(xf, ld_in, ob, ld_out, cols);
     RT_POST_LAUNCH();
   });
 }

@@ -25,6 +25,7 @@ class Segment:
     out_col0: int = 0
     norm_w: Optional[torch.Tensor] = None
     scatter: bool = False                # sequence-parallel: head blocks go to gemm(..., sp_out=[...]) buffers
+    out_f32: bool = False                # `out` is float32: the accumulator leaves without a bf16 rounding
 
 
 @dataclass
@@ -74,6 +75,8 @@ def _fill_problem(dst: L.GemmProblem, p: Problem, keep: list) -> None:
         sg.out_col0 = s.out_col0
         sg.norm_w = L.ptr(s.norm_w)
         sg.scatter = int(s.scatter)
+        sg.out_f32 = int(s.out_f32)
+        assert s.scatter or s.out.dtype == (torch.float32 if s.out_f32 else A.dtype)
     dst.gate = L.ptr(p.gate)
     dst.gate_ld = p.gate.stride(0) if p.gate is not None else 0
     dst.extra = L.ptr(p.extra)
@@ -280,6 +283,16 @@ def upsample_nearest2x_nhwc(x: torch.Tensor, hw: Sequence[int]) -> torch.Tensor:
     assert x.is_contiguous() and HW == hw[0] * hw[1]
     out = torch.empty(B, 4 * HW, Cc, dtype=x.dtype, device=x.device)
     L.check(L.lib().rt_upsample_nearest2x_nhwc(L.ptr(x), L.ptr(out), B, hw[0], hw[1], Cc, L.stream_ptr()))
+    return out
+
+
+def softmax_rows_f32(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """Softmax over the last dimension of a float32 [rows, cols] matrix, written as bf16 to ``out`` [rows, cols] (row
+    strides free): the logits never see a bf16 rounding."""
+    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and x.stride(-1) == 1 and out.stride(-1) == 1
+    assert x.dim() == 2 and out.shape == x.shape
+    L.check(L.lib().rt_softmax_rows_f32(L.ptr(x), x.shape[0], x.shape[1], x.stride(0), L.ptr(out), out.stride(0),
+                                        L.stream_ptr()))
     return out
 
 

@@ -321,16 +321,23 @@ class AutoencoderKL:
             ops.Segment(W=self._p(p + "to_k.weight"), bias=self._p(p + "to_k.bias"), out=k)])], B, x.dtype)
         wv = self._p(p + "to_v.weight")[None]                                         # [1, C, C]
         vt = torch.empty(1, Cc, S, dtype=x.dtype, device=x.device)
-        sc = torch.empty(1, S, S, dtype=x.dtype, device=x.device)
+        # The logits stay in fp32 from the accumulator to the softmax, like the reference's SDPA (a bf16 rounding of a
+        # logit of magnitude 16 would already be a 3 % error of its weight); queries go through in chunks so that the fp32
+        # score block stays <= 1 GB whatever the image size.
+        rows = max(256, min(S, (1 << 28) // S // 256 * 256))
+        sc = torch.empty(1, rows, S, dtype=torch.float32, device=x.device)
+        pr = torch.empty(1, rows, S, dtype=x.dtype, device=x.device)
         o = torch.empty(B, S, Cc, dtype=x.dtype, device=x.device)
         for b in range(B):
             # v^T [C, S] = W_v [C, C] . t^T  (bias folded into to_out)
             ops.gemm([ops.Problem(A=wv, segs=[ops.Segment(W=t[b], out=vt)])], 1, x.dtype)
-            # S = q k^T / sqrt(C)
-            ops.gemm([ops.Problem(A=q[b:b + 1], scale=Cc ** -0.5,
-                                  segs=[ops.Segment(W=k[b], out=sc, mode=L.EPI_SCALE_MASK)])], 1, x.dtype)
-            ops.softmax_rows_(sc)
-            ops.gemm([ops.Problem(A=sc, segs=[ops.Segment(W=vt[0], out=o[b:b + 1])])], 1, x.dtype)
+            for r0 in range(0, S, rows):
+                n = min(rows, S - r0)
+                # S = q k^T / sqrt(C), fp32 out
+                ops.gemm([ops.Problem(A=q[b:b + 1], a_row0=r0, m_rows=n, scale=Cc ** -0.5,
+                                      segs=[ops.Segment(W=k[b], out=sc, mode=L.EPI_SCALE_MASK, out_f32=True)])], 1, x.dtype)
+                ops.softmax_rows_f32(sc[0, :n], pr[0, :n])
+                ops.gemm([ops.Problem(A=pr, m_rows=n, out_row0=r0, segs=[ops.Segment(W=vt[0], out=o[b:b + 1])])], 1, x.dtype)
         return self._linear(o, self._p(p + "to_out.0.weight"), self._p(p + "to_out.0.bias_folded"), residual_into=x)
 
     def _mid(self, x, hw, side):

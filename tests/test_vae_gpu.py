@@ -151,6 +151,40 @@ def test_upsample_softmax_layout_posterior(ops):
     assert torch.equal(ops.vae_posterior_sample(mom, (16, 16), 16, None, BF).float(), m[:, :16])
 
 
+def test_fp32_scores_and_softmax(ops):
+    """The VAE mid block's attention keeps its logits in fp32 from the accumulator to the softmax (rt_gemm_segment::out_f32,
+    rt_softmax_rows_f32), like the reference's SDPA.  With LARGE logits (|q . k| / sqrt(C) up to ~40) a bf16 score matrix
+    is visibly wrong while the fp32 path matches torch."""
+    from reptext_b200 import _lib as L
+    S, Cc = 1024, 512
+    q, k = _rand((1, S, Cc), 31, scale=1.6), _rand((1, S, Cc), 32, scale=1.6)
+    want = torch.matmul(q.float(), k.float().transpose(1, 2)) * Cc ** -0.5
+    sc = torch.empty(1, S, S, dtype=torch.float32, device="cuda")
+    ops.gemm([ops.Problem(A=q, scale=Cc ** -0.5, segs=[ops.Segment(W=k[0], out=sc, mode=L.EPI_SCALE_MASK, out_f32=True)])], 1, BF)
+    assert float((sc - want).abs().max()) < 2e-3 * float(want.abs().max())       # fp32 accumulation order only
+    # rows [256, 768) only, written at rows 0.. of the destination (the chunked form vae.py uses)
+    part = torch.zeros(1, 512, S, dtype=torch.float32, device="cuda")
+    ops.gemm([ops.Problem(A=q, a_row0=256, m_rows=512, scale=Cc ** -0.5,
+                          segs=[ops.Segment(W=k[0], out=part, mode=L.EPI_SCALE_MASK, out_f32=True)])], 1, BF)
+    assert torch.equal(part[0], sc[0, 256:768])
+    p = torch.empty(S, S, dtype=BF, device="cuda")
+    ops.softmax_rows_f32(sc[0], p)
+    ref = torch.softmax(want[0], dim=-1)
+    e32 = rel_l2(p, ref)
+    sb = want.to(BF)[0].clone()
+    ops.softmax_rows_(sb)
+    e16 = rel_l2(sb, ref)
+    print(f"softmax of logits up to {float(want.abs().max()):.0f}: fp32 scores {e32:.2e}, bf16 scores {e16:.2e}")
+    assert e32 < 4e-3 and e16 > 4 * e32
+    for cols in (8, 1000, 4096, 36864):                                             # every kernel instantiation, ragged tails
+        x = _rand((5, cols), 40 + cols % 7, scale=4.0, dtype=torch.float32)
+        o = torch.empty(5, cols, dtype=BF, device="cuda")
+        ops.softmax_rows_f32(x, o)
+        assert rel_l2(o, torch.softmax(x, dim=-1)) < 4e-3
+    with pytest.raises(RuntimeError, match="out_f32"):
+        ops.gemm([ops.Problem(A=q, segs=[ops.Segment(W=k[0], out=sc, mode=L.EPI_GELU, out_f32=True)])], 1, BF, impl=2)
+
+
 def test_conv_rejects_unsupported_shapes(ops):
     x = _rand((1, 24 * 24, 64), 19)
     wk = ops.pack_conv3x3_weight(_rand((64, 64, 3, 3), 20))
