@@ -773,6 +773,7 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
 
 #ifdef RT_AB_VARIANTS
 #include "attn_decoupled_sm100.cuh"
+#include "attn_rr_sm100.cuh"
 #include "attn_variants_sm100.cuh"
 #endif
 
@@ -848,6 +849,37 @@ static void launch_attention_variant(const AttnParams& P, const AttnArgs& a, cud
   if (attrH_set.first()) {
     for (int i = 0; i < kNumVariantsH; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(tableH[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesHalfRow));
+  }
+  if (variant >= 90) {
+    // round-robin decoupled kernel (one thread per row, two softmax warpgroups per query tile take the key blocks in
+    // turn): variant 90 + i; polynomial share 25 / 0 / 37.5 / 50 %; 94: 25 % + hand-off trace
+    // 95-99: the ONE-pass form of the same (block j exponentiated against block j - 1's reference), same order
+    static const KernelFn table9[] = {attn_tc_kernel_v9<0x88>, attn_tc_kernel_v9<0x00>, attn_tc_kernel_v9<0x92>,
+                                      attn_tc_kernel_v9<0xAA>, attn_tc_kernel_v9<0x88, true>,
+                                      attn_tc_kernel_v9<0x88, false, true>, attn_tc_kernel_v9<0x00, false, true>,
+                                      attn_tc_kernel_v9<0x92, false, true>, attn_tc_kernel_v9<0xAA, false, true>,
+                                      attn_tc_kernel_v9<0x88, true, true>};
+    constexpr int kNumVariants9 = sizeof(table9) / sizeof(table9[0]);
+    RT_REQUIRE(variant - 90 < kNumVariants9, "attention: unknown variant");
+    RT_REQUIRE(P.sp_txt == 0, "attention: variant 9x walks the keys in buffer order only");
+    static PerDeviceOnce attr9_set;
+    if (attr9_set.first()) {
+      for (int i = 0; i < kNumVariants9; ++i)
+        RT_CHECK_CUDA(cudaFuncSetAttribute(table9[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes9));
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((long long)P.n_qpairs * a.heads * a.batch));
+    cfg.blockDim = dim3(kThreads9);
+    cfg.dynamicSmemBytes = kSmemBytes9;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = get_option("no_pdl") ? 0 : 1;
+    RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, table9[variant - 90], P));
+    count_launch();
+    return;
   }
   if (variant >= 80) {
     // decoupled kernel (P through shared memory, two threads per row): variant 80 + i; polynomial share 25 / 0 / 37.5 /

@@ -85,6 +85,11 @@ def softmax_rows_(x):
     return x
 
 
+def softmax_rows_f32(x, out):
+    out.copy_(torch.softmax(x.double(), dim=-1).to(out.dtype))
+    return out
+
+
 def im2col3x3_nhwc(x, hw, C_used, out_hw, stride, pad_lo, Kp=None):
     Kp = Kp or (9 * C_used + 7) // 8 * 8
     return _im2col(x, hw[0], hw[1], C_used, out_hw[0], out_hw[1], stride, pad_lo, Kp)
@@ -149,6 +154,6 @@ def embedding(table, ids, pos_table=None):
 
 
 def install(monkeypatch, ops_module):
-    for name in ("gemm", "groupnorm_nhwc", "upsample_nearest2x_nhwc", "softmax_rows_", "im2col3x3_nhwc", "nchw_to_nhwc",
+    for name in ("gemm", "groupnorm_nhwc", "upsample_nearest2x_nhwc", "softmax_rows_", "softmax_rows_f32", "im2col3x3_nhwc", "nchw_to_nhwc",
                  "nhwc_to_nchw", "vae_posterior_sample", "norm_rows", "text_attention", "glu_act", "embedding"):
         monkeypatch.setattr(ops_module, name, globals()[name])
