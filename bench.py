@@ -726,6 +726,10 @@ def run_b200(args, wl):
                                                  "never reads (i // ceil(19 / 6): sample 5) are not run; latents are "
                                                  "bit-identical (tests/test_fullsize_gpu.py); --full-controlnet runs all 6; "
                                                  "utilisation figures count only the FLOPs executed"),
+                                step_invariant_cache=("OFF in the device-timed loop (`value`: every step recomputes "
+                                                      "context_embedder, the rotary table and the guidance / pooled "
+                                                      "linears, like the reference); ON in `e2e`, the pipelines' default "
+                                                      "(once per image, bit-identical latents, SURVEY 8f.2: 0.15 % of a step)"),
                                 images_per_s=value / STEPS_PER_IMAGE,
                                 tensor_util_whole_step=flops / gpus_per_sample / (step_ms / 1000.0) / 1e12 / pk["bf16_sustained"],
                                 finite_output=finite),

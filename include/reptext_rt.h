@@ -158,6 +158,19 @@ RT_API int rt_controlnet_forward(rt_model* m, const rt_forward_args* a, const vo
  * the lists to `transformer(...)`, set it from the transformer's layer counts. */
 RT_API int rt_controlnet_set_live(rt_model* m, int live_layers, int live_single_layers);
 
+/* Step-invariant inputs.  Of what a forward computes, three things depend only on the prompt
+ * embeddings, the pooled / guidance vectors and the position ids - which are the same in all 28 steps of an image -
+ * and not on the latents or the timestep: context_embedder(encoder_hidden_states) (RepText/controlnet_flux.py:292), the
+ * FluxPosEmbed table (:316-317) and the first linears of the guidance and pooled-text embedders (:282-291; the reference
+ * even rebuilds the guidance tensor every step, pipeline_flux_controlnet.py:1029).  mode 1: the first forward after this
+ * call computes them into model-owned device memory, later forwards reuse them for as long as the
+ * encoder_hidden_states / pooled_projections / guidance / txt_ids / img_ids POINTERS and the shapes are the ones of
+ * that first forward (the text rows are copied into the residual stream: same bits as the GEMM that produced them, so
+ * results are bit-identical).  The caller owns validity: call again (any mode) whenever the CONTENTS behind those
+ * pointers change - every call invalidates.  mode 0 (the default) computes everything in every forward.  Not used by
+ * the lock-step entry points.  The first forward after an invalidation may allocate: keep it out of a stream capture. */
+RT_API int rt_model_set_step_invariant_cache(rt_model* m, int mode);
+
 /* FluxTransformer2DModel.forward (diffusers 0.36.0) as called at
  * RepText/pipeline_flux_controlnet.py:1092-1104.  controlnet_*_samples are host arrays of device
  * pointers to [batch, n_img, D] tensors (or NULL / 0); sample i//ceil(L/n) is added after block i,

@@ -75,6 +75,9 @@ class RepTextPipelineBase(DiffusionPipeline):
     _callback_tensor_inputs = ["latents", "prompt_embeds"]
     _inpaint = False
     skip_unconsumed_controlnet_blocks = True
+    # what a forward derives from the prompt embeddings / ids alone is computed once per image, not once per step
+    # (models.set_step_invariant_cache; bit-identical latents)
+    cache_step_invariants = True
 
     # ---- RepText/infer.py:31-33: FluxControlNetPipeline.from_pretrained(base_model, controlnet=..., torch_dtype=...) --
     @classmethod
@@ -365,6 +368,10 @@ class RepTextPipelineBase(DiffusionPipeline):
         for net in (self.controlnet, getattr(self, "controlnet_inpaint", None)):
             if net is not None and hasattr(net, "set_consumer"):
                 net.set_consumer(*consumer)
+        nets = [n for n in (self.controlnet, getattr(self, "controlnet_inpaint", None), self.transformer)
+                if n is not None and hasattr(n, "set_step_invariant_cache")]
+        for net in nets:
+            net.set_step_invariant_cache(self.cache_step_invariants)
         do_cfg = self._inpaint and self.do_classifier_free_guidance
         guidance_const = None
         if self.transformer.config.guidance_embeds:
@@ -431,6 +438,8 @@ class RepTextPipelineBase(DiffusionPipeline):
                     sp.check()       # a timed-out barrier surfaces within the step (the abort is sticky on the device)
                 if i == len(timesteps) - 1 or ((i + 1) > num_warmup_steps and (i + 1) % self.scheduler.order == 0):
                     progress_bar.update()
+        for net in nets:
+            net.release_step_invariants()   # the prompt tensors are no longer pinned; the next image starts cold
         if sp is not None:
             from .parallel import gather_tokens
             latents = gather_tokens(latents, sp.group)

@@ -75,8 +75,25 @@ struct rt_model {
   // second block: they are computed on a side stream, under the first block's tensor-core kernels.
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Step-invariant inputs (rt_model_set_step_invariant_cache): what a forward derives from the prompt
+  // embeddings, the pooled / guidance vectors and the position ids alone - context_embedder(enc)
+  // (controlnet_flux.py:292), the FluxPosEmbed table (:316-317), the first linears of the guidance and pooled-text MLPs
+  // (:282-291) - is the same in all 28 steps of an image: computed on the first forward after an invalidation, kept in
+  // model-owned memory, reused while the input pointers and shapes stay the same.
+  struct StepInvariants {
+    int mode = 0;        // 0 = off (the C-ABI default), 1 = on
+    bool valid = false;
+    const void *enc = nullptr, *pooled = nullptr, *guidance = nullptr, *txt_ids = nullptr, *img_ids = nullptr;
+    int B = 0, T = 0, N = 0;
+    char* buf = nullptr;
+    size_t bytes = 0;
+    char* ctx = nullptr;     // [B, T, D] model dtype
+    float2* rope = nullptr;  // [T + N, head_dim / 2]
+    float* hid = nullptr;    // [B, 3 D]: h_t (every step) | h_g | h_p (kept)
+  } inv;
 
   ~rt_model() {
+    if (inv.buf) cudaFree(inv.buf);
     if (jobs_dev) cudaFree(jobs_dev);
     if (prefix_dev) cudaFree(prefix_dev);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -185,6 +202,7 @@ struct Ctx {
   char* peer_qkv[RT_SP_MAX_RANKS] = {};
   char* peer_cat[RT_SP_MAX_RANKS] = {};
   float* peer_mod[RT_SP_MAX_RANKS] = {};
+  bool inv_on = false, inv_hit = false;  // step-invariant cache in use / its contents are current (StepInvariants)
   bool mod_sharded = false;       // this forward computed only its row shard of the AdaLN vectors (peer stores)
   bool mod_join_pending = false;  // the AdaLN vectors of blocks 1.. are still being computed on the side stream
   long long sD() const { return (long long)S * D; }
@@ -215,13 +233,16 @@ void time_text_and_modulation(Ctx& c, const rt_forward_args& a) {
   const int D = c.D, B = c.B, P = m.cfg.pooled_projection_dim;
   const bool has_g = m.cfg.guidance_embeds != 0;
   launch_time_sinusoid(c.dt, a.timestep, a.t_batch, B, w.sin_t, c.st);
-  if (has_g) launch_time_sinusoid(c.dt, a.guidance, a.t_batch, B, w.sin_g, c.st);
-  launch_cast_to_f32(c.dt, a.pooled_projections, w.pooled, (long long)B * P, c.st);
-  // first linears (+ SiLU) into hid = [h_t | h_g | h_p]
+  // first linears (+ SiLU) into hid = [h_t | h_g | h_p]; h_g and h_p do not depend on the step (kept when cached)
   launch_gemv_grouped(c.dt, w.sin_t, 256, B, 256, m.jobs_dev + 0, m.prefix_dev, 1, D, w.hid, 3 * D, 1, 0, c.st);
-  if (has_g)
-    launch_gemv_grouped(c.dt, w.sin_g, 256, B, 256, m.jobs_dev + 1, m.prefix_dev, 1, D, w.hid, 3 * D, 1, 0, c.st);
-  launch_gemv_grouped(c.dt, w.pooled, P, B, P, m.jobs_dev + 2, m.prefix_dev, 1, D, w.hid, 3 * D, 1, 0, c.st);
+  if (!c.inv_hit) {
+    if (has_g) {
+      launch_time_sinusoid(c.dt, a.guidance, a.t_batch, B, w.sin_g, c.st);
+      launch_gemv_grouped(c.dt, w.sin_g, 256, B, 256, m.jobs_dev + 1, m.prefix_dev, 1, D, w.hid, 3 * D, 1, 0, c.st);
+    }
+    launch_cast_to_f32(c.dt, a.pooled_projections, w.pooled, (long long)B * P, c.st);
+    launch_gemv_grouped(c.dt, w.pooled, P, B, P, m.jobs_dev + 2, m.prefix_dev, 1, D, w.hid, 3 * D, 1, 0, c.st);
+  }
   // second linears accumulate into temb
   launch_gemv_grouped(c.dt, w.hid, 3 * D, B, D, m.jobs_dev + 3, m.prefix_dev, 1, D, w.temb, D, 0, 0, c.st);
   if (has_g)
@@ -267,17 +288,24 @@ void join_modulation(Ctx& c) {
   c.mod_join_pending = false;
 }
 
-void embed_inputs(const Ctx& c, const rt_forward_args& a, const void* cond, int cond_batch) {
+void embed_inputs(const Ctx& c, rt_model* mm, const rt_forward_args& a, const void* cond, int cond_batch) {
   const rt_model& m = c.m;
   const int D = c.D, T = c.T, N = c.N, J = m.cfg.joint_attention_dim, Cin = m.cfg.in_channels;
-  // context_embedder (controlnet_flux.py:292) -> text rows of x
-  {
+  // context_embedder (controlnet_flux.py:292) -> text rows of x; with the step-invariant cache the GEMM runs once per
+  // image into model-owned memory and every forward copies its rows (the same bits) into the residual stream
+  if (!c.inv_hit) {
     GemmLaunch L{};
     L.dtype = c.dt; L.batch = c.B; L.nprob = 1;
     L.prob[0] = make_prob(a.encoder_hidden_states, (long long)T * J, J, 0, T, T, 0, J);
     L.prob[0].nseg = 1;
-    L.prob[0].seg[0] = make_seg(m.ctx_emb, 0, EPI_BIAS, c.ws.x, c.sD(), D, 0);
+    L.prob[0].seg[0] = c.inv_on ? make_seg(m.ctx_emb, 0, EPI_BIAS, mm->inv.ctx, (long long)T * D, D, 0)
+                                : make_seg(m.ctx_emb, 0, EPI_BIAS, c.ws.x, c.sD(), D, 0);
     launch_gemm(L, c.st);
+  }
+  if (c.inv_on) {
+    RT_CHECK_CUDA(cudaMemcpy2DAsync(c.ws.x, (size_t)c.sD() * c.es, mm->inv.ctx, (size_t)T * D * c.es, (size_t)T * D * c.es,
+                                    (size_t)c.B, cudaMemcpyDeviceToDevice, c.st));
+    mm->inv.valid = true;  // rope, h_g | h_p (begin_forward) and ctx are all on their way
   }
   // x_embedder (:277) -> image rows of x; batch-1 latents broadcast against batch-2 embeddings
   {
@@ -495,9 +523,38 @@ Ctx begin_forward(rt_model* m, const rt_forward_args* a) {
       c.peer_mod[i] = pw.mod;
     }
   }
+  // Step-invariant cache (one model per call only: lock-step ranks share the model object)
+  rt_model::StepInvariants& inv = m->inv;
+  if (inv.mode && !(a->sp && a->sp->lockstep)) {
+    c.inv_on = true;
+    c.inv_hit = inv.valid && inv.enc == a->encoder_hidden_states && inv.pooled == a->pooled_projections &&
+                inv.guidance == a->guidance && inv.txt_ids == a->txt_ids && inv.img_ids == a->img_ids &&
+                inv.B == c.B && inv.T == c.T && inv.N == c.N;
+    if (!c.inv_hit) {
+      inv.valid = false;
+      const size_t ctx_b = align_up((size_t)c.B * c.T * c.D * c.es), rope_b = align_up((size_t)c.S * (m->hd / 2) * 8),
+                   hid_b = align_up((size_t)c.B * 3 * c.D * 4);
+      if (inv.bytes < ctx_b + rope_b + hid_b) {
+        if (inv.buf) RT_CHECK_CUDA(cudaFree(inv.buf));  // (synchronises: only when an image is larger than any before)
+        inv.buf = nullptr; inv.bytes = 0;
+        RT_CHECK_CUDA(cudaMalloc(&inv.buf, ctx_b + rope_b + hid_b));
+        inv.bytes = ctx_b + rope_b + hid_b;
+      }
+      inv.ctx = inv.buf;
+      inv.rope = reinterpret_cast<float2*>(inv.buf + ctx_b);
+      inv.hid = reinterpret_cast<float*>(inv.buf + ctx_b + rope_b);
+      inv.enc = a->encoder_hidden_states; inv.pooled = a->pooled_projections; inv.guidance = a->guidance;
+      inv.txt_ids = a->txt_ids; inv.img_ids = a->img_ids;
+      inv.B = c.B; inv.T = c.T; inv.N = c.N;
+    }
+    c.ws.rope = inv.rope;
+    c.ws.hid = inv.hid;
+  }
   // FluxPosEmbed over cat(txt_ids, img_ids) (controlnet_flux.py:316-317)
-  launch_rope_table(a->txt_ids, c.T, m->cfg.axes_dims_rope, ws.rope, c.st);
-  launch_rope_table(a->img_ids, c.N, m->cfg.axes_dims_rope, ws.rope + (size_t)c.T * (m->hd / 2), c.st);
+  if (!c.inv_hit) {
+    launch_rope_table(a->txt_ids, c.T, m->cfg.axes_dims_rope, c.ws.rope, c.st);
+    launch_rope_table(a->img_ids, c.N, m->cfg.axes_dims_rope, c.ws.rope + (size_t)c.T * (m->hd / 2), c.st);
+  }
   time_text_and_modulation(c, *a);
   return c;
 }
@@ -547,7 +604,7 @@ void controlnet_forward_impl(rt_model* m, const std::vector<const rt_controlnet_
     RT_REQUIRE(m->cfg.num_layers == 0 || k->block_samples, "block_samples is null");
     RT_REQUIRE(m->cfg.num_single_layers == 0 || k->single_block_samples, "single_block_samples is null");
     cs.push_back(begin_forward(m, &k->a));
-    embed_inputs(cs.back(), k->a, k->controlnet_cond, k->cond_batch);
+    embed_inputs(cs.back(), m, k->a, k->controlnet_cond, k->cond_batch);
   }
   auto zero_linear = [&](const Ctx& c, const rt_controlnet_call& k, const Lin& zl, void* base, int idx) {
     // controlnet_flux.py:385-396 (+ the pipelines' regional mask and multi-line sum)
@@ -596,7 +653,7 @@ void transformer_forward_impl(rt_model* m, const std::vector<const rt_transforme
     RT_REQUIRE(k->n_block_samples == calls[0]->n_block_samples &&
                    k->n_single_block_samples == calls[0]->n_single_block_samples, "ranks disagree on the sample counts");
     cs.push_back(begin_forward(m, &k->a));
-    embed_inputs(cs.back(), k->a, nullptr, 0);
+    embed_inputs(cs.back(), m, k->a, nullptr, 0);
   }
   const int nl = m->cfg.num_layers, ns = m->cfg.num_single_layers;
   const int nbs = calls[0]->n_block_samples, nss = calls[0]->n_single_block_samples;
@@ -786,6 +843,15 @@ int rt_controlnet_set_live(rt_model* m, int live_layers, int live_single_layers)
     RT_REQUIRE(m && m->cfg.kind == RT_CONTROLNET, "set_live: not a ControlNet model");
     m->live_layers = live_layers;
     m->live_single = live_single_layers;
+  });
+}
+
+int rt_model_set_step_invariant_cache(rt_model* m, int mode) {
+  return guarded([&] {
+    RT_REQUIRE(m, "set_step_invariant_cache: null model");
+    RT_REQUIRE(mode == 0 || mode == 1, "set_step_invariant_cache: mode must be 0 (off) or 1 (on)");
+    m->inv.mode = mode;
+    m->inv.valid = false;  // every call invalidates: the next forward recomputes
   });
 }
 

@@ -308,3 +308,54 @@ def test_unconsumed_controlnet_blocks_are_skipped_bit_identically():
     cn.set_consumer(None)
     again, _ = cn(controlnet_cond=c(x["conds"][0]), conditioning_scale=0.9, regional_mask=c(x["masks"][0]), return_dict=False, **kw)
     assert torch.equal(again[4], full[4])
+
+
+def test_step_invariant_cache_is_bit_identical_and_follows_its_inputs():
+    """SURVEY.md 8f.2 (controlnet_flux.py:280-292, :316-317; pipeline_flux_controlnet.py:1029): with
+    set_step_invariant_cache(True) the second forward on the same prompt tensors (a) launches fewer kernels, (b) returns
+    the same bits as the uncached model at ANY timestep / latents, and (c) recomputes when a keyed tensor is replaced or
+    modified in place (the key holds data_ptr and _version)."""
+    from reptext_b200 import _lib, config
+    TR, CN = config.SMALL128_TRANSFORMER, config.SMALL128_CONTROLNET
+    dtype, dev = torch.bfloat16, "cuda"
+    tr, cn, _, _ = _build(TR, CN, dtype)
+    x = synth_inputs(TR, CN, 256, 256, 128, seed=31, batch=1)
+    c = lambda v: v.to(dev, dtype)
+    enc = c(x["prompt_embeds"])
+    base = dict(encoder_hidden_states=enc, pooled_projections=c(x["pooled"]), img_ids=c(x["img_ids"]),
+                txt_ids=c(x["txt_ids"]), guidance=torch.tensor([3.5], device=dev))
+
+    def step(t, lat):
+        kw = dict(base, hidden_states=lat, timestep=c(torch.tensor([t])))
+        n0 = _lib.launch_count()
+        blocks, _ = cn(controlnet_cond=c(x["conds"][0]), conditioning_scale=0.9, return_dict=False, **kw)
+        v = tr(controlnet_block_samples=blocks, return_dict=False, **kw)[0]
+        torch.cuda.synchronize()
+        return [b.clone() for b in blocks], v.clone(), _lib.launch_count() - n0
+
+    lat0, lat1 = c(x["latents"]), c(torch.randn_like(x["latents"]))
+    ref0, ref1 = step(0.9, lat0), step(0.4, lat1)
+    for net in (cn, tr):
+        net.set_step_invariant_cache(True)
+    got0, got1 = step(0.9, lat0), step(0.4, lat1)       # miss (fills the cache), then hit with other latents / timestep
+    for ref, got in ((ref0, got0), (ref1, got1)):
+        assert all(torch.equal(a, b) for a, b in zip(ref[0], got[0])) and torch.equal(ref[1], got[1])
+    assert got1[2] < ref1[2], (got1[2], ref1[2])           # rope x2, guidance / pooled first linears, ... not relaunched
+    # in-place change of a keyed tensor: _version moves, the cache must not be used
+    enc.mul_(0.5)
+    got2 = step(0.4, lat1)
+    for net in (cn, tr):
+        net.set_step_invariant_cache(False)
+    ref2 = step(0.4, lat1)
+    assert all(torch.equal(a, b) for a, b in zip(ref2[0], got2[0])) and torch.equal(ref2[1], got2[1])
+    assert not torch.equal(ref2[1], ref1[1])
+    # a replaced tensor (new storage) and a different token count
+    for net in (cn, tr):
+        net.set_step_invariant_cache(True)
+    step(0.4, lat1)
+    base["encoder_hidden_states"] = c(torch.randn_like(x["prompt_embeds"]))
+    got3 = step(0.4, lat1)
+    for net in (cn, tr):
+        net.set_step_invariant_cache(False)
+    ref3 = step(0.4, lat1)
+    assert torch.equal(ref3[1], got3[1]) and all(torch.equal(a, b) for a, b in zip(ref3[0], got3[0]))
