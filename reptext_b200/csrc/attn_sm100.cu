@@ -131,7 +131,7 @@ __device__ long long g_attn_trace[128 * 32];
 #define RT_ATTN_TRACE_STORE(j, slot) (void)0
 #endif
 template <int kDebug, int kPolyEvery, bool kPacked = false, int kPolyMask8 = 0, bool kSplitP = false,
-          bool kElect = false, bool kHalfRow = false, bool kTrace = false, bool kEarly = false>
+          bool kElect = false, bool kHalfRow = false, bool kTrace = false, bool kEarly = false, bool kPipe = false>
 __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
     attn_tc_kernel(const __grid_constant__ AttnParams P) {
   constexpr int kBackoff = (kDebug & 8) ? 20 : (kDebug & 16) ? 100 : 0;  // A/B: sleep between barrier polls
@@ -584,6 +584,99 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
         }
         // ---- P = 2^(S c - m) on pairs; bf16 P overwrites the first 64 columns of S
         const float2 nm2 = make_float2(-m_ref, -m_ref);
+        if constexpr (kPipe) {
+          // SOFTWARE-PIPELINED form (tools/softmax_rate_probe.cu, profiles/r2_softmax_pipelined_probe.txt): with one or
+          // two warps on a scheduler the straight-line form below runs at 10-18 cycles per key - the MUFU pipe (8 cycles
+          // per exponential instruction) and the FMA pipe take turns instead of running side by side, because nothing
+          // fixes the distance between an exponential and its consumers.  Here a ROLLED loop walks the row in 16-key
+          // chunks and every half-iteration interleaves three stages of three different chunks: the exponentials of
+          // chunk ch, the scale-subtract of chunk ch + 1, the row sum / bf16 packing / store of chunk ch - 1 - every
+          // consumer sits a whole half-iteration behind its producer.  The loop needs dynamic addressing, so the scores
+          // come from tensor memory a second time (16 columns per load, issued one half-iteration ahead; the first two
+          // chunks are still in registers from the maximum pass).  P chunk ch - 1 (8 columns) lands on score columns
+          // that were read at least two half-iterations earlier.  Same arithmetic in the same order as the
+          // straight-line form: bit-identical results.
+          float2 lsum[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+          float2 xA[8], eA[8], xB[8], eB[8];
+          uint32_t rawA[16], rawB[16];
+          const uint32_t s_base = __shfl_sync(0xffffffffu, s_addr, 0);  // warp-uniform, and the compiler can see it
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            xA[i] = __ffma2_rn(make_float2(__uint_as_float(s0[2 * i]), __uint_as_float(s0[2 * i + 1])), c2, nm2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rawB[i] = s0[16 + i];
+          // one half-iteration: exps of chunk ch (xc -> ec) | scale-subtract of chunk ch + 1 (rawn -> xn) | sum / pack /
+          // store of chunk ch - 1 (ep).  kFirst: no chunk ch - 1; kLast: no chunk ch + 1.  The raw set `rawf` - its last
+          // reader ran a half-iteration ago - receives chunk pf (ch + 2; past the end a harmless reload of chunk 7).
+          auto half = [&](auto first_tag, auto last_tag, auto masked_tag, float2 (&xc)[8], float2 (&ec)[8],
+                          uint32_t (&rawn)[16], float2 (&xn)[8], float2 (&ep)[8], uint32_t (&rawf)[16], int ch) {
+            constexpr bool kFirst = decltype(first_tag)::value, kLast = decltype(last_tag)::value;
+            constexpr bool kMasked = decltype(masked_tag)::value;
+            if constexpr (!kLast) {
+              ptx::tmem_ld_wait();
+              const int pf = ch + 2 < 8 ? ch + 2 : 7;
+              ptx::tmem_ld_32x32b_x16(s_base + pf * 16, rawf);
+              if constexpr (kMasked) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if ((ch + 1) * 16 + i >= n_valid) rawn[i] = 0xff800000u;  // -inf
+              }
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              constexpr int kM = kPolyMask8;
+              const bool poly = (kM >> (i & 7)) & 1;
+              if (!poly) ec[i].x = ptx::ex2_approx(xc[i].x);
+              if constexpr (!kLast)
+                xn[i] = __ffma2_rn(make_float2(__uint_as_float(rawn[2 * i]), __uint_as_float(rawn[2 * i + 1])), c2, nm2);
+              if constexpr (!kFirst) lsum[i & 3] = __fadd2_rn(lsum[i & 3], ep[i]);
+              if (!poly) ec[i].y = ptx::ex2_approx(xc[i].y);
+              else ec[i] = exp2_poly2(xc[i]);
+              if constexpr (!kFirst) pk[i] = ptx::pack_bf16x2(ep[i].x, ep[i].y);
+            }
+            if constexpr (!kFirst) ptx::tmem_st_32x32b_x8(s_base + (ch - 1) * 8, pk);
+          };
+          auto run = [&](auto masked_tag) {
+            using T = std::true_type;
+            using F = std::false_type;
+            half(T{}, F{}, masked_tag, xA, eA, rawB, xB, eB, rawA, 0);
+#pragma unroll 1
+            for (int ch = 1; ch < 7; ch += 2) {
+              half(F{}, F{}, masked_tag, xB, eB, rawA, xA, eA, rawB, ch);
+              half(F{}, F{}, masked_tag, xA, eA, rawB, xB, eB, rawA, ch + 1);
+              if constexpr (kSplitP) {
+                if (ch == 3) {  // P chunks 0..3 (keys 0-63) are on their way: P V may start on them
+                  ptx::tmem_st_wait();
+                  ptx::tc_fence_before();
+                  ptx::mbar_arrive(&p_half[t]);
+                  if (quad == 0) trace(j, 10 + t * 4);
+                }
+              }
+            }
+            half(F{}, T{}, masked_tag, xB, eB, rawA, xA, eA, rawB, 7);
+          };
+          if (n_valid < BKV) run(std::true_type{});
+          else run(std::false_type{});
+          {  // drain: chunk 7
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              lsum[i & 3] = __fadd2_rn(lsum[i & 3], eB[i]);
+              pk[i] = ptx::pack_bf16x2(eB[i].x, eB[i].y);
+            }
+            ptx::tmem_st_32x32b_x8(s_addr + 7 * 8, pk);
+          }
+          {
+            const float2 a = __fadd2_rn(lsum[0], lsum[1]), b2 = __fadd2_rn(lsum[2], lsum[3]);
+            l += (a.x + a.y) + (b2.x + b2.y);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&p_full[t]);
+          if (quad == 0) trace(j, 11 + t * 4);
+          continue;
+        }
         // four independent partial sums: one warp per tile and scheduler is latency-bound, a single FADD2 chain of 64
         // links per block is one of the latencies
         float2 lsum[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -849,6 +942,35 @@ static void launch_attention_variant(const AttnParams& P, const AttnArgs& a, cud
   if (attrH_set.first()) {
     for (int i = 0; i < kNumVariantsH; ++i)
       RT_CHECK_CUDA(cudaFuncSetAttribute(tableH[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesHalfRow));
+  }
+  if (variant >= 110) {
+    // the product's structure with the SOFTWARE-PIPELINED exponential loop (kPipe): 110 = 25 % polynomial, 111 = none,
+    // 112 = 37.5 %, 113 = 50 %, 114 = 25 % + hand-off trace
+    static const KernelFn tableP[] = {attn_tc_kernel<0, 0, true, 0x88, true, false, false, false, false, true>,
+                                      attn_tc_kernel<0, 0, true, 0x00, true, false, false, false, false, true>,
+                                      attn_tc_kernel<0, 0, true, 0x92, true, false, false, false, false, true>,
+                                      attn_tc_kernel<0, 0, true, 0xAA, true, false, false, false, false, true>,
+                                      attn_tc_kernel<0, 0, true, 0x88, true, false, false, true, false, true>};
+    constexpr int kNumVariantsP = sizeof(tableP) / sizeof(tableP[0]);
+    RT_REQUIRE(variant - 110 < kNumVariantsP, "attention: unknown variant");
+    static PerDeviceOnce attrP_set;
+    if (attrP_set.first()) {
+      for (int i = 0; i < kNumVariantsP; ++i)
+        RT_CHECK_CUDA(cudaFuncSetAttribute(tableP[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((long long)P.n_qpairs * a.heads * a.batch));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = get_option("no_pdl") ? 0 : 1;
+    RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tableP[variant - 110], P));
+    count_launch();
+    return;
   }
   if (variant >= 90) {
     // round-robin decoupled kernel (one thread per row, two softmax warpgroups per query tile take the key blocks in

@@ -130,6 +130,171 @@ __global__ void __launch_bounds__(512, 1) probe(const float* in, int rounds, flo
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+
+// Straight-line form over registers (the product's) with CHAINED references: the scale-subtract of chunk k takes its
+// reference through fma(e, 0, -m) from an exponential of chunk k - kLag, which equals -m but is only available once that
+// chunk's exponentials have been issued - the scheduler can no longer hoist every FFMA2 to the front and leave the
+// MUFU-bound tail on its own.  Same values.
+template <int kMask8, int kCh, int kLag>
+__global__ void __launch_bounds__(512, 1) probe_chained(const float* in, int rounds, float* out, long long* cyc) {
+  float s[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) s[i] = in[(threadIdx.x * 128 + i) & 4095];
+  float c = in[4096], m = in[4097];
+  float2 lsum0 = make_float2(0.f, 0.f), lsum1 = make_float2(0.f, 0.f);
+  uint32_t keep = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int r = 0; r < rounds; ++r) {
+    const float2 c2 = make_float2(c, c);
+    constexpr int kNC = 128 / kCh, kP = kCh / 2;
+    float tail[kNC];   // one exponential of every chunk
+#pragma unroll
+    for (int k = 0; k < kNC; ++k) {
+      float nm = -m;
+      if (k >= kLag) nm = fmaf(tail[k - kLag], 0.f, nm);
+      const float2 nm2 = make_float2(nm, nm);
+#pragma unroll
+      for (int i = 0; i < kP; ++i) {
+        const int p = k * kP + i;
+        float2 x = __ffma2_rn(make_float2(s[2 * p], s[2 * p + 1]), c2, nm2);
+        float2 e;
+        if ((kMask8 >> (i & 7)) & 1) {
+          e = exp2_poly2(x);
+        } else {
+          e.x = ptx::ex2_approx(x.x);
+          e.y = ptx::ex2_approx(x.y);
+        }
+        if (i & 1) lsum1 = __fadd2_rn(lsum1, e);
+        else lsum0 = __fadd2_rn(lsum0, e);
+        keep ^= ptx::pack_bf16x2(e.x, e.y);
+        if (i == kP - 1) tail[k] = e.y;
+      }
+    }
+    m += 1e-6f;
+  }
+  const long long t1 = clock64();
+  float acc = lsum0.x + lsum0.y + lsum1.x + lsum1.y + __uint_as_float(keep & 0x007fffffu);
+#pragma unroll
+  for (int i = 0; i < 128; ++i) acc += s[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int kMask8, int kCh, int kLag>
+void run_chained(const char* name, const float* in, float* out, long long* cyc, int rounds) {
+  for (int threads : {128, 256, 512}) {
+    for (int rep = 0; rep < 2; ++rep) probe_chained<kMask8, kCh, kLag><<<1, threads>>>(in, rounds, out, cyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("%s: %s\n", name, cudaGetErrorString(e));
+      exit(1);
+    }
+    long long h;
+    cudaMemcpy(&h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    const int warps_per_smsp = threads / 128;
+    printf("%-44s %d warp(s) / SMSP: %6.2f cycles per 32-lane element step per SMSP  (%7.0f cycles per 128-key row block per warp)\n",
+           name, warps_per_smsp, (double)h / ((double)rounds * 128 * warps_per_smsp), (double)h / rounds);
+  }
+}
+
+// Software-pipelined form of the same step, the way a kernel that reads S from tensor memory and writes P back can run
+// it: a ROLLED loop over chunks of kCh keys (shared memory stands in for tensor memory: dynamic addresses, static
+// registers).  Iteration c issues the exponentials of chunk c, the scale-subtract of chunk c + 1 and the row sum / bf16
+// packing / store of chunk c - 1: every consumer sits one whole iteration behind its producer, so one warp alone can keep
+// the MUFU pipe and the FMA pipe busy at the same time (the straight-line form above leaves that to the scheduler's
+// luck: 15-18 cycles per key with one warp).
+template <int kMask8, int kCh>
+__global__ void __launch_bounds__(512, 1) probe_pipelined(const float* in, int rounds, int zero, float* out, long long* cyc) {
+  extern __shared__ float4 sm[];
+  constexpr int kP = kCh / 2;                           // pairs per chunk
+  constexpr int kNC = 128 / kCh;                        // chunks per 128-key block
+  float4* s_in = sm;                                    // [kCh / 4][blockDim]
+  uint4* s_out = reinterpret_cast<uint4*>(sm + (kCh / 4) * blockDim.x);  // [kCh / 8][blockDim]
+  for (int k = 0; k < kCh / 4; ++k)
+    s_in[k * blockDim.x + threadIdx.x] = make_float4(in[(threadIdx.x * 4 + k) & 4095], in[(threadIdx.x * 4 + k + 1) & 4095],
+                                                     in[(threadIdx.x * 4 + k + 2) & 4095], in[(threadIdx.x * 4 + k + 3) & 4095]);
+  float c = in[4096], m = in[4097];
+  float2 lsum0 = make_float2(0.f, 0.f), lsum1 = make_float2(0.f, 0.f);
+  __syncthreads();
+  auto load = [&](float2 (&raw)[kP], int ch) {
+    const float4* src = s_in + (ch * zero) * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < kCh / 4; ++k) {
+      const float4 v = src[k * blockDim.x];
+      raw[2 * k] = make_float2(v.x, v.y);
+      raw[2 * k + 1] = make_float2(v.z, v.w);
+    }
+  };
+  const long long t0 = clock64();
+  for (int r = 0; r < rounds; ++r) {
+    const float2 c2 = make_float2(c, c), nm2 = make_float2(-m, -m);
+    // two register sets (A / B) alternate roles, so that the rolled loop needs no register moves:
+    //   half-iteration on (cur, nxt): exponentials of cur.x -> cur.e, scale-subtract nxt.raw -> nxt.x, then load the
+    //   chunk after next into cur.raw... each pair's three stages are INTERLEAVED in the source (one basic block).
+    float2 rawA[kP], xA[kP], eA[kP], rawB[kP], xB[kP], eB[kP];
+    load(rawA, 0);
+#pragma unroll
+    for (int i = 0; i < kP; ++i) xA[i] = __ffma2_rn(rawA[i], c2, nm2);
+    load(rawB, 1);
+#pragma unroll
+    for (int i = 0; i < kP; ++i) eB[i] = make_float2(0.f, 0.f);
+    auto half = [&](float2 (&xc)[kP], float2 (&ec)[kP], float2 (&rawn)[kP], float2 (&xn)[kP], float2 (&ep)[kP], int ch) {
+      // exps of chunk ch (xc -> ec) | scale-subtract of chunk ch + 1 (rawn -> xn) | sum / pack / store of chunk ch - 1 (ep)
+      uint32_t pk[kP];
+#pragma unroll
+      for (int i = 0; i < kP; ++i) {
+        const bool poly = (kMask8 >> (i & 7)) & 1;
+        if (!poly) ec[i].x = ptx::ex2_approx(xc[i].x);
+        xn[i] = __ffma2_rn(rawn[i], c2, nm2);
+        if (i & 1) lsum1 = __fadd2_rn(lsum1, ep[i]);
+        else lsum0 = __fadd2_rn(lsum0, ep[i]);
+        if (!poly) ec[i].y = ptx::ex2_approx(xc[i].y);
+        else ec[i] = exp2_poly2(xc[i]);
+        pk[i] = ptx::pack_bf16x2(ep[i].x, ep[i].y);
+      }
+      uint4* dst = s_out + (ch * zero) * blockDim.x + threadIdx.x;
+#pragma unroll
+      for (int k = 0; k < kP / 4; ++k) dst[k * blockDim.x] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+    };
+#pragma unroll 1
+    for (int ch = 0; ch < kNC; ch += 2) {
+      half(xA, eA, rawB, xB, eB, ch);       // (the first pass sums / stores zeros: the pipeline's fill)
+      load(rawA, ch + 2);
+      half(xB, eB, rawA, xA, eA, ch + 1);
+      load(rawB, ch + 3);
+    }
+#pragma unroll
+    for (int i = 0; i < kP; ++i) {          // drain: the last chunk's sum
+      if (i & 1) lsum1 = __fadd2_rn(lsum1, eB[i]);
+      else lsum0 = __fadd2_rn(lsum0, eB[i]);
+    }
+    m += 1e-6f;
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = lsum0.x + lsum0.y + lsum1.x + lsum1.y + __uint_as_float(s_out[threadIdx.x].x & 0x007fffffu);
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int kMask8, int kCh>
+void run_pipelined(const char* name, const float* in, float* out, long long* cyc, int rounds) {
+  cudaFuncSetAttribute(probe_pipelined<kMask8, kCh>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  for (int threads : {128, 256, 512}) {
+    const size_t smem = (size_t)(kCh / 4 + kCh / 8) * threads * 16;
+    for (int rep = 0; rep < 2; ++rep) probe_pipelined<kMask8, kCh><<<1, threads, smem>>>(in, rounds, 0, out, cyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("%s: %s\n", name, cudaGetErrorString(e));
+      exit(1);
+    }
+    long long h;
+    cudaMemcpy(&h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    const int warps_per_smsp = threads / 128;
+    printf("%-44s %d warp(s) / SMSP: %6.2f cycles per 32-lane element step per SMSP  (%7.0f cycles per 128-key row block per warp)\n",
+           name, warps_per_smsp, (double)h / ((double)rounds * 128 * warps_per_smsp), (double)h / rounds);
+  }
+}
+
 template <int kMask8, bool kSum, bool kPack, int kMode>
 void run(const char* name, const float* in, float* out, long long* cyc, int rounds) {
   for (int threads : {128, 256, 512}) {
@@ -161,6 +326,20 @@ int main(int argc, char** argv) {
   cudaMemcpy(in, h.data(), 4100 * sizeof(float), cudaMemcpyHostToDevice);
   cudaMalloc(&out, 512 * sizeof(float));
   cudaMalloc(&cyc, sizeof(long long));
+  run_chained<0x88, 16, 1>("CHAINED 16-key chunks lag 1, 25 % poly", in, out, cyc, rounds);
+  run_chained<0x88, 16, 2>("CHAINED 16-key chunks lag 2, 25 % poly", in, out, cyc, rounds);
+  run_chained<0x88, 8, 2>("CHAINED 8-key chunks lag 2, 25 % poly", in, out, cyc, rounds);
+  run_chained<0x88, 8, 3>("CHAINED 8-key chunks lag 3, 25 % poly", in, out, cyc, rounds);
+  run_chained<0x88, 32, 1>("CHAINED 32-key chunks lag 1, 25 % poly", in, out, cyc, rounds);
+  run_chained<0x00, 16, 2>("CHAINED 16-key chunks lag 2, MUFU only", in, out, cyc, rounds);
+  run_chained<0xAA, 16, 2>("CHAINED 16-key chunks lag 2, 50 % poly", in, out, cyc, rounds);
+  run_pipelined<0x00, 32>("PIPELINED 32-key chunks, MUFU only", in, out, cyc, rounds);
+  run_pipelined<0x88, 32>("PIPELINED 32-key chunks, 25 % polynomial", in, out, cyc, rounds);
+  run_pipelined<0x92, 32>("PIPELINED 32-key chunks, 37.5 % polynomial", in, out, cyc, rounds);
+  run_pipelined<0xAA, 32>("PIPELINED 32-key chunks, 50 % polynomial", in, out, cyc, rounds);
+  run_pipelined<0x00, 16>("PIPELINED 16-key chunks, MUFU only", in, out, cyc, rounds);
+  run_pipelined<0x88, 16>("PIPELINED 16-key chunks, 25 % polynomial", in, out, cyc, rounds);
+  run_pipelined<0xAA, 16>("PIPELINED 16-key chunks, 50 % polynomial", in, out, cyc, rounds);
   run<0x00, true, true, 0>("softmax step, MUFU only", in, out, cyc, rounds);
   run<0x88, true, true, 0>("softmax step, 25 % polynomial (product)", in, out, cyc, rounds);
   run<0xAA, true, true, 0>("softmax step, 50 % polynomial", in, out, cyc, rounds);
