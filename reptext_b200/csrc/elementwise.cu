@@ -367,31 +367,38 @@ __global__ void __launch_bounds__(256, 1) ln_mod_rows2_kernel(const bf16* __rest
     }
     auto lo = [](uint32_t w) { return __uint_as_float(w << 16); };
     auto hi = [](uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); };
-    float2 sa = f2(0.f, 0.f), sb = f2(0.f, 0.f);
+    // four independent partial sums per row, pieces x / y / z / w: the same order as ln_mod_row1_kernel (same bits)
+    float2 sa[4] = {f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f)};
+    float2 sb[4] = {f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f)};
 #pragma unroll
     for (int i = 0; i < kV; ++i) {
       const uint32_t wa[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w}, wb[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        sa = __fadd2_rn(sa, f2(lo(wa[j]), hi(wa[j])));
-        sb = __fadd2_rn(sb, f2(lo(wb[j]), hi(wb[j])));
+        sa[j] = __fadd2_rn(sa[j], f2(lo(wa[j]), hi(wa[j])));
+        sb[j] = __fadd2_rn(sb[j], f2(lo(wb[j]), hi(wb[j])));
       }
     }
-    const float mean_a = warp_sum(sa.x + sa.y) * inv_d, mean_b = warp_sum(sb.x + sb.y) * inv_d;
+    const float2 sta = __fadd2_rn(__fadd2_rn(sa[0], sa[1]), __fadd2_rn(sa[2], sa[3]));
+    const float2 stb = __fadd2_rn(__fadd2_rn(sb[0], sb[1]), __fadd2_rn(sb[2], sb[3]));
+    const float mean_a = warp_sum(sta.x + sta.y) * inv_d, mean_b = warp_sum(stb.x + stb.y) * inv_d;
     const float2 na = f2(-mean_a, -mean_a), nb = f2(-mean_b, -mean_b);
-    float2 qa = f2(0.f, 0.f), qb = f2(0.f, 0.f);
+    float2 qa[4] = {f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f)};
+    float2 qb[4] = {f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f)};
 #pragma unroll
     for (int i = 0; i < kV; ++i) {
       const uint32_t wa[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w}, wb[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 da = __fadd2_rn(f2(lo(wa[j]), hi(wa[j])), na), db = __fadd2_rn(f2(lo(wb[j]), hi(wb[j])), nb);
-        qa = __ffma2_rn(da, da, qa);
-        qb = __ffma2_rn(db, db, qb);
+        qa[j] = __ffma2_rn(da, da, qa[j]);
+        qb[j] = __ffma2_rn(db, db, qb[j]);
       }
     }
-    const float rstd_a = rsqrtf(warp_sum(qa.x + qa.y) * inv_d + 1e-6f);
-    const float rstd_b = rsqrtf(warp_sum(qb.x + qb.y) * inv_d + 1e-6f);
+    const float2 qta = __fadd2_rn(__fadd2_rn(qa[0], qa[1]), __fadd2_rn(qa[2], qa[3]));
+    const float2 qtb = __fadd2_rn(__fadd2_rn(qb[0], qb[1]), __fadd2_rn(qb[2], qb[3]));
+    const float rstd_a = rsqrtf(warp_sum(qta.x + qta.y) * inv_d + 1e-6f);
+    const float rstd_b = rsqrtf(warp_sum(qtb.x + qtb.y) * inv_d + 1e-6f);
     const float2 rsa = f2(rstd_a, rstd_a), rsb = f2(rstd_b, rstd_b);
     bf16* oa = out + (long long)b * o_bs + (long long)r * o_ld + lane * 8;
     bf16* ob = oa + o_ld;
@@ -441,6 +448,125 @@ static void launch_ln_rows2(const void* x, long long x_bs, int x_ld, void* out, 
   count_launch();
 }
 
+// v4: one warp per ROW, 16 warps per CTA (v3: a PAIR of rows per warp, 8 warps).  ncu on v3 (profiles/
+// r2_ncu_full_step_kernels.txt): 11 % warp occupancy, one instruction issued per warp every 10 cycles - two warps per
+// scheduler, each walking a 940-instruction chain whose sums hang on ONE accumulator - so the kernel is bound by
+// dependent-issue latency, not by bytes.  Here a scheduler has four warps with half the chain each, and the two
+// reductions run on four independent partial sums.  Same staging of the modulation vectors, same one wave of CTAs.
+template <int kV>
+__global__ void __launch_bounds__(512, 1) ln_mod_row1_kernel(const bf16* __restrict__ x, long long x_bs, int x_ld,
+                                                             bf16* __restrict__ out, long long o_bs, int o_ld, int D,
+                                                             const LnSegs segs) {
+  extern __shared__ float ln_smem[];  // [D] 1 + scale | [D] shift
+  float* s_sc = ln_smem;
+  float* s_sh = ln_smem + D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int b = 0, r0 = 0, r_end = 0;
+  const float *gsc = nullptr, *gsh = nullptr;
+#pragma unroll
+  for (int i = 0; i < kLnMaxSegs; ++i) {
+    if (i < segs.n && (int)blockIdx.x >= segs.s[i].cta_begin) {
+      b = segs.s[i].batch;
+      r0 = segs.s[i].row_begin + ((int)blockIdx.x - segs.s[i].cta_begin) * segs.rows_per_cta;
+      r_end = segs.s[i].row_end;
+      gsc = segs.s[i].scale;
+      gsh = segs.s[i].shift;
+    }
+  }
+  r_end = min(r_end, r0 + segs.rows_per_cta);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    const float4 a = *reinterpret_cast<const float4*>(gsc + i);
+    const float4 h = *reinterpret_cast<const float4*>(gsh + i);
+    *reinterpret_cast<float4*>(s_sc + i) = make_float4(1.f + a.x, 1.f + a.y, 1.f + a.z, 1.f + a.w);
+    *reinterpret_cast<float4*>(s_sh + i) = h;
+  }
+  __syncthreads();
+  const float inv_d = 1.f / (float)D;
+  // volatile: each pass unpacks again (2 ALU ops per pair) instead of keeping 8 kV fp32 values alive across the passes
+  auto lo = [](uint32_t w) {
+    uint32_t o;
+    asm volatile("shl.b32 %0, %1, 16;" : "=r"(o) : "r"(w));
+    return __uint_as_float(o);
+  };
+  auto hi = [](uint32_t w) {
+    uint32_t o;
+    asm volatile("and.b32 %0, %1, 0xffff0000;" : "=r"(o) : "r"(w));
+    return __uint_as_float(o);
+  };
+  for (int r = r0 + warp; r < r_end; r += 16) {
+    uint4 ra[kV];
+    {
+      const bf16* xa = x + (long long)b * x_bs + (long long)r * x_ld + lane * 8;
+#pragma unroll
+      for (int i = 0; i < kV; ++i) ra[i] = *reinterpret_cast<const uint4*>(xa + i * 256);
+    }
+    float2 sa[4] = {f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f)};
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      sa[0] = __fadd2_rn(sa[0], f2(lo(ra[i].x), hi(ra[i].x)));
+      sa[1] = __fadd2_rn(sa[1], f2(lo(ra[i].y), hi(ra[i].y)));
+      sa[2] = __fadd2_rn(sa[2], f2(lo(ra[i].z), hi(ra[i].z)));
+      sa[3] = __fadd2_rn(sa[3], f2(lo(ra[i].w), hi(ra[i].w)));
+    }
+    const float2 st = __fadd2_rn(__fadd2_rn(sa[0], sa[1]), __fadd2_rn(sa[2], sa[3]));
+    const float mean = warp_sum(st.x + st.y) * inv_d;
+    const float2 nm = f2(-mean, -mean);
+    float2 qa[4] = {f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f)};
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const uint32_t w[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 d = __fadd2_rn(f2(lo(w[j]), hi(w[j])), nm);
+        qa[j] = __ffma2_rn(d, d, qa[j]);
+      }
+    }
+    const float2 qt = __fadd2_rn(__fadd2_rn(qa[0], qa[1]), __fadd2_rn(qa[2], qa[3]));
+    const float rstd = rsqrtf(warp_sum(qt.x + qt.y) * inv_d + 1e-6f);
+    const float2 rs = f2(rstd, rstd);
+    bf16* oa = out + (long long)b * o_bs + (long long)r * o_ld + lane * 8;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int c = i * 256 + lane * 8;
+      const float4 c0 = *reinterpret_cast<const float4*>(s_sc + c), c1 = *reinterpret_cast<const float4*>(s_sc + c + 4);
+      const float4 h0 = *reinterpret_cast<const float4*>(s_sh + c), h1 = *reinterpret_cast<const float4*>(s_sh + c + 4);
+      const float2 sc[4] = {f2(c0.x, c0.y), f2(c0.z, c0.w), f2(c1.x, c1.y), f2(c1.z, c1.w)};
+      const float2 sh[4] = {f2(h0.x, h0.y), f2(h0.z, h0.w), f2(h1.x, h1.y), f2(h1.z, h1.w)};
+      const uint32_t w[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 d = __fadd2_rn(f2(lo(w[j]), hi(w[j])), nm);
+        const float2 y = __ffma2_rn(d, __fmul2_rn(rs, sc[j]), sh[j]);
+        __nv_bfloat162 hh = __float22bfloat162_rn(y);
+        pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      *reinterpret_cast<uint4*>(oa + i * 256) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (i % 2 == 1) asm volatile("" ::: "memory");  // keeps the modulation loads of later pieces from piling up in registers
+    }
+  }
+}
+
+template <int kV>
+static void launch_ln_row1(const void* x, long long x_bs, int x_ld, void* out, long long o_bs, int o_ld, int D,
+                           const LnSegs& S, int grid, cudaStream_t stream) {
+  const int smem = 2 * D * (int)sizeof(float);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = get_option("no_pdl") ? 0 : 1;
+  RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_mod_row1_kernel<kV>, (const bf16*)x, x_bs, x_ld, (bf16*)out, o_bs, o_ld, D, S));
+  count_launch();
+}
+
 void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out, long long o_bs, int o_ld, int batch,
                    int D, int ngroups, const LnModGroup* groups, cudaStream_t stream) {
   RT_REQUIRE(ngroups >= 1 && ngroups <= kLnMaxGroups, "ln_mod: 1..2 row groups");
@@ -457,12 +583,17 @@ void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out
   const long long total = (long long)batch * rows_total;
   // bf16, D = kV * 256: the warp-per-row-pair kernel
   if (dtype == RT_BF16 && D % 256 == 0 && D <= 4096 && (D / 256) % 4 == 0 && batch * ngroups <= kLnMaxSegs &&
-      x_ld % 8 == 0 && o_ld % 8 == 0 && get_option("ln_impl") == 0) {
+      x_ld % 8 == 0 && o_ld % 8 == 0 && (get_option("ln_impl") == 0 || get_option("ln_impl") == 3)) {
     LnSegs S{};
-    // one wave of CTAs (the kernel keeps two whole rows per lane in registers: one CTA per SM)
+    // one wave of CTAs (the kernels keep whole rows in registers: one CTA per SM)
     int rpc = (int)((total + sm_count() - 1) / sm_count());
     rpc = (rpc + 1) / 2 * 2;
+    const bool big = rpc > 64;   // more than one wave
     rpc = rpc < 2 ? 2 : (rpc > 64 ? 64 : rpc);
+    // v4 (one row per warp, 16 warps) up to one wave of 64-row CTAs and D <= 3072 (128 registers hold the row), v3 (a
+    // pair of rows per warp) beyond; ln_impl = 3 forces v3.  Both compute a row with the same operations in the same
+    // order, so the choice never shows in the results (a sharded run must equal the unsharded one bit for bit).
+    const bool row1 = get_option("ln_impl") == 0 && D <= 3072 && !big;
     S.rows_per_cta = rpc;
     int cta = 0;
     for (int b = 0; b < batch; ++b)
@@ -475,6 +606,14 @@ void launch_ln_mod(int dtype, const void* x, long long x_bs, int x_ld, void* out
         e.shift = groups[g].shift + (long long)b * groups[g].ld;
         cta += (rows + rpc - 1) / rpc;
       }
+    if (row1) {
+      switch (D / 256) {
+        case 4: launch_ln_row1<4>(x, x_bs, x_ld, out, o_bs, o_ld, D, S, cta, stream); return;
+        case 8: launch_ln_row1<8>(x, x_bs, x_ld, out, o_bs, o_ld, D, S, cta, stream); return;
+        case 12: launch_ln_row1<12>(x, x_bs, x_ld, out, o_bs, o_ld, D, S, cta, stream); return;
+        default: break;
+      }
+    }
     switch (D / 256) {
       case 4: launch_ln_rows2<4>(x, x_bs, x_ld, out, o_bs, o_ld, D, S, cta, stream); return;
       case 8: launch_ln_rows2<8>(x, x_bs, x_ld, out, o_bs, o_ld, D, S, cta, stream); return;
