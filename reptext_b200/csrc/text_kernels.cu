@@ -12,6 +12,7 @@
 #include <cmath>
 
 #include "dtype_utils.cuh"
+#include "ptx_sm100.cuh"
 #include "rt_internal.h"
 
 namespace rt {
@@ -303,6 +304,228 @@ __global__ void __launch_bounds__(128) text_attn_mma_kernel(TextAttnArgs a) {
   }
 }
 
+// ---- the same attention on the 5th-generation tensor cores: tcgen05.mma with the accumulators in tensor memory, Q / K /
+// V tiles fetched by TMA straight from the fused projection buffer (128B swizzle), the structure of the hot path's
+// attn_tc_kernel cut down to what 512 tokens need.  CTA = (128 query rows, head, batch); key blocks of 128:
+//   warp 0  TMA producer (Q once, K / V through a ring of two stages)
+//   warp 1  MMA issuer: S = Q K^T (SS, 4 k-steps of 16) -> tensor memory; O += P V (TS: P read from tensor memory, V
+//           MN-major, 8 k-steps) -> tensor memory; also allocates / frees the 256 columns (S 128, O 64)
+//   warps 2-5  softmax, one thread per query row: the 128 scores of the block in registers, log2-domain scale +
+//           relative-position bias (T5: a [2 S - 1] row of this head, staged in shared memory, indexed by key - query) or
+//           causal mask (CLIP), online maximum with an exact rescale of O in tensor memory (skipped while the maximum
+//           stands), P = 2^(x - m) as bf16 back over the score columns, row sum in fp32
+// One CTA per SM and no ping-pong: the tensor pipe waits while the softmax runs - this path is < 3 % of an encoder's
+// FLOPs and 24 x 256 CTAs per prompt; the point is the datapath, not the last 2x.
+constexpr int kTT_Threads = 192;
+constexpr int kTT_TileBytes = 128 * 64 * 2;   // 128 rows x 64 head-dim columns, bf16: 16 KB
+constexpr int kTT_BarOff = 5 * kTT_TileBytes;
+constexpr int kTT_BiasOff = kTT_BarOff + 128;
+
+struct TextTcParams {
+  CUtensorMap tm;   // 3-D (columns of the projection buffer, rows, batch), box (64, 128, 1)
+  TextAttnArgs a;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(kTT_Threads, 2) text_attn_tc_kernel(const __grid_constant__ TextTcParams P) {
+  extern __shared__ uint8_t tt_smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(tt_smem_raw);
+  uint8_t* smem = tt_smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint8_t* smem_q = smem;
+  uint8_t* smem_k = smem + kTT_TileBytes;        // 2 stages
+  uint8_t* smem_v = smem + 3 * kTT_TileBytes;    // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTT_BarOff);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* v_full = bars + 3;     // [2]
+  uint64_t* kv_empty = bars + 5;   // [2] P V of the block has completed: K and V of the stage are free
+  uint64_t* s_full = bars + 7;
+  uint64_t* p_full = bars + 8;     // 128 arrivals
+  uint64_t* o_done = bars + 9;     // O += P V of the block has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* Bs = reinterpret_cast<float*>(smem + kTT_BiasOff);
+  const TextAttnArgs& a = P.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * 128;
+  const int k_end = a.causal ? min(a.S, q0 + 128) : a.S;
+  const int n_kv = (k_end + 127) / 128;
+
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&P.tm);
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&kv_empty[i], 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(o_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<1>(tmem_slot, 256);
+  if (a.rel_bias) {   // this head's bias row, already in the log2 domain
+    const float* src = a.rel_bias + (long long)h * (2 * a.S - 1);
+    for (int e = threadIdx.x; e < 2 * a.S - 1; e += kTT_Threads) Bs[e] = src[e] * 1.4426950408889634f;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(q_full, kTT_TileBytes);
+      ptx::tma_load_3d(&P.tm, q_full, smem_q, a.q_col0 + h * 64, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1, ph = (j >> 1) & 1;
+        ptx::mbar_wait(&kv_empty[st], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&k_full[st], kTT_TileBytes);
+        ptx::tma_load_3d(&P.tm, &k_full[st], smem_k + st * kTT_TileBytes, a.k_col0 + h * 64, j * 128, b);
+        ptx::mbar_arrive_expect_tx(&v_full[st], kTT_TileBytes);
+        ptx::tma_load_3d(&P.tm, &v_full[st], smem_v + st * kTT_TileBytes, a.v_col0 + h * 64, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(128, 128, 0, 0);  // A, B K-major
+    constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, 64, 0, 1);   // A (= P) from tensor memory, B (= V) MN-major
+    const uint64_t q_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_q), 0, 1024);
+    const uint64_t k_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_k), 0, 1024);
+    const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_v), kTT_TileBytes, 1024);
+    constexpr uint32_t kTile16 = kTT_TileBytes >> 4;
+    ptx::mbar_wait(q_full, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1, ph = (j >> 1) & 1;
+      ptx::mbar_wait(&k_full[st], ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // 16 of the 64 head-dim columns = 32 B inside the 128-byte swizzle row
+          ptx::mma_bf16_ss<1>(tmem, q_desc + 2 * kk, k_desc + (uint64_t)(st * kTile16) + 2 * kk, idesc_qk, kk != 0 ? 1u : 0u);
+        ptx::mma_commit(s_full);
+      }
+      __syncwarp();
+      ptx::mbar_wait(p_full, j & 1);
+      ptx::mbar_wait(&v_full[st], ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // 16 keys = 8 packed columns of P = two 8-row groups of V (2048 B)
+          ptx::mma_bf16_ts(tmem + 128, tmem + kk * 8, v_desc + (uint64_t)(st * kTile16) + (uint64_t)(kk * 128), idesc_pv,
+                           (j > 0 || kk > 0) ? 1u : 0u);
+        ptx::mma_commit(&kv_empty[st]);
+        ptx::mma_commit(o_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;   // tensor-memory lane quadrant of this warp (warps 2, 3, 4, 5 -> 2, 3, 0, 1)
+    const int row = quad * 32 + lane, qrow = q0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t s_addr = tmem + lane_off, o_addr = tmem + lane_off + 128;
+    const int bias_base = a.S - 1 - min(qrow, a.S - 1);   // Bs[key + bias_base] = bias(key - query)
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      ptx::mbar_wait(s_full, j & 1);
+      ptx::tc_fence_after();
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      ptx::tmem_ld_32x32b_x32(s_addr, s0);
+      ptx::tmem_ld_32x32b_x32(s_addr + 32, s1);
+      ptx::tmem_ld_32x32b_x32(s_addr + 64, s2);
+      ptx::tmem_ld_32x32b_x32(s_addr + 96, s3);
+      ptx::tmem_ld_wait();
+      // scores -> log2-domain logits (bias, masks), running maximum on four independent chains (one softmax warp per
+      // scheduler: every dependent chain is exposed latency)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      const bool full = j * 128 + 128 <= a.S && !(a.causal && j * 128 + 127 > q0);   // no key of this block is masked
+      auto prep = [&](uint32_t (&sv)[32], int c0) {
+        const float* bs = Bs + j * 128 + c0 + bias_base;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(sv[i]) * P.scale_log2;
+          if (full) {
+            if (a.rel_bias) x += bs[i];
+          } else {
+            const int key = j * 128 + c0 + i;
+            if (a.rel_bias && key < a.S) x += bs[i];
+            if (key >= a.S || (a.causal && key > qrow)) x = -INFINITY;
+          }
+          sv[i] = __float_as_uint(x);
+          mx4[i & 3] = fmaxf(mx4[i & 3], x);
+        }
+      };
+      prep(s0, 0);
+      prep(s1, 32);
+      prep(s2, 64);
+      prep(s3, 96);
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float m_new = fmaxf(m, mx);     // finite: every row sees at least one unmasked key in every block it visits
+      const float corr = ptx::ex2_approx(m - m_new);
+      if (j > 0 && __any_sync(0xffffffffu, m_new != m)) {   // the maximum moved for some row of this warp: rescale O
+        ptx::mbar_wait(o_done, (j - 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(o_addr + ch * 16, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+          ptx::tmem_st_32x32b_x16(o_addr + ch * 16, r);
+        }
+      }
+      float2 ps2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 nm2 = make_float2(-m_new, -m_new);
+      auto expo = [&](const uint32_t (&sv)[32], int col) {   // P = 2^(x - m) -> bf16 pairs over the score columns
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 x = __fadd2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), nm2);
+          float2 e;
+          e.x = ptx::ex2_approx(x.x);
+          e.y = ptx::ex2_approx(x.y);
+          ps2[i & 1] = __fadd2_rn(ps2[i & 1], e);
+          pk[i] = ptx::pack_bf16x2(e.x, e.y);
+        }
+        ptx::tmem_st_32x32b_x16(s_addr + col, pk);
+      };
+      expo(s0, 0);
+      expo(s1, 16);
+      expo(s2, 32);
+      expo(s3, 48);
+      l = l * corr + ((ps2[0].x + ps2[0].y) + (ps2[1].x + ps2[1].y));
+      m = m_new;
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(p_full);
+    }
+    ptx::mbar_wait(o_done, (n_kv - 1) & 1);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    bf16* dst = a.out + (long long)b * a.out_batch_stride + (long long)qrow * a.out_ld + a.out_col0 + h * 64;
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(o_addr + ch * 32, r);
+      ptx::tmem_ld_wait();
+      if (qrow < a.S) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = ptx::pack_bf16x2(__uint_as_float(r[8 * i + 0]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
+          u.y = ptx::pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
+          u.z = ptx::pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
+          u.w = ptx::pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + ch * 32 + i * 8) = u;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<1>(tmem, 256);
+}
+
 // ---- gated activation: kind 0: out = in[:, :F] * in[:, F:2F]; kind 1: out = quick_gelu(in[:, :F]) = x * sigmoid(1.702 x)
 __global__ void __launch_bounds__(256) glu_act_kernel(const bf16* __restrict__ in, long long in_ld, bf16* __restrict__ out,
                                                       long long out_ld, int F, int kind, long long total_vecs) {
@@ -393,7 +616,23 @@ int rt_text_attention(const void* qkv, int64_t batch_stride, int ld, int q_col0,
     const bool aligned = ld % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0 && out_ld % 8 == 0 &&
                          out_col0 % 8 == 0 && batch_stride % 8 == 0 && out_batch_stride % 8 == 0 &&
                          (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    if (!get_option("text_attn_simt")) {
+    if (!get_option("text_attn_simt") && !get_option("text_attn_mma") && aligned) {
+      // tcgen05 / TMEM / TMA form
+      TextTcParams T{};
+      T.a = a;
+      T.scale_log2 = scale * 1.4426950408889634f;
+      uint64_t dims[3] = {(uint64_t)ld, (uint64_t)S, (uint64_t)batch};
+      uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)batch_stride * 2};
+      uint32_t box[3] = {64, 128, 1};
+      encode_tmap_bf16(&T.tm, qkv, 3, dims, strides, box);
+      const size_t smem = (size_t)kTT_BiasOff + (size_t)(rel_bias ? 2 * S - 1 : 0) * sizeof(float) + 1024 + 16;
+      RT_REQUIRE(smem <= 227 * 1024, "text_attention: the relative-bias row does not fit into shared memory");
+      static PerDeviceOnce attr;
+      if (attr.first())
+        RT_CHECK_CUDA(cudaFuncSetAttribute(text_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      dim3 grid((S + 127) / 128, heads, batch);
+      text_attn_tc_kernel<<<grid, kTT_Threads, smem, s>>>(T);
+    } else if (!get_option("text_attn_simt")) {
       RT_REQUIRE(aligned, "text_attention: pointers / strides / column offsets must be multiples of 8 elements");
       const size_t smem = kTA_SmemFixed + (size_t)(rel_bias ? 2 * S - 1 : 0) * sizeof(float);
       static PerDeviceOnce attr;

@@ -49,7 +49,7 @@ def test_norm_rows(ops, D, center):
 
 
 @pytest.mark.parametrize("B,S,H,mode", [(2, 512, 4, "bias"), (1, 77, 12, "causal"), (2, 40, 2, "bias"), (1, 33, 2, "plain"),
-                                        (1, 100, 3, "causal")])
+                                        (1, 100, 3, "causal"), (1, 300, 2, "causal"), (2, 257, 3, "bias"), (1, 640, 2, "plain")])
 def test_text_attention(ops, B, S, H, mode):
     D = H * 64
     qkv = _rand((B, S, 3 * D), 4, 0.5)
@@ -65,14 +65,16 @@ def test_text_attention(ops, B, S, H, mode):
         s = s + torch.full((S, S), float("-inf"), device="cuda").triu(1)
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, S, D)
     assert rel_l2(out, ref) < 4e-3
-    # the CUDA-core form of the same kernel (option text_attn_simt), kept for A/B
+    # the default is the tcgen05 / TMEM / TMA kernel; the warp-level MMA form (option text_attn_mma) and the CUDA-core
+    # form (option text_attn_simt) of the same attention are kept for A/B
     from reptext_b200 import _lib
-    _lib.set_option("text_attn_simt", 1)
-    try:
-        out2 = ops.text_attention(qkv, H, scale, rel_bias=bias, causal=(mode == "causal"))
-    finally:
-        _lib.set_option("text_attn_simt", 0)
-    assert rel_l2(out2, ref) < 4e-3
+    for opt in ("text_attn_mma", "text_attn_simt"):
+        _lib.set_option(opt, 1)
+        try:
+            out2 = ops.text_attention(qkv, H, scale, rel_bias=bias, causal=(mode == "causal"))
+        finally:
+            _lib.set_option(opt, 0)
+        assert rel_l2(out2, ref) < 4e-3, opt
 
 
 def test_glu_act_and_embedding(ops):

@@ -20,8 +20,9 @@ ic = SyntheticTokenizer("clip", 49408, 77)([p], padding="max_length", max_length
 t5(i5), clip(ic)
 torch.cuda.synchronize()
 for name, fn in (("t5_xxl", lambda: t5(i5)), ("clip_l", lambda: clip(ic))):
-    for simt in (0, 1):
-        _lib.set_option("text_attn_simt", simt)
+    for simt in (0, 1, 2):     # 0: tcgen05 attention (the product), 1: CUDA cores, 2: warp-level mma.sync
+        _lib.set_option("text_attn_simt", int(simt == 1))
+        _lib.set_option("text_attn_mma", int(simt == 2))
         _lib.set_option("profile", 1)
         _lib.profile_reset()
         fn()
@@ -32,5 +33,6 @@ for name, fn in (("t5_xxl", lambda: t5(i5)), ("clip_l", lambda: clip(ic))):
         rec = {k: dict(ms=round(v[0], 3), launches=v[2],
                        achieved=round(v[1] / (v[0] / 1e3) / (1e9 if k in ("elementwise",) else 1e12), 2),
                        unit="GB/s" if k in ("elementwise",) else "TFLOP/s") for k, v in prof.items()}
-        print(json.dumps({name + ("_simt_attention" if simt else ""): rec}), flush=True)
+        print(json.dumps({name + ("", "_simt_attention", "_mma_sync_attention")[simt]: rec}), flush=True)
 _lib.set_option("text_attn_simt", 0)
+_lib.set_option("text_attn_mma", 0)
