@@ -396,6 +396,16 @@ def sp_leg(args, tr, cn, TR, CN, pipe, dev, rank, world, pk, barrier):
                       guidance, sig, tsd, dict(sp=sp))
     msN, twoN, _ = timed(stepN, sh(lat))
     sp.check()
+    # same-box A/B of the two sequence-parallel design choices (same process, same weights, same inputs): the phase
+    # synchronisation as stand-alone barrier kernels instead of inside the neighbouring kernels, and 256-wide GEMM tiles
+    # everywhere instead of the run-time tile width; both leave the latents bit-identical
+    ab = {}
+    for name, opt, val in (("phase_sync_as_barrier_kernels", "sp_sync_kernels", 1), ("static_256_wide_gemm_tiles", "gemm_dyn_bn", -1)):
+        _lib.set_option(opt, val)
+        ms_ab, two_ab, _ = timed(stepN, sh(lat))
+        _lib.set_option(opt, 0)
+        sp.check()
+        ab[name] = dict(ms_per_step=ms_ab, same_latents=bool(torch.equal(two_ab, twoN)))
     _, _, prof = timed(stepN, sh(lat), prof=True)      # separate pass: events around every launch
     sp.check()
     twoN = parallel.gather_tokens(twoN)
@@ -413,7 +423,8 @@ def sp_leg(args, tr, cn, TR, CN, pipe, dev, rank, world, pk, barrier):
     bar_us = e0.elapsed_time(e1) / 200 * 1000.0
     sp.close()
     flops = step_flops(TR, CN, N, T, cn_live_layers=cn_live(TR, CN))
-    n_bar = 2 * (cn_live(TR, CN) + TR["num_layers"] + TR["num_single_layers"]) + 6
+    n_sync = 2 * (cn_live(TR, CN) + TR["num_layers"] + TR["num_single_layers"])  # two phase hand-offs per block
+    n_bar = 4                                                                    # AdaLN row-shard exchange, 2 per forward
     breakdown = {}
     for k, v in (prof or {}).items():
         tensor = "gemm" in k or "attention" in k
@@ -424,8 +435,8 @@ def sp_leg(args, tr, cn, TR, CN, pipe, dev, rank, world, pk, barrier):
                 one_gpu_ms_per_step=ms1, speedup=ms1 / msN, strong_scaling_efficiency=ms1 / msN / world,
                 target_ms_per_step=27.1 if world == 8 else None, flops_per_step=flops,
                 tensor_util_per_gpu=flops / world / (msN / 1000.0) / 1e12 / pk["bf16_sustained"],
-                latents_rel_l2_vs_one_gpu_after_2_steps=err, barrier_us=bar_us, barriers_per_step=n_bar,
-                barrier_ms_per_step=bar_us * n_bar / 1000.0, breakdown=breakdown,
+                latents_rel_l2_vs_one_gpu_after_2_steps=err, in_kernel_phase_syncs_per_step=n_sync,
+                barrier_kernels_per_step=n_bar, barrier_kernel_us=bar_us, ab=ab, breakdown=breakdown,
                 how="same weights, same inputs, same process group as the headline run; one-GPU figure = every rank runs "
                     "the whole sample itself (max over ranks); device-timed, 3 warm-up steps, barrier + synchronize on "
                     "both sides")

@@ -62,6 +62,11 @@ RT_API long long rt_launch_count(void); /* number of this library's kernels laun
  * "no_pdl" (1 = plain stream-ordered launches instead of programmatic dependent launch),
  * "gemm_band" (tile order of the tcgen05 GEMM: 0 = auto - row tiles fastest unless A is too large to stay in L2 between
  * waves, then bands of row tiles swept over all column tiles; -1 = always row tiles fastest; n > 0 = bands of n row tiles),
+ * "gemm_dyn_bn" (tile width of single-segment tcgen05 GEMM launches: 0 = auto - 256 columns unless a narrower tile fills
+ * the last wave of the persistent grid better, as on the 1216-row shards of the sequence-parallel mode; -1 = always 256;
+ * n = tiles of n columns where eligible; bit-identical results),
+ * "sp_sync_kernels" (1 = the sequence-parallel phase barriers as stand-alone kernels instead of at the head of the
+ * attention / output-projection kernels; same protocol, same results),
  * "gemm_debug" (bit 1: no epilogue, bit 2: k-block 0 only - timing experiments with WRONG results;
  * bit 4: direct row-per-thread epilogue stores instead of the staged coalesced ones - same results) */
 RT_API int rt_set_option(const char* name, int value);
@@ -113,7 +118,9 @@ typedef struct rt_forward_args {
  *      every rank's workspace mapped in every process (rt_ipc_*).  RoPE follows the ids each rank passes, so
  *      img_ids / txt_ids are simply the shard's rows. */
 #define RT_SP_MAX_RANKS 8
-#define RT_SP_FLAG_WORDS 16 /* [0..7] arrival epochs written by rank i, [8] this rank's epoch, [9] time-out flag */
+#define RT_SP_FLAG_WORDS 16 /* [0..7] arrival epochs written by rank i, [8] this rank's epoch, [9] time-out flag,
+                               [11], [12] the epochs announced for the barriers that run inside the attention /
+                               output-projection kernels (csrc/sp_sync.cuh) */
 typedef struct rt_sp_group {
   int world, rank;
   void* peer_workspace[RT_SP_MAX_RANKS];               /* rank i's workspace as mapped in this process ([rank] = own) */

@@ -7,6 +7,7 @@
 
 #include "dtype_utils.cuh"
 #include "rt_internal.h"
+#include "sp_sync.cuh"
 
 namespace rt {
 
@@ -15,7 +16,7 @@ void set_last_error(const std::string& msg) { t_last_error = msg; }
 
 static std::map<std::string, int>& options() {
   static std::map<std::string, int> o = {{"force_simt", 0}, {"gemm_cta_group", 0}, {"attn_variant", 0},
-                                         {"profile", 0}, {"ln_warp_rows", 0}, {"gemv_single_row", 0}, {"gemm_debug", 0}, {"mod_inline", 0}, {"sp_replicate_mod", 0}, {"no_pdl", 0}, {"ln_impl", 0}, {"text_attn_simt", 0}, {"text_attn_mma", 0}, {"gemm_band", 0}, {"euler_dt_host", 0}};
+                                         {"profile", 0}, {"ln_warp_rows", 0}, {"gemv_single_row", 0}, {"gemm_debug", 0}, {"mod_inline", 0}, {"sp_replicate_mod", 0}, {"no_pdl", 0}, {"ln_impl", 0}, {"text_attn_simt", 0}, {"text_attn_mma", 0}, {"gemm_band", 0}, {"gemm_dyn_bn", 0}, {"sp_sync_kernels", 0}, {"euler_dt_host", 0}};
   return o;
 }
 int device_sm_count() {
@@ -64,24 +65,39 @@ static double gemm_flops(const GemmLaunch& g) {
   return f;
 }
 
-void launch_gemm(const GemmLaunch& g, cudaStream_t stream) {
+// `sync` (sequence-parallel mode): the kernel runs the phase barrier at its head and / or announces the next barrier's
+// epoch (sp_sync.cuh).  Only the tcgen05 kernels carry that; on any other path the same two steps run as stand-alone
+// kernels before / after the launch - every rank takes the same path (same shapes), so the epochs stay in step.
+void launch_gemm(const GemmLaunch& g, cudaStream_t stream, const SpSyncParams* sync) {
   if (!get_option("force_simt") && gemm_tc_supported(g, nullptr)) {
     ProfScope ps(PROF_GEMM_TC, gemm_flops(g), stream);
-    launch_gemm_tc(g, stream, get_option("gemm_cta_group"));
+    launch_gemm_tc(g, stream, get_option("gemm_cta_group"), sync);
   } else {
-    ProfScope ps(PROF_GEMM_SIMT, gemm_flops(g), stream);
-    launch_gemm_simt(g, stream);
+    if (sync) launch_sp_sync_before(*sync, stream);
+    {
+      ProfScope ps(PROF_GEMM_SIMT, gemm_flops(g), stream);
+      launch_gemm_simt(g, stream);
+    }
+    if (sync) launch_sp_sync_after(*sync, stream);
   }
 }
 
-void launch_attention(const AttnArgs& a, cudaStream_t stream) {
+void launch_attention(const AttnArgs& a, cudaStream_t stream, const SpSyncParams* sync) {
   const double flops = 4.0 * a.batch * a.heads * (double)a.S * a.S * a.hd;
-  if (!get_option("force_simt") && attention_tc_supported(a, nullptr)) {
+  const int variant = get_option("attn_variant");
+  if (!get_option("force_simt") && attention_tc_supported(a, nullptr) && (!sync || variant == 0)) {
     ProfScope ps(PROF_ATTN_TC, flops, stream);
-    launch_attention_tc(a, stream, get_option("attn_variant"));
+    launch_attention_tc(a, stream, variant, sync);
   } else {
-    ProfScope ps(PROF_ATTN_SIMT, flops, stream);
-    launch_attention_simt(a, stream);
+    if (sync) launch_sp_sync_before(*sync, stream);
+    if (!get_option("force_simt") && attention_tc_supported(a, nullptr)) {
+      ProfScope ps(PROF_ATTN_TC, flops, stream);
+      launch_attention_tc(a, stream, variant);
+    } else {
+      ProfScope ps(PROF_ATTN_SIMT, flops, stream);
+      launch_attention_simt(a, stream);
+    }
+    if (sync) launch_sp_sync_after(*sync, stream);
   }
 }
 

@@ -24,6 +24,7 @@
 #include "dtype_utils.cuh"
 #include "ptx_sm100.cuh"
 #include "rt_internal.h"
+#include "sp_sync.cuh"
 
 namespace rt {
 namespace {
@@ -58,6 +59,9 @@ struct AttnParams {
   bf16* sp_out[RT_SP_MAX_RANKS];
   // sequence-parallel mode, keys in the unsharded order (0 = off): text rows per shard, text key blocks in total
   int sp_txt, sp_txt_blocks;
+  // sequence-parallel phase barrier at the head of this kernel (sp_sync.cuh): the TMA warp waits for the peers' q | k | v
+  // stores; world == 0: none
+  SpSyncParams sync;
 };
 
 // Row coordinate(s) of key block j in the (rank-major) buffer.  Plain launches and sp_txt == 0: rows j*128 .. +127 as
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(kHalfRow ? kThreadsHalfRow : kThreads, 1)
       if (j + 1 < n_kv) { ptx::mbar_wait<kBackoff>(&s_full[1], (j + 1) & 1); trace(j, 25); }
     }
   }
+  if (warp == 0) spsync::sp_barrier_head(P.sync, lane, blockIdx.x == 0);  // the peers' q | k | v stores (sp_sync.cuh)
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     ptx::mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
@@ -1144,11 +1149,15 @@ bool attention_tc_supported(const AttnArgs& a, std::string* why) {
   return true;
 }
 
-void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant) {
+void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant, const SpSyncParams* sync) {
   std::string why;
   if (!attention_tc_supported(a, &why)) throw Error(RT_ERR_UNSUPPORTED, "tcgen05 attention: " + why);
   if (a.batch == 0) return;
   AttnParams P{};
+  if (sync) {
+    RT_REQUIRE(variant == 0, "attention: in-kernel phase synchronisation exists in the product kernel only");
+    P.sync = *sync;
+  }
   const int cols = a.ld;  // the map spans whole rows of the projection buffer; q / k / v are column offsets
   uint64_t dims[3] = {(uint64_t)cols, (uint64_t)a.S, (uint64_t)a.batch};
   uint64_t strides[2] = {(uint64_t)a.ld * 2, (uint64_t)a.batch_stride * 2};

@@ -23,6 +23,7 @@
 #include "dtype_utils.cuh"
 #include "ptx_sm100.cuh"
 #include "rt_internal.h"
+#include "sp_sync.cuh"
 
 namespace rt {
 
@@ -72,6 +73,8 @@ struct alignas(64) TcParams {
   // sequence-parallel scatter (rt_gemm_segment::scatter): destination buffers, columns per destination, row offset
   bf16* sp_out[RT_SP_MAX_RANKS];
   int sp_cols, sp_row0;
+  SpSyncParams sync;  // sequence-parallel phase synchronisation inside this kernel (sp_sync.cuh); world == 0: none
+  int bn;     // kDynN kernels: the tile width of THIS launch (a multiple of 32, <= 256); the last column tile may be partial
   int debug;  // option "gemm_debug": 1 = no epilogue, 2 = every k-block loads k = 0 (timing experiments, wrong
               // results); 4 = direct row-per-thread epilogue stores instead of the staged ones, 8 = L2 eviction
               // hints on the TMA loads (A/B, same results)
@@ -366,30 +369,36 @@ __device__ __forceinline__ void stage_get32(const uint8_t* stage, int lane, int 
   }
 }
 // g: (first row of this warp, first column of the 64-column group); 8 passes of 4 rows x 128 B
-__device__ __forceinline__ void stage_store(const uint8_t* stage, int lane, bf16* g, long long ld, int rows_valid) {
+// chunks: 16-byte chunks of the 64-column group that exist (8, or 4 when a kDynN tile ends on half a group)
+__device__ __forceinline__ void stage_store(const uint8_t* stage, int lane, bf16* g, long long ld, int rows_valid,
+                                            int chunks = 8) {
   const int rr = lane >> 3, ch = lane & 7;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + rr;
-    if (r < rows_valid)
+    if (r < rows_valid && ch < chunks)
       *reinterpret_cast<uint4*>(g + (long long)r * ld + ch * 8) =
           *reinterpret_cast<const uint4*>(stage + r * kStagePitch + ch * 16);
   }
 }
-__device__ __forceinline__ void stage_load(uint8_t* stage, int lane, const bf16* g, long long ld, int rows_valid) {
+__device__ __forceinline__ void stage_load(uint8_t* stage, int lane, const bf16* g, long long ld, int rows_valid,
+                                           int chunks = 8) {
   const int rr = lane >> 3, ch = lane & 7;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + rr;
-    if (r < rows_valid)
+    if (r < rows_valid && ch < chunks)
       *reinterpret_cast<uint4*>(stage + r * kStagePitch + ch * 16) =
           *reinterpret_cast<const uint4*>(g + (long long)r * ld + ch * 8);
   }
 }
 
-template <int BN>
+// kDynN: the tile is `ncols` (a multiple of 32) columns wide instead of BN - the launch's run-time tile width, or what
+// is left of the segment in its last column tile (single-segment BIAS / GELU / GATE_RESID / SCALE_MASK launches only).
+template <int BN, bool kDynN = false>
 __device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const TcProblem& pr, const TcSegment& sg,
-                                                     uint32_t tacc, int b, int m0w, int lane, int n0, uint8_t* stage) {
+                                                     uint32_t tacc, int b, int m0w, int lane, int n0, uint8_t* stage,
+                                                     int ncols = BN) {
   const int m = m0w + lane;
   const bool row_ok = m < pr.m_rows;
   const int rows_valid = min(max(pr.m_rows - m0w, 0), 32);
@@ -473,15 +482,18 @@ __device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const Tc
     if (pr.mask && row_ok) mk *= __bfloat162float(pr.mask[m]);
   }
   const bool resid = sg.mode == EPI_GATE_RESID || (sg.mode == EPI_SCALE_MASK && pr.accumulate);
+  const int n_groups = kDynN ? (ncols + 63) / 64 : BN / 64;
 #pragma unroll 1
-  for (int g = 0; g < BN / 64; ++g) {
+  for (int g = 0; g < n_groups; ++g) {
     bf16* gp = gptr(nl0 + g * 64);
+    const int n_half = kDynN ? min(2, (ncols - g * 64) / 32) : 2;
+    const int chunks = kDynN ? n_half * 4 : 8;
     if (resid) {
-      stage_load(stage, lane, gp, sg.out_ld, rows_valid);
+      stage_load(stage, lane, gp, sg.out_ld, rows_valid, chunks);
       __syncwarp();
     }
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < n_half; ++half) {
       const int c = g * 2 + half;
       float v[32];
       tmem_load_f32x32(tacc + c * 32, v);
@@ -521,15 +533,22 @@ __device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const Tc
       stage_put32(stage, lane, half, v);
     }
     __syncwarp();
-    stage_store(stage, lane, gp, sg.out_ld, rows_valid);
+    stage_store(stage, lane, gp, sg.out_ld, rows_valid, chunks);
     __syncwarp();
   }
 }
 
 // -------------------------------------------------------------------------------------------------
-template <int BN, int kCtaGroup>
+// kDynN (instantiated for BN = 256 only): the shared-memory ring and the accumulator stride keep the BN = 256 layout,
+// but a tile is P.bn <= 256 columns wide (TMA box, expected bytes, instruction descriptor and epilogue follow P.bn).
+// The host takes this form when a narrower tile fills the last wave better (launch_gemm_tc: sequence-parallel shards
+// of 1216 rows x N = 3072 are 120 tiles of 256 columns for 148 SMs, but 140 tiles of 224).  An output element's
+// arithmetic does not depend on the tile width: results are bit-identical to the BN = 256 kernel.
+template <int BN, int kCtaGroup, bool kDynN = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
   using C = Cfg<BN, kCtaGroup>;
+  static_assert(!kDynN || BN == 256, "the run-time tile width lives in the BN = 256 layout");
+  const int bn = kDynN ? P.bn : BN;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
@@ -591,14 +610,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // row tiles of its wave, and evict_first drops it before the neighbours have fetched it.
     const uint64_t pol_a = (P.debug & 8) ? ptx::kL2EvictLast : ptx::kL2EvictNormal;
     const uint64_t pol_w = (P.debug & 8) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
+    // sequence-parallel: A holds rows the peers' attention epilogues stored - the phase barrier runs here (sp_sync.cuh)
+    spsync::sp_barrier_head(P.sync, lane, blockIdx.x == 0);
     int stage = 0, phase = 0;
+    // bytes one CTA's two loads of a stage deliver (out-of-bounds box rows are zero-filled AND counted)
+    const uint32_t stage_tx = kDynN ? (uint32_t)(C::kABytes + (bn / kCtaGroup) * BK * 2) : (uint32_t)C::kStageBytes;
     for (int t = cluster_id; t < P.total_tiles; t += num_clusters) {
-      const TileCoord tc = decode_tile(P, t, BN, kRowsPerTile);
+      const TileCoord tc = decode_tile(P, t, bn, kRowsPerTile);
       const TcProblem& pr = P.prob[tc.p];
       const TcSegment& sg = pr.seg[tc.seg];
       const int a_row = pr.a_row0 + tc.m0 + (int)cta_rank * BM;
       const int a_b = pr.a_bcast ? 0 : tc.b;
-      const int w_row = (tc.n0 - sg.n_begin) + (int)cta_rank * C::kBRows;
+      const int w_row = (tc.n0 - sg.n_begin) + (int)cta_rank * (kDynN ? bn / kCtaGroup : C::kBRows);
       const int nkb = (pr.K + BK - 1) / BK;
       for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -613,20 +636,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const int tap = kb / pr.conv_kcb, cb = kb - tap * pr.conv_kcb;
             const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
             if constexpr (kCtaGroup == 1) {
-              ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
               ptx::tma_load_4d(&pr.tmA, &full_bar[stage], sa, cb * BK, x + dx, y + dy, a_b);
               ptx::tma_load_2d(&sg.tmW, &full_bar[stage], sb, k0, w_row);
             } else {
-              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
               ptx::tma_load_4d_2sm(&pr.tmA, &full_bar[stage], sa, cb * BK, x + dx, y + dy, a_b);
               ptx::tma_load_2d_2sm(&sg.tmW, &full_bar[stage], sb, k0, w_row);
             }
           } else if constexpr (kCtaGroup == 1) {
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
             ptx::tma_load_3d_hint(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b, pol_a);
             ptx::tma_load_2d_hint(&sg.tmW, &full_bar[stage], sb, k0, w_row, pol_w);
           } else {
-            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
             ptx::tma_load_3d_2sm_hint(&pr.tmA, &full_bar[stage], sa, k0, a_row, a_b, pol_a);
             ptx::tma_load_2d_2sm_hint(&sg.tmW, &full_bar[stage], sb, k0, w_row, pol_w);
           }
@@ -637,13 +660,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1 && leader) {
     // ===================== MMA issuer (leader CTA only; whole warp runs the loop, one elected lane issues) =====
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * kCtaGroup, BN, 0, 0);
+    const uint32_t idesc = ptx::make_idesc_bf16(BM * kCtaGroup, kDynN ? bn : BN, 0, 0);
     // stage 0 descriptors; a stage advances the 14-bit (addr >> 4) field (the ring is < 256 KB: no carry out of it)
     const uint64_t adesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a), 0, 1024);
     const uint64_t bdesc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b), 0, 1024);
     int stage = 0, phase = 0, iter = 0;
     for (int t = cluster_id; t < P.total_tiles; t += num_clusters, ++iter) {
-      const TileCoord tc = decode_tile(P, t, BN, kRowsPerTile);
+      const TileCoord tc = decode_tile(P, t, bn, kRowsPerTile);
       const int nkb = (P.prob[tc.p].K + BK - 1) / BK;
       const int as = iter & 1, aphase = (iter >> 1) & 1;
       ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -677,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int quad = warp & 3;
     int iter = 0;
     for (int t = cluster_id; t < P.total_tiles; t += num_clusters, ++iter) {
-      const TileCoord tc = decode_tile(P, t, BN, kRowsPerTile);
+      const TileCoord tc = decode_tile(P, t, bn, kRowsPerTile);
       const TcProblem& pr = P.prob[tc.p];
       const int as = iter & 1, aphase = (iter >> 1) & 1;
       ptx::mbar_wait(&tfull_bar[as], aphase);
@@ -686,6 +709,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const int m0w = tc.m0 + (int)cta_rank * BM + quad * 32;
       if (P.debug & 1) {
         // timing experiment: accumulators are dropped
+      } else if constexpr (kDynN) {
+        const TcSegment& sg = pr.seg[0];  // single-segment launches only
+        epilogue_tile_staged<BN, true>(P, pr, sg, tacc, tc.b, m0w, lane, tc.n0,
+                                       smem + C::kEpiStageOff + quad * kStageWarpBytes, min(bn, sg.n_end - tc.n0));
       } else if ((P.debug & 4) || pr.seg[tc.seg].out_f32) {
         epilogue_tile<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w + lane, tc.n0);
       } else {
@@ -846,12 +873,12 @@ bool gemm_tc_supported(const GemmLaunch& L, std::string* why) {
   return true;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool kDynN = false>
 static void launch_cfg(const TcParams& P, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN, CG>;
   static PerDeviceOnce attr_set;
   if (attr_set.first()) {
-    RT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, kDynN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::kSmemBytes));
   }
   int clusters = num_sms / CG;
@@ -870,11 +897,45 @@ static void launch_cfg(const TcParams& P, int num_sms, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = get_option("no_pdl") ? 1 : 2;
-  RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, P));
+  RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, kDynN>, P));
   count_launch();
 }
 
-void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_group) {
+// Run-time tile width (kDynN kernels).  A persistent launch takes ceil(tiles / slots) tile times; a tile's time grows
+// with its width as (bn + 64) - measured, profiles/r2_gemm_dyn_tile_width.txt: a 128 x N x 16 tcgen05.mma takes
+// ~23 + 0.41 N cycles, and every tile pays the same A traffic - so 256-wide tiles that leave the last wave mostly empty
+// lose to narrower ones that fill it (1216 rows x N = 3072 on CTA pairs: 60 tiles of 256 for 74 pairs, or 70 tiles of
+// 224: measured 36.1 -> 30.4 us at K = 3072, 102.9 -> 90.2 us at K = 15360), while a narrower tile that only adds waves
+// loses.  Only
+// launches whose every problem is ONE segment with a column-local epilogue qualify (no per-head RMSNorm, no scatter to
+// 128-column destinations, no fp32 output), and only a clear win (>= 5 %) switches.  Returns 256 to keep the static form.
+static int pick_dyn_bn(const GemmLaunch& L, int cg, int num_sms) {
+  const int opt = get_option("gemm_dyn_bn");  // 0 = auto, -1 = never, n = force tiles of n columns where eligible
+  if (opt < 0 || (get_option("gemm_debug") & 4)) return 256;
+  for (int p = 0; p < L.nprob; ++p) {
+    const GemmProblem& G = L.prob[p];
+    if (G.nseg != 1 || G.conv_w > 0) return 256;
+    const GemmSegment& S = G.seg[0];
+    if (S.scatter || S.out_f32 || S.mode == EPI_QKNORM_ROPE || (S.n_end - S.n_begin) % 32) return 256;
+  }
+  const int slots = num_sms / cg;
+  auto cost = [&](int bn) {
+    long long t = 0;
+    for (int p = 0; p < L.nprob; ++p)
+      t += (long long)((L.prob[p].m_rows + BM * cg - 1) / (BM * cg)) * ((gemm_total_n(L.prob[p]) + bn - 1) / bn) * L.batch;
+    return (double)((t + slots - 1) / slots) * (bn + 64);
+  };
+  if (opt > 0) return (opt % 32 == 0 && opt >= 64 * cg && opt <= 256) ? opt : 256;
+  int best = 256;
+  double best_cost = cost(256) * 0.95;
+  for (int bn : {224, 192, 160}) {
+    const double c = cost(bn);
+    if (c < best_cost) { best = bn; best_cost = c; }
+  }
+  return best;
+}
+
+void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_group, const SpSyncParams* sync) {
   std::string why;
   if (!gemm_tc_supported(L, &why)) throw Error(RT_ERR_UNSUPPORTED, "tcgen05 GEMM: " + why);
   if (L.batch == 0) return;
@@ -914,7 +975,14 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
     }
   }
 
+  // narrower run-time tiles when they fill the last wave better (bit-identical results; see pick_dyn_bn)
+  const int dyn_bn = bn == 256 ? pick_dyn_bn(L, cg, num_sms) : 256;
+  const bool dyn = dyn_bn != 256;
+  if (dyn) bn = dyn_bn;
+
   TcParams P{};
+  if (sync) P.sync = *sync;
+  P.bn = bn;
   P.nprob = L.nprob;
   P.batch = L.batch;
   P.rope = reinterpret_cast<const float2*>(L.rope);
@@ -961,7 +1029,7 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
     }
     const int rows_per_tile = BM * cg;
     T.tiles_m = (G.m_rows + rows_per_tile - 1) / rows_per_tile;
-    T.tiles_n = gemm_total_n(G) / bn;
+    T.tiles_n = (gemm_total_n(G) + bn - 1) / bn;  // exact unless dyn (pick_bn)
     T.tile_base = tile_base;
     T.num_tiles = T.tiles_m * T.tiles_n * L.batch;
     // option "gemm_band": 0 = auto, -1 = never, n > 0 = bands of n row tiles for every problem (tests, A/B)
@@ -982,6 +1050,11 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
   P.total_tiles = tile_base;
   if (P.total_tiles == 0) return;
 
+  if (dyn) {
+    if (cg == 1) launch_cfg<256, 1, true>(P, num_sms, stream);
+    else launch_cfg<256, 2, true>(P, num_sms, stream);
+    return;
+  }
 #define RT_GEMM_CASE(BN_, CG_) \
   if (bn == BN_ && cg == CG_) { launch_cfg<BN_, CG_>(P, num_sms, stream); return; }
   RT_GEMM_CASE(256, 1)

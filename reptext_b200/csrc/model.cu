@@ -18,6 +18,7 @@
 
 #include "dtype_utils.cuh"
 #include "rt_internal.h"
+#include "sp_sync.cuh"
 
 namespace rt {
 namespace {
@@ -205,6 +206,16 @@ struct Ctx {
   bool inv_on = false, inv_hit = false;  // step-invariant cache in use / its contents are current (StepInvariants)
   bool mod_sharded = false;       // this forward computed only its row shard of the AdaLN vectors (peer stores)
   bool mod_join_pending = false;  // the AdaLN vectors of blocks 1.. are still being computed on the side stream
+  // Real multi-process group: the two phase barriers of a block run INSIDE the consuming kernels (sp_sync.cuh): the QKV
+  // GEMM announces the pre-attention barrier's epoch, attention runs that barrier at its head and announces the next,
+  // the output projection runs the post-attention barrier at its head - unless option "sp_sync_kernels" asks for the
+  // stand-alone barrier kernels (A/B).
+  bool fused_sync = false;
+  SpSyncParams sync_announce{}, sync_attn{}, sync_post{};
+  const SpSyncParams* sync(int which /*0 QKV GEMM, 1 attention, 2 output projection*/) const {
+    if (!fused_sync) return nullptr;
+    return which == 0 ? &sync_announce : which == 1 ? &sync_attn : &sync_post;
+  }
   long long sD() const { return (long long)S * D; }
 };
 
@@ -349,7 +360,7 @@ void run_attention(const Ctx& c) {
     t.sp_txt_rows = c.T;  // keys in the unsharded order when the shard sizes allow it: same bits as on one GPU
     for (int i = 0; i < c.P; ++i) t.sp_out[i] = c.peer_cat[i];
   }
-  launch_attention(t, c.st);
+  launch_attention(t, c.st, c.sync(1));  // sequence-parallel: the pre-attention barrier runs at its head
 }
 
 // FluxTransformerBlock (diffusers).  `extra`: ControlNet residual added to the image rows
@@ -380,7 +391,7 @@ void double_block_pre(const Ctx& c, const DoubleBlk& k) {
     pi.seg[0] = make_qkv_seg(c, k.q, 0, k.nq);
     pi.seg[1] = make_qkv_seg(c, k.k, 1, k.nk);
     pi.seg[2] = make_qkv_seg(c, k.v, 2, nullptr);
-    launch_gemm(L, c.st);
+    launch_gemm(L, c.st, c.sync(0));  // sequence-parallel: announces the pre-attention barrier's epoch
   }
 }
 
@@ -401,7 +412,7 @@ void double_block_post(const Ctx& c, const DoubleBlk& k, const void* extra) {
     L.prob[1].nseg = 1;
     L.prob[1].seg[0] = make_seg(k.o, 0, EPI_GATE_RESID, w.x, sD, D, 0);
     L.prob[1].gate = mi + 2 * D; L.prob[1].gate_ld = ld;
-    launch_gemm(L, c.st);
+    launch_gemm(L, c.st, c.sync(2));  // sequence-parallel: the post-attention barrier runs at its head
   }
   {
     LnModGroup g[2] = {{0, T, mc + 3 * D, mc + 4 * D, ld}, {T, S, mi + 3 * D, mi + 4 * D, ld}};
@@ -460,7 +471,7 @@ void single_block_pre(const Ctx& c, const SingleBlk& k) {
     p.seg[1] = make_qkv_seg(c, k.k, 1, k.nk);
     p.seg[2] = make_qkv_seg(c, k.v, 2, nullptr);
     p.seg[3] = make_seg(k.mlp, 3 * D, EPI_GELU, w.cat, s5D, 5 * D, D);
-    launch_gemm(L, c.st);
+    launch_gemm(L, c.st, c.sync(0));  // sequence-parallel: announces the pre-attention barrier's epoch
   }
 }
 
@@ -480,7 +491,7 @@ void single_block_post(const Ctx& c, const SingleBlk& k, const void* extra) {
     if (extra) {
       p.extra = extra; p.extra_batch_stride = (long long)N * D; p.extra_ld = D; p.extra_row0 = T;
     }
-    launch_gemm(L, c.st);
+    launch_gemm(L, c.st, c.sync(2));  // sequence-parallel: the post-attention barrier runs at its head
   }
 }
 
@@ -521,6 +532,18 @@ Ctx begin_forward(rt_model* m, const rt_forward_args* a) {
       c.peer_qkv[i] = pw.qkv;
       c.peer_cat[i] = pw.cat;
       c.peer_mod[i] = pw.mod;
+    }
+    if (!g.lockstep && !get_option("sp_sync_kernels")) {
+      c.fused_sync = true;
+      SpSyncParams d{};
+      d.world = g.world;
+      d.rank = g.rank;
+      for (int i = 0; i < g.world; ++i) d.flags[i] = g.peer_flags[i];
+      c.sync_announce = c.sync_attn = c.sync_post = d;
+      c.sync_announce.announce_word = 11;
+      c.sync_attn.barrier_word = 11;
+      c.sync_attn.announce_word = 12;
+      c.sync_post.barrier_word = 12;
     }
   }
   // Step-invariant cache (one model per call only: lock-step ranks share the model object)
@@ -567,12 +590,16 @@ Ctx begin_forward(rt_model* m, const rt_forward_args* a) {
 void phase_sync(const std::vector<Ctx>& cs) {
   if (cs.size() == 1 && cs[0].P > 1 && !cs[0].sp->lockstep) launch_sp_barrier(*cs[0].sp, cs[0].st);
 }
+// between pre | attention | post: inside the neighbouring kernels when the context says so (Ctx::fused_sync)
+void block_phase_sync(const std::vector<Ctx>& cs) {
+  if (!(cs.size() == 1 && cs[0].fused_sync)) phase_sync(cs);
+}
 template <class Pre, class Post>
 void run_block(std::vector<Ctx>& cs, Pre pre, Post post) {
   for (size_t i = 0; i < cs.size(); ++i) pre(cs[i], i);
-  phase_sync(cs);
+  block_phase_sync(cs);
   for (size_t i = 0; i < cs.size(); ++i) run_attention(cs[i]);
-  phase_sync(cs);
+  block_phase_sync(cs);
   for (size_t i = 0; i < cs.size(); ++i) post(cs[i], i);
   // after the FIRST block (no-op later): the AdaLN vectors of blocks 1.. are needed from here on
   bool sharded = false;

@@ -88,8 +88,11 @@ int gemm_total_n(const GemmProblem& p);
 // kernels (each launches on `stream`; throws rt::Error)
 void launch_gemm_simt(const GemmLaunch& g, cudaStream_t stream);
 bool gemm_tc_supported(const GemmLaunch& g, std::string* why);
-void launch_gemm_tc(const GemmLaunch& g, cudaStream_t stream, int force_cta_group /*0 auto,1,2*/);
-void launch_gemm(const GemmLaunch& g, cudaStream_t stream);  // picks tcgen05 when supported
+struct SpSyncParams;  // sp_sync.cuh: sequence-parallel phase synchronisation inside the tcgen05 kernels (null: none)
+void launch_gemm_tc(const GemmLaunch& g, cudaStream_t stream, int force_cta_group /*0 auto,1,2*/,
+                    const SpSyncParams* sync = nullptr);
+// picks tcgen05 when supported; `sync` on the other paths becomes stand-alone kernels (same protocol)
+void launch_gemm(const GemmLaunch& g, cudaStream_t stream, const SpSyncParams* sync = nullptr);
 extern long long g_launch_count;                             // kernels launched by this library
 
 // ------------------------------------------------------------------ other kernels
@@ -107,8 +110,8 @@ void launch_qknorm_rope(int dtype, void* buf, long long bs, int ld, int col0, in
 using AttnArgs = rt_attention_args;
 void launch_attention_simt(const AttnArgs& a, cudaStream_t stream);
 bool attention_tc_supported(const AttnArgs& a, std::string* why);
-void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant);
-void launch_attention(const AttnArgs& a, cudaStream_t stream);
+void launch_attention_tc(const AttnArgs& a, cudaStream_t stream, int variant, const SpSyncParams* sync = nullptr);
+void launch_attention(const AttnArgs& a, cudaStream_t stream, const SpSyncParams* sync = nullptr);
 
 // grouped GEMV: out[b, off + r] = dot(act(x[b, :]), W[r, :]) + bias[r]   (fp32 in/out, weights dtype T)
 struct GemvJob {
@@ -147,6 +150,8 @@ void launch_copy_rows(int dtype, const void* src, long long s_bs, int s_ld, int 
 
 // cross-GPU flag barrier of the sequence-parallel mode (sp.cu)
 void launch_sp_barrier(const rt_sp_group& g, cudaStream_t stream);
+void launch_sp_sync_before(const SpSyncParams& s, cudaStream_t stream);  // the in-kernel form's barrier / announcement
+void launch_sp_sync_after(const SpSyncParams& s, cudaStream_t stream);   // as kernels (launches off the tcgen05 path)
 
 // ------------------------------------------------------------------ per-class device timing (option "profile")
 // When the option is on, every launch of a class is bracketed by CUDA events on ITS stream; bench.py reads

@@ -7,6 +7,8 @@
 
 #include "dtype_utils.cuh"
 #include "rt_internal.h"
+#include "sp_sync.cuh"
+#include "sp_sync.cuh"
 
 namespace rt {
 namespace {
@@ -93,6 +95,25 @@ void launch_sp_barrier(const rt_sp_group& g, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = get_option("no_pdl") ? 0 : 1;
   RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sp_barrier_kernel, p));
+  count_launch();
+}
+
+// The in-kernel form's two steps as kernels, for launches that do not take the tcgen05 path (sp_sync.cuh): the barrier
+// kernel draws the same epoch the announced word holds (word 8 + 1), the announcement is a one-thread kernel.
+__global__ void sp_announce_kernel(unsigned long long* mine, int word) { mine[word] = mine[8] + 1; }
+
+void launch_sp_sync_before(const SpSyncParams& s, cudaStream_t stream) {
+  if (s.world == 0 || s.barrier_word == 0) return;
+  rt_sp_group g{};
+  g.world = s.world;
+  g.rank = s.rank;
+  for (int i = 0; i < s.world && i < RT_SP_MAX_RANKS; ++i) g.peer_flags[i] = s.flags[i];
+  launch_sp_barrier(g, stream);
+}
+void launch_sp_sync_after(const SpSyncParams& s, cudaStream_t stream) {
+  if (s.world == 0 || s.announce_word == 0) return;
+  sp_announce_kernel<<<1, 1, 0, stream>>>(s.flags[s.rank], s.announce_word);
+  RT_CHECK_CUDA(cudaGetLastError());
   count_launch();
 }
 

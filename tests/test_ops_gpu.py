@@ -148,6 +148,45 @@ def test_gemm_banded_tile_order(ops, case, band):
         L.set_option("gemm_band", 0)
 
 
+@pytest.mark.parametrize("bn", [224, 192, 160])
+@pytest.mark.parametrize("impl", [2, 3], ids=["tc1", "tc2"])
+@pytest.mark.parametrize("mode", ["bias", "gelu", "gate", "mask"])
+def test_gemm_runtime_tile_width(ops, bn, impl, mode):
+    """Option gemm_dyn_bn: single-segment launches on tiles of a run-time width (gemm_tc_kernel<256, cg, true>), the last
+    column tile partial (768 = 3 x 224 + 96 = 4 x 160 + 128: whole and half 64-column store groups); against the fp32
+    statement of the epilogue, the untouched window, and two problems with different weights in one launch."""
+    from reptext_b200 import _lib as L
+    L.set_option("gemm_dyn_bn", bn)
+    try:
+        test_gemm(ops, ("dyn", torch.bfloat16, impl, 2, 300, [768], 320, [mode]))
+        test_gemm_two_problems_joint_rows(ops, impl)
+    finally:
+        L.set_option("gemm_dyn_bn", 0)
+
+
+@pytest.mark.parametrize("shape", [(1216, 3072, 3072), (1152, 12288, 3072), (1216, 3072, 15360), (2432, 3072, 3072)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_gemm_auto_tile_width_on_shard_shapes(ops, shape):
+    """The row counts of the sequence-parallel shards (1216 = 9728 / 8 rows per rank, 2432 at four ranks) leave the last
+    wave of 256-wide tiles mostly empty; such launches pick a narrower run-time tile on their own.  Bit-identical to the
+    256-wide kernel (an element's arithmetic does not depend on the tile that holds it), in place (gate + residual)."""
+    from reptext_b200 import _lib as L
+    dt = torch.bfloat16
+    M, N, K = shape
+    A, W = _rand((1, M, K), dt, 1), _rand((N, K), dt, 2, K ** -0.5)
+    b, gate, res0 = _rand((N,), dt, 3, 0.1), _rand((1, N), torch.float32, 4), _rand((1, M, N), dt, 5)
+    outs = []
+    for opt in (0, -1, 224):
+        L.set_option("gemm_dyn_bn", opt)
+        out = res0.clone()
+        ops.gemm([ops.Problem(A=A, segs=[ops.Segment(W=W, bias=b, out=out, mode=L.EPI_GATE_RESID)], gate=gate)], 1, dt)
+        outs.append(out)
+    L.set_option("gemm_dyn_bn", 0)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    want = res0[:, :256].float() + gate[:, None] * (A[:, :256].float() @ W.float().t() + b.float())
+    assert rel_l2(outs[0][:, :256].float(), want) < 4e-3
+
+
 def test_gemm_auto_band_on_the_long_k_shape(ops):
     """(4608, 3072, 15360): A is 141 MB, three waves - the launch bands itself (6 row tiles); bit-identical to the
     row-tiles-fastest order (the order changes which CTA computes a tile, not the arithmetic of a tile)."""
