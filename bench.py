@@ -498,6 +498,8 @@ def run_b200(args, wl):
     else:
         raise SystemExit("bench workloads use the FLUX.1-dev text widths (4096 / 768)")
     pipe = FluxControlNetPipeline(sch, vae, clip, tok, t5, tok2, tr, cn)
+    if args.no_mod_table:
+        pipe.precompute_modulation = False
     pipe.skip_unconsumed_controlnet_blocks = not args.full_controlnet
     mask = pipe._regional_masks([mask_img], dev, dt)[0]
     lat, pe, po, cond = [t.to(dev, non_blocking=True) for t in (h_lat, h_pe, h_po, h_cond)]
@@ -741,6 +743,12 @@ def run_b200(args, wl):
                                                       "context_embedder, the rotary table and the guidance / pooled "
                                                       "linears, like the reference); ON in `e2e`, the pipelines' default "
                                                       "(once per image, bit-identical latents, SURVEY 8f.2: 0.15 % of a step)"),
+                                modulation_table=("OFF in the device-timed loop (`value`: every step runs the timestep / "
+                                                  "guidance / pooled embedders and streams the 6.5 GB of AdaLN weights, "
+                                                  "like the reference); ON in `e2e`, the pipelines' default: the AdaLN "
+                                                  "vectors of all 28 steps are computed in one pass inside the timed "
+                                                  "call, before the loop (weights read once per image, bit-identical "
+                                                  "latents, tests/test_pipeline_gpu.py)"),
                                 images_per_s=value / STEPS_PER_IMAGE,
                                 tensor_util_whole_step=flops / gpus_per_sample / (step_ms / 1000.0) / 1e12 / pk["bf16_sustained"],
                                 finite_output=finite),
@@ -770,6 +778,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the pipeline end-to-end leg (profiling runs only)")
     ap.add_argument("--full-controlnet", action="store_true", help="run every ControlNet block like the reference (A/B of the unconsumed-block skip)")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-mod-table", action="store_true", help="e2e leg: AdaLN vectors computed per step instead of once per image (A/B of pipe.precompute_modulation)")
     ap.add_argument("--no-sp", action="store_true", help="skip the cfg5 sequence-parallel record of multi-GPU runs")
     args = ap.parse_args()
     wl = workload(args.workload)

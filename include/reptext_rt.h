@@ -178,6 +178,24 @@ RT_API int rt_controlnet_set_live(rt_model* m, int live_layers, int live_single_
  * the lock-step entry points.  The first forward after an invalidation may allocate: keep it out of a stream capture. */
 RT_API int rt_model_set_step_invariant_cache(rt_model* m, int mode);
 
+/* The AdaLN vectors of ALL the steps of an image in one pass.  What a forward derives from (timestep, guidance,
+ * pooled_projections) alone - CombinedTimestepGuidanceTextProjEmbeddings (RepText/controlnet_flux.py:282-291) and the
+ * AdaLayerNorm linears of every block, 6.5 GB of weights streamed per FLUX.1-dev forward - does not depend on the
+ * latents, and a denoising loop knows its timesteps before it starts (pipeline_flux_controlnet.py:1017: `for i, t in
+ * enumerate(timesteps)`).  rt_model_build_modulation_table computes that chain for `steps` x `batch` rows at once into
+ * `table` - caller-owned device memory of rt_model_modulation_table_bytes(m, steps, batch) bytes, 256-byte aligned, that
+ * must stay alive and untouched while a row is selected (timesteps / guidance: [steps * batch] in the model dtype, row s * batch + b = what step s passes
+ * for batch element b, i.e. timestep / 1000; pooled_projections: [steps * batch, pooled_projection_dim]); the weights
+ * are read from DRAM once instead of once per step.  rt_model_select_modulation(m, s) makes the following forwards of
+ * this model (batch must match) use row s and skip the chain (their `timestep` / `guidance` / `pooled_projections`
+ * arguments are then ignored - the caller owns the correspondence); -1 returns to computing per forward (the C-ABI
+ * default).  Every row holds the bits the forward's own chain produces: results are bit-identical. */
+RT_API int64_t rt_model_modulation_table_bytes(const rt_model* m, int steps, int batch);
+RT_API int rt_model_build_modulation_table(rt_model* m, const void* timesteps, const void* guidance,
+                                           const void* pooled_projections, int steps, int batch, void* table,
+                                           int64_t table_bytes, void* stream);
+RT_API int rt_model_select_modulation(rt_model* m, int step);
+
 /* FluxTransformer2DModel.forward (diffusers 0.36.0) as called at
  * RepText/pipeline_flux_controlnet.py:1092-1104.  controlnet_*_samples are host arrays of device
  * pointers to [batch, n_img, D] tensors (or NULL / 0); sample i//ceil(L/n) is added after block i,

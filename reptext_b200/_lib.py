@@ -25,6 +25,7 @@ EXPORTS = [
     "rt_profile_reset", "rt_profile_read",
     "rt_model_create", "rt_model_set_weight", "rt_model_finalize", "rt_model_destroy", "rt_model_workspace_bytes",
     "rt_controlnet_forward", "rt_transformer_forward", "rt_controlnet_set_live", "rt_model_set_step_invariant_cache",
+    "rt_model_modulation_table_bytes", "rt_model_build_modulation_table", "rt_model_select_modulation",
     "rt_controlnet_forward_lockstep", "rt_transformer_forward_lockstep",
     "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free", "rt_sp_barrier", "rt_sp_status", "rt_sp_reset",
     "rt_euler_step", "rt_cfg_combine", "rt_cfg_euler_step", "rt_mask_scale_add", "rt_glyph_init_blend",
@@ -152,6 +153,11 @@ def lib() -> C.CDLL:
                                          C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
     L.rt_controlnet_set_live.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.rt_model_set_step_invariant_cache.argtypes = [C.c_void_p, C.c_int]
+    L.rt_model_modulation_table_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.rt_model_modulation_table_bytes.restype = C.c_int64
+    L.rt_model_build_modulation_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                  C.c_int64, C.c_void_p]
+    L.rt_model_select_modulation.argtypes = [C.c_void_p, C.c_int]
     L.rt_controlnet_forward_lockstep.argtypes = [C.c_void_p, C.c_int, C.POINTER(ControlNetCall)]
     L.rt_transformer_forward_lockstep.argtypes = [C.c_void_p, C.c_int, C.POINTER(TransformerCall)]
     L.rt_ipc_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]

@@ -78,6 +78,10 @@ class RepTextPipelineBase(DiffusionPipeline):
     # what a forward derives from the prompt embeddings / ids alone is computed once per image, not once per step
     # (models.set_step_invariant_cache; bit-identical latents)
     cache_step_invariants = True
+    # the AdaLN vectors of all steps of an image computed in ONE pass before the loop (models.build_modulation_table:
+    # the loop's timesteps are known up front; 6.5 GB of modulation weights read once instead of 28 times; bit-identical
+    # latents)
+    precompute_modulation = True
 
     # ---- RepText/infer.py:31-33: FluxControlNetPipeline.from_pretrained(base_model, controlnet=..., torch_dtype=...) --
     @classmethod
@@ -396,10 +400,20 @@ class RepTextPipelineBase(DiffusionPipeline):
                 control_image_inpaint = shard_tokens(control_image_inpaint, r, w)
             sp_kw = dict(sp=sp)
             common.update(sp_kw)
+        mod_nets = []
+        if self.precompute_modulation and len(timesteps) > 0:
+            # what every step below passes as `timestep` / `guidance` / `pooled_projections`, for all steps at once
+            ts_all = torch.stack([t.expand(latents.shape[0]).to(latents.dtype) / 1000 for t in timesteps])
+            g_all = guidance_const.expand(latents.shape[0]) if guidance_const is not None else None
+            mod_nets = [n for n in nets if hasattr(n, "build_modulation_table")]
+            for net in mod_nets:
+                net.build_modulation_table(ts_all, g_all, pooled_prompt_embeds)
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(timesteps):
                 if self.interrupt:
                     continue
+                for net in mod_nets:
+                    net.select_modulation(i)
                 timestep = t.expand(latents.shape[0]).to(latents.dtype)
                 guidance = guidance_const.expand(latents.shape[0]) if guidance_const is not None else None
                 step_kw = dict(hidden_states=latents, timestep=timestep / 1000, guidance=guidance,
@@ -438,6 +452,8 @@ class RepTextPipelineBase(DiffusionPipeline):
                     sp.check()       # a timed-out barrier surfaces within the step (the abort is sticky on the device)
                 if i == len(timesteps) - 1 or ((i + 1) > num_warmup_steps and (i + 1) % self.scheduler.order == 0):
                     progress_bar.update()
+        for net in mod_nets:
+            net.select_modulation(None)
         for net in nets:
             net.release_step_invariants()   # the prompt tensors are no longer pinned; the next image starts cold
         if sp is not None:

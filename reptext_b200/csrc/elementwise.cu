@@ -808,6 +808,94 @@ __global__ void __launch_bounds__(256) gemv_grouped_rows_kernel(const float* __r
   }
 }
 
+// The same rows for MANY activation vectors (the AdaLN vectors of all the steps of an image in one pass,
+// rt_model_build_modulation_table): kR consecutive rows per warp as above, and the warp walks the batch in tiles of NB
+// vectors - the first tile streams the rows' weights from HBM, the others find them in L1 / L2 (kR rows of K bf16 =
+// 24 KB per warp), so the 6.5 GB of AdaLN weights are read from DRAM once for the whole table instead of once per step.
+// Every (row, vector) accumulator sees the same operations in the same order as in gemv_grouped_rows_kernel: the table
+// holds the bits a per-step launch would produce (tests/test_model_gpu.py).
+template <typename T, int NB, int kR>
+__global__ void __launch_bounds__(256) gemv_grouped_rows_table_kernel(const float* __restrict__ x, int x_ld, int batch, int K,
+                                                                      const GemvJob* __restrict__ jobs,
+                                                                      const int* __restrict__ prefix, int njobs,
+                                                                      int total_rows, float* __restrict__ out, int out_ld) {
+  constexpr int N = VecT<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = (blockIdx.x * wpb + (threadIdx.x >> 5)) * kR; row < total_rows; row += gridDim.x * wpb * kR) {
+    int lo = 0, hi = njobs - 1;  // last job with prefix[j] <= row
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (prefix[mid] <= row) lo = mid; else hi = mid - 1;
+    }
+    const GemvJob J = jobs[lo];
+    const int r = row - prefix[lo];
+    const T* w = reinterpret_cast<const T*>(J.W) + (long long)r * K;
+    for (int b0 = 0; b0 < batch; b0 += NB) {
+      float acc[kR][NB];
+#pragma unroll
+      for (int i = 0; i < kR; ++i)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[i][b] = 0.f;
+      for (int c = lane * N; c < K; c += 32 * N) {
+        float wv[kR][N];
+#pragma unroll
+        for (int i = 0; i < kR; ++i) ldvec(w + (long long)i * K + c, wv[i]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int bb = b0 + b < batch ? b0 + b : batch - 1;  // (tail tile: a valid vector again, result dropped)
+          const float* xb = x + (long long)bb * x_ld + c;
+#pragma unroll
+          for (int j = 0; j < N; j += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(xb + j);
+#pragma unroll
+            for (int i = 0; i < kR; ++i)
+              acc[i][b] += wv[i][j] * xv.x + wv[i][j + 1] * xv.y + wv[i][j + 2] * xv.z + wv[i][j + 3] * xv.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kR; ++i)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[i][b] = warp_sum(acc[i][b]);
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+          const float bias = J.bias ? to_f(reinterpret_cast<const T*>(J.bias)[r + i]) : 0.f;
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            if (b0 + b < batch) out[(long long)(b0 + b) * out_ld + J.out_off + r + i] = acc[i][b] + bias;
+        }
+      }
+    }
+  }
+}
+
+#define RT_TABLE_CASE(NB_, KR_) \
+    gemv_grouped_rows_table_kernel<T, NB_, KR_><<<blocks, threads, 0, stream>>>(x, x_ld, batch, K, jobs_dev, prefix_dev, njobs, \
+                                                                              total_rows, out, out_ld)
+void launch_gemv_grouped_table(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
+                               const int* prefix_dev, int njobs, int total_rows, float* out, int out_ld,
+                               cudaStream_t stream) {
+  if (batch == 0 || total_rows == 0) return;
+  ProfScope ps(PROF_GEMV, (double)total_rows * K * dtype_size(wdtype), stream);
+  RT_REQUIRE(x_ld % 4 == 0 && total_rows % 4 == 0, "gemv table: x_ld and the row count must be multiples of 4");
+  const int threads = 256, wpb = threads / 32;
+  // 8 rows x 4 vectors per warp pass: measured best of (rows, vectors) = (4, 7) 16.8 ms, (4, 14) 10.0, (8, 7) 9.8,
+  // (8, 4) 7.8 for the FLUX.1-dev transformer's 28-step table (profiles/r2_modulation_table.txt); (4, 7) when a model's
+  // row count is not a multiple of 8
+  const int kRr = total_rows % 8 == 0 ? 8 : 4;
+  int blocks = (total_rows / kRr + wpb - 1) / wpb;
+  const int cap = sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  RT_DISPATCH_DTYPE(wdtype, T, {
+    RT_REQUIRE(K % VecT<T>::N == 0, "gemv: K must be a multiple of the vector width");
+    if (kRr == 8) RT_TABLE_CASE(4, 8);
+    else RT_TABLE_CASE(7, 4);
+    RT_POST_LAUNCH();
+  });
+}
+
 void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
                          const int* prefix_dev, int njobs, int total_rows, float* out, int out_ld, int silu_out,
                          int accumulate, cudaStream_t stream, bool rows_multiple_of_4, int row_base,

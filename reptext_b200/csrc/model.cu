@@ -93,6 +93,17 @@ struct rt_model {
     float* hid = nullptr;    // [B, 3 D]: h_t (every step) | h_g | h_p (kept)
   } inv;
 
+  // AdaLN vectors of ALL the steps of an image (rt_model_build_modulation_table): the timesteps of a denoising loop are
+  // known before it starts, the guidance and pooled vectors do not change - so the time / guidance / pooled-text MLPs and
+  // the AdaLN linears of every block (6.5 GB of weights per forward, a GEMV) can run for all steps in ONE pass that
+  // reads the weights once.  A forward with a selected row (rt_model_select_modulation) points its `mod` at the table
+  // and skips that whole chain.
+  struct ModTable {
+    float* mod = nullptr;  // [rows, mod_total], inside the caller's buffer
+    int steps = 0, batch = 0;
+    int sel = -1;          // the step the next forwards use; -1: compute per forward
+  } modtab;
+
   ~rt_model() {
     if (inv.buf) cudaFree(inv.buf);
     if (jobs_dev) cudaFree(jobs_dev);
@@ -297,6 +308,60 @@ void join_modulation(Ctx& c) {
   if (!c.mod_join_pending) return;
   RT_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.m.ev_join, 0));
   c.mod_join_pending = false;
+}
+
+// The chain of time_text_and_modulation for `rows` = steps x batch (timestep, guidance, pooled) triples at once, into
+// model-owned memory.  Same kernels and the same arithmetic per row as a forward's own chain (the small MLPs in batch
+// passes, the AdaLN linears through the table GEMV that keeps every accumulator's operation order): a forward that uses
+// row i is bit-identical to one that computes it.
+size_t modulation_table_layout(const rt_model& m, size_t rows, size_t* o /*[7]*/) {
+  const size_t D = m.D, P = m.cfg.pooled_projection_dim;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t at = off; off = align_up(off + bytes); return at; };
+  const size_t at[7] = {take(rows * 256 * 4), take(rows * 256 * 4), take(rows * align_up(P, 4) * 4), take(rows * 3 * D * 4),
+                        take(rows * D * 4), take(rows * D * 4), take(rows * m.mod_total * 4)};
+  if (o) for (int i = 0; i < 7; ++i) o[i] = at[i];
+  return off;
+}
+
+void build_modulation_table(rt_model& m, const void* timesteps, const void* guidance, const void* pooled, int steps,
+                            int batch, char* buf, size_t buf_bytes, cudaStream_t st) {
+  const int D = m.D, P = m.cfg.pooled_projection_dim, dt = m.cfg.dtype;
+  const bool has_g = m.cfg.guidance_embeds != 0;
+  const size_t rows = (size_t)steps * batch;
+  rt_model::ModTable& t = m.modtab;
+  t.sel = -1;
+  t.mod = nullptr;
+  t.steps = 0;
+  size_t o[7];
+  RT_REQUIRE(buf && (reinterpret_cast<uintptr_t>(buf) & 255) == 0 && buf_bytes >= modulation_table_layout(m, rows, o),
+             "build_modulation_table: buffer missing, not 256-byte aligned or too small (rt_model_modulation_table_bytes)");
+  const size_t o_sin_t = o[0], o_sin_g = o[1], o_pool = o[2], o_hid = o[3], o_temb = o[4], o_temb_s = o[5], o_mod = o[6];
+  float* sin_t = (float*)(buf + o_sin_t); float* sin_g = (float*)(buf + o_sin_g);
+  float* poolf = (float*)(buf + o_pool);  float* hid = (float*)(buf + o_hid);
+  float* temb = (float*)(buf + o_temb);   float* temb_s = (float*)(buf + o_temb_s);
+  t.mod = (float*)(buf + o_mod);
+  const int R = (int)rows;
+  launch_time_sinusoid(dt, timesteps, R, R, sin_t, st);
+  launch_gemv_grouped(dt, sin_t, 256, R, 256, m.jobs_dev + 0, m.prefix_dev, 1, D, hid, 3 * D, 1, 0, st);
+  if (has_g) {
+    launch_time_sinusoid(dt, guidance, R, R, sin_g, st);
+    launch_gemv_grouped(dt, sin_g, 256, R, 256, m.jobs_dev + 1, m.prefix_dev, 1, D, hid, 3 * D, 1, 0, st);
+  }
+  launch_cast_to_f32(dt, pooled, poolf, (long long)rows * P, st);
+  launch_gemv_grouped(dt, poolf, P, R, P, m.jobs_dev + 2, m.prefix_dev, 1, D, hid, 3 * D, 1, 0, st);
+  launch_gemv_grouped(dt, hid, 3 * D, R, D, m.jobs_dev + 3, m.prefix_dev, 1, D, temb, D, 0, 0, st);
+  if (has_g) launch_gemv_grouped(dt, hid + D, 3 * D, R, D, m.jobs_dev + 4, m.prefix_dev, 1, D, temb, D, 0, 1, st);
+  launch_gemv_grouped(dt, hid + 2 * D, 3 * D, R, D, m.jobs_dev + 5, m.prefix_dev, 1, D, temb, D, 0, 1, st);
+  launch_silu_f32(temb, temb_s, (long long)rows * D, st);
+  if (D % 4 == 0 && m.mod_rows % 4 == 0)
+    launch_gemv_grouped_table(dt, temb_s, D, R, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, m.mod_rows, t.mod,
+                              m.mod_total, st);
+  else
+    launch_gemv_grouped(dt, temb_s, D, R, D, m.jobs_dev + 6, m.prefix_dev + 1, m.n_mod_jobs, m.mod_rows, t.mod,
+                        m.mod_total, 0, 0, st);
+  t.steps = steps;
+  t.batch = batch;
 }
 
 void embed_inputs(const Ctx& c, rt_model* mm, const rt_forward_args& a, const void* cond, int cond_batch) {
@@ -578,7 +643,13 @@ Ctx begin_forward(rt_model* m, const rt_forward_args* a) {
     launch_rope_table(a->txt_ids, c.T, m->cfg.axes_dims_rope, c.ws.rope, c.st);
     launch_rope_table(a->img_ids, c.N, m->cfg.axes_dims_rope, c.ws.rope + (size_t)c.T * (m->hd / 2), c.st);
   }
-  time_text_and_modulation(c, *a);
+  if (m->modtab.sel >= 0) {
+    // this step's AdaLN vectors were computed with the whole table: nothing of the timestep chain runs
+    RT_REQUIRE(m->modtab.batch == c.B, "modulation table: built for another batch size");
+    c.ws.mod = m->modtab.mod + (size_t)m->modtab.sel * c.B * m->mod_total;
+  } else if (!get_option("mod_debug_skip")) {  // (timing experiment: stale AdaLN vectors)
+    time_text_and_modulation(c, *a);
+  }
   return c;
 }
 
@@ -879,6 +950,31 @@ int rt_model_set_step_invariant_cache(rt_model* m, int mode) {
     RT_REQUIRE(mode == 0 || mode == 1, "set_step_invariant_cache: mode must be 0 (off) or 1 (on)");
     m->inv.mode = mode;
     m->inv.valid = false;  // every call invalidates: the next forward recomputes
+  });
+}
+
+int64_t rt_model_modulation_table_bytes(const rt_model* m, int steps, int batch) {
+  if (!m || !m->finalized || steps < 1 || batch < 1) return -1;
+  return (int64_t)modulation_table_layout(*m, (size_t)steps * batch, nullptr);
+}
+
+int rt_model_build_modulation_table(rt_model* m, const void* timesteps, const void* guidance, const void* pooled_projections,
+                                    int steps, int batch, void* table, int64_t table_bytes, void* stream) {
+  return guarded([&] {
+    RT_REQUIRE(m && m->finalized, "build_modulation_table: model is null or not finalized");
+    RT_REQUIRE(steps >= 1 && batch >= 1 && timesteps && pooled_projections, "build_modulation_table: bad argument");
+    RT_REQUIRE(!m->cfg.guidance_embeds || guidance, "build_modulation_table: this model has guidance_embeds");
+    build_modulation_table(*m, timesteps, guidance, pooled_projections, steps, batch, (char*)table, (size_t)table_bytes,
+                           (cudaStream_t)stream);
+  });
+}
+
+int rt_model_select_modulation(rt_model* m, int step) {
+  return guarded([&] {
+    RT_REQUIRE(m, "select_modulation: null model");
+    RT_REQUIRE(step == -1 || (step >= 0 && step < m->modtab.steps && m->modtab.mod != nullptr),
+               "select_modulation: no table, or the step is outside it");
+    m->modtab.sel = step;
   });
 }
 

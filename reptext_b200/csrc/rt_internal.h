@@ -128,6 +128,10 @@ void launch_gemv_grouped(int wdtype, const float* x, int x_ld, int batch, int K,
                          const int* job_row_prefix_dev, int njobs, int total_rows, float* out, int out_ld,
                          int silu_out, int accumulate, cudaStream_t stream, bool rows_multiple_of_4 = false,
                          int row_base = 0, const GemvPeers* peers = nullptr);
+// the same rows for `batch` activation vectors, weights read from DRAM once (4-row jobs; absolute rows, no accumulate)
+void launch_gemv_grouped_table(int wdtype, const float* x, int x_ld, int batch, int K, const GemvJob* jobs_dev,
+                               const int* job_row_prefix_dev, int njobs, int total_rows, float* out, int out_ld,
+                               cudaStream_t stream);
 void launch_silu_f32(const float* x, float* out, long long n, cudaStream_t stream);
 
 void launch_time_sinusoid(int dtype, const void* t, int t_batch, int batch, float* out /*[batch,256]*/,

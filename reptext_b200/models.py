@@ -209,6 +209,55 @@ class _RuntimeModel:
         if self._handle is not None:
             L.check(L.lib().rt_model_set_step_invariant_cache(self._handle, int(self._inv_on)))
 
+    # ---- the AdaLN vectors of every step of an image in one pass ---------------------------------------
+    def build_modulation_table(self, timesteps: torch.Tensor, guidance: Optional[torch.Tensor],
+                               pooled_projections: torch.Tensor) -> int:
+        """``timesteps``: [steps, batch or 1] - what each step of a denoising loop will pass as ``timestep`` (already
+        divided by 1000, RepText/pipeline_flux_controlnet.py:1043); ``guidance``: [batch] or [1] (or None);
+        ``pooled_projections``: [batch, P].  Runs the time / guidance / pooled-text embedders and the AdaLN linears of
+        every block (RepText/controlnet_flux.py:282-291 and the blocks' ``norm1`` / ``norm``) for all steps at once
+        (``rt_model_build_modulation_table``): the 6.5 GB of modulation weights are read once per image instead of once per
+        step.  ``select_modulation(i)`` then makes the forwards use step i's vectors; results are bit-identical to
+        forwards that compute them.  Returns the number of steps."""
+        if self._handle is None:
+            raise RuntimeError("model has no weights: call load_state_dict() or use random_init()")
+        c = self._cfg
+        if timesteps.dim() != 2:
+            raise ValueError("`timesteps` must be [steps, batch]")
+        K, Bt = timesteps.shape
+        pooled = self._check("pooled_projections", pooled_projections, c["pooled_projection_dim"])
+        B = pooled.shape[0]
+        if Bt not in (1, B):   # (batch-1 latents against batch-2 embeddings: the inpaint pipeline's true-CFG call)
+            raise ValueError("timesteps must have 1 or batch elements per step")
+        ts = self._check("timesteps", timesteps.expand(K, B)).reshape(-1)
+        pooled = pooled.repeat(K, 1).contiguous()
+        g = None
+        if c.get("guidance_embeds", False):
+            if guidance is None:
+                raise ValueError("this model was built with guidance_embeds=True: `guidance` is required")
+            g = self._check("guidance", guidance.reshape(-1))
+            if g.numel() not in (1, B):
+                raise ValueError("guidance must have 1 or batch elements")
+            g = g.expand(B).repeat(K).contiguous()
+        lib = L.lib()
+        need = int(lib.rt_model_modulation_table_bytes(self._handle, K, B)) + 256
+        buf = getattr(self, "_modtab_buf", None)
+        if buf is None or buf.numel() < need:
+            self.select_modulation(None)
+            self._modtab_buf = buf = torch.empty(need, dtype=torch.uint8, device=self._device)   # kept across images
+        base = (buf.data_ptr() + 255) // 256 * 256
+        with torch.cuda.device(self._device):
+            L.check(lib.rt_model_build_modulation_table(self._handle, L.ptr(ts), L.ptr(g) if g is not None else None,
+                                                        L.ptr(pooled), K, B, base, buf.numel() - (base - buf.data_ptr()),
+                                                        L.stream_ptr()))
+        return K
+
+    def select_modulation(self, step: Optional[int]) -> None:
+        """Use row ``step`` of the table for the following forwards (their ``timestep`` / ``guidance`` /
+        ``pooled_projections`` are then not read); ``None``: compute per forward again."""
+        if self._handle is not None:
+            L.check(L.lib().rt_model_select_modulation(self._handle, -1 if step is None else int(step)))
+
     @staticmethod
     def _tensor_key(t):
         return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype, t.device)

@@ -359,3 +359,47 @@ def test_step_invariant_cache_is_bit_identical_and_follows_its_inputs():
         net.set_step_invariant_cache(False)
     ref3 = step(0.4, lat1)
     assert torch.equal(ref3[1], got3[1]) and all(torch.equal(a, b) for a, b in zip(ref3[0], got3[0]))
+
+
+@pytest.mark.parametrize("batch", [1, 2])
+def test_modulation_table_rows_are_the_bits_a_forward_computes(batch):
+    """rt_model_build_modulation_table (controlnet_flux.py:282-291 + the AdaLN linears of every block, for all steps of
+    an image in one pass): a forward that uses row i of the table returns the same bits as a forward that computes its
+    modulation from (timestep_i, guidance, pooled) - ControlNet and transformer, batch 1 and the true-CFG batch 2 with a
+    one-element timestep - launches fewer kernels, and ignores the timestep it is handed while a row is selected."""
+    from reptext_b200 import _lib, config
+    TR, CN = config.SMALL128_TRANSFORMER, config.SMALL128_CONTROLNET
+    dtype, dev = torch.bfloat16, "cuda"
+    tr, cn, _, _ = _build(TR, CN, dtype)
+    x = synth_inputs(TR, CN, 256, 256, 128, seed=57, batch=batch)
+    c = lambda v: v.to(dev, dtype)
+    base = dict(encoder_hidden_states=c(x["prompt_embeds"]), pooled_projections=c(x["pooled"]), img_ids=c(x["img_ids"]),
+                txt_ids=c(x["txt_ids"]), guidance=torch.tensor([3.5], device=dev))
+    steps = torch.tensor([1.0, 0.8125, 0.53, 0.2578, 0.0371])
+    lats = [c(torch.randn_like(x["latents"][:1])) for _ in steps]       # batch-1 latents broadcast when batch == 2
+
+    def step(t, lat):
+        kw = dict(base, hidden_states=lat, timestep=c(torch.tensor([t])))
+        n0 = _lib.launch_count()
+        blocks, _ = cn(controlnet_cond=c(x["conds"][0][:1]), conditioning_scale=0.9, return_dict=False, **kw)
+        v = tr(controlnet_block_samples=blocks, return_dict=False, **kw)[0]
+        torch.cuda.synchronize()
+        return [b.clone() for b in blocks], v.clone(), _lib.launch_count() - n0
+
+    ref = [step(float(t), lat) for t, lat in zip(steps, lats)]
+    ts_all = c(steps)[:, None]                                          # [steps, 1]: broadcast over the batch
+    for net in (cn, tr):
+        assert net.build_modulation_table(ts_all, base["guidance"], base["pooled_projections"]) == len(steps)
+    for i in (3, 0, 4, 1, 2):
+        for net in (cn, tr):
+            net.select_modulation(i)
+        got = step(0.999 if i else 0.001, lats[i])                      # the timestep argument is not read
+        assert all(torch.equal(a, b) for a, b in zip(ref[i][0], got[0])), i
+        assert torch.equal(ref[i][1], got[1]), i
+        assert got[2] < ref[i][2], (got[2], ref[i][2])
+    for net in (cn, tr):
+        net.select_modulation(None)
+    back = step(float(steps[2]), lats[2])
+    assert torch.equal(back[1], ref[2][1]) and back[2] == ref[2][2]
+    with pytest.raises(ValueError):
+        tr.select_modulation(len(steps))

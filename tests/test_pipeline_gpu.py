@@ -240,6 +240,45 @@ def test_pipeline_argument_errors():
         pipe(prompt="x", height=256, width=256, max_sequence_length=1024, control_image=[], control_position=[])
 
 
+def test_precomputed_modulation_leaves_the_latents_bit_identical():
+    """`pipe.precompute_modulation` (the AdaLN vectors of all steps in one pass before the loop,
+    models.build_modulation_table) on / off through the public __call__: same latents bit for bit at every step, fewer
+    launches."""
+    from reptext_b200 import _lib
+    pipe, TR, CN, _, _ = _tiny_pipe(torch.bfloat16, TRname="SMALL128_TRANSFORMER", CNname="SMALL128_CONTROLNET")
+    H = W = 256
+    x = synth_inputs(TR, CN, H, W, 128, seed=43, n_lines=2)
+    lh, lw = 2 * (H // 16), 2 * (W // 16)
+    imgs, poss, masks = [], [], []
+    for li, cond in enumerate(x["conds"]):
+        z = _unpack_cond(cond, lh, lw)
+        imgs.append(z[:, :16].cuda())
+        poss.append(z[:, 16:].cuda())
+        y0 = (H // 4) * (li + 1) - H // 8
+        masks.append(box_mask(H, W, (y0, y0 + H // 6, W // 5, W - W // 5)))
+
+    def run(on):
+        taps = []
+        pipe.precompute_modulation = on
+        n0 = _lib.launch_count()
+        out = pipe(prompt_embeds=x["prompt_embeds"].cuda().bfloat16(), pooled_prompt_embeds=x["pooled"].cuda().bfloat16(),
+                   height=H, width=W, num_inference_steps=6, guidance_scale=3.5, control_image=imgs,
+                   control_position=poss, control_mask=masks, controlnet_conditioning_scale=1.0,
+                   latents=x["latents"].cuda().bfloat16(), output_type="latent",
+                   callback_on_step_end=lambda p, i, t, kw: taps.append(kw["latents"].clone()) or {})
+        torch.cuda.synchronize()
+        return taps, out.images, _lib.launch_count() - n0
+
+    try:
+        off, on = run(False), run(True)
+    finally:
+        pipe.precompute_modulation = True
+    assert len(off[0]) == len(on[0]) == 6
+    for a, b in zip(off[0], on[0]):
+        assert torch.equal(a, b)
+    assert torch.equal(off[1], on[1]) and on[2] < off[2], (on[2], off[2])
+
+
 def test_step_invariant_cache_leaves_the_latents_bit_identical():
     """SURVEY.md 8f.2 through the public __call__ (two text lines: the ControlNet runs twice per step on the same prompt
     tensors): `pipe.cache_step_invariants` on / off give the same latents bit for bit at every step, and the cached
