@@ -401,8 +401,11 @@ class RepTextPipelineBase(DiffusionPipeline):
             sp_kw = dict(sp=sp)
             common.update(sp_kw)
         mod_nets = []
-        if self.precompute_modulation and len(timesteps) > 0:
-            # what every step below passes as `timestep` / `guidance` / `pooled_projections`, for all steps at once
+        if self.precompute_modulation and len(timesteps) > 1:
+            # what every step below passes as `timestep` / `guidance` / `pooled_projections`, for all steps at once.
+            # (Built on the caller's stream, 10 ms for 28 steps.  On a side stream under step 0's kernels the build's ~47
+            # dependent launches starve behind the step's back-to-back persistent kernels: measured, intermittent stalls
+            # of 300-500 ms.)
             ts_all = torch.stack([t.expand(latents.shape[0]).to(latents.dtype) / 1000 for t in timesteps])
             g_all = guidance_const.expand(latents.shape[0]) if guidance_const is not None else None
             mod_nets = [n for n in nets if hasattr(n, "build_modulation_table")]
