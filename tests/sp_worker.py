@@ -54,6 +54,55 @@ def main():
     pipe.enable_sequence_parallel(sp)
     multi = run()
     multi2 = run()                          # the epoch counters keep growing across calls
+    # the phase barriers as stand-alone kernels instead of at the head of the attention / output-projection kernels
+    # (csrc/sp_sync.cuh): same protocol, same epochs - the two forms mix in one stream - same bits
+    from reptext_b200 import _lib
+    _lib.set_option("sp_sync_kernels", 1)
+    multi_k = run()
+    _lib.set_option("sp_sync_kernels", 0)
+    multi_b = run()
+    forms = torch.equal(multi_k, multi) and torch.equal(multi_b, multi)
+    print(f"[rank {rank}] barrier forms (kernels / in-kernel / back) agree: {forms}", flush=True)
+    # one sequence-parallel denoising step captured into a CUDA graph on every rank and replayed on new latents: the
+    # in-kernel barriers take their epochs from the flag block on the device, so a replay synchronises like the eager run
+    from reptext_b200 import ops
+    shard = lambda t, d=1: parallel.shard_tokens(t.to(dev), rank, world, d)
+    ids_i = pipe._prepare_latent_image_ids(1, 2 * (H // 16), 2 * (W // 16), dev, dt)
+    ids_t = torch.zeros(T, 3, device=dev, dtype=dt)
+    condp = torch.randn(1, N, CN["in_channels"] + CN["extra_condition_channels"], generator=g).to(dt)
+    tt, gg = torch.tensor([0.62], device=dev, dtype=dt), torch.tensor([3.5], device=dev)
+
+    pe_s, po_d, ii_s, ti_s, cond_s = (shard(pe).contiguous(), po.to(dev), shard(ids_i, 0).float().contiguous(),
+                                      shard(ids_t, 0).float().contiguous(), shard(condp).contiguous())
+
+    def sp_step(z):
+        kw = dict(hidden_states=z, encoder_hidden_states=pe_s, pooled_projections=po_d, timestep=tt,
+                  guidance=gg.to(dt), img_ids=ii_s, txt_ids=ti_s, sp=sp)
+        bl, _ = cn(controlnet_cond=cond_s, conditioning_scale=0.9, return_dict=False, **kw)
+        v = tr(controlnet_block_samples=bl, return_dict=False, **kw)[0]
+        return ops.euler_step(v, z, 0.62, 0.55)
+
+    z1, z2 = shard(lat).contiguous(), shard(torch.randn(1, N, TR["in_channels"], generator=g).to(dt)).contiguous()
+    eager1, eager2 = sp_step(z1).clone(), sp_step(z2).clone()
+    static_in = z1.clone()
+    cs = torch.cuda.Stream(dev)
+    cs.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(cs):
+        sp_step(static_in)
+    torch.cuda.current_stream(dev).wait_stream(cs)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=cs):
+        static_out = sp_step(static_in)
+    graph.replay()
+    torch.cuda.synchronize()
+    g_ok = torch.equal(static_out, eager1)
+    static_in.copy_(z2)
+    graph.replay()
+    torch.cuda.synchronize()
+    g_ok = g_ok and torch.equal(static_out, eager2)
+    sp.check()
+    print(f"[rank {rank}] CUDA-graph replay of a sequence-parallel step equals the eager step: {g_ok}", flush=True)
+    del graph
     pipe.enable_sequence_parallel(None)
     # ---- the inpaint pipeline (second ControlNet, true CFG at effective batch 2) the same way
     from reptext_b200.pipeline_flux_controlnet_inpaint import FluxControlNetPipeline as InpaintPipeline
@@ -86,7 +135,7 @@ def main():
           f"rel_l2(run2, run1)={rel_l2(multi2, multi):.3e}", flush=True)
     exact = torch.equal(multi, single) and torch.equal(i_multi, i_single)
     print(f"[rank {rank}] sp world={world} bit-identical to the single-GPU run: {exact}", flush=True)
-    ok = finite and exact and repeat and torch.isfinite(i_multi.float()).all().item()
+    ok = finite and exact and repeat and forms and g_ok and torch.isfinite(i_multi.float()).all().item()
     flag = torch.tensor([int(ok)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     # every rank holds the same gathered latents
