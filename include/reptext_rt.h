@@ -67,6 +67,8 @@ RT_API long long rt_launch_count(void); /* number of this library's kernels laun
  * n = tiles of n columns where eligible; bit-identical results),
  * "sp_sync_kernels" (1 = the sequence-parallel phase barriers as stand-alone kernels instead of at the head of the
  * attention / output-projection kernels; same protocol, same results),
+ * "gemm_epi_warps" (0 = auto: eight epilogue warps on the CTA-pair tcgen05 GEMM kernels, four on the others; 4 = four
+ * everywhere - A/B, same results),
  * "mod_debug_skip" (1 = forwards skip the timestep / AdaLN chain and run on whatever vectors the workspace holds - a
  * timing experiment with WRONG results: what that chain costs inside a step),
  * "gemm_debug" (bit 1: no epilogue, bit 2: k-block 0 only - timing experiments with WRONG results;

@@ -16,7 +16,7 @@ void set_last_error(const std::string& msg) { t_last_error = msg; }
 
 static std::map<std::string, int>& options() {
   static std::map<std::string, int> o = {{"force_simt", 0}, {"gemm_cta_group", 0}, {"attn_variant", 0},
-                                         {"profile", 0}, {"ln_warp_rows", 0}, {"gemv_single_row", 0}, {"gemm_debug", 0}, {"mod_inline", 0}, {"sp_replicate_mod", 0}, {"no_pdl", 0}, {"ln_impl", 0}, {"text_attn_simt", 0}, {"text_attn_mma", 0}, {"gemm_band", 0}, {"gemm_dyn_bn", 0}, {"sp_sync_kernels", 0}, {"mod_debug_skip", 0}, {"euler_dt_host", 0}};
+                                         {"profile", 0}, {"ln_warp_rows", 0}, {"gemv_single_row", 0}, {"gemm_debug", 0}, {"mod_inline", 0}, {"sp_replicate_mod", 0}, {"no_pdl", 0}, {"ln_impl", 0}, {"text_attn_simt", 0}, {"text_attn_mma", 0}, {"gemm_band", 0}, {"gemm_dyn_bn", 0}, {"sp_sync_kernels", 0}, {"mod_debug_skip", 0}, {"gemm_epi_warps", 0}, {"euler_dt_host", 0}};
   return o;
 }
 int device_sm_count() {

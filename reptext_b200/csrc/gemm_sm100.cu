@@ -32,7 +32,7 @@ namespace {
 constexpr int BM = 128;       // rows per CTA tile (= TMEM lanes)
 constexpr int BK = 64;        // k-block: 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;      // 4 epilogue warps; the 8-warp form (kEpiWarps = 8) launches 384
 constexpr int kEpiThreads = 128;
 constexpr int kMaxSeg = 4;
 
@@ -80,19 +80,21 @@ struct alignas(64) TcParams {
               // hints on the TMA loads (A/B, same results)
 };
 
-template <int BN, int kCtaGroup>
+template <int BN, int kCtaGroup, int kEpiWarps = 4>
 struct Cfg {
   static constexpr int kBRows = BN / kCtaGroup;             // W rows each CTA loads
   static constexpr int kABytes = BM * BK * 2;               // 16 KB
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
+  // 192 KB of ring with four epilogue warps; eight warps need twice the staging tiles: 176 KB of ring
+  static constexpr int kRingBytes = (kEpiWarps == 8 ? 176 : 192) * 1024;
+  static constexpr int kStages = kRingBytes / kStageBytes > 8 ? 8 : kRingBytes / kStageBytes;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (kAccStages * BN <= 32) ? 32 : (kAccStages * BN <= 64) ? 64
                                    : (kAccStages * BN <= 128) ? 128 : (kAccStages * BN <= 256) ? 256 : 512;
   static constexpr int kBarBytes = ((2 * kStages + 2 * kAccStages) * 8 + 16 + 127) / 128 * 128;
   static constexpr int kEpiStageOff = kStages * kStageBytes + kBarBytes;  // per-warp epilogue staging tiles
-  static constexpr int kSmemBytes = kEpiStageOff + 4 * 32 * 144 + 1024;    // + alignment slack
+  static constexpr int kSmemBytes = kEpiStageOff + kEpiWarps * 32 * 144 + 1024;  // + alignment slack
 };
 
 struct TileCoord {
@@ -183,9 +185,14 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   return 0.5f * x * (1.0f + ptx::tanh_approx(inner));
 }
 
+// part / nparts: the eight-warp epilogue gives every TMEM lane quadrant TWO warps, each takes half of the tile's columns
+// (whole heads for the per-head mode, whole 64-column store groups otherwise)
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const TcParams& P, const TcProblem& pr, const TcSegment& sg,
-                                              uint32_t tacc, int b, int m, int n0) {
+                                              uint32_t tacc, int b, int m, int n0, int part = 0, int nparts = 1) {
+  constexpr int kChunks = BN / 32, kHeads = BN / 128;
+  const int c_per = (kChunks + nparts - 1) / nparts, c_begin = part * c_per, c_end = min(kChunks, c_begin + c_per);
+  const int h_per = (kHeads + nparts - 1) / nparts, h_begin = part * h_per, h_end = min(kHeads, h_begin + h_per);
   const bool row_ok = m < pr.m_rows;
   const int nl0 = n0 - sg.n_begin;  // column within the segment
   bf16* orow = sg.out + (long long)b * sg.out_bs + (long long)(pr.out_row0 + m) * sg.out_ld + sg.out_col0 + nl0;
@@ -206,7 +213,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const TcProblem
                   sg.out_col0 + nl0;
     const float sc = sg.mode == EPI_SCALE_MASK ? pr.scale : 1.f;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       float v[32];
       tmem_load_f32x32(tacc + c * 32, v);
       if (bias) {
@@ -227,7 +234,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const TcProblem
     // one head = 128 columns; two passes over TMEM (reads are cheap) instead of 128 live registers
     const float2* rp = P.rope ? P.rope + (long long)(pr.out_row0 + m) * 64 : nullptr;
 #pragma unroll 1
-    for (int hc = 0; hc < BN / 128; ++hc) {
+    for (int hc = h_begin; hc < h_end; ++hc) {
       bf16* ohead = out_chunk(nl0 + hc * 128);
       float ss = 0.f;
 #pragma unroll 1
@@ -286,7 +293,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const TcProblem
     if (pr.mask && row_ok) mk *= __bfloat162float(pr.mask[m]);
   }
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     float v[32];
     tmem_load_f32x32(tacc + c * 32, v);
     if (bias) {
@@ -398,7 +405,7 @@ __device__ __forceinline__ void stage_load(uint8_t* stage, int lane, const bf16*
 template <int BN, bool kDynN = false>
 __device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const TcProblem& pr, const TcSegment& sg,
                                                      uint32_t tacc, int b, int m0w, int lane, int n0, uint8_t* stage,
-                                                     int ncols = BN) {
+                                                     int ncols = BN, int part = 0, int nparts = 1) {
   const int m = m0w + lane;
   const bool row_ok = m < pr.m_rows;
   const int rows_valid = min(max(pr.m_rows - m0w, 0), 32);
@@ -418,8 +425,10 @@ __device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const Tc
   if (sg.mode == EPI_QKNORM_ROPE) {
     // one head = 128 columns; two passes over TMEM (reads are cheap) instead of 128 live registers
     const float2* rp = P.rope ? P.rope + (long long)(pr.out_row0 + m) * 64 : nullptr;
+    constexpr int kHeads = BN / 128;
+    const int h_per = (kHeads + nparts - 1) / nparts, h_begin = part * h_per, h_end = min(kHeads, h_begin + h_per);
 #pragma unroll 1
-    for (int hc = 0; hc < BN / 128; ++hc) {
+    for (int hc = h_begin; hc < h_end; ++hc) {
       float ss = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -483,8 +492,9 @@ __device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const Tc
   }
   const bool resid = sg.mode == EPI_GATE_RESID || (sg.mode == EPI_SCALE_MASK && pr.accumulate);
   const int n_groups = kDynN ? (ncols + 63) / 64 : BN / 64;
+  const int g_per = (n_groups + nparts - 1) / nparts, g_begin = part * g_per, g_end = min(n_groups, g_begin + g_per);
 #pragma unroll 1
-  for (int g = 0; g < n_groups; ++g) {
+  for (int g = g_begin; g < g_end; ++g) {
     bf16* gp = gptr(nl0 + g * 64);
     const int n_half = kDynN ? min(2, (ncols - g * 64) / 32) : 2;
     const int chunks = kDynN ? n_half * 4 : 8;
@@ -544,9 +554,12 @@ __device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const Tc
 // The host takes this form when a narrower tile fills the last wave better (launch_gemm_tc: sequence-parallel shards
 // of 1216 rows x N = 3072 are 120 tiles of 256 columns for 148 SMs, but 140 tiles of 224).  An output element's
 // arithmetic does not depend on the tile width: results are bit-identical to the BN = 256 kernel.
-template <int BN, int kCtaGroup, bool kDynN = false>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
-  using C = Cfg<BN, kCtaGroup>;
+// kEpiWarps = 8: two epilogue warps per TMEM lane quadrant (warps 4-7 take the first half of a tile's columns, warps
+// 8-11 the second).  The epilogue of a CTA's LAST tile is not hidden behind the next tile's MMAs: with four warps it is
+// 3-6 % of the large launches' time and 12 % of (4608, 3072, 3072) (option gemm_debug = 1 removes it).
+template <int BN, int kCtaGroup, bool kDynN = false, int kEpiWarps = 4>
+__global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
+  using C = Cfg<BN, kCtaGroup, kEpiWarps>;
   static_assert(!kDynN || BN == 256, "the run-time tile width lives in the BN = 256 layout");
   const int bn = kDynN ? P.bn : BN;
   extern __shared__ uint8_t smem_raw[];
@@ -590,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     for (int i = 0; i < C::kAccStages; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);                         // one tcgen05.commit
-      ptx::mbar_init(&tempty_bar[i], kCtaGroup * kEpiThreads);  // every epilogue thread of the pair
+      ptx::mbar_init(&tempty_bar[i], kCtaGroup * 32 * kEpiWarps);  // every epilogue thread of the pair
     }
     ptx::fence_barrier_init();
   }
@@ -698,6 +711,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int quad = warp & 3;
+    constexpr int kParts = kEpiWarps / 4;
+    const int part = (warp - 4) >> 2;
+    uint8_t* stage_w = smem + C::kEpiStageOff + (warp - 4) * kStageWarpBytes;
     int iter = 0;
     for (int t = cluster_id; t < P.total_tiles; t += num_clusters, ++iter) {
       const TileCoord tc = decode_tile(P, t, bn, kRowsPerTile);
@@ -711,13 +727,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         // timing experiment: accumulators are dropped
       } else if constexpr (kDynN) {
         const TcSegment& sg = pr.seg[0];  // single-segment launches only
-        epilogue_tile_staged<BN, true>(P, pr, sg, tacc, tc.b, m0w, lane, tc.n0,
-                                       smem + C::kEpiStageOff + quad * kStageWarpBytes, min(bn, sg.n_end - tc.n0));
+        epilogue_tile_staged<BN, true>(P, pr, sg, tacc, tc.b, m0w, lane, tc.n0, stage_w, min(bn, sg.n_end - tc.n0), part,
+                                       kParts);
       } else if ((P.debug & 4) || pr.seg[tc.seg].out_f32) {
-        epilogue_tile<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w + lane, tc.n0);
+        epilogue_tile<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w + lane, tc.n0, part, kParts);
       } else {
-        epilogue_tile_staged<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w, lane, tc.n0,
-                                 smem + C::kEpiStageOff + quad * kStageWarpBytes);
+        epilogue_tile_staged<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w, lane, tc.n0, stage_w, BN, part, kParts);
       }
       ptx::tc_fence_before();
       // The hand-off's payload is TMEM (tcgen05.ld completed by tcgen05.wait::ld, ordered by the fence above), so the
@@ -873,19 +888,19 @@ bool gemm_tc_supported(const GemmLaunch& L, std::string* why) {
   return true;
 }
 
-template <int BN, int CG, bool kDynN = false>
+template <int BN, int CG, bool kDynN = false, int kEpiWarps = 4>
 static void launch_cfg(const TcParams& P, int num_sms, cudaStream_t stream) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, kEpiWarps>;
   static PerDeviceOnce attr_set;
   if (attr_set.first()) {
-    RT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, kDynN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, kDynN, kEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::kSmemBytes));
   }
   int clusters = num_sms / CG;
   if (clusters > P.total_tiles) clusters = P.total_tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(128 + 32 * kEpiWarps);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -897,7 +912,7 @@ static void launch_cfg(const TcParams& P, int num_sms, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = get_option("no_pdl") ? 1 : 2;
-  RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, kDynN>, P));
+  RT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, kDynN, kEpiWarps>, P));
   count_launch();
 }
 
@@ -1050,11 +1065,16 @@ void launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream, int force_cta_grou
   P.total_tiles = tile_base;
   if (P.total_tiles == 0) return;
 
+  // option "gemm_epi_warps": 0 = auto (eight epilogue warps on the CTA-pair kernels), 4 = four everywhere (A/B)
+  const bool epi8 = cg == 2 && get_option("gemm_epi_warps") != 4;
   if (dyn) {
     if (cg == 1) launch_cfg<256, 1, true>(P, num_sms, stream);
+    else if (epi8) launch_cfg<256, 2, true, 8>(P, num_sms, stream);
     else launch_cfg<256, 2, true>(P, num_sms, stream);
     return;
   }
+  if (epi8 && bn == 256) { launch_cfg<256, 2, false, 8>(P, num_sms, stream); return; }
+  if (epi8 && bn == 128) { launch_cfg<128, 2, false, 8>(P, num_sms, stream); return; }
 #define RT_GEMM_CASE(BN_, CG_) \
   if (bn == BN_ && cg == CG_) { launch_cfg<BN_, CG_>(P, num_sms, stream); return; }
   RT_GEMM_CASE(256, 1)
