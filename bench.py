@@ -556,7 +556,12 @@ def run_b200(args, wl):
 
     # ---- warm-up, then EXACTLY K timed steps between barriers, CUDA events on the launch stream
     x = lat
-    for i in range(max(args.warmup, 3)):
+    # W warm-up steps, at least 15 (one second of the cfg-2 step): the power controller needs about that long to settle
+    # after the low-power set-up phase - a timed region that starts 0.2 s into the first GEMM-heavy work catches its
+    # overshoot (SM clock 1365 MHz against the steady 1440-1500, 70.5 against 68.6 ms per step on one box).  A fixed
+    # count: the sequence-parallel ranks must run the same number of steps.
+    n_warm = max(args.warmup, 15)
+    for i in range(n_warm):
         x = one_step(i, x)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -771,7 +776,7 @@ def run_b200(args, wl):
             v_cpu, sample = cpu_oracle_steps_per_s(wl)
             cpu = dict(value=v_cpu, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample)
         step_ms = ms_total / args.steps
-        line = dict(metric=METRIC.replace("1024x1024", f"{H}x{W}"), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        line = dict(metric=METRIC.replace("1024x1024", f"{H}x{W}"), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=n_warm,
                     ms_per_step=step_ms, higher_is_better=True, scaling="strong" if sp is not None else "weak",
                     vs_baseline=None, dtype="bf16",
                     data="synthetic (random-init weights of the named architecture, randn latents / embeddings)",
@@ -796,7 +801,7 @@ def run_b200(args, wl):
                                                   "vectors of all 28 steps are computed in one pass inside the timed "
                                                   "call, before the loop (weights read once per image, bit-identical "
                                                   "latents, tests/test_pipeline_gpu.py)"),
-                                device_loop_with_modulation_table=with_table_ms,
+                                device_loop_with_modulation_table=with_table_ms, warmup_steps_run=n_warm,
                                 images_per_s=value / STEPS_PER_IMAGE,
                                 tensor_util_whole_step=flops / gpus_per_sample / (step_ms / 1000.0) / 1e12 / pk["bf16_sustained"],
                                 finite_output=finite),
