@@ -400,12 +400,62 @@ __device__ __forceinline__ void stage_load(uint8_t* stage, int lane, const bf16*
   }
 }
 
+// the same 4 rows x 128 B pattern, global -> registers now and registers -> staging tile later: the next group's residual
+// travels while the current group is being stored
+__device__ __forceinline__ void stage_fetch(uint4 (&r)[8], int lane, const bf16* g, long long ld, int rows_valid, int chunks) {
+  const int rr = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + rr;
+    if (row < rows_valid && ch < chunks) r[it] = *reinterpret_cast<const uint4*>(g + (long long)row * ld + ch * 8);
+  }
+}
+__device__ __forceinline__ void stage_commit(uint8_t* stage, int lane, const uint4 (&r)[8], int rows_valid, int chunks) {
+  const int rr = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + rr;
+    if (row < rows_valid && ch < chunks) *reinterpret_cast<uint4*>(stage + row * kStagePitch + ch * 16) = r[it];
+  }
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// What a tile's epilogue needs besides the accumulator - the residual rows of its first 64-column group, the bias and
+// gate lines of its columns - does not depend on the tile's MMAs: the epilogue warps fetch it BEFORE they wait for the
+// accumulator (staging tile / L1), so that the epilogue of a CTA's last tile, which nothing hides, starts with its
+// operands on the SM instead of with an L2 round trip per step of a dependent chain.  Returns true when the first
+// group's residual is staged.  Same values, same arithmetic as the unprefetched form.
+template <int BN, bool kDynN>
+__device__ __forceinline__ bool epilogue_prefetch(const TcParams& P, const TcProblem& pr, const TcSegment& sg, int b, int m0w,
+                                                  int lane, int n0, uint8_t* stage, int ncols, int part, int nparts) {
+  const int rows_valid = min(max(pr.m_rows - m0w, 0), 32);
+  if (rows_valid == 0 || sg.mode == EPI_QKNORM_ROPE || sg.out_f32 || sg.scatter) return false;  // warp-uniform
+  const int n_groups = kDynN ? (ncols + 63) / 64 : BN / 64;
+  const int g_per = (n_groups + nparts - 1) / nparts, g_begin = part * g_per, g_end = min(n_groups, g_begin + g_per);
+  if (g_begin >= g_end) return false;
+  const int nl0 = n0 - sg.n_begin;
+  const int c0 = g_begin * 64, c1 = min(kDynN ? ncols : BN, g_end * 64);  // this warp's columns of the tile
+  if (sg.bias && c0 + lane * 64 < c1) prefetch_l1(sg.bias + nl0 + c0 + lane * 64);
+  if (sg.mode == EPI_GATE_RESID && pr.gate && c0 + lane * 32 < c1)
+    prefetch_l1(pr.gate + (long long)b * pr.gate_ld + n0 + c0 + lane * 32);
+  const bool resid = sg.mode == EPI_GATE_RESID || (sg.mode == EPI_SCALE_MASK && pr.accumulate);
+  if (!resid) return false;
+  const bf16* gp = sg.out + (long long)b * sg.out_bs + (long long)(pr.out_row0 + m0w) * sg.out_ld + sg.out_col0 + nl0 + c0;
+  const int chunks = kDynN ? min(2, (ncols - c0) / 32) * 4 : 8;
+  stage_load(stage, lane, gp, sg.out_ld, rows_valid, chunks);
+  __syncwarp();
+  return true;
+}
+
 // kDynN: the tile is `ncols` (a multiple of 32) columns wide instead of BN - the launch's run-time tile width, or what
 // is left of the segment in its last column tile (single-segment BIAS / GELU / GATE_RESID / SCALE_MASK launches only).
 template <int BN, bool kDynN = false>
 __device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const TcProblem& pr, const TcSegment& sg,
                                                      uint32_t tacc, int b, int m0w, int lane, int n0, uint8_t* stage,
-                                                     int ncols = BN, int part = 0, int nparts = 1) {
+                                                     int ncols = BN, int part = 0, int nparts = 1,
+                                                     bool first_staged = false) {
   const int m = m0w + lane;
   const bool row_ok = m < pr.m_rows;
   const int rows_valid = min(max(pr.m_rows - m0w, 0), 32);
@@ -493,12 +543,13 @@ __device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const Tc
   const bool resid = sg.mode == EPI_GATE_RESID || (sg.mode == EPI_SCALE_MASK && pr.accumulate);
   const int n_groups = kDynN ? (ncols + 63) / 64 : BN / 64;
   const int g_per = (n_groups + nparts - 1) / nparts, g_begin = part * g_per, g_end = min(n_groups, g_begin + g_per);
+  bool staged = first_staged;  // this group's residual is already in the staging tile (epilogue_prefetch / the previous group)
 #pragma unroll 1
   for (int g = g_begin; g < g_end; ++g) {
     bf16* gp = gptr(nl0 + g * 64);
     const int n_half = kDynN ? min(2, (ncols - g * 64) / 32) : 2;
     const int chunks = kDynN ? n_half * 4 : 8;
-    if (resid) {
+    if (resid && !staged) {
       stage_load(stage, lane, gp, sg.out_ld, rows_valid, chunks);
       __syncwarp();
     }
@@ -543,8 +594,19 @@ __device__ __forceinline__ void epilogue_tile_staged(const TcParams& P, const Tc
       stage_put32(stage, lane, half, v);
     }
     __syncwarp();
+    // the next group's residual leaves global memory now and lands in the staging tile once this group has left it
+    const bool next = resid && g + 1 < g_end;
+    uint4 nxt[8];
+    const int n_chunks = kDynN ? min(2, (ncols - (g + 1) * 64) / 32) * 4 : 8;
+    if (next) stage_fetch(nxt, lane, gptr(nl0 + (g + 1) * 64), sg.out_ld, rows_valid, n_chunks);
     stage_store(stage, lane, gp, sg.out_ld, rows_valid, chunks);
     __syncwarp();
+    staged = false;
+    if (next) {
+      stage_commit(stage, lane, nxt, rows_valid, n_chunks);
+      __syncwarp();
+      staged = true;
+    }
   }
 }
 
@@ -719,20 +781,23 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_tc_kernel(const 
       const TileCoord tc = decode_tile(P, t, bn, kRowsPerTile);
       const TcProblem& pr = P.prob[tc.p];
       const int as = iter & 1, aphase = (iter >> 1) & 1;
+      const int m0w = tc.m0 + (int)cta_rank * BM + quad * 32;
+      const TcSegment& sgt = pr.seg[tc.seg];
+      const int ncols_t = kDynN ? min(bn, sgt.n_end - tc.n0) : BN;
+      // operands of the epilogue that do not depend on the accumulator, fetched while the tile's MMAs still run
+      const bool direct = (P.debug & 4) || sgt.out_f32;
+      const bool first_staged = (P.debug & 1) || direct || (P.debug & 16)
+                                    ? false
+                                    : epilogue_prefetch<BN, kDynN>(P, pr, sgt, tc.b, m0w, lane, tc.n0, stage_w, ncols_t, part, kParts);
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      const int m0w = tc.m0 + (int)cta_rank * BM + quad * 32;
       if (P.debug & 1) {
         // timing experiment: accumulators are dropped
-      } else if constexpr (kDynN) {
-        const TcSegment& sg = pr.seg[0];  // single-segment launches only
-        epilogue_tile_staged<BN, true>(P, pr, sg, tacc, tc.b, m0w, lane, tc.n0, stage_w, min(bn, sg.n_end - tc.n0), part,
-                                       kParts);
-      } else if ((P.debug & 4) || pr.seg[tc.seg].out_f32) {
-        epilogue_tile<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w + lane, tc.n0, part, kParts);
+      } else if (direct) {
+        epilogue_tile<BN>(P, pr, sgt, tacc, tc.b, m0w + lane, tc.n0, part, kParts);
       } else {
-        epilogue_tile_staged<BN>(P, pr, pr.seg[tc.seg], tacc, tc.b, m0w, lane, tc.n0, stage_w, BN, part, kParts);
+        epilogue_tile_staged<BN, kDynN>(P, pr, sgt, tacc, tc.b, m0w, lane, tc.n0, stage_w, ncols_t, part, kParts, first_staged);
       }
       ptx::tc_fence_before();
       // The hand-off's payload is TMEM (tcgen05.ld completed by tcgen05.wait::ld, ordered by the fence above), so the

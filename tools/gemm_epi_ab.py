@@ -9,9 +9,10 @@ import torch
 from reptext_b200 import ops, _lib as L
 
 
-def bench(M, N, K, mode, opt, iters=30, copies=4):
+def bench(M, N, K, mode, opt, iters=30, copies=4, debug=0):
     dt = torch.bfloat16
     L.set_option("gemm_epi_warps", opt)
+    L.set_option("gemm_debug", debug)
     A = [torch.randn(1, M, K, device="cuda", dtype=dt) for _ in range(copies)]
     W = [torch.randn(N, K, device="cuda", dtype=dt) * K ** -0.5 for _ in range(copies)]
     b = torch.randn(N, device="cuda", dtype=dt)
@@ -31,6 +32,7 @@ def bench(M, N, K, mode, opt, iters=30, copies=4):
     e1.record()
     torch.cuda.synchronize()
     L.set_option("gemm_epi_warps", 0)
+    L.set_option("gemm_debug", 0)
     ms = e0.elapsed_time(e1) / iters
     return ms * 1e3, 2.0 * M * N * K / ms / 1e9
 
@@ -42,7 +44,12 @@ if __name__ == "__main__":
     for rep in range(2):
         for (M, N, K, mode) in shapes:
             line = f"M={M:5d} N={N:5d} K={K:5d}:"
-            for opt in (4, 0, 4, 0):
+            for opt in (4, 0):
                 us, tf = bench(M, N, K, mode, opt)
                 line += f"  {'four ' if opt == 4 else 'eight'}: {us:7.1f} us {tf:5.0f} TF/s |"
+            for dbg in (16, 0, 16, 0):                    # 16: no operand prefetch ahead of the accumulator
+                us, tf = bench(M, N, K, mode, 0, debug=dbg)
+                line += f"  eight{', no prefetch' if dbg else ''}: {us:7.1f} us |"
+            us, tf = bench(M, N, K, mode, 0, debug=1)     # accumulators dropped: what the epilogue still costs
+            line += f"  no epilogue: {us:7.1f} us |"
             print(line, flush=True)
