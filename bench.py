@@ -748,16 +748,23 @@ def run_b200(args, wl):
         gpus_per_sample = world if sp is not None else 1
         gem = prof.get("gemm_tcgen05", (0.0, 0.0, 0))
         roof = None
-        traffic = None   # ncu dram__bytes_read + write per GEMM launch, averaged over the 188 launches of one cfg2 step
-        tpath = os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")
-        if args.workload == "cfg2" and os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            traffic = (tj.get("banded_long_k") or tj["no_l2_hints"])["bytes_per_launch"]
+        # ncu dram__bytes_read + write per GEMM launch, averaged over the GEMM launches of one cfg2 step (tools/gpu.sh traffic)
+        traffic, traffic_file = None, None
+        if args.workload == "cfg2":
+            for name in ("r2_gemm_dram_traffic.json", "r1_gemm_dram_traffic.json"):
+                tpath = os.path.join(ROOT, "profiles", name)
+                if not os.path.exists(tpath):
+                    continue
+                tj = json.load(open(tpath))
+                fam = tj.get("families", {}).get("gemm_tc_kernel") or tj.get("banded_long_k") or tj.get("no_l2_hints")
+                if fam:
+                    traffic, traffic_file = fam["bytes_per_launch"], name
+                    break
         if gem[0] > 0:
             ach = gem[1] / (gem[0] / 1000.0) / 1e12
             roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 + TMA, fused epilogues)", achieved=ach,
                         peak=pk["bf16_sustained"], unit="TFLOP/s", frac=ach / pk["bf16_sustained"], traffic=traffic,
-                        traffic_unit="bytes of DRAM traffic per launch (ncu, profiles/r1_gemm_dram_traffic.json); "
+                        traffic_unit=f"bytes of DRAM traffic per launch (ncu, profiles/{traffic_file}); "
                                      "algorithmic operand bytes per launch: 203e6",
                         peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)",
                         frac_of_burst=ach / pk["bf16_burst"], launches=gem[2], ms_per_step=gem[0] / args.steps,

@@ -3,6 +3,7 @@
 
     python tools/ncu_summary.py launches gpurun_out/launches.csv          > profiles/rNN_launches.txt
     python tools/ncu_summary.py full     gpurun_out/prof_gemm.ncu-rep     > profiles/rNN_ncu_gemm.txt
+    python tools/ncu_summary.py traffic  gpurun_out/traffic.csv           > profiles/rNN_gemm_dram_traffic.json
 """
 import collections
 import csv
@@ -60,5 +61,37 @@ def full(path):
                 print(f"{k:100s} {r[i]:>16s} {units[i]}")
 
 
+def traffic(path):
+    """CSV of `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv` -> one JSON record:
+    DRAM bytes per launch of every kernel family captured (the bench line's `roofline.traffic` reads the GEMM's)."""
+    import json
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    hdr = rows[hi]
+    ii, ki, mi, vi, ui = (hdr.index(c) for c in ("ID", "Kernel Name", "Metric Name", "Metric Value", "Metric Unit"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0,
+             "ms": 1e3, "msecond": 1e3}
+    per = collections.OrderedDict()   # launch id -> (family, {metric: value})
+    for r in rows[hi + 1:]:
+        if len(r) <= vi:
+            continue
+        fam = r[ki].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("unnamed>::", "").replace("void ", "").replace("rt::", "")
+        fam = fam.split("(")[0].split("<")[0].strip()
+        d = per.setdefault(r[ii], (fam, {}))[1]
+        d[r[mi]] = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
+    out = collections.OrderedDict()
+    for fam, d in per.values():
+        a = out.setdefault(fam, dict(launches=0, dram_read_gb=0.0, dram_write_gb=0.0, time_ms_under_ncu=0.0))
+        a["launches"] += 1
+        a["dram_read_gb"] += d.get("dram__bytes_read.sum", 0.0) / 1e9
+        a["dram_write_gb"] += d.get("dram__bytes_write.sum", 0.0) / 1e9
+        a["time_ms_under_ncu"] += d.get("gpu__time_duration.sum", 0.0) / 1e3
+    for a in out.values():
+        a["bytes_per_launch"] = (a["dram_read_gb"] + a["dram_write_gb"]) * 1e9 / a["launches"]
+    print(json.dumps(dict(what="ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum "
+                               "--clock-control none over the launches of ONE cfg2 step of bench.py (the first timed step; "
+                               "warm-up launches skipped with --launch-skip)", families=out), indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
