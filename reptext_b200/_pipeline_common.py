@@ -16,6 +16,7 @@ true-CFG step 0 predicts zero; inpaint residuals are dropped when no text-line r
 from __future__ import annotations
 
 import os
+import re
 import warnings
 from typing import List, Optional, Union
 
@@ -187,16 +188,35 @@ class RepTextPipelineBase(DiffusionPipeline):
         if max_sequence_length is not None and max_sequence_length > 512:
             raise ValueError(f"`max_sequence_length` cannot be greater than 512 but is {max_sequence_length}")
 
+    def _locate_text_to_render(self, prompt, text_input_ids):
+        """``:257-280``: where the tokens of the text to render sit in the T5 ids of the prompt -> (start, end).  The text is
+        the first ``'...'`` group of ``prompt[0]`` (``"..."`` when there is none; neither: IndexError, as upstream), tokenised on
+        its own, WITHOUT its first token and its EOS; the ids of all prompts are searched as one flat sequence.  No window
+        matching raises ValueError; several make ``.item()`` raise, as upstream."""
+        quoted = re.findall(r"'[^']*'", prompt[0]) or re.findall(r'"[^"]*"', prompt[0])
+        ids = self.tokenizer_2(quoted[0], padding="max_length", max_length=self.tokenizer_max_length, truncation=True,
+                               return_tensors="pt")["input_ids"]
+        first_pad = torch.where(ids == 0)[1][0].item()
+        needle = ids[:, 1:first_pad - 1].flatten()
+        hit = (text_input_ids.flatten().unfold(0, needle.size(0), 1) == needle).all(dim=1)
+        if not torch.any(hit):
+            raise ValueError("No match found in the input IDs.")
+        start = torch.nonzero(hit).item()
+        return start, start + needle.size(0)
+
     def _get_t5_prompt_embeds(self, prompt, num_images_per_prompt: int = 1, max_sequence_length: int = 512, device=None,
-                              dtype=None):
+                              dtype=None, get_text_to_render: bool = False):
         """``:232-304``: tokenizer_2 (padding to ``max_sequence_length``, truncation) -> ``text_encoder_2(ids)[0]``; no
-        attention mask is passed, as upstream."""
+        attention mask is passed, as upstream.  ``get_text_to_render``: also returns the token span of the quoted text
+        (``_locate_text_to_render``) - (embeddings, start, end) as upstream."""
         device = device or self._execution_device
         prompt = [prompt] if isinstance(prompt, str) else list(prompt)
         batch_size = len(prompt)
         text_inputs = self.tokenizer_2(prompt, padding="max_length", max_length=max_sequence_length, truncation=True,
                                        return_length=False, return_overflowing_tokens=False, return_tensors="pt")
         text_input_ids = text_inputs.input_ids
+        if get_text_to_render:
+            span = self._locate_text_to_render(prompt, text_input_ids)
         untruncated_ids = self.tokenizer_2(prompt, padding="longest", return_tensors="pt").input_ids
         if untruncated_ids.shape[-1] >= text_input_ids.shape[-1] and not torch.equal(text_input_ids, untruncated_ids):
             warnings.warn(f"part of the prompt was truncated: `max_sequence_length` is {max_sequence_length} tokens")
@@ -204,7 +224,8 @@ class RepTextPipelineBase(DiffusionPipeline):
         prompt_embeds = prompt_embeds.to(dtype=self.text_encoder_2.dtype, device=device)
         _, seq_len, _ = prompt_embeds.shape
         prompt_embeds = prompt_embeds.repeat(1, num_images_per_prompt, 1)
-        return prompt_embeds.view(batch_size * num_images_per_prompt, seq_len, -1)
+        prompt_embeds = prompt_embeds.view(batch_size * num_images_per_prompt, seq_len, -1)
+        return (prompt_embeds, *span) if get_text_to_render else prompt_embeds
 
     def _get_clip_prompt_embeds(self, prompt, num_images_per_prompt: int = 1, device=None):
         """``:307-347``: tokenizer (77 tokens) -> ``text_encoder(ids).pooler_output``."""
@@ -222,15 +243,22 @@ class RepTextPipelineBase(DiffusionPipeline):
         pooled = pooled.repeat(1, num_images_per_prompt)
         return pooled.view(batch_size * num_images_per_prompt, -1)
 
-    def _encode_text(self, prompt, num_images_per_prompt, max_sequence_length, clip_prompt=None):
+    def _encode_text(self, prompt, num_images_per_prompt, max_sequence_length, clip_prompt=None, get_text_to_render=False):
         """Prompt(s) -> (T5 embeddings [B, L, 4096], CLIP pooled [B, 768]).  With tokenizers and both encoders attached
         this is the reference's path (``:349-456``: CLIP on ``prompt``, T5 on ``prompt_2``); a single object with an
-        ``encode(prompts, L)`` method in the ``text_encoder`` slot is the synthetic stand-in."""
+        ``encode(prompts, L)`` method in the ``text_encoder`` slot is the synthetic stand-in.  ``get_text_to_render``
+        (``:423-430``; needs the tokenizers): the T5 token span of the quoted text follows -> (embeddings, pooled, start, end)."""
         enc = getattr(self, "text_encoder", None)
         if all(getattr(self, n, None) is not None for n in ("tokenizer", "tokenizer_2", "text_encoder_2")) and enc is not None:
             pooled = self._get_clip_prompt_embeds(clip_prompt if clip_prompt is not None else prompt, num_images_per_prompt)
+            if get_text_to_render:
+                pe, start, end = self._get_t5_prompt_embeds(prompt, num_images_per_prompt, max_sequence_length,
+                                                            get_text_to_render=True)
+                return pe, pooled, start, end
             pe = self._get_t5_prompt_embeds(prompt, num_images_per_prompt, max_sequence_length)
             return pe, pooled
+        if get_text_to_render:
+            raise ValueError("`get_text_to_render` needs tokenizer_2 / text_encoder_2: the span is found in the T5 token ids")
         if enc is None or not hasattr(enc, "encode"):
             raise ValueError("no text encoder is attached to this pipeline: pass `prompt_embeds` and "
                              "`pooled_prompt_embeds`, or attach tokenizer / tokenizer_2 / text_encoder / text_encoder_2")

@@ -31,13 +31,21 @@ class FluxControlNetPipeline(RepTextPipelineBase):
         self._setup()
 
     def encode_prompt(self, prompt, prompt_2, device=None, num_images_per_prompt: int = 1, prompt_embeds=None,
-                      pooled_prompt_embeds=None, max_sequence_length: int = 512, lora_scale=None):
-        """``:349-456``: returns (prompt_embeds [B, L, 4096], pooled [B, 768], text_ids [L, 3] zeros)."""
+                      pooled_prompt_embeds=None, max_sequence_length: int = 512, lora_scale=None,
+                      get_text_to_render: bool = False):
+        """``:349-456``: returns (prompt_embeds [B, L, 4096], pooled [B, 768], text_ids [L, 3] zeros), followed by the T5
+        token span (start, end) of the quoted text when ``get_text_to_render`` is set (``:423-430``, ``:453-454``; as
+        upstream the span only exists when the prompt is encoded here, not with ``prompt_embeds`` passed in)."""
         device = device or self._execution_device
+        span = ()
         if prompt_embeds is None:
-            prompt_embeds, pooled_prompt_embeds = self._encode_text(prompt_2 or prompt, num_images_per_prompt,
-                                                                    max_sequence_length, clip_prompt=prompt)
-        return prompt_embeds, pooled_prompt_embeds, self._text_ids(prompt_embeds.shape[1], device)
+            prompt_embeds, pooled_prompt_embeds, *span = self._encode_text(
+                prompt_2 or prompt, num_images_per_prompt, max_sequence_length, clip_prompt=prompt,
+                get_text_to_render=get_text_to_render)
+        elif get_text_to_render:
+            raise ValueError("`get_text_to_render` needs the prompt to be encoded here (upstream fails with an unbound "
+                             "`t5_start_index` when `prompt_embeds` is passed)")
+        return (prompt_embeds, pooled_prompt_embeds, self._text_ids(prompt_embeds.shape[1], device), *span)
 
     @torch.no_grad()
     def __call__(

@@ -111,3 +111,50 @@ def test_models_refuse_cpu_and_missing_library(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/librt_reptext.so")
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def test_text_to_render_span_host_logic():
+    """``get_text_to_render`` (pipeline_flux_controlnet.py:257-280): the span is where the quoted text's tokens - without the
+    first one and the EOS - sit in the prompt's T5 ids; ``'...'`` before ``"..."``; no window / no quotes raise as upstream
+    (ValueError / IndexError); without tokenizers the option is refused."""
+    from types import SimpleNamespace
+    from reptext_b200.pipeline_flux_controlnet import FluxControlNetPipeline as P
+    from reptext_b200.pipeline_utils import SyntheticTokenizer
+
+    class Enc:
+        dtype = torch.float32
+
+        def __call__(self, ids, output_hidden_states=False):
+            h = ids.float()[..., None].expand(*ids.shape, 8)
+            return _Out(h)
+
+    class _Out(tuple):
+        def __new__(cls, h):
+            o = super().__new__(cls, (h,))
+            o.pooler_output = h[:, 0]
+            return o
+
+    tok2 = SyntheticTokenizer("t5", 1000, 512)
+    mine = SimpleNamespace(tokenizer=SyntheticTokenizer("clip", 1000, 77), tokenizer_2=tok2, text_encoder=Enc(),
+                           text_encoder_2=Enc(), tokenizer_max_length=77, _execution_device=torch.device("cpu"))
+    for name in ("_locate_text_to_render", "_get_t5_prompt_embeds", "_get_clip_prompt_embeds", "_encode_text", "_text_ids"):
+        setattr(mine, name, getattr(RepTextPipelineBase, name).__get__(mine))
+    prompt = "a sign that says ' hello big world ' and \" not this \" in the city"
+    pe, po, ids, start, end = P.encode_prompt(mine, prompt, None, device="cpu", max_sequence_length=32, get_text_to_render=True)
+    words = prompt.split()
+    assert (start, end) == (words.index("hello"), words.index("hello") + 4)      # hello big world ' (the closing quote stays)
+    row = tok2([prompt], padding="max_length", max_length=32, truncation=True).input_ids[0]
+    assert torch.equal(row[start:end], tok2(["hello big world '"]).input_ids[0][:4])
+    assert pe.shape == (1, 32, 8) and po.shape == (1, 8) and ids.shape == (32, 3)
+    assert P.encode_prompt(mine, 'say " only double quotes here " now', None, device="cpu", max_sequence_length=32,
+                           get_text_to_render=True)[3:] == (2, 7)
+    assert len(P.encode_prompt(mine, prompt, None, device="cpu", max_sequence_length=32)) == 3
+    with pytest.raises(ValueError, match="No match found"):
+        P.encode_prompt(mine, "says 'hello big world'now", None, device="cpu", max_sequence_length=32, get_text_to_render=True)
+    with pytest.raises(IndexError):
+        P.encode_prompt(mine, "no quotes at all", None, device="cpu", max_sequence_length=32, get_text_to_render=True)
+    with pytest.raises(ValueError, match="encoded here"):
+        P.encode_prompt(mine, prompt, None, device="cpu", prompt_embeds=pe, pooled_prompt_embeds=po, get_text_to_render=True)
+    mine.tokenizer_2 = None
+    with pytest.raises(ValueError):
+        P.encode_prompt(mine, prompt, None, device="cpu", max_sequence_length=32, get_text_to_render=True)

@@ -192,3 +192,40 @@ def test_oracle_preparation_equals_reference_run(name):
     assert torch.allclose(ts, z["timesteps"], rtol=1e-6) and torch.allclose(sg, z["sigmas"], rtol=1e-6, atol=1e-7)
     assert torch.equal(O.prepare_latent_image_ids(2 * (H // 16), 2 * (W // 16)), z["img_ids"])
     assert torch.equal(torch.zeros(case["T"], 3), z["txt_ids"])
+
+
+# ------------------------------------------------------------------ reference == product host logic (text-to-render span)
+@needs_ref
+def test_text_to_render_span_equals_reference_run():
+    """``encode_prompt(..., get_text_to_render=True)`` (pipeline_flux_controlnet.py:257-280, :423-454): the reference's own
+    method, run on its own pipeline object, against the product's host logic on the same tokenizers and the same
+    (transformers) encoders - embeddings, pooled vector, text ids and the (start, end) span of the quoted text; and the
+    reference's error when the quoted text is not found as a token window."""
+    from types import SimpleNamespace
+    from reptext_b200._pipeline_common import RepTextPipelineBase as B
+    from reptext_b200.pipeline_flux_controlnet import FluxControlNetPipeline as P
+    torch.set_num_threads(8)
+    case = F.CASES["ref_tiny_t2i"]
+    ref = F.reference_pipeline(case)
+    mine = SimpleNamespace(tokenizer=ref.tokenizer, tokenizer_2=ref.tokenizer_2, text_encoder=ref.text_encoder,
+                           text_encoder_2=ref.text_encoder_2, tokenizer_max_length=ref.tokenizer_max_length,
+                           _execution_device=torch.device("cpu"))
+    for name in ("_locate_text_to_render", "_get_t5_prompt_embeds", "_get_clip_prompt_embeds", "_encode_text", "_text_ids"):
+        setattr(mine, name, getattr(B, name).__get__(mine))
+    for prompt in ("a street sign that says ' hello big world ' in the city, film grain",
+                   'a shop front with " open all night " written above the door'):
+        with torch.no_grad():
+            want = ref.encode_prompt(prompt, None, device="cpu", max_sequence_length=case["T"], get_text_to_render=True)
+            got = P.encode_prompt(mine, prompt, None, device="cpu", max_sequence_length=case["T"], get_text_to_render=True)
+        assert len(want) == len(got) == 5 and tuple(got[3:]) == tuple(want[3:]) and got[4] > got[3] > 0
+        for w, g in zip(want[:3], got[:3]):
+            assert w.shape == g.shape and w.dtype == g.dtype and torch.equal(w, g)
+    with torch.no_grad():
+        plain = P.encode_prompt(mine, "no quotes needed here", None, device="cpu", max_sequence_length=case["T"])
+    assert len(plain) == 3
+    # the quoted text tokenises differently on its own than inside the prompt (no break after the closing quote): both raise
+    bad = "a sign that says 'hello big world'now in the city"
+    for call in (lambda: ref.encode_prompt(bad, None, device="cpu", max_sequence_length=case["T"], get_text_to_render=True),
+                 lambda: P.encode_prompt(mine, bad, None, device="cpu", max_sequence_length=case["T"], get_text_to_render=True)):
+        with pytest.raises(ValueError, match="No match found"):
+            call()
