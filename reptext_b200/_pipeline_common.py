@@ -74,6 +74,7 @@ def _load_tokenizer(dirpath: str, class_name: Optional[str]):
 
 class RepTextPipelineBase(DiffusionPipeline):
     _callback_tensor_inputs = ["latents", "prompt_embeds"]
+    _optional_components: List[str] = []
     _inpaint = False
     skip_unconsumed_controlnet_blocks = True
     # what a forward derives from the prompt embeddings / ids alone is computed once per image, not once per step
@@ -163,6 +164,15 @@ class RepTextPipelineBase(DiffusionPipeline):
         return self._interrupt
 
     # ---- once-per-call helpers ----------------------------------------------------------------------
+    def get_timesteps(self, num_inference_steps, strength, device):
+        """``:474-484`` (both pipelines carry it, neither ``__call__`` uses it): the tail of the schedule an img2img run of
+        ``strength`` would keep -> (timesteps, number of steps); the scheduler's begin index moves with it."""
+        first = int(max(num_inference_steps - min(num_inference_steps * strength, num_inference_steps), 0))
+        timesteps = self.scheduler.timesteps[first * self.scheduler.order:]
+        if hasattr(self.scheduler, "set_begin_index"):
+            self.scheduler.set_begin_index(first * self.scheduler.order)
+        return timesteps, num_inference_steps - first
+
     def check_inputs(self, prompt, prompt_2, height, width, prompt_embeds=None, pooled_prompt_embeds=None,
                      callback_on_step_end_tensor_inputs=None, max_sequence_length=None):
         """Same conditions and exception types as ``pipeline_flux_controlnet.py:486-531``."""

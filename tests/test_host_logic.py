@@ -158,3 +158,15 @@ def test_text_to_render_span_host_logic():
     mine.tokenizer_2 = None
     with pytest.raises(ValueError):
         P.encode_prompt(mine, prompt, None, device="cpu", max_sequence_length=32, get_text_to_render=True)
+
+
+def test_get_timesteps_tail_of_the_schedule():
+    """``get_timesteps`` (pipeline_flux_controlnet.py:474-484): strength 1 keeps every step, 0.5 the second half, 0 none;
+    the scheduler's begin index follows."""
+    from types import SimpleNamespace
+    sch = FlowMatchEulerDiscreteScheduler()
+    sch.set_timesteps(sigmas=np.linspace(1.0, 1 / 10, 10), mu=1.0)
+    me = SimpleNamespace(scheduler=sch)
+    for strength, first in ((1.0, 0), (0.5, 5), (0.26, 7), (0.0, 10), (1.7, 0)):
+        ts, n = RepTextPipelineBase.get_timesteps(me, 10, strength, "cpu")
+        assert n == 10 - first and torch.equal(ts, sch.timesteps[first:]) and sch.begin_index == first
