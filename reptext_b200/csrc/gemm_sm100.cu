@@ -683,8 +683,10 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_tc_kernel(const 
     // L2 eviction hints (activations evict_last, weights evict_first) are OFF by default: measured with ncu over the
     // 188 GEMM launches of a step they RAISE DRAM reads from 52 GB to 74 GB - a weight tile is shared by the 16-18
     // row tiles of its wave, and evict_first drops it before the neighbours have fetched it.
-    const uint64_t pol_a = (P.debug & 8) ? ptx::kL2EvictLast : ptx::kL2EvictNormal;
-    const uint64_t pol_w = (P.debug & 8) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
+    // (bits 32 / 64: the opposite polarity for the long-K problems, whose W is re-read once per band of row tiles -
+    //  W evict_last with A normal / A evict_first; A/B, same results)
+    const uint64_t pol_a = (P.debug & 8) ? ptx::kL2EvictLast : (P.debug & 64) ? ptx::kL2EvictFirst : ptx::kL2EvictNormal;
+    const uint64_t pol_w = (P.debug & 8) ? ptx::kL2EvictFirst : (P.debug & (32 | 64)) ? ptx::kL2EvictLast : ptx::kL2EvictNormal;
     // sequence-parallel: A holds rows the peers' attention epilogues stored - the phase barrier runs here (sp_sync.cuh)
     spsync::sp_barrier_head(P.sync, lane, blockIdx.x == 0);
     int stage = 0, phase = 0;

@@ -12,9 +12,13 @@ for (M, N, K) in [(4608, 3072, 15360), (4096, 3072, 12288)]:
     b = torch.randn(N, device="cuda", dtype=dt)
     out = torch.zeros(1, M, N, device="cuda", dtype=dt)
     gate = torch.ones(1, N, device="cuda")
-    for band in (-1, 0, -1, 0):
+    # launches per shape: band off, band auto, then band auto with the L2 hints of gemm_debug 32 (W evict_last) and
+    # 64 (W evict_last, A evict_first), twice each
+    for band, dbg in ((-1, 0), (0, 0), (0, 32), (0, 64), (-1, 0), (0, 0), (0, 32), (0, 64)):
         L.set_option("gemm_band", band)
+        L.set_option("gemm_debug", dbg)
         ops.gemm([ops.Problem(A=A, segs=[ops.Segment(W=W, bias=b, out=out, mode=L.EPI_GATE_RESID)], gate=gate)], 1, dt, impl=3)
     torch.cuda.synchronize()
 L.set_option("gemm_band", 0)
+L.set_option("gemm_debug", 0)
 print("done")
