@@ -72,7 +72,9 @@ RT_API long long rt_launch_count(void); /* number of this library's kernels laun
  * "mod_debug_skip" (1 = forwards skip the timestep / AdaLN chain and run on whatever vectors the workspace holds - a
  * timing experiment with WRONG results: what that chain costs inside a step),
  * "gemm_debug" (bit 1: no epilogue, bit 2: k-block 0 only - timing experiments with WRONG results;
- * bit 4: direct row-per-thread epilogue stores instead of the staged coalesced ones - same results) */
+ * bit 4: direct row-per-thread epilogue stores instead of the staged coalesced ones; bits 8 / 32 / 64: L2 eviction hints
+ * on the TMA loads - A evict_last + W evict_first / W evict_last / W evict_last + A evict_first - same results, all
+ * measured neutral or worse, off by default) */
 RT_API int rt_set_option(const char* name, int value);
 RT_API int rt_get_option(const char* name, int* value);
 
