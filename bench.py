@@ -318,11 +318,19 @@ def elementwise_leg(dev, pk):
 def make_step(tr, cn, ops, pe, po, cond, mask, img_ids, txt_ids, guidance, sig, tsd, sp_kw):
     dt = torch.bfloat16
 
+    # `cond` / `mask`: one tensor each, or a list with one entry per text line (cfg 2b: the ControlNet runs once per line
+    # and the masked samples are summed - pipeline_flux_controlnet.py:1060-1087 - here inside the zero-linear epilogue)
+    conds, masks = (cond, mask) if isinstance(cond, (list, tuple)) else ([cond], [mask])
+
     def one_step(i, latents):
         j = i % STEPS_PER_IMAGE
         kw = dict(hidden_states=latents, encoder_hidden_states=pe, pooled_projections=po,
                   timestep=(tsd[j].expand(1).to(dt)) / 1000, guidance=guidance, img_ids=img_ids, txt_ids=txt_ids)
-        bl, sl = cn(controlnet_cond=cond, conditioning_scale=1.0, regional_mask=mask, return_dict=False, **kw, **sp_kw)
+        acc = None
+        for c, m in zip(conds, masks):
+            bl, sl = cn(controlnet_cond=c, conditioning_scale=1.0, regional_mask=m, accumulate_into=acc,
+                        return_dict=False, **kw, **sp_kw)
+            acc = (bl[0]._rt_stacked if bl is not None else None, sl[0]._rt_stacked if sl is not None else None)
         v = tr(controlnet_block_samples=bl, controlnet_single_block_samples=sl, return_dict=False, **kw, **sp_kw)[0]
         return ops.euler_step(v, latents, sig[j], sig[j + 1])
     return one_step
@@ -547,7 +555,17 @@ def run_b200(args, wl):
     if not args.full_controlnet:
         # what the pipelines do by default: ControlNet blocks whose sample the transformer never reads are not run
         cn.set_consumer(TR["num_layers"], TR["num_single_layers"])
-    one_step = make_step(tr, cn, ops, pe, po, cond, mask, img_ids, txt_ids, guidance, sig, tsd, sp_kw)
+    L_lines = max(1, args.lines)
+    mask_imgs, conds_l, masks_l = [mask_img], [cond], [mask]
+    for li in range(1, L_lines):     # cfg 2b: further text lines, each with its own condition and box (stacked below line 1)
+        top = (H // 3 + li * (H // 5)) % (H - H // 6)
+        mask_imgs.append(box_mask(H, W, (top, top + H // 6, W // 5, W - W // 5)))
+        conds_l.append(torch.randn(cond.shape, generator=g).to(dt).to(dev))
+        masks_l.append(pipe._regional_masks([mask_imgs[-1]], dev, dt)[0])
+    if L_lines > 1:
+        assert sp is None, "--lines > 1 is a single-GPU-per-sample measurement"
+    one_step = make_step(tr, cn, ops, pe, po, conds_l if L_lines > 1 else cond, masks_l if L_lines > 1 else mask,
+                         img_ids, txt_ids, guidance, sig, tsd, sp_kw)
 
     def barrier():
         if world > 1:
@@ -635,6 +653,7 @@ def run_b200(args, wl):
     h_tap = torch.empty(1, N // (world if sp is not None else 1), TR["in_channels"], dtype=dt).pin_memory()
     canny = pin(torch.rand(1, 3, H, W, generator=g) * 2 - 1)
     pos = pin((torch.from_numpy(mask_img)[None, None].float() / 255.0) * 2 - 1)
+    poss = [pos] + [pin((torch.from_numpy(m)[None, None].float() / 255.0) * 2 - 1) for m in mask_imgs[1:]]
     d2h = [0]
 
     def tap(p, i, t, kw):
@@ -644,7 +663,7 @@ def run_b200(args, wl):
 
     def one_image(steps):
         out = pipe(prompt=PROMPT, max_sequence_length=T, height=H, width=W, num_inference_steps=steps,
-                   guidance_scale=3.5, control_image=[canny], control_position=[pos], control_mask=[mask_img],
+                   guidance_scale=3.5, control_image=[canny] * L_lines, control_position=poss, control_mask=mask_imgs,
                    controlnet_conditioning_scale=1.0, latents=h_lat, output_type="pt", callback_on_step_end=tap)
         res = out.images.to("cpu", non_blocking=False)     # the decoded image [1, 3, H, W]
         return res
@@ -664,7 +683,8 @@ def run_b200(args, wl):
         if world > 1:
             dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         e2e_value = n_samples * STEPS_PER_IMAGE / (float(e2e_ms.item()) / 1000.0)
-        h2d_total = sum(t.numel() * t.element_size() for t in (h_lat, canny, pos)) + mask_img.size * 4 + (T + 77) * 8
+        h2d_total = (sum(t.numel() * t.element_size() for t in (h_lat, *([canny] * L_lines), *poss))
+                     + sum(m.size for m in mask_imgs) * 4 + (T + 77) * 8)
         h2d_step = h2d_total / STEPS_PER_IMAGE
         d2h_step = (d2h[0] + res.numel() * res.element_size()) / STEPS_PER_IMAGE
 
@@ -725,7 +745,7 @@ def run_b200(args, wl):
     pk = peaks()
     # ---- the kernel to beat, same box, same inputs: the reference path through stock torch in bf16
     gpu_base = None
-    if world == 1 and sp is None and not args.no_gpu_baseline:
+    if world == 1 and sp is None and not args.no_gpu_baseline and L_lines == 1:
         try:
             gpu_base = gpu_baseline_leg(tr, cn, TR, CN, lat, pe, po, cond, mask, img_ids, txt_ids, sch.sigmas, tsd,
                                         max(2, min(args.steps, 6)), one_step(0, lat))
@@ -743,14 +763,14 @@ def run_b200(args, wl):
 
     if rank == 0:
         live = None if args.full_controlnet else cn_live(TR, CN)
-        flops = step_flops(TR, CN, N, T, cn_live_layers=live)
-        flops_reference = step_flops(TR, CN, N, T)
+        flops = step_flops(TR, CN, N, T, lines=L_lines, cn_live_layers=live)
+        flops_reference = step_flops(TR, CN, N, T, lines=L_lines)
         gpus_per_sample = world if sp is not None else 1
         gem = prof.get("gemm_tcgen05", (0.0, 0.0, 0))
         roof = None
         # ncu dram__bytes_read + write per GEMM launch, averaged over the GEMM launches of one cfg2 step (tools/gpu.sh traffic)
         traffic, traffic_file = None, None
-        if args.workload == "cfg2":
+        if args.workload == "cfg2" and L_lines == 1:
             for name in ("r2_gemm_dram_traffic.json", "r1_gemm_dram_traffic.json"):
                 tpath = os.path.join(ROOT, "profiles", name)
                 if not os.path.exists(tpath):
@@ -764,8 +784,8 @@ def run_b200(args, wl):
             ach = gem[1] / (gem[0] / 1000.0) / 1e12
             roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 + TMA, fused epilogues)", achieved=ach,
                         peak=pk["bf16_sustained"], unit="TFLOP/s", frac=ach / pk["bf16_sustained"], traffic=traffic,
-                        traffic_unit=f"bytes of DRAM traffic per launch (ncu, profiles/{traffic_file}); "
-                                     "algorithmic operand bytes per launch: 203e6",
+                        traffic_unit=(f"bytes of DRAM traffic per launch (ncu, profiles/{traffic_file}); "
+                                      "algorithmic operand bytes per launch: 203e6") if traffic else None,
                         peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)",
                         frac_of_burst=ach / pk["bf16_burst"], launches=gem[2], ms_per_step=gem[0] / args.steps,
                         flops_per_step=gem[1] / args.steps)
@@ -787,7 +807,7 @@ def run_b200(args, wl):
                     ms_per_step=step_ms, higher_is_better=True, scaling="strong" if sp is not None else "weak",
                     vs_baseline=None, dtype="bf16",
                     data="synthetic (random-init weights of the named architecture, randn latents / embeddings)",
-                    config=dict(workload=wl["name"],
+                    config=dict(workload=wl["name"] if L_lines == 1 else wl["name"].replace("1 text line", f"{L_lines} text lines (cfg 2b)"),
                                 parallelism=(f"sp{world} (one sample; tokens and attention heads sharded; peer stores + flag "
                                              "barriers, NCCL only gathers the final latents)" if sp is not None else
                                              f"dp{world} (independent samples, no data-path collective)"),
@@ -839,6 +859,7 @@ def main():
     ap.add_argument("--full-controlnet", action="store_true", help="run every ControlNet block like the reference (A/B of the unconsumed-block skip)")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-mod-table", action="store_true", help="e2e leg: AdaLN vectors computed per step instead of once per image (A/B of pipe.precompute_modulation)")
+    ap.add_argument("--lines", type=int, default=1, help="text lines per image (cfg 2b = 2: the ControlNet runs once per line); the baselines are measured at 1 only")
     ap.add_argument("--no-sp", action="store_true", help="skip the cfg5 sequence-parallel record of multi-GPU runs")
     args = ap.parse_args()
     wl = workload(args.workload)
