@@ -126,6 +126,40 @@ def test_t5_xxl_width_two_layers_vs_oracle():
     assert e < 1e-2
 
 
+def test_t5_xxl_full_depth_vs_oracle_and_stock_torch_bf16():
+    """T5-v1.1-XXL as the pipeline runs it (24 blocks, d_model 4096, 64 heads, d_ff 10240, the 32128-row vocabulary, 512
+    tokens; 4.7 B random parameters drawn on the device in bf16): the CUDA encoder against the fp32 oracle reading the SAME
+    bf16 weights, and against what stock torch does with the oracle in bf16 (the reference's own numerics on this GPU).
+    Bars: <= 3e-2 against fp32 after 24 residual blocks, and never worse than 1.25 x stock torch bf16."""
+    from oracle import text_oracle as TO
+    from reptext_b200 import text_encoders as TE
+    cfg = dict(TO.T5_XXL_CONFIG)
+    sd = TE.random_weights(TE.t5_param_shapes(TE.T5_XXL_CONFIG), 21, "cuda")
+    assert len(sd) == len(TO.t5_param_shapes(cfg)) and sum(v.numel() for v in sd.values()) > 4.5e9
+
+    class F32View(dict):                     # one fp32 copy of one tensor at a time (the whole model would be 19 GB)
+        def __getitem__(self, k):
+            return dict.__getitem__(self, k).float()
+
+    m = TE.T5EncoderModel(None, sd, device="cuda")
+    ids = torch.randint(2, cfg["vocab_size"], (1, 512), generator=torch.Generator().manual_seed(22)).cuda()
+    ids[:, 40:] = 0                          # a 39-token prompt + EOS, padded to 512 like the pipeline's tokenizer call
+    ids[:, 39] = 1
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = TO.t5_encoder(F32View(sd), cfg, ids)
+            stock = TO.t5_encoder(sd, cfg, ids)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    out = m(ids)[0]
+    assert out.shape == (1, 512, 4096) and out.dtype == BF and stock.dtype == BF
+    e, e_stock = rel_l2(out, want), rel_l2(stock, want)
+    print(f"T5-XXL, all 24 blocks, 512 tokens: rel-L2 against fp32 {e:.2e}; stock torch bf16 {e_stock:.2e} (ratio {e / e_stock:.2f})")
+    assert e < 3e-2 and e <= 1.25 * e_stock
+
+
 def test_clip_l_full_vs_oracle():
     """CLIP ViT-L/14 text model at full size (12 blocks, 768 wide, 77 tokens): hidden states and pooler_output."""
     from oracle import text_oracle as TO
