@@ -215,10 +215,14 @@ def run_reference(args, wl):
     cores = torch.get_num_threads()
     sample = desc + f"; {len(secs)} samples timed in {timed:.1f} s, min {min(secs):.2f} / mean {mean:.2f} / max {max(secs):.2f} s"
     line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=len(secs), warmup=args.warmup,
-                ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", config=dict(workload=wl["name"], note="CPU arm does not scale with --gpus",
+                # a "step" of this arm is ONE bounded sample (what was really run and timed: steps x ms_per_step = the
+                # timed region); `value` is the whole-step rate those samples imply (sample time x FLOP ratio)
+                ms_per_step=1000.0 * mean, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=dict(workload=wl["name"], note="CPU arm does not scale with --gpus; each timed "
+                                              "step is one bounded sample (sample_fraction_of_step of a step's FLOPs), "
+                                              "value = 1 / ms_per_whole_step_extrapolated",
                                               sample_fraction_of_step=f_sample / f_step, timed_region_s=timed,
-                                              samples_timed=len(secs)),
+                                              samples_timed=len(secs), ms_per_whole_step_extrapolated=1000.0 / v),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 images_per_s=v / STEPS_PER_IMAGE)
