@@ -308,12 +308,22 @@ def elementwise_leg(dev, pk):
         nz, gl = torch.randn(B, 16, 128, 128, device=dev, dtype=dt), torch.randn(B, 16, 128, 128, device=dev, dtype=dt)
         gm = (torch.rand(B, 16, 128, 128, device=dev) > 0.5).to(torch.uint8)
         e = 2
+        T = 512
+        xs = torch.randn(B, T + N, D, device=dev, dtype=dt)
+        xo = torch.empty_like(xs)
+        md = torch.randn(B, 4 * D, device=dev) * 0.3
+        ln_groups = [(0, T, md[:, :D], md[:, D:2 * D]), (T, T + N, md[:, 2 * D:3 * D], md[:, 3 * D:])]
         out[f"B{B}"] = dict(
+            layernorm_modulate=t(lambda: ops.layernorm_modulate(xs, ln_groups, out=xo), 2 * xs.numel() * e),
             euler_step=t(lambda: ops.euler_step(v, x, 0.9, 0.85), 3 * v.numel() * e),
             cfg_euler_step=t(lambda: ops.cfg_euler_step(v2, x, 3.5, False, 0.9, 0.85), (v2.numel() + 2 * x.numel()) * e),
             mask_scale_add=t(lambda: ops.mask_scale_add(s6, m, acc, 0.9), 3 * s6.numel() * e),
             glyph_init_blend=t(lambda: ops.glyph_init_blend(nz, gl, gm, 0.10, 1.00), 3 * nz.numel() * e + gm.numel()))
-    out["note"] = ("bytes = algorithmic reads + writes; at B = 1 the Euler / CFG tensors are 0.5 MB each: the figure is launch "
+    out["note"] = ("layernorm_modulate: the step's LN + AdaLN kernel alone at the joint sequence (512 + 4096 rows), L2 "
+                   "flushed before every launch - the `breakdown` figure of the same kernel carries the CUDA-event brackets "
+                   "of the profiling pass, and so does this one (an event pair around ONE launch adds ~5 us: ncu times the "
+                   "B = 1 launch at 15.2 us, here ~20; at B = 8 the same kernel streams 453 MB at 0.77 of the copy bandwidth); "
+                   "bytes = algorithmic reads + writes; at B = 1 the Euler / CFG tensors are 0.5 MB each: the figure is launch "
                    "latency (~2-3 us), not bandwidth; mask_scale_add is the UNFUSED form of the regional-mask multiply and "
                    "multi-line sum (the product fuses both into the zero-linear GEMM epilogue)")
     return out
