@@ -229,3 +229,22 @@ def test_text_to_render_span_equals_reference_run():
                  lambda: P.encode_prompt(mine, bad, None, device="cpu", max_sequence_length=case["T"], get_text_to_render=True)):
         with pytest.raises(ValueError, match="No match found"):
             call()
+
+
+@needs_ref
+def test_get_timesteps_equals_reference_run():
+    """``get_timesteps`` (pipeline_flux_controlnet.py:474-484), the reference's own method on its own pipeline object and
+    scheduler, against the product's on the product's scheduler: same tail of the schedule, same count, same begin index."""
+    from types import SimpleNamespace
+    from reptext_b200._pipeline_common import RepTextPipelineBase as B
+    from reptext_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    ref = F.reference_pipeline(F.CASES["ref_tiny_t2i"])
+    sig = np.linspace(1.0, 1 / 12, 12)
+    mine = SimpleNamespace(scheduler=FlowMatchEulerDiscreteScheduler())
+    for strength in (1.0, 0.75, 0.3, 0.05, 0.0):
+        ref.scheduler.set_timesteps(sigmas=sig, mu=0.8)
+        mine.scheduler.set_timesteps(sigmas=sig, mu=0.8)
+        want_ts, want_n = ref.get_timesteps(12, strength, "cpu")
+        got_ts, got_n = B.get_timesteps(mine, 12, strength, "cpu")
+        assert got_n == want_n and torch.allclose(got_ts.float(), want_ts.float(), rtol=0, atol=1e-4)
+        assert mine.scheduler.begin_index == ref.scheduler.begin_index
