@@ -248,3 +248,34 @@ def test_get_timesteps_equals_reference_run():
         got_ts, got_n = B.get_timesteps(mine, 12, strength, "cpu")
         assert got_n == want_n and torch.allclose(got_ts.float(), want_ts.float(), rtol=0, atol=1e-4)
         assert mine.scheduler.begin_index == ref.scheduler.begin_index
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["ref_tiny_t2i", "ref_tiny_inpaint"])
+def test_check_inputs_accepts_and_rejects_like_the_reference_run(kind):
+    """``check_inputs`` of both pipelines (pipeline_flux_controlnet.py:486-531, the inpaint file's copy): every argument set
+    the reference's own method accepts is accepted, every one it rejects is rejected with the same exception type."""
+    from reptext_b200._pipeline_common import RepTextPipelineBase as B
+    ref = F.reference_pipeline(F.CASES[kind])
+    mine = B.__new__(B)
+    e = torch.zeros(1, 4, 8)
+    ok = dict(prompt="a", prompt_2=None, height=256, width=256)
+    cases = [ok, dict(ok, prompt=["a", "b"], prompt_2=["c", "d"]), dict(ok, prompt_2="b", max_sequence_length=512),
+             dict(ok, prompt=None, prompt_embeds=e, pooled_prompt_embeds=e), dict(ok, height=1000, width=760),
+             dict(ok, callback_on_step_end_tensor_inputs=["latents", "prompt_embeds"]),
+             dict(ok, height=250), dict(ok, width=12), dict(ok, prompt=None), dict(ok, prompt=3), dict(ok, prompt_2=3.5),
+             dict(ok, prompt_embeds=e), dict(ok, prompt=None, prompt_2="b", prompt_embeds=e, pooled_prompt_embeds=e),
+             dict(ok, prompt=None, prompt_embeds=e), dict(ok, max_sequence_length=513),
+             dict(ok, callback_on_step_end_tensor_inputs=["noise_pred"])]
+    outcomes = []
+    for kw in cases:
+        res = []
+        for obj in (ref, mine):
+            try:
+                obj.check_inputs(**kw)
+                res.append(None)
+            except Exception as ex:          # noqa: BLE001 - the TYPE is what is compared
+                res.append(type(ex))
+        assert res[0] is res[1], (kw, res)
+        outcomes.append(res[0])
+    assert outcomes.count(None) == 6 and outcomes.count(ValueError) == 10
