@@ -279,3 +279,65 @@ def test_check_inputs_accepts_and_rejects_like_the_reference_run(kind):
         assert res[0] is res[1], (kw, res)
         outcomes.append(res[0])
     assert outcomes.count(None) == 6 and outcomes.count(ValueError) == 10
+
+
+@needs_ref
+def test_pack_unpack_ids_shift_equal_reference_functions():
+    """The once-per-call helpers, reference function against product function on the same CPU tensors, bit for bit:
+    ``_pack_latents`` / ``_unpack_latents`` / ``_prepare_latent_image_ids`` (pipeline_flux_controlnet.py:535-570),
+    ``calculate_shift`` (:78-88) and ``retrieve_timesteps`` with custom sigmas (:104-160) - for both pipeline files."""
+    from reptext_b200 import _pipeline_common as PC
+    from reptext_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    R = ref_run.load()
+    B = PC.RepTextPipelineBase
+    g = torch.Generator().manual_seed(5)
+    for mod in (R.t2i, R.inpaint):
+        RP = mod.FluxControlNetPipeline
+        for (b, c, h, w) in ((1, 16, 32, 32), (2, 16, 24, 40), (3, 4, 2, 6)):
+            x = torch.randn(b, c, h, w, generator=g)
+            p_ref, p_mine = RP._pack_latents(x, b, c, h, w), B._pack_latents(x, b, c, h, w)
+            assert torch.equal(p_ref, p_mine)
+            assert torch.equal(RP._unpack_latents(p_ref, h * 8, w * 8, 16), B._unpack_latents(p_mine, h * 8, w * 8, 16))
+            ids_ref = RP._prepare_latent_image_ids(b, h, w, "cpu", torch.float32)
+            ids_mine = B._prepare_latent_image_ids(b, h, w, "cpu", torch.float32)
+            assert ids_ref.shape == ids_mine.shape and torch.equal(ids_ref, ids_mine)
+        for n in (256, 1024, 4096, 9216):
+            assert mod.calculate_shift(n) == PC.calculate_shift(n)
+            assert mod.calculate_shift(n, 256, 4096, 0.5, 1.16) == PC.calculate_shift(n, 256, 4096, 0.5, 1.16)
+    # the schedule through retrieve_timesteps (custom sigmas + mu), shim scheduler under the reference function
+    from diffusers.schedulers import FlowMatchEulerDiscreteScheduler as ShimScheduler
+    for steps, n in ((4, 256), (28, 4096), (30, 9216)):
+        sig = np.linspace(1.0, 1 / steps, steps)
+        mu = PC.calculate_shift(n)
+        s_ref, s_mine = ShimScheduler(**F.config.SCHEDULER), FlowMatchEulerDiscreteScheduler()
+        t_ref, n_ref = R.t2i.retrieve_timesteps(s_ref, steps, "cpu", None, sig, mu=mu)
+        t_mine, n_mine = PC.retrieve_timesteps(s_mine, steps, "cpu", None, sig, mu=mu)
+        assert n_ref == n_mine == steps and torch.equal(t_ref, t_mine) and torch.equal(s_ref.sigmas, s_mine.sigmas)
+    with pytest.raises(ValueError):
+        PC.retrieve_timesteps(FlowMatchEulerDiscreteScheduler(), 4, "cpu", [1, 2], [0.5, 0.1])
+    with pytest.raises(ValueError):
+        R.t2i.retrieve_timesteps(ShimScheduler(**F.config.SCHEDULER), 4, "cpu", [1, 2], [0.5, 0.1])
+
+
+@needs_ref
+def test_prepare_latents_equals_reference_run():
+    """``prepare_latents`` (pipeline_flux_controlnet.py:573-606): the reference's own method on its pipeline object against
+    the product's, same seeded generators (one, and a list of one per sample), passed-in latents, and the length check."""
+    from reptext_b200._pipeline_common import RepTextPipelineBase as B
+    ref = F.reference_pipeline(F.CASES["ref_tiny_t2i"])
+    mine = B.__new__(B)
+    mine.vae_scale_factor = ref.vae_scale_factor
+    gens = lambda seeds: [torch.Generator().manual_seed(s) for s in seeds]
+    for (b, h, w, seeds) in ((1, 256, 256, None), (2, 256, 384, None), (2, 200, 136, [3, 4])):
+        g_ref = gens(seeds) if seeds else torch.Generator().manual_seed(7)
+        g_mine = gens(seeds) if seeds else torch.Generator().manual_seed(7)
+        l_ref, i_ref = ref.prepare_latents(b, 16, h, w, torch.float32, "cpu", g_ref)
+        l_mine, i_mine = mine.prepare_latents(b, 16, h, w, torch.float32, "cpu", g_mine)
+        assert l_ref.shape == l_mine.shape and torch.equal(l_ref, l_mine) and torch.equal(i_ref, i_mine)
+        given = torch.randn_like(l_ref)
+        k_ref, _ = ref.prepare_latents(b, 16, h, w, torch.float32, "cpu", None, latents=given)
+        k_mine, _ = mine.prepare_latents(b, 16, h, w, torch.float32, "cpu", None, latents=given)
+        assert torch.equal(k_ref, k_mine) and torch.equal(k_mine, given)
+    for obj in (ref, mine):
+        with pytest.raises(ValueError):
+            obj.prepare_latents(3, 16, 256, 256, torch.float32, "cpu", gens([1, 2]))
