@@ -400,3 +400,60 @@ def test_product_condition_preparation_equals_reference_run_on_cpu(kind):
         want, ids_w = ref.prepare_latents_reptext(glyph_r, *args, torch.Generator().manual_seed(3))
         got, ids_g = mine.prepare_latents_reptext(glyph_m, *args, torch.Generator().manual_seed(3))
         assert torch.equal(want, got) and torch.equal(ids_w, ids_g)
+
+
+# ------------------------------------------------------------------ reference script == product host glyph path (8f row 4)
+def _infer_script_pieces():
+    """The reference's own ``infer.py`` code, unmodified, as executable pieces: its helper functions (``contains_chinese``,
+    ``canny``), the per-text-line ``for`` loop (:71-100), the statements after it up to the prompt (:102-113).  The script
+    itself cannot be imported (it loads checkpoints at ``__main__`` and imports diffusers-bound modules at the top)."""
+    import ast
+    src = open(os.path.join(ref_run.REF, "infer.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef)
+            or (isinstance(n, (ast.Import, ast.ImportFrom)) and "controlnet" not in ast.unparse(n))]
+    main = [n for n in tree.body if isinstance(n, ast.If)][0].body
+    loop_at = [i for i, n in enumerate(main) if isinstance(n, ast.For)][0]
+    tail = []
+    for n in main[loop_at + 1:]:
+        if isinstance(n, ast.Assign) and "Generator" in ast.unparse(n):
+            break
+        if not (isinstance(n, ast.Expr) and "print" in ast.unparse(n)):
+            tail.append(n)
+    mod = lambda nodes: compile(ast.fix_missing_locations(ast.Module(body=nodes, type_ignores=[])), "infer.py", "exec")
+    return mod(keep), mod([main[loop_at]]), mod(tail)
+
+
+@needs_ref
+def test_glyph_conditions_and_prompt_equal_the_reference_script():
+    """``reptext_b200.glyphs.build_conditions`` / ``build_prompt`` / ``canny`` / ``contains_chinese`` against the code of
+    ``RepText/infer.py`` itself (:11-22, :71-113), executed from the file with the same font, lines, positions and colours:
+    Canny, position, regional-mask and accumulated glyph images pixel for pixel, and the prompt string."""
+    cv2 = pytest.importorskip("cv2")
+    from PIL import ImageFont
+    from reptext_b200 import glyphs
+    helpers, loop, tail = _infer_script_pieces()
+    for (W, H, size, texts, poss, cols) in (
+            (512, 384, 48, ["Shakker Labs", "RepText"], [(60, 80), (60, 200)], [(255, 255, 255), (255, 200, 40)]),
+            (256, 256, 32, ["B200"], [(40, 100)], [(255, 255, 255)]),
+            (384, 256, 40, ["哩布哩布", "Lovart AI"], [(30, 40), (30, 140)], [(255, 255, 255), (200, 255, 255)])):
+        font = ImageFont.load_default(size)
+        ns = dict(width=W, height=H, font=font, text_list=texts, text_position_list=poss, text_color_list=cols,
+                  control_image_list=[], control_position_list=[], control_mask_list=[],
+                  control_glyph_all=np.zeros([H, W, 3], dtype=np.uint8))
+        exec(helpers, ns)
+        exec(loop, ns)
+        exec(tail, ns)
+        got = glyphs.build_conditions(texts, poss, cols, W, H, font)
+        for name, mine in (("control_image_list", got.control_image), ("control_position_list", got.control_position),
+                           ("control_mask_list", got.control_mask)):
+            assert len(ns[name]) == len(mine) == len(texts)
+            for a, b in zip(ns[name], mine):
+                assert a.mode == b.mode and a.size == b.size and np.array_equal(np.array(a), np.array(b)), name
+        assert np.array_equal(np.array(ns["control_glyph_all"]), np.array(got.control_glyph))
+        assert ns["prompt"] == glyphs.build_prompt("a street sign in city", texts,
+                                                   ", filmfotos, film grain, reversal film photography")
+        for t in texts + ["مرحبا", "abc 漢"]:
+            assert ns["contains_chinese"](t) == glyphs.contains_chinese(t)
+        rnd = np.random.RandomState(0).randint(0, 255, (64, 96, 3)).astype(np.uint8)
+        assert np.array_equal(ns["canny"](rnd), glyphs.canny(rnd))
