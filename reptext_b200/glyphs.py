@@ -78,10 +78,35 @@ class GlyphConditions:
     bboxes: List[Tuple[int, int, int, int]] = field(default_factory=list)
 
 
+def resize_img(input_image: Image.Image, max_side: int = 1280, min_side: int = 1024, size=None,
+               pad_to_max_side: bool = False, mode=Image.BILINEAR, base_pixel_number: int = 64) -> Image.Image:
+    """``infer_inpaint.py:25-46``: the source photograph of the inpaint script brought to the model's sizes - the short side
+    to ``min_side``, then the long side to ``max_side`` (two resizes, as upstream), both sides rounded DOWN to multiples of
+    ``base_pixel_number``; ``size`` overrides; ``pad_to_max_side`` centres the result on a white square."""
+    w, h = input_image.size
+    if size is not None:
+        w_new, h_new = size
+    else:
+        ratio = min_side / min(h, w)
+        w, h = round(ratio * w), round(ratio * h)
+        ratio = max_side / max(h, w)
+        input_image = input_image.resize([round(ratio * w), round(ratio * h)], mode)
+        w_new = (round(ratio * w) // base_pixel_number) * base_pixel_number
+        h_new = (round(ratio * h) // base_pixel_number) * base_pixel_number
+    input_image = input_image.resize([w_new, h_new], mode)
+    if pad_to_max_side:
+        canvas = np.ones([max_side, max_side, 3], dtype=np.uint8) * 255
+        ox, oy = (max_side - w_new) // 2, (max_side - h_new) // 2
+        canvas[oy:oy + h_new, ox:ox + w_new] = np.array(input_image)
+        input_image = Image.fromarray(canvas)
+    return input_image
+
+
 def build_conditions(text_list: Sequence[str], text_position_list: Sequence[Tuple[int, int]],
                      text_color_list: Sequence[Tuple[int, int, int]], width: int, height: int, font,
-                     mask_margin: int = 5) -> GlyphConditions:
-    """The per-line loop of ``infer.py:64-104`` (one ControlNet pass per line in the pipeline)."""
+                     mask_margin: int = 5, position_margin: int = 0) -> GlyphConditions:
+    """The per-line loop of ``infer.py:64-104`` (one ControlNet pass per line in the pipeline).  ``position_margin``: the
+    inpaint script grows the POSITION box by 5 pixels as well (``infer_inpaint.py:99``); ``infer.py`` does not."""
     if not (len(text_list) == len(text_position_list) == len(text_color_list)):
         raise ValueError("text_list, text_position_list and text_color_list must have the same length")
     out = GlyphConditions()
@@ -95,7 +120,7 @@ def build_conditions(text_list: Sequence[str], text_position_list: Sequence[Tupl
         x0, y0, x1, y1 = max(x0, 0), max(y0, 0), min(x1, width), min(y1, height)
         out.bboxes.append((x0, y0, x1, y1))
         position = np.zeros([height, width], dtype=np.uint8)
-        position[y0:y1, x0:x1] = 255
+        position[max(y0 - position_margin, 0):y1 + position_margin, max(x0 - position_margin, 0):x1 + position_margin] = 255
         out.control_position.append(Image.fromarray(position))
         mask = np.zeros([height, width], dtype=np.uint8)
         mask[max(y0 - mask_margin, 0):y1 + mask_margin, max(x0 - mask_margin, 0):x1 + mask_margin] = 255

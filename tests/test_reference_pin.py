@@ -457,3 +457,41 @@ def test_glyph_conditions_and_prompt_equal_the_reference_script():
             assert ns["contains_chinese"](t) == glyphs.contains_chinese(t)
         rnd = np.random.RandomState(0).randint(0, 255, (64, 96, 3)).astype(np.uint8)
         assert np.array_equal(ns["canny"](rnd), glyphs.canny(rnd))
+
+
+@needs_ref
+def test_inpaint_script_helpers_equal_the_reference_script():
+    """``glyphs.resize_img`` and ``build_conditions(position_margin=5)`` against the code of ``RepText/infer_inpaint.py``
+    itself (:25-46, the per-line loop at :84-117 whose POSITION box is grown by 5 pixels like the mask), executed from
+    the file."""
+    pytest.importorskip("cv2")
+    import ast
+    from PIL import Image, ImageFont
+    from reptext_b200 import glyphs
+    tree = ast.parse(open(os.path.join(ref_run.REF, "infer_inpaint.py")).read())
+    fns = [n for n in tree.body if (isinstance(n, ast.FunctionDef) and n.name in ("resize_img", "canny", "contains_chinese"))
+           or (isinstance(n, (ast.Import, ast.ImportFrom)) and not any(w in ast.unparse(n) for w in ("controlnet", "diffusers")))]
+    main = [n for n in tree.body if isinstance(n, ast.If)][0].body
+    loop = [n for n in main if isinstance(n, ast.For)][0]
+    mod = lambda nodes: compile(ast.fix_missing_locations(ast.Module(body=nodes, type_ignores=[])), "infer_inpaint.py", "exec")
+    ns = {}
+    exec(mod(fns), ns)
+    rs = np.random.RandomState(1)
+    for (w, h), kw in (((1600, 1067), {}), ((900, 1400), {}), ((640, 480), dict(size=(512, 384))),
+                       ((1500, 1000), dict(pad_to_max_side=True)), ((333, 517), dict(max_side=768, min_side=512, base_pixel_number=16))):
+        img = Image.fromarray(rs.randint(0, 255, (h, w, 3)).astype(np.uint8))
+        a, b = ns["resize_img"](img, **kw), glyphs.resize_img(img, **kw)
+        assert a.size == b.size and np.array_equal(np.array(a), np.array(b)), ((w, h), kw)
+    W, H, texts, poss, cols = 512, 384, ["Shakker Labs", "RepText"], [(60, 80), (60, 200)], [(0, 255, 0), (255, 255, 255)]
+    font = ImageFont.load_default(48)
+    ns.update(width=W, height=H, font=font, text_list=texts, text_position_list=poss, text_color_list=cols,
+              control_image_list=[], control_position_list=[], control_mask_list=[],
+              control_glyph_all=np.zeros([H, W, 3], dtype=np.uint8))
+    exec(mod([loop]), ns)
+    got = glyphs.build_conditions(texts, poss, cols, W, H, font, position_margin=5)
+    for name, mine in (("control_image_list", got.control_image), ("control_position_list", got.control_position),
+                       ("control_mask_list", got.control_mask)):
+        for a, b in zip(ns[name], mine):
+            assert np.array_equal(np.array(a), np.array(b)), name
+    assert np.array_equal(np.array(ns["control_position_list"][0]), np.array(ns["control_mask_list"][0]))
+    assert np.array_equal(np.array(ns["control_glyph_all"]), np.array(got.control_glyph))
