@@ -51,3 +51,15 @@ def test_infer_shaped_driver_runs_end_to_end(tmp_path):
     assert img.size == (256, 256) and out.exists()
     lat = infer.main(["--config", "tiny", "--text", "RepText", "--steps", "2", "--output-type", "latent", "--no-glyph-init"])
     assert torch.isfinite(lat.float()).all() and tuple(lat.shape) == (1, 256, 64)
+
+
+@pytest.mark.gpu
+def test_infer_inpaint_shaped_driver_runs_end_to_end(tmp_path):
+    """``examples/infer_inpaint.py`` (the flow of RepText/infer_inpaint.py: synthetic photograph, grown position box, true CFG,
+    second ControlNet) - the command verified on a B200 at the end of round 2."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    import infer_inpaint
+    out = tmp_path / "result_inpaint.png"
+    img = infer_inpaint.main(["--config", "small", "--steps", "3", "--text", "RepText", "--text", "B200", "--out", str(out)])
+    assert img.size == (256, 256) and out.exists()
